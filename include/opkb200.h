@@ -1,0 +1,236 @@
+/*
+ * opkb200.h -- C ABI of libopkb200.so: the B200 (sm_100a) implementation of
+ * the per-iteration vector algebra of OptimPackNextGen.jl's `vmlmb`/`vmlmb!`
+ * and `spg`/`spg!`.
+ *
+ * This is the drop-in boundary.  A Julia host (`ccall`) or the Python twin in
+ * optimpacknextgen.jl_b200/ runs the reference's driver loop, line searches and
+ * convergence tests on the scalars these entry points return; every n-vector
+ * lives in device memory behind an opaque handle.  Citations `file:line` are
+ * relative to the reference tree (emmt/OptimPackNextGen.jl v0.4.3); the style
+ * (opaque handles, `double` scalars, out-pointers, int status) follows the
+ * reference's own C FFI, src/wrappers.jl:52-141, :560-628, :1238-1299.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative OPKB_E* code otherwise;
+ *    opkb_last_error() gives the text (thread-local).  NaN/Inf in the data are
+ *    not errors (IEEE propagation, src/bounds.jl:41,53).
+ *  - all scalars are `double` (`Float = Cdouble`, src/OptimPackNextGen.jl:42);
+ *    scalars that multiply a vector are converted to the element type first
+ *    (test/vectors-tests.jl:33,46,79).
+ *  - a bound is an array when its vector handle is non-NULL, else the scalar
+ *    value (+-Inf = no bound), as `lower=`/`upper=` of src/quasinewton.jl:228-229.
+ *  - reductions are deterministic (fixed grid, fixed tree, fixed rank order),
+ *    accumulate exact products in double whatever the element type, and are
+ *    GLOBAL over all ranks once opkb_comm_init() has been called: each rank
+ *    holds a contiguous shard and one small packed all-gather per call
+ *    combines the partials (no other data-path communication exists).
+ *  - calls are synchronous w.r.t. returned scalars and asynchronous (stream
+ *    ordered) otherwise; a context is not re-entrant.
+ *  - there is no CPU fallback: every entry point needs a CUDA device.
+ */
+#ifndef OPKB200_H
+#define OPKB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OPKB_VERSION 100
+
+/* element types: OPK_FLOAT / OPK_DOUBLE of src/wrappers.jl:226-229 */
+#define OPKB_FLOAT  0
+#define OPKB_DOUBLE 1
+
+/* status codes (cf. opk_status, src/wrappers.jl:110-141) */
+#define OPKB_SUCCESS          0
+#define OPKB_EINVAL          -1  /* invalid argument */
+#define OPKB_ECUDA           -2  /* CUDA runtime error */
+#define OPKB_ENCCL           -3  /* NCCL error / NCCL not available */
+#define OPKB_ENOMEM          -4
+#define OPKB_EBOUNDS         -5  /* "invalid bounds", src/bounds.jl:339, :450 */
+#define OPKB_EORIENT         -6  /* "invalid orientation", src/bounds.jl:223-225 */
+
+/* orientation of project_direction / step_limits: `+` or `-`
+ * (src/bounds.jl:218-229; OPK_ASCENT/OPK_DESCENT of src/wrappers.jl:1296-1299) */
+#define OPKB_FORWARD   1
+#define OPKB_BACKWARD -1
+
+/* optimisation method, src/quasinewton.jl:273 */
+#define OPKB_METHOD_LBFGS 0
+#define OPKB_METHOD_BLMVM 1
+#define OPKB_METHOD_VMLMB 2
+
+/* built-in objectives with a fused f + gradient kernel */
+#define OPKB_OBJ_USER       0  /* gradient written by the caller between trial_begin/trial_end */
+#define OPKB_OBJ_ROSENBROCK 1  /* test/rosenbrock.jl:16-29 */
+#define OPKB_OBJ_QUADRATIC  2  /* f = 1/2 sum a_i (x_i - c_i)^2 (BASELINE.json north_star) */
+
+typedef struct opkb_context_ opkb_context;
+typedef struct opkb_vector_  opkb_vector;
+typedef struct opkb_vmlmb_   opkb_vmlmb;
+typedef struct opkb_spg_     opkb_spg;
+
+const char* opkb_last_error(void);
+int         opkb_version(void);
+
+/* ---- Tier 0: lifecycle --------------------------------------------------- */
+/* One context per process and GPU (device < 0: current device). */
+int opkb_context_create(opkb_context** ctx, int device);
+int opkb_context_destroy(opkb_context* ctx);
+int opkb_context_synchronize(opkb_context* ctx);
+int opkb_context_device(const opkb_context* ctx);
+int opkb_context_sm_count(const opkb_context* ctx);
+/* number of kernels launched by this context so far (bench `gpu_launches`) */
+int64_t opkb_context_launch_count(const opkb_context* ctx);
+/* CUDA-event timer on the context's stream */
+int opkb_timer_start(opkb_context* ctx);
+int opkb_timer_stop(opkb_context* ctx, double* milliseconds);
+/* write `bytes` of scratch memory (> L2) to flush the L2 between timed runs */
+int opkb_flush_l2(opkb_context* ctx);
+
+/* Multi-GPU: rank 0 obtains a 128-byte id, the host broadcasts it (e.g.
+ * torch.distributed / MPI.jl), every rank calls opkb_comm_init. */
+int opkb_comm_unique_id(void* id128);
+int opkb_comm_init(opkb_context* ctx, const void* id128, int rank, int nranks);
+int opkb_comm_rank(const opkb_context* ctx);
+int opkb_comm_size(const opkb_context* ctx);
+
+/* vcreate (doc/algebra.md:27): a vector of `n` local elements (this rank's
+ * shard).  The library owns the memory; host arrays are only borrowed during
+ * upload/download. */
+int     opkb_vector_create(opkb_context* ctx, int eltype, int64_t n, opkb_vector** v);
+int     opkb_vector_destroy(opkb_vector* v);
+int64_t opkb_vector_length(const opkb_vector* v);
+int     opkb_vector_eltype(const opkb_vector* v);
+void*   opkb_vector_data(const opkb_vector* v); /* device pointer */
+int     opkb_vector_upload(opkb_vector* v, const void* host, int64_t offset, int64_t count);
+int     opkb_vector_download(const opkb_vector* v, void* host, int64_t offset, int64_t count);
+int     opkb_vector_fill(opkb_vector* v, double value);              /* vfill! */
+/* x[i] = lo + (hi - lo) * u(seed, first + i), u = splitmix64-based uniform in [0,1)
+ * (SURVEY 8(d) synthetic inputs; bit-identical to the host generator in the package);
+ * if `log_scale` != 0: x[i] = lo * (hi/lo)^u. */
+int     opkb_vector_fill_random(opkb_vector* v, uint64_t seed, int64_t first,
+                                double lo, double hi, int log_scale);
+
+/* ---- Tier 1: LazyAlgebra / SimpleBounds primitives, one-for-one ----------- */
+/* vdot(x,y), src/quasinewton.jl:45-53 */
+int opkb_vdot(opkb_context* ctx, const opkb_vector* x, const opkb_vector* y, double* result);
+/* vdot(sel,x,y) with sel = {i : w[i] != 0}, src/quasinewton.jl:55-65, src/bounds.jl:701-714 */
+int opkb_vdot_masked(opkb_context* ctx, const opkb_vector* w, const opkb_vector* x,
+                     const opkb_vector* y, double* result);
+/* vnorm2(x), src/quasinewton.jl:68-69; vnorminf(x), src/spg.jl:262 */
+int opkb_vnorm2(opkb_context* ctx, const opkb_vector* x, double* result);
+int opkb_vnorminf(opkb_context* ctx, const opkb_vector* x, double* result);
+/* vcopy!(dst,src); vscale!(x,alpha); vupdate!(y,alpha,x); vupdate!(y,sel,alpha,x);
+ * vcombine!(dst,alpha,x,beta,y); vproduct!(dst,x,y)  (doc/algebra.md:84-105) */
+int opkb_vcopy(opkb_context* ctx, opkb_vector* dst, const opkb_vector* src);
+int opkb_vscale(opkb_context* ctx, opkb_vector* x, double alpha);
+int opkb_vupdate(opkb_context* ctx, opkb_vector* y, double alpha, const opkb_vector* x);
+int opkb_vupdate_masked(opkb_context* ctx, opkb_vector* y, const opkb_vector* w,
+                        double alpha, const opkb_vector* x);
+int opkb_vcombine(opkb_context* ctx, opkb_vector* dst, double alpha, const opkb_vector* x,
+                  double beta, const opkb_vector* y);
+int opkb_vproduct(opkb_context* ctx, opkb_vector* dst, const opkb_vector* x, const opkb_vector* y);
+/* project_variables!(dst,src,lo,hi), src/bounds.jl:137-213 */
+int opkb_project_variables(opkb_context* ctx, opkb_vector* dst, const opkb_vector* src,
+                           const opkb_vector* lo, double lo_val,
+                           const opkb_vector* hi, double hi_val);
+/* project_direction!(dst,x,lo,hi,orient,d), src/bounds.jl:321-409 */
+int opkb_project_direction(opkb_context* ctx, opkb_vector* dst, const opkb_vector* x,
+                           const opkb_vector* lo, double lo_val,
+                           const opkb_vector* hi, double hi_val,
+                           int orient, const opkb_vector* d);
+/* step_limits(x,lo,hi,orient,d) -> (smin, smax), src/bounds.jl:431-624 */
+int opkb_step_limits(opkb_context* ctx, const opkb_vector* x,
+                     const opkb_vector* lo, double lo_val,
+                     const opkb_vector* hi, double hi_val,
+                     int orient, const opkb_vector* d, double* smin, double* smax);
+/* get_free_variables!(sel,gp), src/bounds.jl:701-714: no index list is built;
+ * the free set is the mask gp != 0.  count = |sel| (global); if `mask_bytes`
+ * is non-NULL it receives this rank's mask as one byte per element (host). */
+int opkb_free_variables(opkb_context* ctx, const opkb_vector* gp, int64_t* count,
+                        uint8_t* mask_bytes);
+/* built-in objectives as stand-alone `fg!(x, g) -> f` (test/rosenbrock.jl:16-29) */
+int opkb_rosenbrock_fg(opkb_context* ctx, const opkb_vector* x, opkb_vector* g, double* f);
+int opkb_quadratic_fg(opkb_context* ctx, const opkb_vector* a, const opkb_vector* c,
+                      const opkb_vector* x, opkb_vector* g, double* f);
+
+/* ---- Tier 2: fused phases of `_vmlmb!` (src/quasinewton.jl:381-601) ------- */
+/* The workspace owns x, g, p, d and the mem pairs S[k], Y[k] (src/quasinewton.jl:358-369).
+ * lo/hi handles must outlive the workspace. */
+int opkb_vmlmb_create(opkb_context* ctx, int eltype, int64_t n, int mem, int method,
+                      const opkb_vector* lo, double lo_val,
+                      const opkb_vector* hi, double hi_val, opkb_vmlmb** ws);
+int opkb_vmlmb_destroy(opkb_vmlmb* ws);
+int opkb_vmlmb_set_objective(opkb_vmlmb* ws, int kind, const opkb_vector* a, const opkb_vector* c);
+/* borrowed handles to the workspace vectors: which = 'x','g','p','d','S','Y' */
+opkb_vector* opkb_vmlmb_vector(opkb_vmlmb* ws, int which, int slot);
+
+/* P1 "trial" = :599, :386, :391 (built-in objective), :396, :399, :427, :432/:434,
+ * :446, :448.  If `initial` the point is x itself (first evaluation), else
+ * x = S[mark] - stp*d.  out[0..7] = { f, |p|^2 (|g|^2 for L-BFGS), g.s, g.d,
+ * |x|^2, |s|^2 (s = x - S[mark]), number of free variables, 0 }. */
+int opkb_vmlmb_trial(opkb_vmlmb* ws, int mark, double stp, int initial, double out[8]);
+/* same, for a user objective: begin computes x; the caller writes g (device)
+ * and passes f to end, which computes p and the reductions. */
+int opkb_vmlmb_trial_begin(opkb_vmlmb* ws, int mark, double stp, int initial);
+int opkb_vmlmb_trial_end(opkb_vmlmb* ws, int mark, double f, int initial, double out[8]);
+
+/* P3 "pair update + sweep" = :512-513 then every inner product apply_lbfgs!
+ * needs (:728, :737, :758-764, :771) in ONE pass: slot `mark` is turned in
+ * place into (S[mark]-x, Y[mark]-g) [Y[mark]-p for BLMVM], then with the m
+ * pairs ordered oldest..newest, slots[j] (j = 0 oldest), the Gram block
+ *   G[r][c], r in {s_0,y_0,s_1,y_1,...} (2m rows), c in {v0,y_0,...,y_{m-1}} (m+1 cols)
+ * restricted to the free set {i : p[i] != 0} for VMLMB (unrestricted otherwise,
+ * v0 = p for VMLMB, g otherwise) is returned row-major in G[2m*(m+1)].  Only
+ * the entries with age(col) >= age(row) and the v0 column are defined. */
+int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots, double* G);
+
+/* P4 "direction" = :525/:528 + the axpys of :729/:738/:761/:768/:772, :535,
+ * :537, :629, :562-563, :577.  d = v0; for j newest..oldest d -= alpha[j]*y_j;
+ * d *= gamma; for j oldest..newest d += c[j]*s_j (free set only for VMLMB; the
+ * rounding sequence of the reference's axpys is kept); d = project_direction(d);
+ * S[mark_next] = x; Y[mark_next] = g (p for BLMVM).  A pair with alpha[j] = c[j] = 0
+ * exactly is skipped (rho <= 0).  out[0..3] = { g.d, |d|^2, smin, smax }. */
+int opkb_vmlmb_direction(opkb_vmlmb* ws, int m, const int* slots, const double* alpha,
+                         const double* c, double gamma, int mark_next, double out[4]);
+/* P4 tail alone, for a direction the caller has already written in d (the
+ * sequential two-loop recursion made of Tier-1 calls): :535, :537, :629,
+ * :562-563, :577.  Same outputs. */
+int opkb_vmlmb_finish_direction(opkb_vmlmb* ws, int mark_next, double out[4]);
+/* P4' "steepest descent" = :554, :562-563, :577: d = p (g for L-BFGS). */
+int opkb_vmlmb_steepest(opkb_vmlmb* ws, int mark_next, double out[4]);
+/* P0 "revert to best" = :490-492: x = project(S[mark] - stp*d). */
+int opkb_vmlmb_revert(opkb_vmlmb* ws, int mark, double stp);
+
+/* ---- Tier 2: fused passes of `_spg!` with the box projection (src/spg.jl:245-380) */
+/* The workspace owns four x buffers and two g buffers: x0/g0 (:322-323) and
+ * xbest (:344) are kept by rotating buffers, never by copying; pg, d, s, y
+ * (:224-226) are recomputed in registers and never stored. */
+int opkb_spg_create(opkb_context* ctx, int eltype, int64_t n,
+                    const opkb_vector* lo, double lo_val,
+                    const opkb_vector* hi, double hi_val, opkb_spg** ws);
+int opkb_spg_destroy(opkb_spg* ws);
+int opkb_spg_set_objective(opkb_spg* ws, int kind, const opkb_vector* a, const opkb_vector* c);
+/* borrowed handles: which = 'x', '0' (x0), 'b' (xbest), 'g', 'G' (g0); they
+ * change at every step/backtrack/mark_best call */
+opkb_vector* opkb_spg_vector(opkb_spg* ws, int which);
+/* Every pass returns out[0..5] = { f, delta = g0.d, |pg|^2, |pg|_inf, s.y, s.s }
+ * with pg = (x - prj(x - eta*g))/eta (:259-262), d = prj(x0 - lambda*g0) - x0
+ * (:327-330), s = x - x0, y = g - g0 (:309-314), all at the NEW point x.
+ * start     :230-241  x = prj(x); f = fg(x, g); xbest = x   (delta, s.y, s.s = 0)
+ * step      :322-330 + :336  x0 = x, g0 = g; x = prj(x0 - lambda*g0); f = fg(x, g)
+ * backtrack :368 + :336      x = x0 + stp*d; f = fg(x, g) */
+int opkb_spg_start(opkb_spg* ws, double eta, double out[8]);
+int opkb_spg_step(opkb_spg* ws, double lambda, double eta, double out[8]);
+int opkb_spg_backtrack(opkb_spg* ws, double lambda, double stp, double eta, double out[8]);
+/* :342-345: xbest = x (no copy; the buffer is simply not reused) */
+int opkb_spg_mark_best(opkb_spg* ws);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPKB200_H */

@@ -1,0 +1,124 @@
+"""ctypes binding of libopkb200.so (the C ABI declared in include/opkb200.h).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is
+present, every entry point raises `OpkbError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libopkb200.so")
+
+FLOAT, DOUBLE = 0, 1
+METHOD_LBFGS, METHOD_BLMVM, METHOD_VMLMB = 0, 1, 2
+OBJ_USER, OBJ_ROSENBROCK, OBJ_QUADRATIC = 0, 1, 2
+FORWARD, BACKWARD = 1, -1
+MEM_MAX = 20
+
+i64 = C.c_int64
+f64 = C.c_double
+vp = C.c_void_p
+Pd = C.POINTER(f64)
+Pi = C.POINTER(C.c_int)
+
+
+class OpkbError(RuntimeError):
+    """Raised for any non-zero status of the library (text of opkb_last_error)."""
+
+    def __init__(self, code, message):
+        super().__init__(f"libopkb200 error {code}: {message}")
+        self.code = code
+
+
+# name -> (restype, argtypes); the list mirrors include/opkb200.h one for one
+_SIGNATURES = {
+    "opkb_last_error": (C.c_char_p, []),
+    "opkb_version": (C.c_int, []),
+    "opkb_context_create": (C.c_int, [C.POINTER(vp), C.c_int]),
+    "opkb_context_destroy": (C.c_int, [vp]),
+    "opkb_context_synchronize": (C.c_int, [vp]),
+    "opkb_context_device": (C.c_int, [vp]),
+    "opkb_context_sm_count": (C.c_int, [vp]),
+    "opkb_context_launch_count": (i64, [vp]),
+    "opkb_timer_start": (C.c_int, [vp]),
+    "opkb_timer_stop": (C.c_int, [vp, Pd]),
+    "opkb_flush_l2": (C.c_int, [vp]),
+    "opkb_comm_unique_id": (C.c_int, [vp]),
+    "opkb_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+    "opkb_comm_rank": (C.c_int, [vp]),
+    "opkb_comm_size": (C.c_int, [vp]),
+    "opkb_vector_create": (C.c_int, [vp, C.c_int, i64, C.POINTER(vp)]),
+    "opkb_vector_destroy": (C.c_int, [vp]),
+    "opkb_vector_length": (i64, [vp]),
+    "opkb_vector_eltype": (C.c_int, [vp]),
+    "opkb_vector_data": (vp, [vp]),
+    "opkb_vector_upload": (C.c_int, [vp, vp, i64, i64]),
+    "opkb_vector_download": (C.c_int, [vp, vp, i64, i64]),
+    "opkb_vector_fill": (C.c_int, [vp, f64]),
+    "opkb_vector_fill_random": (C.c_int, [vp, C.c_uint64, i64, f64, f64, C.c_int]),
+    "opkb_vdot": (C.c_int, [vp, vp, vp, Pd]),
+    "opkb_vdot_masked": (C.c_int, [vp, vp, vp, vp, Pd]),
+    "opkb_vnorm2": (C.c_int, [vp, vp, Pd]),
+    "opkb_vnorminf": (C.c_int, [vp, vp, Pd]),
+    "opkb_vcopy": (C.c_int, [vp, vp, vp]),
+    "opkb_vscale": (C.c_int, [vp, vp, f64]),
+    "opkb_vupdate": (C.c_int, [vp, vp, f64, vp]),
+    "opkb_vupdate_masked": (C.c_int, [vp, vp, vp, f64, vp]),
+    "opkb_vcombine": (C.c_int, [vp, vp, f64, vp, f64, vp]),
+    "opkb_vproduct": (C.c_int, [vp, vp, vp, vp]),
+    "opkb_project_variables": (C.c_int, [vp, vp, vp, vp, f64, vp, f64]),
+    "opkb_project_direction": (C.c_int, [vp, vp, vp, vp, f64, vp, f64, C.c_int, vp]),
+    "opkb_step_limits": (C.c_int, [vp, vp, vp, f64, vp, f64, C.c_int, vp, Pd, Pd]),
+    "opkb_free_variables": (C.c_int, [vp, vp, C.POINTER(i64), vp]),
+    "opkb_rosenbrock_fg": (C.c_int, [vp, vp, vp, Pd]),
+    "opkb_quadratic_fg": (C.c_int, [vp, vp, vp, vp, vp, Pd]),
+    "opkb_vmlmb_create": (C.c_int, [vp, C.c_int, i64, C.c_int, C.c_int, vp, f64, vp, f64,
+                                    C.POINTER(vp)]),
+    "opkb_vmlmb_destroy": (C.c_int, [vp]),
+    "opkb_vmlmb_set_objective": (C.c_int, [vp, C.c_int, vp, vp]),
+    "opkb_vmlmb_vector": (vp, [vp, C.c_int, C.c_int]),
+    "opkb_vmlmb_trial": (C.c_int, [vp, C.c_int, f64, C.c_int, Pd]),
+    "opkb_vmlmb_trial_begin": (C.c_int, [vp, C.c_int, f64, C.c_int]),
+    "opkb_vmlmb_trial_end": (C.c_int, [vp, C.c_int, f64, C.c_int, Pd]),
+    "opkb_vmlmb_gram": (C.c_int, [vp, C.c_int, C.c_int, Pi, Pd]),
+    "opkb_vmlmb_direction": (C.c_int, [vp, C.c_int, Pi, Pd, Pd, f64, C.c_int, Pd]),
+    "opkb_vmlmb_finish_direction": (C.c_int, [vp, C.c_int, Pd]),
+    "opkb_vmlmb_steepest": (C.c_int, [vp, C.c_int, Pd]),
+    "opkb_vmlmb_revert": (C.c_int, [vp, C.c_int, f64]),
+    "opkb_spg_create": (C.c_int, [vp, C.c_int, i64, vp, f64, vp, f64, C.POINTER(vp)]),
+    "opkb_spg_destroy": (C.c_int, [vp]),
+    "opkb_spg_set_objective": (C.c_int, [vp, C.c_int, vp, vp]),
+    "opkb_spg_vector": (vp, [vp, C.c_int]),
+    "opkb_spg_start": (C.c_int, [vp, f64, Pd]),
+    "opkb_spg_step": (C.c_int, [vp, f64, f64, Pd]),
+    "opkb_spg_backtrack": (C.c_int, [vp, f64, f64, f64, Pd]),
+    "opkb_spg_mark_best": (C.c_int, [vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_LIB = None
+
+
+def lib():
+    """Load libopkb200.so (once).  Fails loudly when the extension is absent."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO_PATH):
+            raise OpkbError(
+                -2, f"{SO_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (nvcc, sm_100a).  There is no CPU fallback.")
+        L = C.CDLL(SO_PATH, mode=C.RTLD_GLOBAL)
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the .so lacks a declared symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _LIB = L
+    return _LIB
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise OpkbError(rc, lib().opkb_last_error().decode(errors="replace"))

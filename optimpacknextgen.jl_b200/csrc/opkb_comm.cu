@@ -1,0 +1,99 @@
+// opkb_comm.cu -- the only communication of the hot path: one small packed
+// all-gather of per-rank reduction partials per phase, over NCCL
+// (NVLink 5 / NVSwitch).  NCCL is loaded with dlopen so that the single-GPU
+// library has no link-time dependency; inside a torch process this resolves to
+// the libnccl.so.2 torch has already loaded.
+#include <dlfcn.h>
+#include <string.h>
+
+#include "opkb_internal.cuh"
+
+// minimal NCCL ABI (nccl.h, stable since 2.x)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64 = 8 };
+
+static struct {
+    void* handle;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
+    const char* (*GetErrorString)(ncclResult_t);
+} g_nccl;
+
+static int load_nccl(void)
+{
+    if (g_nccl.handle) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so", NULL};
+    void* h = NULL;
+    for (int i = 0; names[i] && !h; ++i) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return opkb_set_error(OPKB_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = (ncclResult_t(*)(ncclUniqueId*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (ncclResult_t(*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (ncclResult_t(*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllGather = (ncclResult_t(*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))
+        dlsym(h, "ncclAllGather");
+    g_nccl.GetErrorString = (const char* (*)(ncclResult_t))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.GetErrorString)
+        return opkb_set_error(OPKB_ENCCL, "libnccl lacks a required symbol");
+    g_nccl.handle = h;
+    return 0;
+}
+
+static int nccl_fail(ncclResult_t r, const char* what)
+{
+    return opkb_set_error(OPKB_ENCCL, "NCCL error %d (%s) in %s", (int)r,
+                          g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?", what);
+}
+
+extern "C" int opkb_comm_unique_id(void* id128)
+{
+    if (!id128) return opkb_set_error(OPKB_EINVAL, "NULL id buffer");
+    int rc = load_nccl();
+    if (rc) return rc;
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != 0) return nccl_fail(r, "ncclGetUniqueId");
+    memcpy(id128, &id, sizeof(id));
+    return 0;
+}
+
+extern "C" int opkb_comm_init(opkb_context* ctx, const void* id128, int rank, int nranks)
+{
+    if (!ctx || !id128) return opkb_set_error(OPKB_EINVAL, "NULL argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return opkb_set_error(OPKB_EINVAL, "invalid rank");
+    if (nranks == 1) {
+        ctx->rank = 0;
+        ctx->nranks = 1;
+        return 0;
+    }
+    int rc = load_nccl();
+    if (rc) return rc;
+    OPKB_CUDA(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclComm_t comm = NULL;
+    ncclResult_t r = g_nccl.CommInitRank(&comm, nranks, id, rank);
+    if (r != 0) return nccl_fail(r, "ncclCommInitRank");
+    ctx->nccl_comm = comm;
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    OPKB_CUDA(cudaMalloc(&ctx->d_all, sizeof(double) * OPKB_NRED_MAX * (size_t)nranks));
+    cudaFreeHost(ctx->h_res);
+    OPKB_CUDA(cudaMallocHost(&ctx->h_res, sizeof(double) * OPKB_NRED_MAX * (size_t)nranks));
+    return 0;
+}
+
+extern "C" int opkb_comm_rank(const opkb_context* ctx) { return ctx ? ctx->rank : -1; }
+extern "C" int opkb_comm_size(const opkb_context* ctx) { return ctx ? ctx->nranks : -1; }
+
+int opkb_nccl_allgather_f64(opkb_context* ctx, const double* send, double* recv, int count)
+{
+    if (!ctx->nccl_comm) return opkb_set_error(OPKB_ENCCL, "communicator not initialised");
+    ncclResult_t r = g_nccl.AllGather(send, recv, (size_t)count, ncclFloat64,
+                                      (ncclComm_t)ctx->nccl_comm, ctx->stream);
+    if (r != 0) return nccl_fail(r, "ncclAllGather");
+    return 0;
+}

@@ -1,0 +1,862 @@
+// opkb_core.cu -- Tier 0 (lifecycle) and Tier 1 (LazyAlgebra / SimpleBounds
+// primitives, one kernel per reference call) of libopkb200.so.
+//
+// Reference semantics: doc/algebra.md:84-116, test/vectors-tests.jl:15-81,
+// src/bounds.jl, src/quasinewton.jl:45-69.  sm_100a only; no CPU fallback.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "opkb_internal.cuh"
+
+// ---------------------------------------------------------------------------
+// errors
+static thread_local char g_errbuf[512] = "";
+
+int opkb_set_error(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_errbuf, sizeof(g_errbuf), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int opkb_check_cuda(cudaError_t err, const char* what)
+{
+    if (err == cudaSuccess) return 0;
+    return opkb_set_error(OPKB_ECUDA, "CUDA error %d (%s) in %s", (int)err,
+                          cudaGetErrorString(err), what);
+}
+
+extern "C" const char* opkb_last_error(void) { return g_errbuf; }
+extern "C" int opkb_version(void) { return OPKB_VERSION; }
+
+// ---------------------------------------------------------------------------
+// context
+extern "C" int opkb_context_create(opkb_context** out, int device)
+{
+    if (!out) return opkb_set_error(OPKB_EINVAL, "NULL context pointer");
+    *out = NULL;
+    int ndev = 0;
+    cudaError_t err = cudaGetDeviceCount(&ndev);
+    if (err != cudaSuccess || ndev <= 0)
+        return opkb_set_error(OPKB_ECUDA,
+                              "no CUDA device available (%s): libopkb200 has no CPU fallback",
+                              cudaGetErrorString(err));
+    if (device < 0) OPKB_CUDA(cudaGetDevice(&device));
+    if (device >= ndev) return opkb_set_error(OPKB_EINVAL, "device %d out of range", device);
+    OPKB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    OPKB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return opkb_set_error(OPKB_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a",
+                              device, prop.major, prop.minor);
+    opkb_context* ctx = (opkb_context*)calloc(1, sizeof(opkb_context));
+    if (!ctx) return opkb_set_error(OPKB_ENOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->rank = 0;
+    ctx->nranks = 1;
+    OPKB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    OPKB_CUDA(cudaMalloc(&ctx->d_part, sizeof(double) * OPKB_MAX_GRID * (size_t)OPKB_NRED_MAX));
+    OPKB_CUDA(cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)));
+    OPKB_CUDA(cudaMemsetAsync(ctx->d_ticket, 0, sizeof(unsigned int), ctx->stream));
+    OPKB_CUDA(cudaMalloc(&ctx->d_res, sizeof(double) * OPKB_NRED_MAX));
+    OPKB_CUDA(cudaMallocHost(&ctx->h_res, sizeof(double) * OPKB_NRED_MAX));
+    OPKB_CUDA(cudaEventCreate(&ctx->ev0));
+    OPKB_CUDA(cudaEventCreate(&ctx->ev1));
+    OPKB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = ctx;
+    return 0;
+}
+
+extern "C" int opkb_context_destroy(opkb_context* ctx)
+{
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_part);
+    cudaFree(ctx->d_ticket);
+    cudaFree(ctx->d_res);
+    if (ctx->d_all) cudaFree(ctx->d_all);
+    if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    cudaFreeHost(ctx->h_res);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    free(ctx);
+    return 0;
+}
+
+extern "C" int opkb_context_synchronize(opkb_context* ctx)
+{
+    if (!ctx) return opkb_set_error(OPKB_EINVAL, "NULL context");
+    OPKB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int opkb_context_device(const opkb_context* ctx) { return ctx ? ctx->device : -1; }
+extern "C" int opkb_context_sm_count(const opkb_context* ctx) { return ctx ? ctx->sm_count : 0; }
+extern "C" int64_t opkb_context_launch_count(const opkb_context* ctx)
+{
+    return ctx ? ctx->launches : 0;
+}
+
+extern "C" int opkb_timer_start(opkb_context* ctx)
+{
+    if (!ctx) return opkb_set_error(OPKB_EINVAL, "NULL context");
+    OPKB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    return 0;
+}
+
+extern "C" int opkb_timer_stop(opkb_context* ctx, double* ms)
+{
+    if (!ctx || !ms) return opkb_set_error(OPKB_EINVAL, "NULL argument");
+    float t = 0;
+    OPKB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    OPKB_CUDA(cudaEventSynchronize(ctx->ev1));
+    OPKB_CUDA(cudaEventElapsedTime(&t, ctx->ev0, ctx->ev1));
+    *ms = (double)t;
+    return 0;
+}
+
+extern "C" int opkb_flush_l2(opkb_context* ctx)
+{
+    if (!ctx) return opkb_set_error(OPKB_EINVAL, "NULL context");
+    if (!ctx->flush_buf) {
+        ctx->flush_bytes = (size_t)256 << 20;  // 256 MiB > 126 MB of L2
+        OPKB_CUDA(cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
+    }
+    OPKB_CUDA(cudaMemsetAsync(ctx->flush_buf, 0, ctx->flush_bytes, ctx->stream));
+    return 0;
+}
+
+int opkb_grid_for(const opkb_context* ctx, int64_t nitems, int ctas_per_sm)
+{
+    // a multiple of the SM count (persistent grid-stride CTAs), shrunk for
+    // small inputs; the grid only depends on (n, device) => deterministic
+    int64_t want = (nitems + OPKB_BLOCK - 1) / OPKB_BLOCK;
+    int64_t full = (int64_t)ctx->sm_count * ctas_per_sm;
+    if (full > OPKB_MAX_GRID) full = OPKB_MAX_GRID;
+    if (want < 1) want = 1;
+    return (int)(want < full ? want : full);
+}
+
+int opkb_finish_reduction(opkb_context* ctx, int nred, const int* kinds, double* out)
+{
+    if (nred > OPKB_NRED_MAX) return opkb_set_error(OPKB_EINVAL, "too many reduced scalars");
+    if (ctx->nranks <= 1) {
+        OPKB_CUDA(cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(double) * nred,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+        OPKB_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int k = 0; k < nred; ++k) out[k] = ctx->h_res[k];
+        return 0;
+    }
+    // one packed all-gather per phase, then a fixed rank-order combination
+    int rc = opkb_nccl_allgather_f64(ctx, ctx->d_res, ctx->d_all, nred);
+    if (rc != 0) return rc;
+    OPKB_CUDA(cudaMemcpyAsync(ctx->h_res, ctx->d_all, sizeof(double) * nred * ctx->nranks,
+                              cudaMemcpyDeviceToHost, ctx->stream));
+    OPKB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < nred; ++k) {
+        int kind = kinds ? kinds[k] : OPKB_RSUM;
+        double a = ctx->h_res[k];
+        for (int r = 1; r < ctx->nranks; ++r) {
+            double b = ctx->h_res[(size_t)r * nred + k];
+            if (kind == OPKB_RSUM) a = a + b;
+            else if (kind == OPKB_RMAX) a = (b > a ? b : a);
+            else a = (b < a ? b : a);
+        }
+        out[k] = a;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// vectors
+static size_t elsize(int eltype) { return eltype == OPKB_DOUBLE ? 8 : 4; }
+
+extern "C" int opkb_vector_create(opkb_context* ctx, int eltype, int64_t n, opkb_vector** out)
+{
+    if (!ctx || !out) return opkb_set_error(OPKB_EINVAL, "NULL argument");
+    if (eltype != OPKB_FLOAT && eltype != OPKB_DOUBLE)
+        return opkb_set_error(OPKB_EINVAL, "invalid element type %d", eltype);
+    if (n < 0) return opkb_set_error(OPKB_EINVAL, "negative length");
+    opkb_vector* v = (opkb_vector*)calloc(1, sizeof(opkb_vector));
+    if (!v) return opkb_set_error(OPKB_ENOMEM, "out of host memory");
+    v->ctx = ctx;
+    v->eltype = eltype;
+    v->n = n;
+    v->owned = 1;
+    size_t bytes = (size_t)(n > 0 ? n : 1) * elsize(eltype);
+    bytes = (bytes + 255) & ~(size_t)255;
+    cudaError_t err = cudaMalloc(&v->data, bytes);
+    if (err != cudaSuccess) {
+        free(v);
+        return opkb_check_cuda(err, "cudaMalloc(vector)");
+    }
+    *out = v;
+    return 0;
+}
+
+extern "C" int opkb_vector_destroy(opkb_vector* v)
+{
+    if (!v) return 0;
+    if (v->owned && v->data) {
+        cudaStreamSynchronize(v->ctx->stream);
+        cudaFree(v->data);
+    }
+    free(v);
+    return 0;
+}
+
+extern "C" int64_t opkb_vector_length(const opkb_vector* v) { return v ? v->n : -1; }
+extern "C" int opkb_vector_eltype(const opkb_vector* v) { return v ? v->eltype : -1; }
+extern "C" void* opkb_vector_data(const opkb_vector* v) { return v ? v->data : NULL; }
+
+extern "C" int opkb_vector_upload(opkb_vector* v, const void* host, int64_t offset, int64_t count)
+{
+    if (!v || (!host && count > 0)) return opkb_set_error(OPKB_EINVAL, "NULL argument");
+    if (offset < 0 || count < 0 || offset + count > v->n)
+        return opkb_set_error(OPKB_EINVAL, "upload range out of bounds");
+    size_t es = elsize(v->eltype);
+    OPKB_CUDA(cudaMemcpyAsync((char*)v->data + offset * es, host, count * es,
+                              cudaMemcpyHostToDevice, v->ctx->stream));
+    OPKB_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    return 0;
+}
+
+extern "C" int opkb_vector_download(const opkb_vector* v, void* host, int64_t offset, int64_t count)
+{
+    if (!v || (!host && count > 0)) return opkb_set_error(OPKB_EINVAL, "NULL argument");
+    if (offset < 0 || count < 0 || offset + count > v->n)
+        return opkb_set_error(OPKB_EINVAL, "download range out of bounds");
+    size_t es = elsize(v->eltype);
+    OPKB_CUDA(cudaMemcpyAsync(host, (const char*)v->data + offset * es, count * es,
+                              cudaMemcpyDeviceToHost, v->ctx->stream));
+    OPKB_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// helpers for the argument checks of Tier 1
+static int same_space(const opkb_vector* a, const opkb_vector* b)
+{
+    return a && b && a->ctx == b->ctx && a->eltype == b->eltype && a->n == b->n;
+}
+
+#define CHECK_CTX(ctx) \
+    if (!(ctx)) return opkb_set_error(OPKB_EINVAL, "NULL context")
+#define CHECK_SAME(a, b) \
+    if (!same_space((a), (b))) return opkb_set_error(OPKB_EINVAL, "vectors of different spaces")
+
+#define LAUNCH(ctx, kernel, grid, ...)                                       \
+    do {                                                                     \
+        kernel<<<(grid), OPKB_BLOCK, 0, (ctx)->stream>>>(__VA_ARGS__);       \
+        (ctx)->launches += 1;                                                \
+        OPKB_CUDA(cudaGetLastError());                                       \
+    } while (0)
+
+static ReduceScratch scratch(opkb_context* ctx)
+{
+    ReduceScratch rs;
+    rs.part = ctx->d_part;
+    rs.ticket = ctx->d_ticket;
+    rs.res = ctx->d_res;
+    return rs;
+}
+
+template <typename T>
+static Bound<T> make_bound(const opkb_vector* arr, double val, bool lower)
+{
+    Bound<T> b;
+    b.arr = arr ? (const T*)arr->data : NULL;
+    b.val = (T)val;
+    b.has = arr ? 1 : (lower ? (b.val > -(T)INFINITY) : (b.val < (T)INFINITY));
+    return b;
+}
+
+static int check_bounds_args(const opkb_vector* x, const opkb_vector* lo, const opkb_vector* hi)
+{
+    if (lo && !same_space(x, lo)) return opkb_set_error(OPKB_EINVAL, "lower bound of a different space");
+    if (hi && !same_space(x, hi)) return opkb_set_error(OPKB_EINVAL, "upper bound of a different space");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// fill kernels
+template <typename T>
+__global__ void k_fill(T* x, int64_t n, T value)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = value;
+}
+
+extern "C" int opkb_vector_fill(opkb_vector* v, double value)
+{
+    if (!v) return opkb_set_error(OPKB_EINVAL, "NULL vector");
+    opkb_context* ctx = v->ctx;
+    int grid = opkb_grid_for(ctx, v->n, 8);
+    if (v->eltype == OPKB_DOUBLE)
+        LAUNCH(ctx, k_fill<double>, grid, (double*)v->data, v->n, value);
+    else
+        LAUNCH(ctx, k_fill<float>, grid, (float*)v->data, v->n, (float)value);
+    return 0;
+}
+
+// splitmix64 of (seed, index): the counter-based generator of SURVEY 8(d);
+// the package's host generator computes the same integers.
+__host__ __device__ __forceinline__ uint64_t opkb_splitmix64(uint64_t seed, uint64_t i)
+{
+    uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+template <typename T>
+__global__ void k_fill_random(T* x, int64_t n, uint64_t seed, int64_t first, double lo, double hi,
+                              int log_scale)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t z = opkb_splitmix64(seed, (uint64_t)(first + i));
+        double u = (double)(z >> 11) * (1.0 / 9007199254740992.0);  // [0,1), 53 bits
+        double r = log_scale ? lo * exp2(u * log2(hi / lo)) : lo + (hi - lo) * u;
+        x[i] = (T)r;
+    }
+}
+
+extern "C" int opkb_vector_fill_random(opkb_vector* v, uint64_t seed, int64_t first, double lo,
+                                       double hi, int log_scale)
+{
+    if (!v) return opkb_set_error(OPKB_EINVAL, "NULL vector");
+    opkb_context* ctx = v->ctx;
+    int grid = opkb_grid_for(ctx, v->n, 8);
+    if (v->eltype == OPKB_DOUBLE)
+        LAUNCH(ctx, k_fill_random<double>, grid, (double*)v->data, v->n, seed, first, lo, hi,
+               log_scale);
+    else
+        LAUNCH(ctx, k_fill_random<float>, grid, (float*)v->data, v->n, seed, first, lo, hi,
+               log_scale);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// reductions: vdot, vdot_masked, vnorm2, vnorminf
+// MODE 0: sum x*y; 1: sum x*y over w != 0; 2: max |x|
+template <typename T, int MODE>
+__global__ void __launch_bounds__(OPKB_BLOCK)
+k_reduce(const T* x, const T* y, const T* w, int64_t n, ReduceScratch rs)
+{
+    constexpr int VEC = VecOf<T>::N;
+    const int64_t nvec = n / VEC;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double acc[1];
+    acc[0] = 0.0;
+    // two packs per trip: 2-4 independent 16-byte loads in flight per stream
+    for (int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += 2 * stride) {
+        const int64_t iv2 = iv + stride;
+        const bool two = iv2 < nvec;
+        Pack<T> a0 = ld_pack<T>(x, iv), a1, b0, b1, w0, w1;
+        if (two) a1 = ld_pack<T>(x, iv2);
+        if (MODE != 2) {
+            b0 = ld_pack<T>(y, iv);
+            if (two) b1 = ld_pack<T>(y, iv2);
+        }
+        if (MODE == 1) {
+            w0 = ld_pack<T>(w, iv);
+            if (two) w1 = ld_pack<T>(w, iv2);
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            if (MODE == 0) acc[0] = dacc(a0.v[e], b0.v[e], acc[0]);
+            if (MODE == 1 && w0.v[e] != T(0)) acc[0] = dacc(a0.v[e], b0.v[e], acc[0]);
+            if (MODE == 2) { double t = fabs((double)a0.v[e]); acc[0] = (t > acc[0] ? t : acc[0]); }
+        }
+        if (two) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                if (MODE == 0) acc[0] = dacc(a1.v[e], b1.v[e], acc[0]);
+                if (MODE == 1 && w1.v[e] != T(0)) acc[0] = dacc(a1.v[e], b1.v[e], acc[0]);
+                if (MODE == 2) { double t = fabs((double)a1.v[e]); acc[0] = (t > acc[0] ? t : acc[0]); }
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int64_t i = nvec * VEC; i < n; ++i) {
+            if (MODE == 0) acc[0] = dacc(x[i], y[i], acc[0]);
+            if (MODE == 1 && w[i] != T(0)) acc[0] = dacc(x[i], y[i], acc[0]);
+            if (MODE == 2) { double t = fabs((double)x[i]); acc[0] = (t > acc[0] ? t : acc[0]); }
+        }
+    }
+    if (MODE == 2)
+        block_reduce_publish<1, 1u, 0u>(acc, rs);
+    else
+        block_reduce_publish<1, 0u, 0u>(acc, rs);
+}
+
+template <int MODE>
+static int reduce_dispatch(opkb_context* ctx, const opkb_vector* x, const opkb_vector* y,
+                           const opkb_vector* w, double* result)
+{
+    int grid = opkb_grid_for(ctx, x->n / (x->eltype == OPKB_DOUBLE ? 2 : 4), 4);
+    if (x->eltype == OPKB_DOUBLE)
+        LAUNCH(ctx, (k_reduce<double, MODE>), grid, (const double*)x->data,
+               y ? (const double*)y->data : NULL, w ? (const double*)w->data : NULL, x->n,
+               scratch(ctx));
+    else
+        LAUNCH(ctx, (k_reduce<float, MODE>), grid, (const float*)x->data,
+               y ? (const float*)y->data : NULL, w ? (const float*)w->data : NULL, x->n,
+               scratch(ctx));
+    int kind = (MODE == 2 ? OPKB_RMAX : OPKB_RSUM);
+    return opkb_finish_reduction(ctx, 1, &kind, result);
+}
+
+extern "C" int opkb_vdot(opkb_context* ctx, const opkb_vector* x, const opkb_vector* y, double* result)
+{
+    CHECK_CTX(ctx);
+    CHECK_SAME(x, y);
+    if (!result) return opkb_set_error(OPKB_EINVAL, "NULL result");
+    return reduce_dispatch<0>(ctx, x, y, NULL, result);
+}
+
+extern "C" int opkb_vdot_masked(opkb_context* ctx, const opkb_vector* w, const opkb_vector* x,
+                                const opkb_vector* y, double* result)
+{
+    CHECK_CTX(ctx);
+    CHECK_SAME(x, y);
+    CHECK_SAME(x, w);
+    if (!result) return opkb_set_error(OPKB_EINVAL, "NULL result");
+    return reduce_dispatch<1>(ctx, x, y, w, result);
+}
+
+extern "C" int opkb_vnorm2(opkb_context* ctx, const opkb_vector* x, double* result)
+{
+    CHECK_CTX(ctx);
+    if (!x || !result) return opkb_set_error(OPKB_EINVAL, "NULL argument");
+    double s = 0;
+    int rc = reduce_dispatch<0>(ctx, x, x, NULL, &s);
+    if (rc == 0) *result = sqrt(s);
+    return rc;
+}
+
+extern "C" int opkb_vnorminf(opkb_context* ctx, const opkb_vector* x, double* result)
+{
+    CHECK_CTX(ctx);
+    if (!x || !result) return opkb_set_error(OPKB_EINVAL, "NULL argument");
+    return reduce_dispatch<2>(ctx, x, NULL, NULL, result);
+}
+
+// ---------------------------------------------------------------------------
+// element-wise primitives.  OP: 0 copy, 1 scale, 2 update (y += a x),
+// 3 masked update, 4 combine (dst = a x + b y), 5 product.
+// CASE selects the special multipliers of test/vectors-tests.jl:26-81.
+struct EwArgs {
+    void* dst;
+    const void* x;
+    const void* y;
+    const void* w;
+    double alpha, beta;
+    int64_t n;
+    int acase, bcase;  // 0: zero, 1: one, 2: minus one, 3: general
+};
+
+template <typename T, int OP>
+__device__ __forceinline__ T ew_apply(T dst, T x, T y, T w, T a, T b, int acase, int bcase)
+{
+    if (OP == 0) return x;
+    if (OP == 1) {  // vscale!(x, alpha): dst aliases x
+        if (acase == 0) return T(0);
+        if (acase == 2) return -x;
+        return a * x;
+    }
+    if (OP == 2 || OP == 3) {  // y += alpha*x (dst aliases y, passed as `dst`)
+        if (OP == 3 && !(w != T(0))) return dst;
+        if (acase == 1) return dst + x;
+        if (acase == 2) return dst - x;
+        return dst + a * x;
+    }
+    if (OP == 4) {
+        if (acase == 0 && bcase == 0) return T(0);
+        if (acase == 0) return b * y;
+        if (bcase == 0) return a * x;
+        return a * x + b * y;  // +-1 multipliers are exact: same bits as x +- y
+    }
+    return x * y;  // OP == 5
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(OPKB_BLOCK) k_elementwise(EwArgs A)
+{
+    constexpr int VEC = VecOf<T>::N;
+    T* dst = (T*)A.dst;
+    const T* x = (const T*)A.x;
+    const T* y = (const T*)A.y;
+    const T* w = (const T*)A.w;
+    const T a = (T)A.alpha, b = (T)A.beta;
+    const int64_t nvec = A.n / VEC;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const bool need_dst = (OP == 2 || OP == 3);
+    const bool need_x = (OP != 4) || A.acase != 0;
+    const bool need_y = (OP == 5) || (OP == 4 && A.bcase != 0);
+    for (int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += stride) {
+        Pack<T> pd = splat_pack<T>(T(0)), px = pd, py = pd, pw = pd, out;
+        if (need_dst) pd = ld_pack<T>(dst, iv);
+        if (need_x) px = ld_pack<T>(x, iv);
+        if (need_y) py = ld_pack<T>(y, iv);
+        if (OP == 3) pw = ld_pack<T>(w, iv);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+            out.v[e] = ew_apply<T, OP>(pd.v[e], px.v[e], py.v[e], pw.v[e], a, b, A.acase, A.bcase);
+        st_pack<T>(dst, iv, out);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int64_t i = nvec * VEC; i < A.n; ++i) {
+            T vd = need_dst ? dst[i] : T(0), vx = need_x ? x[i] : T(0), vy = need_y ? y[i] : T(0);
+            T vw = (OP == 3) ? w[i] : T(0);
+            dst[i] = ew_apply<T, OP>(vd, vx, vy, vw, a, b, A.acase, A.bcase);
+        }
+    }
+}
+
+static int mult_case(double a) { return a == 0 ? 0 : (a == 1 ? 1 : (a == -1 ? 2 : 3)); }
+
+template <int OP>
+static int ew_dispatch(opkb_context* ctx, opkb_vector* dst, const opkb_vector* x, const opkb_vector* y,
+                       const opkb_vector* w, double alpha, double beta)
+{
+    EwArgs A;
+    A.dst = dst->data;
+    A.x = x ? x->data : NULL;
+    A.y = y ? y->data : NULL;
+    A.w = w ? w->data : NULL;
+    A.alpha = alpha;
+    A.beta = beta;
+    A.n = dst->n;
+    A.acase = mult_case(alpha);
+    A.bcase = mult_case(beta);
+    int grid = opkb_grid_for(ctx, dst->n / (dst->eltype == OPKB_DOUBLE ? 2 : 4), 8);
+    if (dst->eltype == OPKB_DOUBLE)
+        LAUNCH(ctx, (k_elementwise<double, OP>), grid, A);
+    else
+        LAUNCH(ctx, (k_elementwise<float, OP>), grid, A);
+    return 0;
+}
+
+extern "C" int opkb_vcopy(opkb_context* ctx, opkb_vector* dst, const opkb_vector* src)
+{
+    CHECK_CTX(ctx);
+    CHECK_SAME(dst, src);
+    if (dst->data == src->data) return 0;
+    return ew_dispatch<0>(ctx, dst, src, NULL, NULL, 1, 0);
+}
+
+extern "C" int opkb_vscale(opkb_context* ctx, opkb_vector* x, double alpha)
+{
+    CHECK_CTX(ctx);
+    if (!x) return opkb_set_error(OPKB_EINVAL, "NULL vector");
+    if (alpha == 1) return 0;
+    return ew_dispatch<1>(ctx, x, x, NULL, NULL, alpha, 0);
+}
+
+extern "C" int opkb_vupdate(opkb_context* ctx, opkb_vector* y, double alpha, const opkb_vector* x)
+{
+    CHECK_CTX(ctx);
+    CHECK_SAME(y, x);
+    if (alpha == 0) return 0;
+    return ew_dispatch<2>(ctx, y, x, NULL, NULL, alpha, 0);
+}
+
+extern "C" int opkb_vupdate_masked(opkb_context* ctx, opkb_vector* y, const opkb_vector* w,
+                                   double alpha, const opkb_vector* x)
+{
+    CHECK_CTX(ctx);
+    CHECK_SAME(y, x);
+    CHECK_SAME(y, w);
+    if (alpha == 0) return 0;
+    // the reference's vupdate!(y, sel, alpha, x) has no +-1 special case that
+    // would change bits: y + 1*x == y + x
+    return ew_dispatch<3>(ctx, y, x, NULL, w, alpha, 0);
+}
+
+extern "C" int opkb_vcombine(opkb_context* ctx, opkb_vector* dst, double alpha, const opkb_vector* x,
+                             double beta, const opkb_vector* y)
+{
+    CHECK_CTX(ctx);
+    CHECK_SAME(dst, x);
+    CHECK_SAME(dst, y);
+    return ew_dispatch<4>(ctx, dst, x, y, NULL, alpha, beta);
+}
+
+extern "C" int opkb_vproduct(opkb_context* ctx, opkb_vector* dst, const opkb_vector* x,
+                             const opkb_vector* y)
+{
+    CHECK_CTX(ctx);
+    CHECK_SAME(dst, x);
+    CHECK_SAME(dst, y);
+    return ew_dispatch<5>(ctx, dst, x, y, NULL, 1, 1);
+}
+
+// ---------------------------------------------------------------------------
+// bounds primitives
+template <typename T>
+__global__ void __launch_bounds__(OPKB_BLOCK)
+k_project_variables(T* dst, const T* src, Bound<T> lo, Bound<T> hi, int64_t n)
+{
+    constexpr int VEC = VecOf<T>::N;
+    const int64_t nvec = n / VEC;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += stride) {
+        Pack<T> s = ld_pack<T>(src, iv), l = lo.pack(iv), h = hi.pack(iv), o;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) o.v[e] = fastclamp(s.v[e], l.v[e], h.v[e]);
+        st_pack<T>(dst, iv, o);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t i = nvec * VEC; i < n; ++i) dst[i] = fastclamp(src[i], lo.at(i), hi.at(i));
+}
+
+extern "C" int opkb_project_variables(opkb_context* ctx, opkb_vector* dst, const opkb_vector* src,
+                                      const opkb_vector* lo, double lo_val, const opkb_vector* hi,
+                                      double hi_val)
+{
+    CHECK_CTX(ctx);
+    CHECK_SAME(dst, src);
+    int rc = check_bounds_args(dst, lo, hi);
+    if (rc) return rc;
+    int grid = opkb_grid_for(ctx, dst->n / (dst->eltype == OPKB_DOUBLE ? 2 : 4), 8);
+    if (dst->eltype == OPKB_DOUBLE)
+        LAUNCH(ctx, k_project_variables<double>, grid, (double*)dst->data, (const double*)src->data,
+               make_bound<double>(lo, lo_val, true), make_bound<double>(hi, hi_val, false), dst->n);
+    else
+        LAUNCH(ctx, k_project_variables<float>, grid, (float*)dst->data, (const float*)src->data,
+               make_bound<float>(lo, lo_val, true), make_bound<float>(hi, hi_val, false), dst->n);
+    return 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(OPKB_BLOCK)
+k_project_direction(T* dst, const T* x, Bound<T> lo, Bound<T> hi, int orient, const T* d, int64_t n)
+{
+    constexpr int VEC = VecOf<T>::N;
+    const int64_t nvec = n / VEC;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += stride) {
+        Pack<T> px = ld_pack<T>(x, iv), pd = ld_pack<T>(d, iv), l = lo.pack(iv), h = hi.pack(iv), o;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+            o.v[e] = projdir(px.v[e], l.v[e], h.v[e], lo.has, hi.has, orient, pd.v[e]);
+        st_pack<T>(dst, iv, o);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t i = nvec * VEC; i < n; ++i)
+            dst[i] = projdir(x[i], lo.at(i), hi.at(i), lo.has, hi.has, orient, d[i]);
+}
+
+static int scalar_bounds_valid(const opkb_vector* lo, double lo_val, const opkb_vector* hi,
+                               double hi_val, int eltype)
+{
+    // `lo <= hi || argument_error("invalid bounds")` (also catches NaN):
+    // only the scalar/scalar methods check, src/bounds.jl:339, :450
+    if (lo || hi) return 1;
+    if (eltype == OPKB_DOUBLE) return lo_val <= hi_val;
+    return (float)lo_val <= (float)hi_val;
+}
+
+extern "C" int opkb_project_direction(opkb_context* ctx, opkb_vector* dst, const opkb_vector* x,
+                                      const opkb_vector* lo, double lo_val, const opkb_vector* hi,
+                                      double hi_val, int orient, const opkb_vector* d)
+{
+    CHECK_CTX(ctx);
+    CHECK_SAME(dst, x);
+    CHECK_SAME(dst, d);
+    int rc = check_bounds_args(dst, lo, hi);
+    if (rc) return rc;
+    if (orient == 0) return opkb_set_error(OPKB_EORIENT, "invalid orientation");
+    if (!scalar_bounds_valid(lo, lo_val, hi, hi_val, dst->eltype))
+        return opkb_set_error(OPKB_EBOUNDS, "invalid bounds");
+    int grid = opkb_grid_for(ctx, dst->n / (dst->eltype == OPKB_DOUBLE ? 2 : 4), 8);
+    if (dst->eltype == OPKB_DOUBLE)
+        LAUNCH(ctx, k_project_direction<double>, grid, (double*)dst->data, (const double*)x->data,
+               make_bound<double>(lo, lo_val, true), make_bound<double>(hi, hi_val, false), orient,
+               (const double*)d->data, dst->n);
+    else
+        LAUNCH(ctx, k_project_direction<float>, grid, (float*)dst->data, (const float*)x->data,
+               make_bound<float>(lo, lo_val, true), make_bound<float>(hi, hi_val, false), orient,
+               (const float*)d->data, dst->n);
+    return 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(OPKB_BLOCK)
+k_step_limits(const T* x, Bound<T> lo, Bound<T> hi, T s, const T* d, int64_t n, ReduceScratch rs)
+{
+    constexpr int VEC = VecOf<T>::N;
+    const int64_t nvec = n / VEC;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    T smin = T(INFINITY), smax = T(0);
+    for (int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += stride) {
+        Pack<T> px = ld_pack<T>(x, iv), pd = ld_pack<T>(d, iv), l = lo.pack(iv), h = hi.pack(iv);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+            step_limit_update(px.v[e], l.v[e], h.v[e], lo.has, hi.has, s * pd.v[e], smin, smax);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t i = nvec * VEC; i < n; ++i)
+            step_limit_update(x[i], lo.at(i), hi.at(i), lo.has, hi.has, s * d[i], smin, smax);
+    double acc[2] = {(double)smin, (double)smax};
+    block_reduce_publish<2, 2u, 1u>(acc, rs);  // slot 0: min, slot 1: max
+}
+
+extern "C" int opkb_step_limits(opkb_context* ctx, const opkb_vector* x, const opkb_vector* lo,
+                                double lo_val, const opkb_vector* hi, double hi_val, int orient,
+                                const opkb_vector* d, double* smin, double* smax)
+{
+    CHECK_CTX(ctx);
+    CHECK_SAME(x, d);
+    int rc = check_bounds_args(x, lo, hi);
+    if (rc) return rc;
+    if (!smin || !smax) return opkb_set_error(OPKB_EINVAL, "NULL result");
+    if (orient == 0) return opkb_set_error(OPKB_EORIENT, "invalid orientation");
+    if (!scalar_bounds_valid(lo, lo_val, hi, hi_val, x->eltype))
+        return opkb_set_error(OPKB_EBOUNDS, "invalid bounds");
+    bool has_lo = lo || (x->eltype == OPKB_DOUBLE ? lo_val > -INFINITY : (float)lo_val > -INFINITY);
+    bool has_hi = hi || (x->eltype == OPKB_DOUBLE ? hi_val < INFINITY : (float)hi_val < INFINITY);
+    if (!has_lo && !has_hi) {  // src/bounds.jl:503-505
+        *smin = INFINITY;
+        *smax = INFINITY;
+        return 0;
+    }
+    int grid = opkb_grid_for(ctx, x->n / (x->eltype == OPKB_DOUBLE ? 2 : 4), 4);
+    if (x->eltype == OPKB_DOUBLE)
+        LAUNCH(ctx, k_step_limits<double>, grid, (const double*)x->data,
+               make_bound<double>(lo, lo_val, true), make_bound<double>(hi, hi_val, false),
+               (double)(orient > 0 ? 1 : -1), (const double*)d->data, x->n, scratch(ctx));
+    else
+        LAUNCH(ctx, k_step_limits<float>, grid, (const float*)x->data,
+               make_bound<float>(lo, lo_val, true), make_bound<float>(hi, hi_val, false),
+               (float)(orient > 0 ? 1 : -1), (const float*)d->data, x->n, scratch(ctx));
+    int kinds[2] = {OPKB_RMIN, OPKB_RMAX};
+    double out[2];
+    rc = opkb_finish_reduction(ctx, 2, kinds, out);
+    if (rc == 0) {
+        *smin = out[0];
+        *smax = out[1];
+    }
+    return rc;
+}
+
+// free-variable mask: count (and optionally the byte mask) of gp != 0
+template <typename T>
+__global__ void __launch_bounds__(OPKB_BLOCK)
+k_free_variables(const T* gp, int64_t n, uint8_t* mask, ReduceScratch rs)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double acc[1] = {0.0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        bool f = (gp[i] != T(0));
+        if (mask) mask[i] = f ? 1 : 0;
+        acc[0] += f ? 1.0 : 0.0;
+    }
+    block_reduce_publish<1, 0u, 0u>(acc, rs);
+}
+
+extern "C" int opkb_free_variables(opkb_context* ctx, const opkb_vector* gp, int64_t* count,
+                                   uint8_t* mask_bytes)
+{
+    CHECK_CTX(ctx);
+    if (!gp || !count) return opkb_set_error(OPKB_EINVAL, "NULL argument");
+    uint8_t* dmask = NULL;
+    if (mask_bytes && gp->n > 0) OPKB_CUDA(cudaMalloc(&dmask, (size_t)gp->n));
+    int grid = opkb_grid_for(ctx, gp->n, 4);
+    if (gp->eltype == OPKB_DOUBLE)
+        LAUNCH(ctx, k_free_variables<double>, grid, (const double*)gp->data, gp->n, dmask, scratch(ctx));
+    else
+        LAUNCH(ctx, k_free_variables<float>, grid, (const float*)gp->data, gp->n, dmask, scratch(ctx));
+    double c = 0;
+    int rc = opkb_finish_reduction(ctx, 1, NULL, &c);
+    if (rc == 0) {
+        *count = (int64_t)c;
+        if (dmask)
+            rc = opkb_check_cuda(cudaMemcpy(mask_bytes, dmask, (size_t)gp->n, cudaMemcpyDeviceToHost),
+                                 "cudaMemcpy(mask)");
+    }
+    if (dmask) cudaFree(dmask);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// stand-alone objectives: fg!(x, g) -> f
+template <typename T, int OBJ>
+__global__ void __launch_bounds__(OPKB_BLOCK)
+k_objective(const T* x, T* g, const T* qa, const T* qc, int64_t n, ReduceScratch rs)
+{
+    constexpr int VEC = VecOf<T>::N;
+    const int64_t nvec = n / VEC;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double acc[2] = {0.0, 0.0};
+    for (int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += stride) {
+        Pack<T> px = ld_pack<T>(x, iv), pg;
+        if (OBJ == OPKB_OBJ_ROSENBROCK) {
+#pragma unroll
+            for (int e = 0; e < VEC; e += 2)
+                rosenbrock_pair(px.v[e], px.v[e + 1], pg.v[e], pg.v[e + 1], acc[0], acc[1]);
+        } else {
+            Pack<T> pa = ld_pack<T>(qa, iv), pc = ld_pack<T>(qc, iv);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) quadratic_elem(px.v[e], pa.v[e], pc.v[e], pg.v[e], acc[0]);
+        }
+        st_pack<T>(g, iv, pg);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (OBJ == OPKB_OBJ_ROSENBROCK) {
+            for (int64_t i = nvec * VEC; i + 1 < n; i += 2)
+                rosenbrock_pair(x[i], x[i + 1], g[i], g[i + 1], acc[0], acc[1]);
+        } else {
+            for (int64_t i = nvec * VEC; i < n; ++i) quadratic_elem(x[i], qa[i], qc[i], g[i], acc[0]);
+        }
+    }
+    block_reduce_publish<2, 0u, 0u>(acc, rs);
+}
+
+extern "C" int opkb_rosenbrock_fg(opkb_context* ctx, const opkb_vector* x, opkb_vector* g, double* f)
+{
+    CHECK_CTX(ctx);
+    CHECK_SAME(x, g);
+    if (!f) return opkb_set_error(OPKB_EINVAL, "NULL result");
+    if (x->n % 2) return opkb_set_error(OPKB_EINVAL, "Rosenbrock needs an even number of variables");
+    int grid = opkb_grid_for(ctx, x->n / (x->eltype == OPKB_DOUBLE ? 2 : 4), 4);
+    if (x->eltype == OPKB_DOUBLE)
+        LAUNCH(ctx, (k_objective<double, OPKB_OBJ_ROSENBROCK>), grid, (const double*)x->data,
+               (double*)g->data, (const double*)NULL, (const double*)NULL, x->n, scratch(ctx));
+    else
+        LAUNCH(ctx, (k_objective<float, OPKB_OBJ_ROSENBROCK>), grid, (const float*)x->data,
+               (float*)g->data, (const float*)NULL, (const float*)NULL, x->n, scratch(ctx));
+    double out[2];
+    int rc = opkb_finish_reduction(ctx, 2, NULL, out);
+    if (rc == 0) *f = out[0] + out[1];
+    return rc;
+}
+
+extern "C" int opkb_quadratic_fg(opkb_context* ctx, const opkb_vector* a, const opkb_vector* c,
+                                 const opkb_vector* x, opkb_vector* g, double* f)
+{
+    CHECK_CTX(ctx);
+    CHECK_SAME(x, g);
+    CHECK_SAME(x, a);
+    CHECK_SAME(x, c);
+    if (!f) return opkb_set_error(OPKB_EINVAL, "NULL result");
+    int grid = opkb_grid_for(ctx, x->n / (x->eltype == OPKB_DOUBLE ? 2 : 4), 4);
+    if (x->eltype == OPKB_DOUBLE)
+        LAUNCH(ctx, (k_objective<double, OPKB_OBJ_QUADRATIC>), grid, (const double*)x->data,
+               (double*)g->data, (const double*)a->data, (const double*)c->data, x->n, scratch(ctx));
+    else
+        LAUNCH(ctx, (k_objective<float, OPKB_OBJ_QUADRATIC>), grid, (const float*)x->data,
+               (float*)g->data, (const float*)a->data, (const float*)c->data, x->n, scratch(ctx));
+    double out[2];
+    int rc = opkb_finish_reduction(ctx, 2, NULL, out);
+    if (rc == 0) *f = 0.5 * out[0];
+    return rc;
+}

@@ -1,0 +1,292 @@
+// opkb_internal.cuh -- shared internals of libopkb200.so (sm_100a only).
+//
+// Built with -fmad=false: `a*x + b*y` written in plain C++ is two roundings,
+// as in the reference's Julia loops (no contraction); the reductions use
+// explicit fma() on exact double products instead.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "opkb200.h"
+
+#define OPKB_BLOCK 256          // threads per CTA of the streaming kernels
+#define OPKB_MAX_GRID 2048      // upper bound of any grid (partials buffer)
+#define OPKB_NRED_MAX 1024      // scalars one launch may reduce
+#define OPKB_MEM_MAX 20         // pairs the fused Gram path supports
+
+// reduction kinds of one scalar slot
+enum { OPKB_RSUM = 0, OPKB_RMAX = 1, OPKB_RMIN = 2 };
+
+struct opkb_context_ {
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+    int rank, nranks;
+    void* nccl_comm;
+    double* d_part;          // [OPKB_MAX_GRID * OPKB_NRED_MAX] per-CTA partials
+    unsigned int* d_ticket;  // last-CTA-done ticket
+    double* d_res;           // [OPKB_NRED_MAX] this rank's reduced scalars
+    double* d_all;           // [nranks * OPKB_NRED_MAX] after the all-gather
+    double* h_res;           // pinned mirror of d_res / d_all
+    cudaEvent_t ev0, ev1;
+    int64_t launches;
+    void* flush_buf;
+    size_t flush_bytes;
+};
+
+struct opkb_vector_ {
+    opkb_context* ctx;
+    int eltype;
+    int64_t n;
+    void* data;
+    int owned;
+};
+
+// error plumbing (opkb_core.cu)
+int opkb_set_error(int code, const char* fmt, ...);
+int opkb_check_cuda(cudaError_t err, const char* what);
+#define OPKB_CUDA(call)                                            \
+    do {                                                           \
+        int rc_ = opkb_check_cuda((call), #call);                  \
+        if (rc_ != 0) return rc_;                                  \
+    } while (0)
+
+// Collect `nred` reduced scalars of this rank (already in ctx->d_res), combine
+// them over the ranks in fixed rank order and return them in out[].  `kinds`
+// gives OPKB_RSUM/RMAX/RMIN per slot (NULL = all sums).
+int opkb_finish_reduction(opkb_context* ctx, int nred, const int* kinds, double* out);
+int opkb_grid_for(const opkb_context* ctx, int64_t nwork_items, int ctas_per_sm);
+
+// NCCL (opkb_comm.cpp, loaded with dlopen)
+int opkb_nccl_allgather_f64(opkb_context* ctx, const double* send, double* recv, int count);
+
+// ---------------------------------------------------------------------------
+// 16-byte packs: 2 doubles or 4 floats per thread and request.
+template <typename T> struct VecOf;
+template <> struct VecOf<double> { static constexpr int N = 2; typedef double2 type; };
+template <> struct VecOf<float>  { static constexpr int N = 4; typedef float4 type; };
+
+template <typename T> struct Pack { T v[VecOf<T>::N]; };
+
+template <typename T>
+__device__ __forceinline__ Pack<T> ld_pack(const T* p, int64_t iv)
+{
+    typedef typename VecOf<T>::type V;
+    union { V q; Pack<T> pk; } u;
+    u.q = reinterpret_cast<const V*>(p)[iv];
+    return u.pk;
+}
+
+template <typename T>
+__device__ __forceinline__ void st_pack(T* p, int64_t iv, const Pack<T>& pk)
+{
+    typedef typename VecOf<T>::type V;
+    union { V q; Pack<T> pk; } u;
+    u.pk = pk;
+    reinterpret_cast<V*>(p)[iv] = u.q;
+}
+
+template <typename T>
+__device__ __forceinline__ Pack<T> splat_pack(T x)
+{
+    Pack<T> pk;
+#pragma unroll
+    for (int e = 0; e < VecOf<T>::N; ++e) pk.v[e] = x;
+    return pk;
+}
+
+// A bound: an array (arr != NULL) or a scalar; `has` tells whether it counts
+// (arrays always do, scalars only when finite: src/quasinewton.jl:248-269,
+// src/bounds.jl:340-341).
+template <typename T> struct Bound {
+    const T* arr;
+    T val;
+    int has;
+    __device__ __forceinline__ T at(int64_t i) const { return arr ? arr[i] : val; }
+    __device__ __forceinline__ Pack<T> pack(int64_t iv) const
+    {
+        return arr ? ld_pack<T>(arr, iv) : splat_pack<T>(val);
+    }
+};
+
+// fastclamp(x, lo, hi) = fastmax(fastmin(x, hi), lo): src/bounds.jl:41, :53, :65-67.
+// NaN in x is kept; an infinite bound never triggers.
+template <typename T>
+__device__ __forceinline__ T fastclamp(T x, T lo, T hi)
+{
+    T t = (x > hi ? hi : x);
+    return (t < lo ? lo : t);
+}
+
+// projdir / can_change: src/bounds.jl:306-311, :638-648.
+template <typename T>
+__device__ __forceinline__ T projdir(T x, T lo, T hi, int has_lo, int has_hi, int orient, T d)
+{
+    bool neg = (orient > 0 ? d < T(0) : d > T(0));  // is_negative(o, d)
+    bool pos = (orient > 0 ? d > T(0) : d < T(0));  // is_positive(o, d)
+    bool ok = (neg && (!has_lo || x > lo)) || (pos && (!has_hi || x < hi));
+    return ok ? d : T(0);
+}
+
+// one element of _step_limits: src/bounds.jl:456-506, :521-551, :566-596, :608-622.
+// `sd` = s*d[i] with s = +-1; smin/smax in the element type.
+template <typename T>
+__device__ __forceinline__ void step_limit_update(T x, T lo, T hi, int has_lo, int has_hi, T sd,
+                                                  T& smin, T& smax)
+{
+    const T inf = T(INFINITY);
+    if (sd > T(0)) {
+        if (has_hi) {
+            T a = (hi - x) / sd;
+            if (T(0) < a && a < smin) smin = a;
+            if (a > smax) smax = a;
+        } else {
+            smax = inf;
+        }
+    } else if (sd < T(0)) {
+        if (has_lo) {
+            T a = (lo - x) / sd;
+            if (T(0) < a && a < smin) smin = a;
+            if (a > smax) smax = a;
+        } else {
+            smax = inf;
+        }
+    }
+}
+
+// exact product accumulated in double whatever T
+template <typename T>
+__device__ __forceinline__ double dacc(T a, T b, double acc)
+{
+    return fma((double)a, (double)b, acc);
+}
+
+// Rosenbrock pair, test/rosenbrock.jl:16-29 (arithmetic in T, no contraction).
+template <typename T>
+__device__ __forceinline__ void rosenbrock_pair(T x1, T x2, T& g1, T& g2, double& f1, double& f2)
+{
+    const T c1 = T(1), c2 = T(2), c10 = T(10), c200 = T(200);
+    T t1 = c1 - x1;
+    T u = x2 - x1 * x1;
+    T t2 = c10 * u;
+    g2 = c200 * u;
+    g1 = -c2 * (x1 * g2 + t1);
+    f1 += (double)(T)(t1 * t1);
+    f2 += (double)(T)(t2 * t2);
+}
+
+// Quadratic element: r = x - c; g = a*r; term = g*r (f = sum(term)/2).
+template <typename T>
+__device__ __forceinline__ void quadratic_elem(T x, T a, T c, T& g, double& f)
+{
+    T r = x - c;
+    g = a * r;
+    f += (double)(T)(g * r);
+}
+
+// ---------------------------------------------------------------------------
+// Deterministic reduction of NR scalars per thread: warp butterfly, fixed
+// order over the warps of the CTA, per-CTA partial in global memory, and the
+// last CTA (ticket) sums the partials of all CTAs in fixed order.
+struct ReduceScratch {
+    double* part;
+    unsigned int* ticket;
+    double* res;
+};
+
+template <int KIND>
+__device__ __forceinline__ double rcombine(double a, double b)
+{
+    if (KIND == OPKB_RSUM) return a + b;
+    if (KIND == OPKB_RMAX) return (b > a ? b : a);
+    return (b < a ? b : a);
+}
+
+template <int KIND> __device__ __forceinline__ double rneutral()
+{
+    if (KIND == OPKB_RSUM) return 0.0;
+    if (KIND == OPKB_RMAX) return -INFINITY;
+    return INFINITY;
+}
+
+__device__ __forceinline__ double rcombine_dyn(int kind, double a, double b)
+{
+    if (kind == OPKB_RSUM) return a + b;
+    if (kind == OPKB_RMAX) return (b > a ? b : a);
+    return (b < a ? b : a);
+}
+
+__device__ __forceinline__ double rneutral_dyn(int kind)
+{
+    if (kind == OPKB_RSUM) return 0.0;
+    if (kind == OPKB_RMAX) return -INFINITY;
+    return INFINITY;
+}
+
+// kind of slot k from the two bit masks (max slots / min slots)
+__host__ __device__ __forceinline__ int rkind(unsigned maxmask, unsigned minmask, int k)
+{
+    return ((maxmask >> k) & 1u) ? OPKB_RMAX : (((minmask >> k) & 1u) ? OPKB_RMIN : OPKB_RSUM);
+}
+
+// All threads of the CTA must call this (blockDim.x = OPKB_BLOCK or less, a
+// multiple of 32).  On return of the LAST CTA, rs.res[0..NR) holds the result.
+template <int NR, unsigned MAXM, unsigned MINM>
+__device__ void block_reduce_publish(double (&v)[NR], const ReduceScratch& rs)
+{
+    __shared__ double sm[NR][32];
+    __shared__ unsigned int s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+        const int kind = rkind(MAXM, MINM, k);
+        double a = v[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double b = __shfl_xor_sync(0xffffffffu, a, off);
+            a = rcombine_dyn(kind, a, b);
+        }
+        if (lane == 0) sm[k][warp] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < NR) {
+        const int k = threadIdx.x;
+        const int kind = rkind(MAXM, MINM, k);
+        double a = sm[k][0];
+        for (int w = 1; w < nwarps; ++w) a = rcombine_dyn(kind, a, sm[k][w]);
+        rs.part[(size_t)blockIdx.x * NR + k] = a;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(rs.ticket, 1u);
+        s_last = (t == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // last CTA: for each slot, strided partial over the CTAs then the same tree
+    for (int k = 0; k < NR; ++k) {
+        const int kind = rkind(MAXM, MINM, k);
+        double a = rneutral_dyn(kind);
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+            a = rcombine_dyn(kind, a, __ldcg(&rs.part[(size_t)b * NR + k]));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double c = __shfl_xor_sync(0xffffffffu, a, off);
+            a = rcombine_dyn(kind, a, c);
+        }
+        __syncthreads();
+        if (lane == 0) sm[0][warp] = a;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double r = sm[0][0];
+            for (int w = 1; w < nwarps; ++w) r = rcombine_dyn(kind, r, sm[0][w]);
+            rs.res[k] = r;
+        }
+    }
+    if (threadIdx.x == 0) *rs.ticket = 0u;
+}

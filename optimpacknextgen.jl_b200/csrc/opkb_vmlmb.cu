@@ -1,0 +1,635 @@
+// opkb_vmlmb.cu -- Tier 2: fused phases of `_vmlmb!` (src/quasinewton.jl:381-601)
+// and of `apply_lbfgs!` (src/quasinewton.jl:703-779).  Every n-vector crosses
+// HBM once per phase:
+//   P1 trial      : x = prj(x0 - stp d); f, g = fg(x); p = projdir(g); 6 reductions
+//   P3 gram       : in-place pair update + all inner products of the two-loop
+//                   recursion in one tall-skinny sweep (opkb_gram.cuh)
+//   P4 direction  : d = H v0 from the host-solved coefficients, projection,
+//                   g.d, |d|^2, step limits, save (x, g) for the next search
+//   P4' steepest, P0 revert
+#include <math.h>
+#include <string.h>
+
+#include "opkb_internal.cuh"
+
+struct opkb_vmlmb_ {
+    opkb_context* ctx;
+    int eltype;
+    int64_t n;
+    int mem;
+    int method;
+    const opkb_vector* lo;
+    double lo_val;
+    const opkb_vector* hi;
+    double hi_val;
+    int obj;
+    const opkb_vector* qa;
+    const opkb_vector* qc;
+    opkb_vector *x, *g, *p, *d;
+    opkb_vector* S[OPKB_MEM_MAX];
+    opkb_vector* Y[OPKB_MEM_MAX];
+};
+
+#define LAUNCHB(ctx, kernel, grid, block, smem, ...)                         \
+    do {                                                                     \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);     \
+        (ctx)->launches += 1;                                                \
+        OPKB_CUDA(cudaGetLastError());                                       \
+    } while (0)
+
+static ReduceScratch scratch(opkb_context* ctx)
+{
+    ReduceScratch rs;
+    rs.part = ctx->d_part;
+    rs.ticket = ctx->d_ticket;
+    rs.res = ctx->d_res;
+    return rs;
+}
+
+template <typename T>
+static Bound<T> make_bound(const opkb_vector* arr, double val, bool lower)
+{
+    Bound<T> b;
+    b.arr = arr ? (const T*)arr->data : NULL;
+    b.val = (T)val;
+    b.has = arr ? 1 : (lower ? (b.val > -(T)INFINITY) : (b.val < (T)INFINITY));
+    return b;
+}
+
+// ---------------------------------------------------------------------------
+// workspace
+extern "C" int opkb_vmlmb_create(opkb_context* ctx, int eltype, int64_t n, int mem, int method,
+                                 const opkb_vector* lo, double lo_val, const opkb_vector* hi,
+                                 double hi_val, opkb_vmlmb** out)
+{
+    if (!ctx || !out) return opkb_set_error(OPKB_EINVAL, "NULL argument");
+    *out = NULL;
+    if (eltype != OPKB_FLOAT && eltype != OPKB_DOUBLE)
+        return opkb_set_error(OPKB_EINVAL, "invalid element type");
+    if (mem < 1 || mem > OPKB_MEM_MAX)
+        return opkb_set_error(OPKB_EINVAL, "mem must be in 1..%d for the fused path", OPKB_MEM_MAX);
+    if (method < 0 || method > 2) return opkb_set_error(OPKB_EINVAL, "invalid method");
+    if ((lo && (lo->n != n || lo->eltype != eltype)) || (hi && (hi->n != n || hi->eltype != eltype)))
+        return opkb_set_error(OPKB_EINVAL, "bounds of a different space");
+    opkb_vmlmb* ws = (opkb_vmlmb*)calloc(1, sizeof(opkb_vmlmb));
+    if (!ws) return opkb_set_error(OPKB_ENOMEM, "out of host memory");
+    ws->ctx = ctx;
+    ws->eltype = eltype;
+    ws->n = n;
+    ws->mem = mem;
+    ws->method = method;
+    ws->lo = lo;
+    ws->lo_val = lo_val;
+    ws->hi = hi;
+    ws->hi_val = hi_val;
+    ws->obj = OPKB_OBJ_USER;
+    int rc = 0;
+    rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->x);
+    rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->g);
+    if (method > 0) rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->p);
+    rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->d);
+    for (int k = 0; k < mem && !rc; ++k) {
+        rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->S[k]);
+        rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->Y[k]);
+    }
+    if (rc) {
+        opkb_vmlmb_destroy(ws);
+        return rc;
+    }
+    *out = ws;
+    return 0;
+}
+
+extern "C" int opkb_vmlmb_destroy(opkb_vmlmb* ws)
+{
+    if (!ws) return 0;
+    opkb_vector_destroy(ws->x);
+    opkb_vector_destroy(ws->g);
+    opkb_vector_destroy(ws->p);
+    opkb_vector_destroy(ws->d);
+    for (int k = 0; k < OPKB_MEM_MAX; ++k) {
+        opkb_vector_destroy(ws->S[k]);
+        opkb_vector_destroy(ws->Y[k]);
+    }
+    free(ws);
+    return 0;
+}
+
+extern "C" int opkb_vmlmb_set_objective(opkb_vmlmb* ws, int kind, const opkb_vector* a,
+                                        const opkb_vector* c)
+{
+    if (!ws) return opkb_set_error(OPKB_EINVAL, "NULL workspace");
+    if (kind == OPKB_OBJ_QUADRATIC) {
+        if (!a || !c || a->n != ws->n || c->n != ws->n || a->eltype != ws->eltype ||
+            c->eltype != ws->eltype)
+            return opkb_set_error(OPKB_EINVAL, "quadratic objective needs a, c of the same space");
+    } else if (kind == OPKB_OBJ_ROSENBROCK) {
+        if (ws->n % 2)
+            return opkb_set_error(OPKB_EINVAL, "Rosenbrock needs an even number of (local) variables");
+    } else if (kind != OPKB_OBJ_USER) {
+        return opkb_set_error(OPKB_EINVAL, "unknown objective");
+    }
+    ws->obj = kind;
+    ws->qa = a;
+    ws->qc = c;
+    return 0;
+}
+
+extern "C" opkb_vector* opkb_vmlmb_vector(opkb_vmlmb* ws, int which, int slot)
+{
+    if (!ws) return NULL;
+    switch (which) {
+    case 'x': return ws->x;
+    case 'g': return ws->g;
+    case 'p': return ws->p;
+    case 'd': return ws->d;
+    case 'S': return (slot >= 0 && slot < ws->mem) ? ws->S[slot] : NULL;
+    case 'Y': return (slot >= 0 && slot < ws->mem) ? ws->Y[slot] : NULL;
+    }
+    return NULL;
+}
+
+// ---------------------------------------------------------------------------
+// P1: trial point, objective, projected gradient, reductions.
+// STAGE 0: everything (built-in objective); 1: x only (user objective, begin);
+// 2: p + reductions from the caller's g (user objective, end).
+template <typename T> struct TrialArgs {
+    const T* x0;   // S[mark]
+    const T* d;
+    T* x;
+    T* g;
+    T* p;          // NULL for L-BFGS
+    const T* qa;
+    const T* qc;
+    Bound<T> lo, hi;
+    T mstp;        // -stp converted to the element type
+    int64_t n;
+    int initial;
+    int bounded;
+};
+
+template <typename T>
+__device__ __forceinline__ T trial_point(const TrialArgs<T>& A, T xin, T x0, T d, T lo, T hi)
+{
+    // vcombine!(x, 1, S[mark], -stp, d) :599 then project_variables! :386
+    T xi = A.initial ? xin : x0 + A.mstp * d;
+    if (A.bounded) xi = fastclamp(xi, lo, hi);
+    return xi;
+}
+
+template <typename T>
+__device__ __forceinline__ void trial_reduce(const TrialArgs<T>& A, T xi, T gi, T x0, T d, T lo, T hi,
+                                             T& pi, double (&acc)[8])
+{
+    // project_direction!(p, x, lo, hi, -, g) :396
+    pi = A.bounded ? projdir(xi, lo, hi, A.lo.has, A.hi.has, -1, gi) : gi;
+    acc[2] = dacc(pi, pi, acc[2]);              // |p|^2 :399
+    acc[7] += (pi != T(0)) ? 1.0 : 0.0;         // |sel| (bounds.jl:701-714)
+    if (!A.initial) {
+        T si = xi - x0;                         // vcombine!(s, 1, x, -1, S[mark]) :427
+        acc[3] = dacc(gi, si, acc[3]);          // vdot(g, s) :432
+        acc[4] = dacc(gi, d, acc[4]);           // vdot(g, d) :434
+        acc[5] = dacc(xi, xi, acc[5]);          // vnorm2(x) :446
+        acc[6] = dacc(si, si, acc[6]);          // vnorm2(s) :448
+    } else {
+        acc[5] = dacc(xi, xi, acc[5]);
+    }
+}
+
+template <typename T, int OBJ, int STAGE>
+__global__ void __launch_bounds__(OPKB_BLOCK) k_trial(TrialArgs<T> A, ReduceScratch rs)
+{
+    constexpr int VEC = VecOf<T>::N;
+    const int64_t nvec = A.n / VEC;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // acc: 0,1 objective partial sums; 2 |p|^2; 3 g.s; 4 g.d; 5 |x|^2; 6 |s|^2; 7 nfree
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += stride) {
+        Pack<T> px0, pd, pxin, pl, ph, px, pg, pp, pa, pc;
+        if (A.initial) {
+            pxin = ld_pack<T>(A.x, iv);
+            px0 = pxin;
+            pd = splat_pack<T>(T(0));
+        } else {
+            px0 = ld_pack<T>(A.x0, iv);
+            pd = ld_pack<T>(A.d, iv);
+            pxin = px0;
+        }
+        if (A.bounded) {
+            pl = A.lo.pack(iv);
+            ph = A.hi.pack(iv);
+        } else {
+            pl = splat_pack<T>(T(0));
+            ph = pl;
+        }
+        if (STAGE == 2) {
+            px = ld_pack<T>(A.x, iv);
+            pg = ld_pack<T>(A.g, iv);
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+                px.v[e] = trial_point(A, pxin.v[e], px0.v[e], pd.v[e], pl.v[e], ph.v[e]);
+            st_pack<T>(A.x, iv, px);
+        }
+        if (STAGE == 0) {
+            if (OBJ == OPKB_OBJ_ROSENBROCK) {
+#pragma unroll
+                for (int e = 0; e < VEC; e += 2)
+                    rosenbrock_pair(px.v[e], px.v[e + 1], pg.v[e], pg.v[e + 1], acc[0], acc[1]);
+            } else {
+                pa = ld_pack<T>(A.qa, iv);
+                pc = ld_pack<T>(A.qc, iv);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e)
+                    quadratic_elem(px.v[e], pa.v[e], pc.v[e], pg.v[e], acc[0]);
+            }
+            st_pack<T>(A.g, iv, pg);
+        }
+        if (STAGE != 1) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+                trial_reduce(A, px.v[e], pg.v[e], px0.v[e], pd.v[e], pl.v[e], ph.v[e], pp.v[e], acc);
+            if (A.p) st_pack<T>(A.p, iv, pp);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // scalar tail (at most VEC-1 elements; an even count for Rosenbrock)
+        for (int64_t i = nvec * VEC; i < A.n; ++i) {
+            T x0 = A.initial ? A.x[i] : A.x0[i];
+            T d = A.initial ? T(0) : A.d[i];
+            T lo = A.bounded ? A.lo.at(i) : T(0), hi = A.bounded ? A.hi.at(i) : T(0);
+            if (STAGE != 2) A.x[i] = trial_point(A, A.x[i], x0, d, lo, hi);
+        }
+        if (STAGE == 0) {
+            if (OBJ == OPKB_OBJ_ROSENBROCK) {
+                for (int64_t i = nvec * VEC; i + 1 < A.n; i += 2)
+                    rosenbrock_pair(A.x[i], A.x[i + 1], A.g[i], A.g[i + 1], acc[0], acc[1]);
+            } else {
+                for (int64_t i = nvec * VEC; i < A.n; ++i)
+                    quadratic_elem(A.x[i], A.qa[i], A.qc[i], A.g[i], acc[0]);
+            }
+        }
+        if (STAGE != 1) {
+            for (int64_t i = nvec * VEC; i < A.n; ++i) {
+                T x0 = A.initial ? A.x[i] : A.x0[i];
+                T d = A.initial ? T(0) : A.d[i];
+                T lo = A.bounded ? A.lo.at(i) : T(0), hi = A.bounded ? A.hi.at(i) : T(0);
+                T pi;
+                trial_reduce(A, A.x[i], A.g[i], x0, d, lo, hi, pi, acc);
+                if (A.p) A.p[i] = pi;
+            }
+        }
+    }
+    if (STAGE != 1) block_reduce_publish<8, 0u, 0u>(acc, rs);
+}
+
+template <typename T>
+static int trial_launch(opkb_vmlmb* ws, int mark, double stp, int initial, int stage)
+{
+    opkb_context* ctx = ws->ctx;
+    TrialArgs<T> A;
+    A.x0 = (const T*)ws->S[mark]->data;
+    A.d = (const T*)ws->d->data;
+    A.x = (T*)ws->x->data;
+    A.g = (T*)ws->g->data;
+    A.p = ws->p ? (T*)ws->p->data : NULL;
+    A.qa = ws->qa ? (const T*)ws->qa->data : NULL;
+    A.qc = ws->qc ? (const T*)ws->qc->data : NULL;
+    A.lo = make_bound<T>(ws->lo, ws->lo_val, true);
+    A.hi = make_bound<T>(ws->hi, ws->hi_val, false);
+    A.mstp = (T)(-stp);
+    A.n = ws->n;
+    A.initial = initial;
+    A.bounded = ws->method > 0;
+    int grid = opkb_grid_for(ctx, ws->n / VecOf<T>::N, 4);
+    ReduceScratch rs = scratch(ctx);
+    if (stage == 1)
+        LAUNCHB(ctx, (k_trial<T, OPKB_OBJ_USER, 1>), grid, OPKB_BLOCK, 0, A, rs);
+    else if (stage == 2)
+        LAUNCHB(ctx, (k_trial<T, OPKB_OBJ_USER, 2>), grid, OPKB_BLOCK, 0, A, rs);
+    else if (ws->obj == OPKB_OBJ_ROSENBROCK)
+        LAUNCHB(ctx, (k_trial<T, OPKB_OBJ_ROSENBROCK, 0>), grid, OPKB_BLOCK, 0, A, rs);
+    else
+        LAUNCHB(ctx, (k_trial<T, OPKB_OBJ_QUADRATIC, 0>), grid, OPKB_BLOCK, 0, A, rs);
+    return 0;
+}
+
+static int trial_collect(opkb_vmlmb* ws, double f_user, int user, double out[8])
+{
+    double r[8];
+    int rc = opkb_finish_reduction(ws->ctx, 8, NULL, r);
+    if (rc) return rc;
+    double f = user ? f_user
+                    : (ws->obj == OPKB_OBJ_ROSENBROCK ? r[0] + r[1] : 0.5 * r[0]);
+    out[0] = f;
+    out[1] = r[2];
+    out[2] = r[3];
+    out[3] = r[4];
+    out[4] = r[5];
+    out[5] = r[6];
+    out[6] = r[7];
+    out[7] = 0;
+    return 0;
+}
+
+static int check_mark(opkb_vmlmb* ws, int mark)
+{
+    if (!ws) return opkb_set_error(OPKB_EINVAL, "NULL workspace");
+    if (mark < 0 || mark >= ws->mem) return opkb_set_error(OPKB_EINVAL, "mark out of range");
+    return 0;
+}
+
+extern "C" int opkb_vmlmb_trial(opkb_vmlmb* ws, int mark, double stp, int initial, double out[8])
+{
+    int rc = check_mark(ws, mark);
+    if (rc) return rc;
+    if (ws->obj == OPKB_OBJ_USER)
+        return opkb_set_error(OPKB_EINVAL, "no built-in objective set: use trial_begin/trial_end");
+    rc = (ws->eltype == OPKB_DOUBLE) ? trial_launch<double>(ws, mark, stp, initial, 0)
+                                     : trial_launch<float>(ws, mark, stp, initial, 0);
+    if (rc) return rc;
+    return trial_collect(ws, 0.0, 0, out);
+}
+
+extern "C" int opkb_vmlmb_trial_begin(opkb_vmlmb* ws, int mark, double stp, int initial)
+{
+    int rc = check_mark(ws, mark);
+    if (rc) return rc;
+    if (initial && ws->method == 0) return 0;  // x unchanged
+    return (ws->eltype == OPKB_DOUBLE) ? trial_launch<double>(ws, mark, stp, initial, 1)
+                                       : trial_launch<float>(ws, mark, stp, initial, 1);
+}
+
+extern "C" int opkb_vmlmb_trial_end(opkb_vmlmb* ws, int mark, double f, int initial, double out[8])
+{
+    int rc = check_mark(ws, mark);
+    if (rc) return rc;
+    rc = (ws->eltype == OPKB_DOUBLE) ? trial_launch<double>(ws, mark, 0.0, initial, 2)
+                                     : trial_launch<float>(ws, mark, 0.0, initial, 2);
+    if (rc) return rc;
+    return trial_collect(ws, f, 1, out);
+}
+
+// ---------------------------------------------------------------------------
+// P3: Gram sweep
+#include "opkb_gram.cuh"
+
+extern "C" int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots, double* G)
+{
+    int rc = check_mark(ws, mark);
+    if (rc) return rc;
+    if (m < 1 || m > ws->mem || !slots || !G) return opkb_set_error(OPKB_EINVAL, "invalid m/slots/G");
+    if (slots[m - 1] != mark)
+        return opkb_set_error(OPKB_EINVAL, "the newest pair (slots[m-1]) must be `mark`");
+    for (int j = 0; j < m; ++j)
+        if (slots[j] < 0 || slots[j] >= ws->mem) return opkb_set_error(OPKB_EINVAL, "slot out of range");
+    const void* Sp[OPKB_MEM_MAX];
+    const void* Yp[OPKB_MEM_MAX];
+    for (int j = 0; j < m; ++j) {
+        Sp[j] = ws->S[slots[j]]->data;
+        Yp[j] = ws->Y[slots[j]]->data;
+    }
+    // v0 = p for VMLMB (mask p != 0), g otherwise; the gradient difference uses
+    // p for BLMVM (src/quasinewton.jl:513)
+    const void* v0 = (ws->method == 2 ? ws->p->data : ws->g->data);
+    const void* gcur = (ws->method == 1 ? ws->p->data : ws->g->data);
+    if (ws->eltype == OPKB_DOUBLE)
+        return gram_run<double>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur,
+                                ws->method == 2, G);
+    return gram_run<float>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur, ws->method == 2, G);
+}
+
+// ---------------------------------------------------------------------------
+// P4: direction assembly + projection + reductions + save
+template <typename T> struct DirArgs {
+    const T* S[OPKB_MEM_MAX];
+    const T* Y[OPKB_MEM_MAX];
+    T ma[OPKB_MEM_MAX];   // -alpha_j in the element type
+    T cc[OPKB_MEM_MAX];   // alpha_j - beta_j in the element type
+    unsigned use;         // bit j: pair j takes part (rho_j > 0)
+    int m;
+    T gamma;
+    const T* v0;          // p (VMLMB) or g
+    const T* x;
+    const T* g;
+    const T* ysrc;        // what is saved in Y[mark_next]: g, or p for BLMVM
+    T* d;
+    T* Snext;
+    T* Ynext;
+    Bound<T> lo, hi;
+    int64_t n;
+    int masked, bounded;
+    int steepest;         // 0: two-loop assembly; 1: d = p|g (:554); 2: d given, finish only
+};
+
+template <typename T>
+__device__ __forceinline__ T dir_elem(const DirArgs<T>& A, T v0, const T* yv, const T* sv)
+{
+    // apply_lbfgs! :716-745 / :747-779 with the scalars solved by the host;
+    // same sequence of roundings as the reference's vupdate!/vscale! calls
+    T v = v0;
+    const bool upd = !A.masked || (v0 != T(0));
+    if (upd) {
+        for (int j = A.m - 1; j >= 0; --j)
+            if ((A.use >> j) & 1u) v = v + A.ma[j] * yv[j];
+    }
+    v = A.gamma * v;
+    if (upd) {
+        for (int j = 0; j < A.m; ++j)
+            if ((A.use >> j) & 1u) v = v + A.cc[j] * sv[j];
+    }
+    return v;
+}
+
+template <typename T, int MB>
+__global__ void __launch_bounds__(OPKB_BLOCK) k_direction(DirArgs<T> A, ReduceScratch rs)
+{
+    constexpr int VEC = VecOf<T>::N;
+    const int64_t nvec = A.n / VEC;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // acc: 0 g.d; 1 |d|^2; 2 smin; 3 smax
+    T smin = T(INFINITY), smax = T(0);
+    double acc[4] = {0, 0, 0, 0};
+    for (int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += stride) {
+        Pack<T> pv = ld_pack<T>(A.v0, iv), px = ld_pack<T>(A.x, iv), pg = ld_pack<T>(A.g, iv);
+        Pack<T> pys = (A.ysrc == A.g) ? pg : ld_pack<T>(A.ysrc, iv);
+        Pack<T> pl, ph, pd;
+        if (A.bounded) {
+            pl = A.lo.pack(iv);
+            ph = A.hi.pack(iv);
+        } else {
+            pl = splat_pack<T>(T(0));
+            ph = pl;
+        }
+        if (A.steepest) {
+            pd = pv;
+        } else {
+            Pack<T> py[MB], ps[MB];
+#pragma unroll
+            for (int j = 0; j < MB; ++j) {
+                if (j < A.m) {
+                    py[j] = ld_pack<T>(A.Y[j], iv);
+                    ps[j] = ld_pack<T>(A.S[j], iv);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                T v = pv.v[e];
+                const bool upd = !A.masked || (v != T(0));
+#pragma unroll
+                for (int j = MB - 1; j >= 0; --j)
+                    if (j < A.m && upd && ((A.use >> j) & 1u)) v = v + A.ma[j] * py[j].v[e];
+                v = A.gamma * v;
+#pragma unroll
+                for (int j = 0; j < MB; ++j)
+                    if (j < A.m && upd && ((A.use >> j) & 1u)) v = v + A.cc[j] * ps[j].v[e];
+                pd.v[e] = v;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            T di = pd.v[e];
+            // project_direction!(d, x, lo, hi, -, d) :535 (skipped for the
+            // steepest descent: p is already projected, :554)
+            if (A.bounded && A.steepest != 1)
+                di = projdir(px.v[e], pl.v[e], ph.v[e], A.lo.has, A.hi.has, -1, di);
+            pd.v[e] = di;
+            acc[0] = dacc(pg.v[e], di, acc[0]);   // vdot(g, d) :537
+            acc[1] = dacc(di, di, acc[1]);        // vnorm2(d) :629
+            if (A.bounded)                        // step_limits(x, lo, hi, -1, d) :577
+                step_limit_update(px.v[e], pl.v[e], ph.v[e], A.lo.has, A.hi.has, -di, smin, smax);
+        }
+        st_pack<T>(A.d, iv, pd);
+        st_pack<T>(A.Snext, iv, px);    // vcopy!(S[mark], x) :562
+        st_pack<T>(A.Ynext, iv, pys);   // vcopy!(Y[mark], g|p) :563
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int64_t i = nvec * VEC; i < A.n; ++i) {
+            T yv[OPKB_MEM_MAX], sv[OPKB_MEM_MAX];
+            T xi = A.x[i], gi = A.g[i], ys = A.ysrc[i], v0 = A.v0[i];
+            T lo = A.bounded ? A.lo.at(i) : T(0), hi = A.bounded ? A.hi.at(i) : T(0);
+            T di;
+            if (A.steepest) {
+                di = v0;
+            } else {
+                for (int j = 0; j < A.m; ++j) {
+                    yv[j] = A.Y[j][i];
+                    sv[j] = A.S[j][i];
+                }
+                di = dir_elem(A, v0, yv, sv);
+            }
+            if (A.bounded && A.steepest != 1) di = projdir(xi, lo, hi, A.lo.has, A.hi.has, -1, di);
+            acc[0] = dacc(gi, di, acc[0]);
+            acc[1] = dacc(di, di, acc[1]);
+            if (A.bounded) step_limit_update(xi, lo, hi, A.lo.has, A.hi.has, -di, smin, smax);
+            A.d[i] = di;
+            A.Snext[i] = xi;
+            A.Ynext[i] = ys;
+        }
+    }
+    acc[2] = (double)smin;
+    acc[3] = (double)smax;
+    block_reduce_publish<4, 8u, 4u>(acc, rs);  // slot 2: min, slot 3: max
+}
+
+template <typename T>
+static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* alpha,
+                         const double* c, double gamma, int mark_next, int steepest, double out[4])
+{
+    opkb_context* ctx = ws->ctx;
+    DirArgs<T> A;
+    memset(&A, 0, sizeof(A));
+    A.m = steepest ? 0 : m;
+    A.use = 0;
+    for (int j = 0; j < A.m; ++j) {
+        A.S[j] = (const T*)ws->S[slots[j]]->data;
+        A.Y[j] = (const T*)ws->Y[slots[j]]->data;
+        A.ma[j] = (T)(-alpha[j]);
+        A.cc[j] = (T)(c[j]);
+        // NaN marks a skipped pair (rho <= 0, src/quasinewton.jl:727, :759)
+        if (alpha[j] == alpha[j]) A.use |= (1u << j);
+    }
+    A.gamma = (T)gamma;
+    A.v0 = (const T*)(ws->method > 0 ? ws->p->data : ws->g->data);
+    if (!steepest && ws->method == 1) A.v0 = (const T*)ws->g->data;  // vcopy!(d, g) :525
+    if (steepest == 2) A.v0 = (const T*)ws->d->data;                 // d already holds H*v
+    A.x = (const T*)ws->x->data;
+    A.g = (const T*)ws->g->data;
+    A.ysrc = (const T*)(ws->method == 1 ? ws->p->data : ws->g->data);
+    A.d = (T*)ws->d->data;
+    A.Snext = (T*)ws->S[mark_next]->data;
+    A.Ynext = (T*)ws->Y[mark_next]->data;
+    A.lo = make_bound<T>(ws->lo, ws->lo_val, true);
+    A.hi = make_bound<T>(ws->hi, ws->hi_val, false);
+    A.n = ws->n;
+    A.masked = (ws->method == 2);
+    A.bounded = (ws->method > 0);
+    A.steepest = steepest;
+    ReduceScratch rs = scratch(ctx);
+    int grid = opkb_grid_for(ctx, ws->n / VecOf<T>::N, 2);
+    if (A.m <= 4)
+        LAUNCHB(ctx, (k_direction<T, 4>), grid, OPKB_BLOCK, 0, A, rs);
+    else if (A.m <= 8)
+        LAUNCHB(ctx, (k_direction<T, 8>), grid, OPKB_BLOCK, 0, A, rs);
+    else if (A.m <= 12)
+        LAUNCHB(ctx, (k_direction<T, 12>), grid, OPKB_BLOCK, 0, A, rs);
+    else if (A.m <= 16)
+        LAUNCHB(ctx, (k_direction<T, 16>), grid, OPKB_BLOCK, 0, A, rs);
+    else
+        LAUNCHB(ctx, (k_direction<T, OPKB_MEM_MAX>), grid, OPKB_BLOCK, 0, A, rs);
+    int kinds[4] = {OPKB_RSUM, OPKB_RSUM, OPKB_RMIN, OPKB_RMAX};
+    int rc = opkb_finish_reduction(ctx, 4, kinds, out);
+    if (rc) return rc;
+    if (!A.bounded) {  // no step limits for L-BFGS (:581-584)
+        out[2] = INFINITY;
+        out[3] = INFINITY;
+    } else if (!A.lo.has && !A.hi.has) {
+        out[2] = INFINITY;
+        out[3] = INFINITY;
+    }
+    return 0;
+}
+
+extern "C" int opkb_vmlmb_direction(opkb_vmlmb* ws, int m, const int* slots, const double* alpha,
+                                    const double* c, double gamma, int mark_next, double out[4])
+{
+    int rc = check_mark(ws, mark_next);
+    if (rc) return rc;
+    if (m < 1 || m > ws->mem || !slots || !alpha || !c || !out)
+        return opkb_set_error(OPKB_EINVAL, "invalid argument");
+    for (int j = 0; j < m; ++j)
+        if (slots[j] < 0 || slots[j] >= ws->mem) return opkb_set_error(OPKB_EINVAL, "slot out of range");
+    return (ws->eltype == OPKB_DOUBLE)
+               ? direction_run<double>(ws, m, slots, alpha, c, gamma, mark_next, 0, out)
+               : direction_run<float>(ws, m, slots, alpha, c, gamma, mark_next, 0, out);
+}
+
+extern "C" int opkb_vmlmb_steepest(opkb_vmlmb* ws, int mark_next, double out[4])
+{
+    int rc = check_mark(ws, mark_next);
+    if (rc) return rc;
+    if (!out) return opkb_set_error(OPKB_EINVAL, "NULL result");
+    return (ws->eltype == OPKB_DOUBLE)
+               ? direction_run<double>(ws, 0, NULL, NULL, NULL, 1.0, mark_next, 1, out)
+               : direction_run<float>(ws, 0, NULL, NULL, NULL, 1.0, mark_next, 1, out);
+}
+
+extern "C" int opkb_vmlmb_finish_direction(opkb_vmlmb* ws, int mark_next, double out[4])
+{
+    int rc = check_mark(ws, mark_next);
+    if (rc) return rc;
+    if (!out) return opkb_set_error(OPKB_EINVAL, "NULL result");
+    return (ws->eltype == OPKB_DOUBLE)
+               ? direction_run<double>(ws, 0, NULL, NULL, NULL, 1.0, mark_next, 2, out)
+               : direction_run<float>(ws, 0, NULL, NULL, NULL, 1.0, mark_next, 2, out);
+}
+
+// ---------------------------------------------------------------------------
+// P0: revert to the best point, :490-492
+extern "C" int opkb_vmlmb_revert(opkb_vmlmb* ws, int mark, double stp)
+{
+    int rc = check_mark(ws, mark);
+    if (rc) return rc;
+    return (ws->eltype == OPKB_DOUBLE) ? trial_launch<double>(ws, mark, stp, 0, 1)
+                                       : trial_launch<float>(ws, mark, stp, 0, 1);
+}

@@ -1,0 +1,793 @@
+"""`vmlmb` / `vmlmb!`: host driver of the reference (src/quasinewton.jl:215-612).
+
+The stage machine, the line searches and the convergence tests run here on
+Float64 scalars; every n-vector stays on the GPU.  Two device back ends exist:
+
+* ``mode="fused"`` (default) -- three kernels per iteration:
+  P1 trial (`opkb_vmlmb_trial`), P3 Gram sweep (`opkb_vmlmb_gram`) and P4
+  direction (`opkb_vmlmb_direction`); the two-loop recursion is solved on the
+  host in coefficient space from the Gram block.
+* ``mode="primitive"`` -- one kernel per reference call (Tier 1), i.e. the
+  reference's own sequence of `v*` / `SimpleBounds` operations; this is the
+  parity-grade path and the one a LazyAlgebra-style plugin would use.
+
+A Julia host does the same through `ccall`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import sys
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, f64, vp
+from .linesearches import LineSearch, MoreThuenteLineSearch, MoreToraldoLineSearch
+from .objectives import is_builtin
+from .vectors import (Context, Vector, default_context, project_direction_, project_variables_,
+                      step_limits, vcombine_, vcopy_, vdot, vnorm2, vscale_, vupdate_, _eltype)
+
+EMULATE_BLMVM = 1  # src/quasinewton.jl:40
+
+
+class BoundedSet:
+    """`BoundedSet(lower, upper)`: the box of `lower=` / `upper=` keywords of
+    `vmlmb` (src/quasinewton.jl:228-229) as one object.  (The reference only
+    sketches it, doc/ConvexSets.md:7-10; semantics are those of src/bounds.jl.)"""
+
+    def __init__(self, lower=-math.inf, upper=math.inf):
+        self.lower = lower
+        self.upper = upper
+
+
+def _jl_max(a, b):
+    if a != a:
+        return a
+    if b != b:
+        return b
+    return a if a > b else b
+
+
+def _jl_min(a, b):
+    if a != a:
+        return a
+    if b != b:
+        return b
+    return a if a < b else b
+
+
+def verbose(verb: int, it: int) -> bool:
+    """src/quasinewton.jl:641-642"""
+    return verb > 0 and it % verb == 0
+
+
+def print_iteration(io, it, ev, rejects, f, gnorm, step):
+    """src/quasinewton.jl:649-660"""
+    if it == 0:
+        io.write("#%s%s\n#%s%s\n" % (" ITER   EVAL   REJECTS", "          F(X)           ||G(X)||    STEP",
+                                     "----------------------",
+                                     "-------------------------------------------"))
+    io.write(" %5d  %5d  %5d  %24.16E %9.2E %9.2E\n" % (it, ev, rejects, f, gnorm, step))
+
+
+def sufficient_descent(gd, eps, gnorm, dnorm) -> bool:
+    """src/quasinewton.jl:631-632"""
+    return (gd <= -eps * dnorm * gnorm) if eps > 0 else (gd < 0)
+
+
+# ---------------------------------------------------------------------------
+# apply_lbfgs! on device vectors, one kernel per reference call
+def apply_lbfgs_(S, Y, rho, H0, m, mark, v, alpha):
+    """src/quasinewton.jl:716-745.  `H0` is a scalar gamma (:703-708), a Vector
+    of diagonal terms (:710-714, vproduct!) or a callable `H0(v)`.  0-based mark."""
+    from .vectors import vproduct_
+    mem = min(len(S), len(Y), len(rho), len(alpha))
+    assert 1 <= m <= mem and 0 <= mark < mem
+    modif = False
+    k = mark + 1
+    for _ in range(m):
+        k = k - 1 if k > 0 else mem - 1
+        if rho[k] > 0:
+            alpha[k] = vdot(S[k], v) / rho[k]
+            vupdate_(v, -alpha[k], Y[k])
+            modif = True
+    if modif:
+        if callable(H0):
+            H0(v)
+        elif isinstance(H0, Vector):
+            vproduct_(v, H0, v)
+        else:
+            assert H0 > 0
+            vscale_(v, H0)
+        for _ in range(m):
+            if rho[k] > 0:
+                beta = vdot(Y[k], v) / rho[k]
+                vupdate_(v, alpha[k] - beta, S[k])
+            k = k + 1 if k < mem - 1 else 0
+    return modif
+
+
+def apply_lbfgs_masked_(S, Y, rho, m, mark, v, alpha, w):
+    """src/quasinewton.jl:747-779; the index list `sel` is the mask w != 0."""
+    mem = min(len(S), len(Y), len(rho), len(alpha))
+    assert 1 <= m <= mem and 0 <= mark < mem
+    gamma = 0.0
+    k = mark + 1
+    for _ in range(m):
+        k = k - 1 if k > 0 else mem - 1
+        rho[k] = vdot(w, Y[k], S[k])
+        if rho[k] > 0:
+            alpha[k] = vdot(w, S[k], v) / rho[k]
+            vupdate_(v, w, -alpha[k], Y[k])
+            if gamma == 0:
+                gamma = rho[k] / vdot(w, Y[k], Y[k])
+    if gamma != 0:
+        vscale_(v, gamma)
+        for _ in range(m):
+            if rho[k] > 0:
+                beta = vdot(w, Y[k], v) / rho[k]
+                vupdate_(v, w, alpha[k] - beta, S[k])
+            k = k + 1 if k < mem - 1 else 0
+    return gamma != 0
+
+
+# ---------------------------------------------------------------------------
+class _PrimitiveOps:
+    """Device back end made of Tier-1 calls only: the reference's sequence."""
+
+    def __init__(self, solver, x: Vector):
+        self.s = solver
+        self.x = x
+        self.g = x.similar()
+        self.p = x.similar() if solver.method > 0 else None
+        self.d = x.similar()
+        self.sv = x.similar()
+        self.S = [x.similar() for _ in range(solver.mem)]
+        self.Y = [x.similar() for _ in range(solver.mem)]
+        self.rho = [0.0] * solver.mem
+        self.alpha = [0.0] * solver.mem
+        self._mark = 0
+
+    def evaluate(self, mark, stp, initial):
+        s = self.s
+        if not initial:
+            vcombine_(self.x, 1, self.S[mark], -stp, self.d)           # :599
+        if s.method > 0:
+            project_variables_(self.x, self.x, s.lo, s.hi)              # :386
+        f = float(s.fg(self.x, self.g))                                 # :391
+        if s.method > 0:
+            project_direction_(self.p, self.x, s.lo, s.hi, "-", self.g)  # :396
+        self._mark = mark
+        return f
+
+    def gnorm(self):
+        return vnorm2(self.p if self.s.method > 0 else self.g)          # :399, :495
+
+    def effective_step(self):
+        vcombine_(self.sv, 1, self.x, -1, self.S[self._mark])           # :427
+
+    def gd_search(self, stp):
+        if self.s.method > 0:
+            return vdot(self.g, self.sv) / stp                          # :432
+        return -vdot(self.g, self.d)                                    # :434
+
+    def xnorm(self):
+        return vnorm2(self.x)                                           # :446
+
+    def snorm(self):
+        return vnorm2(self.sv)                                          # :448
+
+    def nfree(self):
+        return None
+
+    def revert(self, mark, stp):
+        vcombine_(self.x, 1, self.S[mark], -stp, self.d)                # :490
+        if self.s.method > 0:
+            project_variables_(self.x, self.x, self.s.lo, self.s.hi)    # :492
+
+    def new_direction(self):
+        s = self.s
+        mark = s.mark
+        vupdate_(self.S[mark], -1, self.x)                              # :512
+        vupdate_(self.Y[mark], -1, self.p if s.method == 1 else self.g)  # :513
+        if s.method < 2:
+            self.rho[mark] = vdot(self.Y[mark], self.S[mark])           # :515
+            if self.rho[mark] > 0:
+                s.gamma = self.rho[mark] / vdot(self.Y[mark], self.Y[mark])  # :518
+        s.m = min(s.m + 1, s.mem)                                       # :521
+        if s.method < 2:
+            vcopy_(self.d, self.g)                                      # :525
+            change = apply_lbfgs_(self.S, self.Y, self.rho, s.gamma, s.m, mark, self.d, self.alpha)
+        else:
+            vcopy_(self.d, self.p)                                      # :528
+            change = apply_lbfgs_masked_(self.S, self.Y, self.rho, s.m, mark, self.d, self.alpha,
+                                         self.p)                        # sel = {p != 0} :530
+        if not change:
+            return False, 0.0, 0.0
+        if s.method > 0:
+            project_direction_(self.d, self.x, s.lo, s.hi, "-", self.d)  # :535
+        gd = -vdot(self.g, self.d)                                      # :537
+        dnorm = vnorm2(self.d)                                          # :629
+        return True, gd, dnorm
+
+    def steepest(self):
+        vcopy_(self.d, self.p if self.s.method > 0 else self.g)         # :554
+
+    def begin_search(self, mark):
+        s = self.s
+        vcopy_(self.S[mark], self.x)                                    # :562
+        vcopy_(self.Y[mark], self.p if s.method == 1 else self.g)       # :563
+        if s.method > 0:
+            return step_limits(self.x, s.lo, s.hi, -1, self.d)          # :577
+        return math.inf, math.inf
+
+    def vector(self, which, slot=0):
+        if which == "S":
+            return self.S[slot]
+        if which == "Y":
+            return self.Y[slot]
+        return {"x": self.x, "g": self.g, "p": self.p, "d": self.d}[which]
+
+
+class _FusedOps:
+    """Device back end made of the fused phases P1 / P3 / P4 (Tier 2)."""
+
+    def __init__(self, solver, ws, x: Vector):
+        self.s = solver
+        self.ws = ws
+        self.L = _lib.lib()
+        self.x = x
+        self.r = [0.0] * 8
+        self._out8 = (f64 * 8)()
+        self._out4 = (f64 * 4)()
+        self._limits = (math.inf, math.inf)
+        self._saved_for = -1
+        self._need_steepest = False
+        self.rho = [0.0] * solver.mem    # per slot, for L-BFGS / BLMVM (:515)
+        self._S = self._Y = self._alpha = None
+        self.g = self._vec("g")
+        self.p = self._vec("p") if solver.method > 0 else None
+        self.d = self._vec("d")
+        self.builtin = is_builtin(solver.fg)
+
+    def _vec(self, which, slot=0):
+        h = self.L.opkb_vmlmb_vector(self.ws, ord(which), slot)
+        return Vector.borrowed(self.s.ctx, h, self)
+
+    def vector(self, which, slot=0):
+        return self._vec(which, slot)
+
+    def evaluate(self, mark, stp, initial):
+        if self.builtin:
+            check(self.L.opkb_vmlmb_trial(self.ws, mark, stp, int(initial), self._out8))
+        else:
+            check(self.L.opkb_vmlmb_trial_begin(self.ws, mark, stp, int(initial)))
+            f = float(self.s.fg(self.x, self.g))
+            check(self.L.opkb_vmlmb_trial_end(self.ws, mark, f, int(initial), self._out8))
+        self.r = list(self._out8)
+        return self.r[0]
+
+    def gnorm(self):
+        return math.sqrt(self.r[1])
+
+    def effective_step(self):
+        pass
+
+    def gd_search(self, stp):
+        if self.s.method > 0:
+            return self.r[2] / stp
+        return -self.r[3]
+
+    def xnorm(self):
+        return math.sqrt(self.r[4])
+
+    def snorm(self):
+        return math.sqrt(self.r[5])
+
+    def nfree(self):
+        return int(self.r[6])
+
+    def revert(self, mark, stp):
+        check(self.L.opkb_vmlmb_revert(self.ws, mark, stp))
+
+    def _solve(self, G, m, slots):
+        """Two-loop recursion in coefficient space (apply_lbfgs!, :716-779) from
+        the Gram block; pairs j = 0 (oldest) .. m-1 (newest)."""
+        s = self.s
+        W = m + 1
+        sv = lambda a: G[2 * a * W]                       # s_a . v0
+        yv = lambda a: G[(2 * a + 1) * W]                 # y_a . v0
+        SY = lambda a, b: G[2 * a * W + 1 + b]            # s_a . y_b, b >= a
+        YY = lambda a, b: (G[(2 * a + 1) * W + 1 + b] if b >= a else G[(2 * b + 1) * W + 1 + a])
+        nan = math.nan
+        if s.method == 2:
+            rho = [SY(j, j) for j in range(m)]            # :758
+        else:
+            newest = m - 1
+            self.rho[slots[newest]] = SY(newest, newest)  # :515
+            if self.rho[slots[newest]] > 0:
+                s.gamma = self.rho[slots[newest]] / YY(newest, newest)  # :518
+            rho = [self.rho[slots[j]] for j in range(m)]
+        alpha = [nan] * m
+        c = [0.0] * m
+        gamma = 0.0
+        for k in range(m - 1, -1, -1):                    # :725-732 / :756-766
+            if rho[k] > 0:
+                acc = sv(k)
+                for j in range(m - 1, k, -1):
+                    if rho[j] > 0:
+                        acc -= alpha[j] * SY(k, j)
+                alpha[k] = acc / rho[k]
+                if gamma == 0:
+                    gamma = rho[k] / YY(k, k)             # :762-764
+        modif = any(r > 0 for r in rho)
+        if s.method < 2:
+            gamma = s.gamma                               # :526 (H0 = gamma*I)
+        if not modif or gamma == 0:
+            return alpha, c, gamma, False
+        for k in range(m):                                # :735-741 / :769-775
+            if rho[k] > 0:
+                acc = yv(k)
+                for j in range(m - 1, -1, -1):
+                    if rho[j] > 0:
+                        acc -= alpha[j] * YY(k, j)
+                acc *= gamma
+                for j in range(k):
+                    if rho[j] > 0:
+                        acc += c[j] * SY(j, k)
+                beta = acc / rho[k]
+                c[k] = alpha[k] - beta
+        return alpha, c, gamma, True
+
+    def _new_direction_sequential(self):
+        """Parity-grade variant: the reference's sequential two-loop recursion
+        (one kernel per vdot / vupdate!, same roundings of the intermediate v in
+        the element type), between the fused P1 and the fused tail of P4."""
+        s = self.s
+        mark = s.mark
+        if self._S is None:
+            self._S = [self._vec("S", k) for k in range(s.mem)]
+            self._Y = [self._vec("Y", k) for k in range(s.mem)]
+            self._alpha = [0.0] * s.mem
+        S, Y = self._S, self._Y
+        vupdate_(S[mark], -1, self.x)                                    # :512
+        vupdate_(Y[mark], -1, self.p if s.method == 1 else self.g)       # :513
+        if s.method < 2:
+            self.rho[mark] = vdot(Y[mark], S[mark])                      # :515
+            if self.rho[mark] > 0:
+                s.gamma = self.rho[mark] / vdot(Y[mark], Y[mark])        # :518
+        s.m = min(s.m + 1, s.mem)
+        if s.method < 2:
+            vcopy_(self.d, self.g)
+            change = apply_lbfgs_(S, Y, self.rho, s.gamma, s.m, mark, self.d, self._alpha)
+        else:
+            vcopy_(self.d, self.p)
+            change = apply_lbfgs_masked_(S, Y, self.rho, s.m, mark, self.d, self._alpha, self.p)
+        self._saved_for = -1
+        if not change:
+            return False, 0.0, 0.0
+        mark_next = mark + 1 if mark < s.mem - 1 else 0
+        check(self.L.opkb_vmlmb_finish_direction(self.ws, mark_next, self._out4))
+        self._limits = (self._out4[2], self._out4[3])
+        self._saved_for = mark_next
+        self._need_steepest = False
+        return True, -self._out4[0], math.sqrt(self._out4[1])
+
+    def new_direction(self):
+        s = self.s
+        if s.twoloop == "sequential":
+            return self._new_direction_sequential()
+        mark = s.mark
+        m = min(s.m + 1, s.mem)                           # :521
+        slots = [(mark - (m - 1) + j) % s.mem for j in range(m)]
+        cslots = (C.c_int * m)(*slots)
+        G = (f64 * (2 * m * (m + 1)))()
+        check(self.L.opkb_vmlmb_gram(self.ws, mark, m, cslots, G))
+        s.m = m
+        alpha, c, gamma, change = self._solve(G, m, slots)
+        self._saved_for = -1
+        if not change:
+            return False, 0.0, 0.0
+        mark_next = mark + 1 if mark < s.mem - 1 else 0
+        check(self.L.opkb_vmlmb_direction(self.ws, m, cslots, (f64 * m)(*alpha), (f64 * m)(*c),
+                                          gamma, mark_next, self._out4))
+        gd = -self._out4[0]
+        dnorm = math.sqrt(self._out4[1])
+        self._limits = (self._out4[2], self._out4[3])
+        self._saved_for = mark_next
+        self._need_steepest = False
+        return True, gd, dnorm
+
+    def steepest(self):
+        self._need_steepest = True
+
+    def begin_search(self, mark):
+        if self._need_steepest or self._saved_for != mark:
+            check(self.L.opkb_vmlmb_steepest(self.ws, mark, self._out4))
+            self._limits = (self._out4[2], self._out4[3])
+            self._need_steepest = False
+        self._saved_for = -1
+        return self._limits
+
+
+# ---------------------------------------------------------------------------
+class VMLMB:
+    """Steppable `_vmlmb!` (src/quasinewton.jl:296-612).
+
+    `step()` performs one trip of the reference's `while true` loop (one
+    evaluation of the objective); `iterate(k)` runs until `iter` has advanced by
+    k; `solve()` runs to termination.  After termination `x` holds the best
+    point (as `vmlmb!` returns it)."""
+
+    def __init__(self, fg, x0, *, mem=5, lower=-math.inf, upper=math.inf, autodiff=False,
+                 blmvm=False, fmin=-math.inf, maxiter=None, maxeval=None, xtol=(0.0, 1e-7),
+                 ftol=(0.0, 1e-8), gtol=(0.0, 1e-6), epsilon=0.0, verb=0, printer=print_iteration,
+                 output=None, lnsrch=None, ctx: Context = None, mode="fused", twoloop=None,
+                 observer=None, nglobal=None):
+        if autodiff:
+            raise NotImplementedError("autodiff is a host-side hook of the reference "
+                                      "(src/autodiff.jl); pass fg(x, g) -> f")
+        if isinstance(lower, BoundedSet):
+            lower, upper = lower.lower, lower.upper
+        self.fg = fg
+        # `mode` may also be a factory `ops = mode(solver, x0)` of a device back
+        # end: the seam the CPU tests of this host logic use (tests/cpu_backend.py)
+        external = callable(mode)
+        self.ctx = None if external else (ctx or (x0.ctx if isinstance(x0, Vector) else default_context()))
+        self._numpy_in = not isinstance(x0, Vector)
+        if self._numpy_in:
+            x0 = np.ascontiguousarray(x0)
+            if x0.dtype not in (np.float32, np.float64):
+                x0 = x0.astype(np.float64)
+            self._shape = x0.shape
+            x0 = x0.reshape(-1)
+        n = len(x0)
+        dtype = x0.dtype
+        self.n = n
+        self.dtype = np.dtype(dtype)
+
+        # vmlmb! :244-293 -------------------------------------------------------
+        bounds = 0
+        self._keep = []
+        lo, hi = lower, upper
+        if isinstance(lo, (int, float, np.floating, np.integer)):
+            lo = float(lo)
+            if lo > -math.inf:
+                bounds |= 1
+        else:
+            lo = lo if external else self._as_vector(lo, n, dtype, "lower")
+            bounds |= 1
+        if isinstance(hi, (int, float, np.floating, np.integer)):
+            hi = float(hi)
+            if hi < math.inf:
+                bounds |= 2
+        else:
+            hi = hi if external else self._as_vector(hi, n, dtype, "upper")
+            bounds |= 2
+        self.lo, self.hi = lo, hi
+        self.method = 0 if bounds == 0 else (1 if blmvm else 2)            # :273
+        if lnsrch is None:                                                 # :276-284
+            if self.method == 0:
+                lnsrch = MoreThuenteLineSearch(ftol=1e-3, gtol=0.9, xtol=0.1)
+            else:
+                lnsrch = MoreToraldoLineSearch(ftol=1e-3, gamma=(0.1, 0.5))
+        if not isinstance(lnsrch, LineSearch):
+            raise TypeError("lnsrch must be a LineSearch")
+        self.lnsrch = lnsrch
+
+        # _vmlmb! :310-379 --------------------------------------------------------
+        big = 2 ** 63 - 1
+        self.maxiter = big if maxiter is None else int(maxiter)
+        self.maxeval = big if maxeval is None else int(maxeval)
+        self.xatol, self.xrtol = float(xtol[0]), float(xtol[1])
+        self.fatol, self.frtol = float(ftol[0]), float(ftol[1])
+        self.gatol, self.grtol = float(gtol[0]), float(gtol[1])
+        self.epsilon = float(epsilon)
+        self.fmin = float(fmin)
+        mem = int(mem)
+        assert mem >= 1 and self.maxiter >= 0 and self.maxeval >= 1
+        assert self.xatol >= 0 and self.xrtol >= 0 and self.fatol >= 0 and self.frtol >= 0
+        assert self.gatol >= 0 and self.grtol >= 0 and 0 <= self.epsilon < 1
+        self.mem = min(mem, int(nglobal) if nglobal is not None else n)   # :328
+        self.mem = max(self.mem, 1)
+        self.fminset = (not math.isnan(self.fmin)) and self.fmin > -math.inf  # :330
+        self.verb = int(verb)
+        self.printer = printer
+        self.output = output if output is not None else sys.stdout
+        self.observer = observer
+        self.reason = ""
+        self.mark = 0
+        self.m = 0
+        self.iter = 0
+        self.eval = 0
+        self.rejects = 0
+        self.f = self.f0 = self.gd = self.gd0 = self.stp = 0.0
+        self.stpmin = self.stpmax = self.smin = self.smax = 0.0
+        self.gamma = 1.0
+        self.gnorm = self.gtest = 0.0
+        self.beststp = self.bestf = self.bestgnorm = 0.0
+        self.stage = 0
+        self.finished = False
+
+        # The fused path evaluates the two-loop recursion either in coefficient
+        # space from one Gram sweep ("gram": 4m+3 passes) or as the reference's
+        # sequence of dots and axpys ("sequential": parity-grade).  In Float32
+        # the roundings of the intermediate vector are part of the result, and
+        # the chaotic Rosenbrock trajectory amplifies a 1-ulp change beyond the
+        # 1e-4 gate within 20 iterations, so "sequential" is the Float32 default.
+        if twoloop is None:
+            twoloop = "gram" if self.dtype == np.float64 else "sequential"
+        if twoloop not in ("gram", "sequential"):
+            raise ValueError("twoloop must be 'gram' or 'sequential'")
+        self.twoloop = twoloop
+
+        # device storage (:358-371) ----------------------------------------------
+        self.mode = mode
+        self._ws = None
+        if external:
+            self.ops = mode(self, x0)
+            self.x = self.ops.x
+            return
+        L = _lib.lib()
+        if mode == "fused":
+            if self.mem > _lib.MEM_MAX:
+                raise ValueError(f"mode='fused' supports mem <= {_lib.MEM_MAX}; use mode='primitive'")
+            ws = vp()
+            lo_h = lo.handle if isinstance(lo, Vector) else None
+            hi_h = hi.handle if isinstance(hi, Vector) else None
+            check(L.opkb_vmlmb_create(self.ctx.handle, _eltype(dtype), n, self.mem, self.method,
+                                      lo_h, lo if lo_h is None else -math.inf,
+                                      hi_h, hi if hi_h is None else math.inf, C.byref(ws)))
+            self._ws = ws
+            self.x = Vector.borrowed(self.ctx, L.opkb_vmlmb_vector(ws, ord("x"), 0), self)
+            if isinstance(x0, Vector):
+                vcopy_(self.x, x0)
+            else:
+                self.x.upload(x0)
+            if is_builtin(fg):
+                a, c = fg.vectors(self.ctx, n, dtype)
+                check(L.opkb_vmlmb_set_objective(ws, fg.kind, a.handle if a else None,
+                                                 c.handle if c else None))
+            else:
+                check(L.opkb_vmlmb_set_objective(ws, _lib.OBJ_USER, None, None))
+            self.ops = _FusedOps(self, ws, self.x)
+        elif mode == "primitive":
+            if isinstance(x0, Vector):
+                self.x = x0                       # vmlmb! works in place
+            else:
+                self.x = self.ctx.from_numpy(x0)
+            if is_builtin(fg):
+                self.fg = _builtin_as_callable(fg, self.ctx, n, dtype)
+            self.ops = _PrimitiveOps(self, self.x)
+        else:
+            raise ValueError("mode must be 'fused' or 'primitive'")
+
+    def _as_vector(self, b, n, dtype, name):
+        if isinstance(b, Vector):
+            if b.n != n or b.dtype != dtype:
+                raise TypeError(f"invalid {name} bound type")
+            return b
+        arr = np.ascontiguousarray(b, dtype=dtype).reshape(-1)
+        if arr.size != n:
+            raise TypeError(f"invalid {name} bound type")
+        v = self.ctx.from_numpy(arr)
+        self._keep.append(v)
+        return v
+
+    def close(self):
+        if self._ws:
+            _lib.lib().opkb_vmlmb_destroy(self._ws)
+            self._ws = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -----------------------------------------------------------------------
+    def step(self) -> bool:
+        """One trip of `while true` (:381-601).  Returns False once finished."""
+        if self.finished:
+            return False
+        o = self.ops
+        ls = self.lnsrch
+        # :385-397 (and :599 of the previous trip, fused into the evaluation)
+        self.f = o.evaluate(self.mark, self.stp, self.eval == 0)
+        self.eval += 1
+        if self.eval == 1 or self.f < self.bestf:                          # :398-419
+            self.gnorm = o.gnorm()
+            self.beststp = self.stp
+            self.bestf = self.f
+            self.bestgnorm = self.gnorm
+            if self.eval == 1:
+                self.gtest = _jl_max(self.gatol, self.grtol * self.gnorm)
+            if self.gnorm <= self.gtest:
+                self.stage = 3
+                if self.gnorm == 0:
+                    self.reason = "a stationary point has been found"
+                elif self.method > 0:
+                    self.reason = "projected gradient norm sufficiently small"
+                else:
+                    self.reason = "gradient norm sufficiently small"
+                if self.eval > 1:
+                    self.iter += 1
+        if self.fminset and self.f < self.fmin:                            # :420-423
+            self.stage = 4
+            self.reason = "f < fmin"
+
+        if self.stage == 1:                                                # :425-474
+            o.effective_step()
+            if ls.usederivatives:
+                self.gd = o.gd_search(self.stp)
+            task = ls.iterate(self.stp, self.f, self.gd)
+            if task == "SEARCH":
+                self.stp = ls.getstep()
+            elif task == "CONVERGENCE":
+                self.iter += 1
+                xtest = _jl_max(self.xatol, 0.0)
+                if self.xrtol > 0:
+                    xtest = _jl_max(xtest, self.xrtol * o.xnorm())
+                if o.snorm() <= xtest:
+                    self.stage = 3
+                    self.reason = "X test satisfied"
+                else:
+                    delta = _jl_max(abs(self.f - self.f0), self.stp * abs(self.gd0))
+                    if delta <= self.fatol:
+                        self.stage = 3
+                        self.reason = "fatol test satisfied"
+                    elif delta <= self.frtol * abs(self.f0):
+                        self.stage = 3
+                        self.reason = "frtol test satisfied"
+                    elif self.iter >= self.maxiter:
+                        self.stage = 4
+                        self.reason = "too many iterations"
+                    elif self.eval >= self.maxeval:
+                        self.stage = 4
+                        self.reason = "too many evaluations"
+                    else:
+                        self.stage = 2
+            else:
+                self.stage = 4
+                self.reason = ls.getreason()
+        if self.stage < 2 and self.eval >= self.maxeval:                   # :475-478
+            self.stage = 4
+            self.reason = "too many evaluations"
+
+        if self.stage != 1:                                                # :480-596
+            if self.stp != self.beststp:                                   # :485-497
+                if self.stage >= 3:
+                    self.stp = self.beststp
+                    self.f = self.bestf
+                    self.gnorm = self.bestgnorm
+                    o.revert(self.mark, self.stp)
+                else:
+                    self.gnorm = o.gnorm()
+            if verbose(self.verb, self.iter):                              # :501-503
+                self.printer(self.output, self.iter, self.eval, self.rejects, self.f, self.gnorm,
+                             self.stp)
+            if self.observer is not None:
+                self.observer(self)
+            if self.stage >= 3:                                            # :504-506
+                self._finish()
+                return False
+
+            if self.stage == 2:                                            # :509-550
+                change, gd, dnorm = o.new_direction()
+                if change:
+                    self.gd = gd
+                    reject = not sufficient_descent(self.gd, self.epsilon, self.gnorm, dnorm)
+                else:
+                    reject = True
+                if reject:
+                    self.stage = 0
+                    self.rejects += 1
+                self.mark = self.mark + 1 if self.mark < self.mem - 1 else 0  # :549
+            if self.stage == 0:                                            # :551-556
+                o.steepest()
+                self.gd = -self.gnorm ** 2
+
+            self.f0 = self.f                                               # :560-563
+            self.gd0 = self.gd
+            self.smin, self.smax = o.begin_search(self.mark)
+
+            if self.stage == 2:                                            # :566-574
+                self.stp = 1.0
+            elif self.fminset and self.fmin < self.f0:
+                self.stp = 2 * (self.fmin - self.f0) / self.gd0
+            else:
+                self.stp = 1 / self.gnorm
+            STPMIN, STPMAX = 1e-20, 1e+20                                  # :321-322
+            if self.method > 0:                                            # :575-584
+                self.stp = _jl_min(self.stp, self.smax)
+                self.stpmin = STPMIN * self.stp
+                self.stpmax = _jl_min(STPMAX * self.stp, self.smax)
+            else:
+                self.stpmin = STPMIN * self.stp
+                self.stpmax = STPMAX * self.stp
+            # :587-594 (start! throws ArgumentError -> ValueError here)
+            task = ls.start(self.f0, self.gd0, self.stp, stpmin=self.stpmin, stpmax=self.stpmax)
+            if task != "SEARCH":
+                self.stage = 4
+                self.reason = ls.getreason()
+                self._finish()
+                return False
+            self.stage = 1
+        return True
+
+    def _finish(self):
+        self.finished = True
+        if verbose(self.verb, 0):                                          # :604-610
+            prefix = "WARNING: " if self.stage > 3 else "CONVERGENCE: "
+            self.output.write("# " + prefix + self.reason + "\n")
+
+    def iterate(self, niter: int = 1) -> bool:
+        """Run until `iter` has advanced by `niter` (or termination)."""
+        target = self.iter + niter
+        while self.iter < target:
+            if not self.step():
+                return False
+        return True
+
+    def solve(self):
+        while self.step():
+            pass
+        return self.x
+
+    def result(self):
+        """The solution as the caller's kind of array."""
+        if self._numpy_in:
+            x = self.x.download() if isinstance(self.x, Vector) else np.array(self.x)
+            return x.reshape(self._shape)
+        return self.x
+
+    def free_mask(self) -> np.ndarray:
+        """Free-variable mask {i : p[i] != 0} of this rank (all True for L-BFGS)."""
+        if self.method == 0:
+            return np.ones(self.n, dtype=bool)
+        p = self.ops.vector("p")
+        return (p.download() if isinstance(p, Vector) else np.asarray(p)) != 0
+
+
+def _builtin_as_callable(obj, ctx, n, dtype):
+    """Stand-alone `fg!(x, g)` of a built-in objective (Tier 1), for mode='primitive'."""
+    L = _lib.lib()
+    a, c = obj.vectors(ctx, n, dtype)
+    r = f64()
+
+    if obj.kind == _lib.OBJ_ROSENBROCK:
+        def fg(x, g):
+            check(L.opkb_rosenbrock_fg(ctx.handle, x.handle, g.handle, C.byref(r)))
+            return r.value
+    else:
+        def fg(x, g):
+            check(L.opkb_quadratic_fg(ctx.handle, a.handle, c.handle, x.handle, g.handle, C.byref(r)))
+            return r.value
+    fg._keep = (a, c)
+    return fg
+
+
+def vmlmb_(fg, x, **kwds):
+    """`vmlmb!(fg!, x; kwds...) -> x` (src/quasinewton.jl:226): the best solution
+    is stored in `x` (a device Vector or a writeable host array) and returned."""
+    solver = VMLMB(fg, x, **kwds)
+    solver.solve()
+    if isinstance(x, Vector):
+        if solver.x is not x:
+            vcopy_(x, solver.x)
+    else:
+        x[...] = solver.result().astype(x.dtype, copy=False)
+    solver.close()
+    return x
+
+
+def vmlmb(fg, x0, **kwds):
+    """`vmlmb(fg!, x0; kwds...) -> x` (src/quasinewton.jl:215): x0 is left unchanged."""
+    if isinstance(x0, Vector):
+        x = vcopy_(x0.similar(), x0)
+    else:
+        x = np.array(x0, copy=True)
+        if x.dtype not in (np.float32, np.float64):
+            x = x.astype(np.float64)
+    return vmlmb_(fg, x, **kwds)

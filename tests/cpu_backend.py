@@ -1,0 +1,167 @@
+"""TEST-ONLY device back end for the host drivers: the same `ops` interface as
+optimpacknextgen.jl_b200/vmlmb.py's _PrimitiveOps / _FusedOps, implemented with
+the CPU oracle's vector operations on numpy arrays.  It lets the CPU suite
+exercise the Python stage machine, the coefficient-space two-loop solver and
+the sharded (world_size > 1, gloo) reduction logic without a GPU.  It is never
+imported by the product package."""
+import math
+
+import numpy as np
+
+import opk_oracle as O
+
+
+class NumpyOps:
+    """1:1 with _PrimitiveOps (reference call sequence)."""
+
+    def __init__(self, solver, x0, obj):
+        self.s = solver
+        self.obj = obj
+        self.x = np.array(x0, copy=True)
+        n = self.x.size
+        self.g = np.empty_like(self.x)
+        self.p = np.empty_like(self.x) if solver.method > 0 else None
+        self.d = np.empty_like(self.x)
+        self.sv = np.empty_like(self.x)
+        self.S = [np.empty_like(self.x) for _ in range(solver.mem)]
+        self.Y = [np.empty_like(self.x) for _ in range(solver.mem)]
+        self.rho = np.zeros(solver.mem)
+        self._mark = 0
+
+    def _fg(self, x, g):
+        if self.obj == "rosenbrock":
+            return O.rosenbrock_fg(x, g)
+        return O.quadratic_fg(self.obj[1], self.obj[2], x, g)
+
+    def _b(self):
+        lo, hi = self.s.lo, self.s.hi
+        lo = None if (np.isscalar(lo) and lo == -math.inf) else lo
+        hi = None if (np.isscalar(hi) and hi == math.inf) else hi
+        return lo, hi
+
+    def evaluate(self, mark, stp, initial):
+        s = self.s
+        lo, hi = self._b()
+        if not initial:
+            O.vcombine(self.x, 1, self.S[mark], -stp, self.d)
+        if s.method > 0:
+            O.project_variables(self.x, self.x, lo, hi)
+        f = self._fg(self.x, self.g)
+        if s.method > 0:
+            O.project_direction(self.p, self.x, lo, hi, -1, self.g)
+        self._mark = mark
+        return f
+
+    def gnorm(self):
+        return O.vnorm2(self.p if self.s.method > 0 else self.g)
+
+    def effective_step(self):
+        O.vcombine(self.sv, 1, self.x, -1, self.S[self._mark])
+
+    def gd_search(self, stp):
+        if self.s.method > 0:
+            return O.vdot(self.g, self.sv) / stp
+        return -O.vdot(self.g, self.d)
+
+    def xnorm(self):
+        return O.vnorm2(self.x)
+
+    def snorm(self):
+        return O.vnorm2(self.sv)
+
+    def revert(self, mark, stp):
+        lo, hi = self._b()
+        O.vcombine(self.x, 1, self.S[mark], -stp, self.d)
+        if self.s.method > 0:
+            O.project_variables(self.x, self.x, lo, hi)
+
+    def new_direction(self):
+        s = self.s
+        mark = s.mark
+        lo, hi = self._b()
+        O.vupdate(self.S[mark], -1, self.x)
+        O.vupdate(self.Y[mark], -1, self.p if s.method == 1 else self.g)
+        if s.method < 2:
+            self.rho[mark] = O.vdot(self.Y[mark], self.S[mark])
+            if self.rho[mark] > 0:
+                s.gamma = self.rho[mark] / O.vdot(self.Y[mark], self.Y[mark])
+        s.m = min(s.m + 1, s.mem)
+        if s.method < 2:
+            self.d[:] = self.g
+            change, _ = O.apply_lbfgs(self.S, self.Y, self.rho, s.gamma, s.m, mark, self.d)
+        else:
+            self.d[:] = self.p
+            sel = O.get_free_variables(self.d)
+            change, _ = O.apply_lbfgs_sel(self.S, self.Y, self.rho, s.m, mark, self.d, sel)
+        if not change:
+            return False, 0.0, 0.0
+        if s.method > 0:
+            O.project_direction(self.d, self.x, lo, hi, -1, self.d)
+        return True, -O.vdot(self.g, self.d), O.vnorm2(self.d)
+
+    def steepest(self):
+        self.d[:] = self.p if self.s.method > 0 else self.g
+
+    def begin_search(self, mark):
+        s = self.s
+        lo, hi = self._b()
+        self.S[mark][:] = self.x
+        self.Y[mark][:] = self.p if s.method == 1 else self.g
+        if s.method > 0:
+            return O.step_limits(self.x, lo, hi, -1, self.d)
+        return math.inf, math.inf
+
+    def vector(self, which, slot=0):
+        if which == "S":
+            return self.S[slot]
+        if which == "Y":
+            return self.Y[slot]
+        return {"x": self.x, "g": self.g, "p": self.p, "d": self.d}[which]
+
+
+class NumpyGramOps(NumpyOps):
+    """Same phases as _FusedOps (Gram block -> host solve -> assembly), with the
+    Gram block and the assembly computed by numpy in place of the kernels; the
+    coefficient-space solver is the product's own (_FusedOps._solve)."""
+
+    def __init__(self, solver, x0, obj):
+        super().__init__(solver, x0, obj)
+        from opkb200.vmlmb import _FusedOps
+        self._solve = lambda G, m, slots: _FusedOps._solve(self, G, m, slots)
+        self.rho = [0.0] * solver.mem
+
+    def new_direction(self):
+        s = self.s
+        mark = s.mark
+        lo, hi = self._b()
+        T = self.x.dtype.type
+        O.vupdate(self.S[mark], -1, self.x)
+        O.vupdate(self.Y[mark], -1, self.p if s.method == 1 else self.g)
+        m = min(s.m + 1, s.mem)
+        s.m = m
+        slots = [(mark - (m - 1) + j) % s.mem for j in range(m)]
+        v0 = self.p if s.method == 2 else self.g
+        free = (v0 != 0) if s.method == 2 else np.ones(v0.size, dtype=bool)
+        W = m + 1
+        G = np.zeros((2 * m, W))
+        cols = [v0] + [self.Y[k] for k in slots]
+        for a, k in enumerate(slots):
+            for ci, cv in enumerate(cols):
+                G[2 * a, ci] = O.vdot_sel(np.flatnonzero(free), self.S[k], cv)
+                G[2 * a + 1, ci] = O.vdot_sel(np.flatnonzero(free), self.Y[k], cv)
+        alpha, c, gamma, change = self._solve(list(G.reshape(-1)), m, slots)
+        if not change:
+            return False, 0.0, 0.0
+        # assembly with the reference's rounding sequence (what k_direction does)
+        v = v0.copy()
+        for j in range(m - 1, -1, -1):
+            if alpha[j] == alpha[j]:
+                v[free] = v[free] + T(-alpha[j]) * self.Y[slots[j]][free]
+        v = T(gamma) * v
+        for j in range(m):
+            if alpha[j] == alpha[j]:
+                v[free] = v[free] + T(c[j]) * self.S[slots[j]][free]
+        self.d[:] = v
+        if s.method > 0:
+            O.project_direction(self.d, self.x, lo, hi, -1, self.d)
+        return True, -O.vdot(self.g, self.d), O.vnorm2(self.d)

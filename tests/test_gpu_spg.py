@@ -1,0 +1,112 @@
+"""SPG parity on the GPU: fused one-pass kernels and the one-kernel-per-call
+path against the oracle's `_spg!` (src/spg.jl:193-403)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from helpers import problem, relerr
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def opk():
+    import opkb200
+    return opkb200
+
+
+def run_gpu(opk, pb, m, mode, **kw):
+    lo = -math.inf if pb["lower"] is None else pb["lower"]
+    hi = math.inf if pb["upper"] is None else pb["upper"]
+    trace = []
+
+    def obs(s):
+        trace.append(dict(iter=s.iter, fcnt=s.fcnt, pcnt=s.pcnt, f=s.f, pgtwon=s.pgtwon, pginfn=s.pginfn))
+    ws = opk.Info()
+    s = opk.SPG(pb["gpu_obj"], opk.BoxProjection(lo, hi), pb["x0"], m, mode=mode, observer=obs, ws=ws, **kw)
+    s.solve()
+    x = s.result()
+    s.close()
+    return x, ws, trace
+
+
+CASES = [
+    ("rosen_lower0", 20, np.float64, 10),
+    ("rosen_box", 1000, np.float64, 10),
+    ("quad_box", 1003, np.float64, 10),
+    ("quad_box", 100001, np.float64, 1),
+    ("quad_upper_scalar", 5000, np.float64, 5),
+    ("quad_box", 100001, np.float32, 10),
+    ("rosen_box", 1000, np.float32, 10),
+]
+
+
+@pytest.mark.parametrize("mode", ["fused", "primitive"])
+@pytest.mark.parametrize("kind,n,dtype,m", CASES)
+def test_spg_trajectory(opk, oracle, kind, n, dtype, m, mode):
+    pb = problem(kind, n, dtype)
+    xo, io, tro = oracle.spg(pb["oracle_obj"], pb["x0"], m, pb["lower"], pb["upper"], trace=True, maxit=25)
+    xg, ws, trg = run_gpu(opk, pb, m, mode, maxit=25)
+    rtol = 1e-10 if dtype == np.float64 else 1e-4
+    assert len(trg) == len(tro)
+    for g, w in zip(trg, tro):
+        if w["iter"] > 20:
+            break
+        assert (g["iter"], g["fcnt"], g["pcnt"]) == (w["iter"], w["fcnt"], w["pcnt"])
+        assert abs(g["f"] - w["f"]) <= rtol * abs(w["f"]) + 1e-300, (w["iter"], g["f"], w["f"])
+        assert abs(g["pgtwon"] - w["pgtwon"]) <= rtol * abs(w["pgtwon"]) + 1e-300
+        assert abs(g["pginfn"] - w["pginfn"]) <= rtol * abs(w["pginfn"]) + 1e-300
+    assert (ws.iter, ws.fcnt, ws.pcnt, ws.status) == (io["iter"], io["fcnt"], io["pcnt"], io["status"])
+    assert relerr(xg, xo) <= rtol
+
+
+@pytest.mark.parametrize("mode", ["fused", "primitive"])
+def test_spg_converges_like_reference_test(opk, oracle, mode):
+    # test/rosenbrock.jl:119-122 runs spg(rosenbrock_fg!, nonnegative!, x0, 10) (never asserted)
+    x0 = opk.Rosenbrock.x0(20, np.float64)
+    ws = opk.Info()
+    x = opk.spg(opk.Rosenbrock(), opk.BoxProjection(0.0, math.inf), x0, 10, ws=ws, mode=mode)
+    assert np.abs(x - 1).max() < 1e-3
+    assert (ws.iter, ws.fcnt, ws.pcnt, ws.status) == (64, 82, 130, opk.SPGModule.INFNORM_CONVERGENCE)
+    assert opk.getreason(ws) == "Convergence with projected gradient infinite-norm"
+
+
+def test_spg_user_projection_and_objective(opk):
+    ctx = opk.default_context()
+    n = 500
+    t = ctx.from_numpy(np.linspace(-1, 2, n))
+
+    def fg(x, g):
+        opk.vcombine_(g, 2, x, -2, t)
+        r = opk.vcombine_(x.similar(), 1, x, -1, t)
+        return opk.vdot(r, r)
+
+    def nonnegative(dst, src):                       # test/rosenbrock.jl:50-58
+        return opk.project_variables_(dst, src, 0.0, None)
+
+    x = opk.spg(fg, nonnegative, np.full(n, 3.0), 10)
+    assert np.abs(x - np.clip(np.linspace(-1, 2, n), 0, None)).max() < 1e-5
+    ws = opk.Info()
+    opk.spg(fg, nonnegative, np.full(n, 3.0), 10, maxfc=3, ws=ws)
+    assert ws.status == opk.SPGModule.TOO_MANY_EVALUATIONS and ws.fcnt == 3
+
+
+def test_spg_golden(opk):
+    with open(os.path.join(GOLDEN, "spg_traces.json")) as fh:
+        gold = json.load(fh)
+    for case in gold["cases"]:
+        dtype = np.dtype(case["dtype"])
+        pb = problem(case["kind"], case["n"], dtype)
+        rtol = 1e-10 if dtype == np.float64 else 1e-4
+        for mode in ("fused", "primitive"):
+            xg, ws, trg = run_gpu(opk, pb, case["m"], mode, maxit=case["maxit"])
+            for g, w in zip(trg, case["trace"]):
+                if w["iter"] > 20:
+                    break
+                assert (g["iter"], g["fcnt"]) == (w["iter"], w["fcnt"])
+                assert abs(g["f"] - w["f"]) <= rtol * abs(w["f"]) + 1e-300
+                assert abs(g["pgtwon"] - w["pgtwon"]) <= rtol * abs(w["pgtwon"]) + 1e-300

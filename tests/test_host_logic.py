@@ -1,0 +1,217 @@
+"""CPU tests of the product's host logic (no GPU, no CUDA calls): the C-ABI
+library loads and exports every declared symbol; the Python line searches match
+the oracle's C state machines step for step; the VMLMB/SPG stage machines and
+the coefficient-space two-loop solver reproduce the oracle driver when run on
+a test-only numpy back end (tests/cpu_backend.py)."""
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+import opkb200 as opk
+from cpu_backend import NumpyGramOps, NumpyOps
+from helpers import compare_traces, gpu_bounds, problem
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    """The shared library loads without a GPU and exports what include/opkb200.h declares."""
+    from opkb200 import _lib
+    L = _lib.lib()
+    header = open(os.path.join(ROOT, "include", "opkb200.h")).read()
+    declared = set(re.findall(r"\b(opkb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in opkb200.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    assert L.opkb_version() == 100
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product fails loudly (no silent CPU path)."""
+    import ctypes
+    from opkb200 import _lib
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    rc = L.opkb_context_create(ctypes.byref(h), -1)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = rc == 0
+    if has_gpu:
+        assert rc == 0
+        L.opkb_context_destroy(h)
+    else:
+        assert rc != 0 and b"no CPU fallback" in L.opkb_last_error()
+        with pytest.raises(opk.OpkbError):
+            opk.vmlmb(opk.Rosenbrock(), np.zeros(4))
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "optimpacknextgen.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "opk_oracle" not in txt and "libopkoracle" not in txt, f
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_linesearches_match_oracle(oracle, seed):
+    """Random 1-D functions: the Python state machines and the C restatement
+    return the same task and step at every call."""
+    rng = np.random.default_rng(seed)
+    O = oracle
+    names = {O.TASK_SEARCH: "SEARCH", O.TASK_CONVERGENCE: "CONVERGENCE", O.TASK_WARNING: "WARNING"}
+    for trial in range(40):
+        a, b, c, w = rng.uniform(0.1, 3), rng.uniform(0.5, 5), rng.uniform(-1, 1), rng.uniform(0.5, 8)
+        phi = lambda t: -a * t + b * t * t + c * math.sin(w * t) + 0.3 * t ** 3
+        dphi = lambda t: -a + 2 * b * t + c * w * math.cos(w * t) + 0.9 * t * t
+        if dphi(0) >= 0:
+            continue
+        stp0 = float(10 ** rng.uniform(-2, 1.5))
+        stpmax = stp0 * float(10 ** rng.uniform(0, 3))
+        for kind, mk in ((O.LS_ARMIJO, lambda: opk.ArmijoLineSearch(ftol=1e-4)),
+                         (O.LS_MORE_TORALDO, lambda: opk.MoreToraldoLineSearch(ftol=1e-3, gamma=(0.1, 0.5))),
+                         (O.LS_MORE_TORALDO, lambda: opk.MoreToraldoLineSearch(ftol=1e-3, strict=True)),
+                         (O.LS_MORE_THUENTE, lambda: opk.MoreThuenteLineSearch(ftol=1e-3, gtol=0.9, xtol=0.1)),
+                         (O.LS_MORE_THUENTE, lambda: opk.MoreThuenteLineSearch(ftol=1e-4, gtol=0.1, xtol=1e-3))):
+            py = mk()
+            kw = {}
+            if kind == O.LS_ARMIJO:
+                kw = dict(ftol=py.ftol)
+            elif kind == O.LS_MORE_TORALDO:
+                kw = dict(ftol=py.ftol, gamma=(py.gamma1, py.gamma2), strict=py.strict)
+            else:
+                kw = dict(ftol=py.ftol, gtol=py.gtol, xtol=py.xtol)
+            cc = O.LineSearch(kind, **kw)
+            t1 = py.start(phi(0), dphi(0), stp0, stpmin=1e-20 * stp0, stpmax=stpmax)
+            t2 = cc.start(phi(0), dphi(0), stp0, 1e-20 * stp0, stpmax)
+            assert t1 == names[t2] == "SEARCH"
+            assert opk.usederivatives(py) == cc.usederivatives
+            for _ in range(60):
+                stp = py.getstep()
+                assert stp == cc.stp
+                t1 = py.iterate(stp, phi(stp), dphi(stp))
+                t2 = cc.iterate(stp, phi(stp), dphi(stp))
+                assert t1 == names[t2]
+                if t1 != "SEARCH":
+                    assert opk.getreason(py) == cc.reason()
+                    break
+
+
+def test_linesearch_errors():
+    ls = opk.MoreToraldoLineSearch(ftol=1e-3)
+    for args, msg in (((1.0, -1.0, 1.0, 2.0, 1.0), "STPMAX < STPMIN"), ((1.0, -1.0, 1.0, -1.0, 2.0), "STPMIN < 0"),
+                      ((1.0, -1.0, 3.0, 0.0, 2.0), "STP > STPMAX"), ((1.0, -1.0, 0.5, 1.0, 2.0), "STP < STPMIN"),
+                      ((1.0, 0.0, 1.0, 0.0, 2.0), "Not a descent direction")):
+        with pytest.raises(ValueError, match=msg):
+            ls.start(args[0], args[1], args[2], stpmin=args[3], stpmax=args[4])
+    with pytest.raises(ValueError, match="descent condition violated"):
+        opk.cstep(False, 0.0, 10.0, 0.0, 1.0, +1.0, 0.0, 1.0, 1.0, 1.0, 0.5, 0.2)
+    ls = opk.ArmijoLineSearch()
+    ls.start(1.0, -1.0, 1.0, stpmin=0.0, stpmax=2.0)
+    with pytest.raises(AssertionError):
+        ls.iterate(0.7, 1.0, 0.0)
+    assert opk.getreason(opk.ArmijoLineSearch()) == "Algorithm not yet started"
+
+
+CASES = [
+    ("rosen_unc", 20, np.float64, dict()),
+    ("rosen_unc", 20, np.float64, dict(mem=15)),
+    ("rosen_unc", 1000, np.float64, dict()),
+    ("rosen_lower0", 20, np.float64, dict()),
+    ("rosen_lower0", 20, np.float64, dict(blmvm=True)),
+    ("rosen_box", 1000, np.float64, dict(mem=7)),
+    ("rosen_box", 1000, np.float64, dict(blmvm=True)),
+    ("quad_box", 1003, np.float64, dict(mem=10)),
+    ("quad_upper_scalar", 500, np.float64, dict(mem=3)),
+    ("rosen_unc", 20, np.float32, dict()),
+    ("rosen_box", 1000, np.float32, dict(mem=7)),
+    ("quad_box", 1003, np.float32, dict(mem=5)),
+]
+
+
+def _run_host(pb, factory, **kw):
+    lo, hi = gpu_bounds(pb)
+    trace = []
+
+    def obs(s):
+        trace.append(dict(iter=s.iter, eval=s.eval, rejects=s.rejects, f=s.f, gnorm=s.gnorm, stp=s.stp,
+                          x=np.array(s.x), mask=s.free_mask()))
+    s = opk.VMLMB(pb["gpu_obj"], pb["x0"], lower=lo, upper=hi, observer=obs,
+                  mode=lambda solver, x0: factory(solver, x0, pb["oracle_obj"]), **kw)
+    s.solve()
+    return s, trace
+
+
+@pytest.mark.parametrize("kind,n,dtype,kw", CASES)
+def test_stage_machine_equals_oracle_driver(oracle, kind, n, dtype, kw):
+    """Python `_vmlmb!` + numpy/oracle vector ops == oracle C driver, bit for bit."""
+    pb = problem(kind, n, dtype)
+    xo, ro, tro = oracle.vmlmb(pb["oracle_obj"], pb["x0"], pb["lower"], pb["upper"], trace=True, **kw)
+    s, tr = _run_host(pb, NumpyOps, **kw)
+    assert (s.iter, s.eval, s.rejects, s.reason) == (ro["iter"], ro["eval"], ro["rejects"], ro["reason"])
+    assert len(tr) == len(tro)
+    for g, w in zip(tr, tro):
+        assert (g["iter"], g["eval"], g["f"], g["gnorm"], g["stp"]) == (w["iter"], w["eval"], w["f"], w["gnorm"], w["stp"])
+        assert np.array_equal(g["x"], w["x"]) and np.array_equal(g["mask"], w["mask"])
+    assert np.array_equal(s.result(), xo)
+
+
+@pytest.mark.parametrize("kind,n,dtype,kw", CASES)
+def test_gram_form_two_loop_within_tolerance(oracle, kind, n, dtype, kw):
+    """The coefficient-space two-loop (Gram block + host solve + assembly with
+    the reference's rounding sequence) keeps the first 20 iterations within the
+    north_star tolerance of the sequential recursion."""
+    pb = problem(kind, n, dtype)
+    kw = dict(kw, maxiter=25)
+    xo, ro, tro = oracle.vmlmb(pb["oracle_obj"], pb["x0"], pb["lower"], pb["upper"], trace=True, **kw)
+    s, tr = _run_host(pb, NumpyGramOps, **kw)
+    if dtype == np.float64:
+        compare_traces(tr, tro, 20, 1e-10)
+    elif kind.startswith("quad"):
+        compare_traces(tr, tro, 20, 1e-4)
+    else:
+        # Float32 + chaotic Rosenbrock: the roundings of the intermediate vector
+        # (absent in coefficient space) are amplified to ~2e-3 by iteration 20,
+        # which is why twoloop="sequential" is the Float32 default
+        compare_traces(tr, tro, 20, 1e-2, check_mask=False)
+
+
+def test_vmlmb_options(oracle):
+    pb = problem("rosen_lower0", 20, np.float64)
+    for kw in (dict(maxeval=7), dict(maxiter=3), dict(fmin=0.0), dict(epsilon=0.01), dict(gtol=(1e-3, 0.0)),
+               dict(xtol=(0.0, 1e-2)), dict(ftol=(1e-4, 0.0)), dict(fmin=300.0)):
+        xo, ro, tro = oracle.vmlmb("rosenbrock", pb["x0"], 0.0, None, **kw)
+        s, tr = _run_host(pb, NumpyOps, **kw)
+        assert (s.iter, s.eval, s.reason, s.stage) == (ro["iter"], ro["eval"], ro["reason"], ro["stage"]), kw
+        assert np.array_equal(s.result(), xo)
+    with pytest.raises(NotImplementedError):
+        opk.VMLMB(opk.Rosenbrock(), pb["x0"], autodiff=True, mode=lambda s, x: None)
+    with pytest.raises(AssertionError):
+        opk.VMLMB(opk.Rosenbrock(), pb["x0"], epsilon=1.5, mode=lambda s, x: None)
+    # print_iteration format (src/quasinewton.jl:649-660)
+    import io
+    buf = io.StringIO()
+    opk.print_iteration(buf, 0, 1, 0, 242.0, 736.39, 0.0)
+    assert buf.getvalue().splitlines()[2] == "     0      1      0    2.4200000000000000E+02  7.36E+02  0.00E+00"
+
+
+def test_shard_ranges():
+    from opkb200.dist import shard_range
+    for n in (1 << 28, 1 << 31, 10 ** 7, 1000003, 10):
+        for world in (1, 2, 4, 8):
+            tot, prev = 0, 0
+            for r in range(world):
+                first, cnt = shard_range(n, r, world)
+                assert first == prev and cnt >= 0
+                if first + cnt < n:
+                    assert cnt % 4 == 0
+                prev = first + cnt
+                tot += cnt
+            assert tot == n

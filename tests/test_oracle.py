@@ -232,3 +232,33 @@ def test_python_callable_objective(oracle):
     assert np.allclose(x, 3.0, atol=1e-6)
     x, res, _ = oracle.vmlmb(fg, np.zeros(7), upper=2.0)
     assert np.allclose(x, 2.0)
+
+
+def test_oracle_reproduces_golden(oracle):
+    """tests/golden/*.json were generated from this oracle (make_golden.py);
+    the GPU suite compares the CUDA path with the same files."""
+    import json
+    import os
+    from helpers import problem
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    with open(os.path.join(gdir, "vmlmb_traces.json")) as fh:
+        gold = json.load(fh)
+    for case in gold["cases"]:
+        pb = problem(case["kind"], case["n"], np.dtype(case["dtype"]))
+        x, res, tr = oracle.vmlmb(pb["oracle_obj"], pb["x0"], pb["lower"], pb["upper"],
+                                  trace=True, maxiter=case["maxiter"], **case["kw"])
+        assert len(tr) == len(case["trace"])
+        for t, w in zip(tr, case["trace"]):
+            assert (t["iter"], t["eval"], t["f"], t["gnorm"], t["stp"]) == \
+                (w["iter"], w["eval"], w["f"], w["gnorm"], w["stp"])
+            assert int(t["mask"].sum()) == w["nfree"]
+    with open(os.path.join(gdir, "spg_traces.json")) as fh:
+        gold = json.load(fh)
+    for case in gold["cases"]:
+        pb = problem(case["kind"], case["n"], np.dtype(case["dtype"]))
+        x, info, tr = oracle.spg(pb["oracle_obj"], pb["x0"], case["m"], pb["lower"], pb["upper"],
+                                 trace=True, maxit=case["maxit"])
+        assert (info["iter"], info["fcnt"], info["status"]) == \
+            (case["final"]["iter"], case["final"]["fcnt"], case["final"]["status"])
+        for t, w in zip(tr, case["trace"]):
+            assert (t["f"], t["pgtwon"], t["pginfn"]) == (w["f"], w["pgtwon"], w["pginfn"])
