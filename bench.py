@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- VMLMB iterations/sec and effective HBM GB/s (BASELINE.json).
+
+A "step" is one VMLMB iteration (an accepted line search, counter `iter` of
+src/quasinewton.jl:443) of the bound-constrained convex quadratic of config C4:
+n = 2^28 Float64, m = 10, array bounds [0, 1], a_i = 1e4^u, c_i = -1 + 3u,
+x0 = 0.5, fused path (P1 trial / P3 Gram sweep / P4 direction).
+With N > 1 (torchrun, one rank per GPU) the SAME n is sharded in contiguous
+blocks over the ranks ("strong" scaling); the only communication is one packed
+all-gather of reduction partials per phase.
+
+    python bench.py --gpus 1 --steps 50 --warmup 3
+    python bench.py --impl reference --steps 5 --warmup 1     # CPU oracle port
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "VMLMB iterations/sec at n=2^28 f64 m=10 (bound-constrained quadratic)"
+UNIT = "iterations/s"
+KAPPA = 1e4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2n", type=int, default=28)
+    ap.add_argument("--mem", type=int, default=10)
+    ap.add_argument("--cpu-log2n", type=int, default=23, help="size of the bounded CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def config(args, n):
+    return {
+        "workload": "C4: VMLMB bound-constrained quadratic n=2^%d Float64 m=%d, array bounds [0,1], "
+                    "More-Toraldo line search, fused P1/P3(Gram)/P4" % (int(math.log2(n)), args.mem),
+        "n": n, "mem": args.mem, "eltype": "Float64", "kappa": KAPPA,
+        "sharding": "contiguous 1-D blocks, %d rank(s), one packed all-gather of partials per phase" % args.gpus,
+        "l2": "no flush needed: every kernel streams >= 18 GiB per rank at N=1 (>> 126 MB L2)",
+    }
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle port ("reference-faithful unfused" C restatement, OpenMP)
+def cpu_run(args, steps, warmup, log2n):
+    """Times `steps` VMLMB iterations of the oracle on the host cores on a
+    bounded sample (n_s = 2^log2n) of the same workload.  Returns it/s at n_s."""
+    import opk_oracle as O
+    O.build()
+    O.set_sum_mode(O.SUM_ACCURATE)
+    O.set_num_threads(0)
+    cores = O.max_threads()
+    ns = 1 << log2n
+    sys.path.insert(0, ROOT)
+    import opkb200 as opk
+    a, c = opk.Quadratic.synthetic(ns, np.float64, kappa=KAPPA)
+    lo, hi = np.zeros(ns), np.ones(ns)
+    x0 = np.full(ns, 0.5)
+    kw = dict(mem=args.mem, xtol=(0, 0), ftol=(0, 0), gtol=(0, 0))
+
+    def run(k):
+        t0 = time.perf_counter()
+        x, res, _ = O.vmlmb(("quadratic", a, c), x0, lo, hi, maxiter=k, **kw)
+        return time.perf_counter() - t0, res
+
+    # warm-up iterations are part of a run (the solver cannot be resumed): time
+    # (warmup + steps) and (warmup) iterations and take the difference
+    tw, _ = run(max(warmup, 1))
+    tt, res = run(max(warmup, 1) + steps)
+    dt = max(tt - tw, 1e-9)
+    its = steps / dt
+    evals_per_iter = res["eval"] / max(res["iter"], 1)
+    return dict(its_at_ns=its, ns=ns, cores=cores, seconds=dt, evals_per_iter=evals_per_iter)
+
+
+def reference_line(args):
+    n = 1 << args.log2n
+    r = cpu_run(args, args.steps, args.warmup, args.cpu_log2n)
+    scale = r["ns"] / n
+    value = r["its_at_ns"] * scale
+    sample = ("oracle port (C restatement of the reference's unfused CPU path, OpenMP, %d threads): "
+              "%d iterations at n_s=2^%d timed (%.2f s), iterations/s scaled by n_s/n to n=2^%d; "
+              "the Julia reference itself cannot run here (no Julia runtime)"
+              % (r["cores"], args.steps, args.cpu_log2n, r["seconds"], args.log2n))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config(args, n),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def summary(self, t0, t1):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if not (t0 <= t <= t1 + 0.3):
+                continue
+            f = [s.strip() for s in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+def traffic_for(kernel, n_local):
+    """dram bytes per launch of `kernel` from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            t = json.load(fh)
+        e = t.get(kernel)
+        if e and int(e["n"]) == int(n_local):
+            return float(e["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
+def ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import opkb200 as opk
+    from opkb200.dist import init_context, shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = init_context(local)
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = 1 << args.log2n
+    first, nloc = shard_range(n, rank, world)
+    dt = np.float64
+    es = 8
+    m = args.mem
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ---- device-resident inputs -------------------------------------------------
+    obj = opk.Quadratic.synthetic_device(ctx, nloc, dt, kappa=KAPPA, first=first)
+    lo = ctx.vector(nloc, dt).fill(0.0)
+    hi = ctx.vector(nloc, dt).fill(1.0)
+    x0 = ctx.vector(nloc, dt).fill(0.5)
+    kw = dict(lower=lo, upper=hi, mem=m, xtol=(0, 0), ftol=(0, 0), gtol=(0, 0), nglobal=n, ctx=ctx)
+
+    solver = opk.VMLMB(obj, x0, **kw)
+    solver.iterate(W)                                   # warm-up (untimed)
+    ctx.profile(True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    l0, e0, i0 = ctx.launch_count, solver.eval, solver.iter
+    t0 = time.perf_counter()
+    ctx.timer_start()
+    alive = solver.iterate(K)                           # EXACTLY K iterations
+    ms = ctx.timer_stop()
+    barrier()
+    t1 = time.perf_counter()
+    ms = max_over_ranks(ms)
+    launches = ctx.launch_count - l0
+    evals = solver.eval - e0
+    iters = solver.iter - i0
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    clocks = sampler.summary(t0, t1) if sampler else None
+    f_final, gnorm_final = solver.f, solver.gnorm
+    solver.close()
+    del solver
+    if not alive or iters != K:
+        raise SystemExit("solver stopped after %d of %d timed iterations" % (iters, K))
+    value = K / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel -------------------------------------------
+    peak, peak_src = measured_peak()
+    # algorithmic passes per launch (array bounds): P1 = 7, P3 = 2m+5, P4 = 2m+8
+    passes = {"trial": 7, "gram": 2 * m + 5, "direction": 2 * m + 8}
+    kern = {}
+    for name, npass in passes.items():
+        if name in prof:
+            tot, cnt = prof[name]
+            avg = tot / cnt
+            ach = npass * es * nloc / (avg * 1e-3) / 1e9
+            kern[name] = {"launches": cnt, "avg_ms": avg, "share_of_step": tot / ms,
+                          "alg_bytes_per_launch": npass * es * nloc, "achieved_gbs": ach,
+                          "frac": ach / peak}
+    dom = max(kern, key=lambda k: kern[k]["avg_ms"] * kern[k]["launches"])
+    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak,
+                "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": traffic_for(dom, nloc),
+                "peak_source": peak_src, "kernels": kern,
+                "iteration": {"alg_bytes": (4 * m + 20) * es * n, "evals_per_iter": evals / K,
+                              "achieved_gbs": (4 * m + 20) * es * n / (ms * 1e-3 / K) / 1e9 / world,
+                              "frac_per_gpu": (4 * m + 20) * es * n / (ms * 1e-3 / K) / 1e9 / world / peak}}
+
+    # ---- e2e: the public call with HOST (pinned) buffers -------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = {}
+        for name, v in (("a", obj.a), ("c", obj.c), ("lo", lo), ("hi", hi), ("x0", x0)):
+            t = torch.empty(nloc, dtype=torch.float64, pin_memory=True)
+            arr = t.numpy()
+            v.download(arr)
+            host[name] = (t, arr)
+        out_t = torch.empty(nloc, dtype=torch.float64, pin_memory=True)
+        del obj, lo, hi, x0
+        barrier()
+        te0 = time.perf_counter()
+        s2 = opk.VMLMB(opk.Quadratic(host["a"][1], host["c"][1]), host["x0"][1], lower=host["lo"][1],
+                       upper=host["hi"][1], mem=m, maxiter=K, xtol=(0, 0), ftol=(0, 0), gtol=(0, 0),
+                       nglobal=n, ctx=ctx)
+        s2.solve()
+        s2.x.download(out_t.numpy())
+        barrier()
+        te = max_over_ranks(time.perf_counter() - te0)
+        e2e = {"value": s2.iter / te, "unit": UNIT, "h2d_bytes_per_step": 5 * nloc * es * world / K,
+               "d2h_bytes_per_step": nloc * es * world / K,
+               "what": "opkb200.VMLMB(Quadratic(a, c), x0, lower, upper, mem=%d, maxiter=%d).solve() "
+                       "with pinned host arrays in, host array out (setup, uploads, %d iterations, "
+                       "download inside the timed region)" % (m, K, s2.iter),
+               "seconds": te}
+        s2.close()
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config(args, n), "roofline": roofline,
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "evals_per_s": evals / (ms * 1e-3), "final": {"f": f_final, "gnorm": gnorm_final},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_run(args, args.cpu_steps, 1, args.cpu_log2n)
+        scale = r["ns"] / n
+        line["cpu_baseline"] = {
+            "value": r["its_at_ns"] * scale, "unit": UNIT, "cores": r["cores"], "kind": "port",
+            "sample": "oracle port (C restatement of the reference's unfused CPU path, OpenMP, %d threads): "
+                      "%d iterations at n_s=2^%d timed (%.2f s), scaled by n_s/n to n=2^%d"
+                      % (r["cores"], args.cpu_steps, args.cpu_log2n, r["seconds"], args.log2n)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            reference_line(args)
+        return
+    ours(args)
+
+
+if __name__ == "__main__":
+    main()

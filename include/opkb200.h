@@ -88,7 +88,14 @@ int64_t opkb_context_launch_count(const opkb_context* ctx);
 /* CUDA-event timer on the context's stream */
 int opkb_timer_start(opkb_context* ctx);
 int opkb_timer_stop(opkb_context* ctx, double* milliseconds);
-/* write `bytes` of scratch memory (> L2) to flush the L2 between timed runs */
+/* per-kernel profile: with the profile enabled every launch is bracketed by a
+ * CUDA-event pair on the launching stream; kernel_class: 0 other, 1 trial (P1),
+ * 2 gram (P3), 3 direction (P4/P4'), 4 spg, 5 reductions, 6 element-wise,
+ * 7 bounds, 8 stand-alone objectives */
+int opkb_profile_enable(opkb_context* ctx, int on);
+int opkb_profile_reset(opkb_context* ctx);
+int opkb_profile_get(opkb_context* ctx, int kernel_class, double* ms_total, int64_t* count);
+/* write 256 MiB of scratch memory (> L2) to flush the L2 between timed runs */
 int opkb_flush_l2(opkb_context* ctx);
 
 /* Multi-GPU: rank 0 obtains a 128-byte id, the host broadcasts it (e.g.

@@ -20,7 +20,8 @@ from .vmlmb import (VMLMB, vmlmb, vmlmb_, BoundedSet, EMULATE_BLMVM, apply_lbfgs
                     apply_lbfgs_masked_, sufficient_descent, print_iteration, verbose)
 from .spg import SPG, spg, spg_, Info, BoxProjection, default_printer
 from .spg import getreason as _spg_getreason
-from . import spg as SPGModule
+from .spg import (SEARCHING, INFNORM_CONVERGENCE, TWONORM_CONVERGENCE, FUNCTION_CONVERGENCE,
+                  TOO_MANY_ITERATIONS, TOO_MANY_EVALUATIONS)
 from . import dist
 
 

@@ -44,6 +44,9 @@ _SIGNATURES = {
     "opkb_context_launch_count": (i64, [vp]),
     "opkb_timer_start": (C.c_int, [vp]),
     "opkb_timer_stop": (C.c_int, [vp, Pd]),
+    "opkb_profile_enable": (C.c_int, [vp, C.c_int]),
+    "opkb_profile_reset": (C.c_int, [vp]),
+    "opkb_profile_get": (C.c_int, [vp, C.c_int, Pd, C.POINTER(i64)]),
     "opkb_flush_l2": (C.c_int, [vp]),
     "opkb_comm_unique_id": (C.c_int, [vp]),
     "opkb_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),

@@ -81,6 +81,13 @@ extern "C" int opkb_context_destroy(opkb_context* ctx)
     cudaFree(ctx->d_res);
     if (ctx->d_all) cudaFree(ctx->d_all);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    if (ctx->prof) {
+        for (int i = 0; i < OPKB_PROF_RING; ++i) {
+            cudaEventDestroy(ctx->prof[i].a);
+            cudaEventDestroy(ctx->prof[i].b);
+        }
+        free(ctx->prof);
+    }
     cudaFreeHost(ctx->h_res);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
@@ -118,6 +125,75 @@ extern "C" int opkb_timer_stop(opkb_context* ctx, double* ms)
     OPKB_CUDA(cudaEventSynchronize(ctx->ev1));
     OPKB_CUDA(cudaEventElapsedTime(&t, ctx->ev0, ctx->ev1));
     *ms = (double)t;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// per-kernel profile: one CUDA-event pair per launch on the launching stream
+static void prof_drain(opkb_context* ctx)
+{
+    if (ctx->prof_n == 0) return;
+    cudaEventSynchronize(ctx->prof[ctx->prof_n - 1].b);
+    for (int i = 0; i < ctx->prof_n; ++i) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->prof[i].a, ctx->prof[i].b) == cudaSuccess) {
+            ctx->prof_ms[ctx->prof[i].cls] += ms;
+            ctx->prof_cnt[ctx->prof[i].cls] += 1;
+        }
+    }
+    ctx->prof_n = 0;
+}
+
+void opkb_prof_begin(opkb_context* ctx, int cls)
+{
+    if (!ctx->prof_on) return;
+    if (ctx->prof_n == OPKB_PROF_RING) prof_drain(ctx);
+    ctx->prof[ctx->prof_n].cls = cls;
+    cudaEventRecord(ctx->prof[ctx->prof_n].a, ctx->stream);
+}
+
+void opkb_prof_end(opkb_context* ctx)
+{
+    if (!ctx->prof_on) return;
+    cudaEventRecord(ctx->prof[ctx->prof_n].b, ctx->stream);
+    ctx->prof_n += 1;
+}
+
+extern "C" int opkb_profile_enable(opkb_context* ctx, int on)
+{
+    if (!ctx) return opkb_set_error(OPKB_EINVAL, "NULL context");
+    if (on && !ctx->prof) {
+        ctx->prof = (opkb_prof_rec*)calloc(OPKB_PROF_RING, sizeof(opkb_prof_rec));
+        if (!ctx->prof) return opkb_set_error(OPKB_ENOMEM, "out of host memory");
+        for (int i = 0; i < OPKB_PROF_RING; ++i) {
+            OPKB_CUDA(cudaEventCreate(&ctx->prof[i].a));
+            OPKB_CUDA(cudaEventCreate(&ctx->prof[i].b));
+        }
+    }
+    if (!on && ctx->prof_on) prof_drain(ctx);
+    ctx->prof_on = on ? 1 : 0;
+    return 0;
+}
+
+extern "C" int opkb_profile_reset(opkb_context* ctx)
+{
+    if (!ctx) return opkb_set_error(OPKB_EINVAL, "NULL context");
+    prof_drain(ctx);
+    for (int k = 0; k < OPKB_K_NCLASS; ++k) {
+        ctx->prof_ms[k] = 0;
+        ctx->prof_cnt[k] = 0;
+    }
+    return 0;
+}
+
+extern "C" int opkb_profile_get(opkb_context* ctx, int kernel_class, double* ms_total, int64_t* count)
+{
+    if (!ctx || !ms_total || !count) return opkb_set_error(OPKB_EINVAL, "NULL argument");
+    if (kernel_class < 0 || kernel_class >= OPKB_K_NCLASS)
+        return opkb_set_error(OPKB_EINVAL, "invalid kernel class");
+    prof_drain(ctx);
+    *ms_total = ctx->prof_ms[kernel_class];
+    *count = ctx->prof_cnt[kernel_class];
     return 0;
 }
 
@@ -251,9 +327,11 @@ static int same_space(const opkb_vector* a, const opkb_vector* b)
 #define CHECK_SAME(a, b) \
     if (!same_space((a), (b))) return opkb_set_error(OPKB_EINVAL, "vectors of different spaces")
 
-#define LAUNCH(ctx, kernel, grid, ...)                                       \
+#define LAUNCH(ctx, cls, kernel, grid, ...)                                  \
     do {                                                                     \
+        opkb_prof_begin((ctx), (cls));                                       \
         kernel<<<(grid), OPKB_BLOCK, 0, (ctx)->stream>>>(__VA_ARGS__);       \
+        opkb_prof_end((ctx));                                                \
         (ctx)->launches += 1;                                                \
         OPKB_CUDA(cudaGetLastError());                                       \
     } while (0)
@@ -299,9 +377,9 @@ extern "C" int opkb_vector_fill(opkb_vector* v, double value)
     opkb_context* ctx = v->ctx;
     int grid = opkb_grid_for(ctx, v->n, 8);
     if (v->eltype == OPKB_DOUBLE)
-        LAUNCH(ctx, k_fill<double>, grid, (double*)v->data, v->n, value);
+        LAUNCH(ctx, OPKB_K_OTHER, k_fill<double>, grid, (double*)v->data, v->n, value);
     else
-        LAUNCH(ctx, k_fill<float>, grid, (float*)v->data, v->n, (float)value);
+        LAUNCH(ctx, OPKB_K_OTHER, k_fill<float>, grid, (float*)v->data, v->n, (float)value);
     return 0;
 }
 
@@ -335,10 +413,10 @@ extern "C" int opkb_vector_fill_random(opkb_vector* v, uint64_t seed, int64_t fi
     opkb_context* ctx = v->ctx;
     int grid = opkb_grid_for(ctx, v->n, 8);
     if (v->eltype == OPKB_DOUBLE)
-        LAUNCH(ctx, k_fill_random<double>, grid, (double*)v->data, v->n, seed, first, lo, hi,
+        LAUNCH(ctx, OPKB_K_OTHER, k_fill_random<double>, grid, (double*)v->data, v->n, seed, first, lo, hi,
                log_scale);
     else
-        LAUNCH(ctx, k_fill_random<float>, grid, (float*)v->data, v->n, seed, first, lo, hi,
+        LAUNCH(ctx, OPKB_K_OTHER, k_fill_random<float>, grid, (float*)v->data, v->n, seed, first, lo, hi,
                log_scale);
     return 0;
 }
@@ -403,11 +481,11 @@ static int reduce_dispatch(opkb_context* ctx, const opkb_vector* x, const opkb_v
 {
     int grid = opkb_grid_for(ctx, x->n / (x->eltype == OPKB_DOUBLE ? 2 : 4), 4);
     if (x->eltype == OPKB_DOUBLE)
-        LAUNCH(ctx, (k_reduce<double, MODE>), grid, (const double*)x->data,
+        LAUNCH(ctx, OPKB_K_REDUCE, (k_reduce<double, MODE>), grid, (const double*)x->data,
                y ? (const double*)y->data : NULL, w ? (const double*)w->data : NULL, x->n,
                scratch(ctx));
     else
-        LAUNCH(ctx, (k_reduce<float, MODE>), grid, (const float*)x->data,
+        LAUNCH(ctx, OPKB_K_REDUCE, (k_reduce<float, MODE>), grid, (const float*)x->data,
                y ? (const float*)y->data : NULL, w ? (const float*)w->data : NULL, x->n,
                scratch(ctx));
     int kind = (MODE == 2 ? OPKB_RMAX : OPKB_RSUM);
@@ -539,9 +617,9 @@ static int ew_dispatch(opkb_context* ctx, opkb_vector* dst, const opkb_vector* x
     A.bcase = mult_case(beta);
     int grid = opkb_grid_for(ctx, dst->n / (dst->eltype == OPKB_DOUBLE ? 2 : 4), 8);
     if (dst->eltype == OPKB_DOUBLE)
-        LAUNCH(ctx, (k_elementwise<double, OP>), grid, A);
+        LAUNCH(ctx, OPKB_K_ELEMENTWISE, (k_elementwise<double, OP>), grid, A);
     else
-        LAUNCH(ctx, (k_elementwise<float, OP>), grid, A);
+        LAUNCH(ctx, OPKB_K_ELEMENTWISE, (k_elementwise<float, OP>), grid, A);
     return 0;
 }
 
@@ -628,10 +706,10 @@ extern "C" int opkb_project_variables(opkb_context* ctx, opkb_vector* dst, const
     if (rc) return rc;
     int grid = opkb_grid_for(ctx, dst->n / (dst->eltype == OPKB_DOUBLE ? 2 : 4), 8);
     if (dst->eltype == OPKB_DOUBLE)
-        LAUNCH(ctx, k_project_variables<double>, grid, (double*)dst->data, (const double*)src->data,
+        LAUNCH(ctx, OPKB_K_BOUNDS, k_project_variables<double>, grid, (double*)dst->data, (const double*)src->data,
                make_bound<double>(lo, lo_val, true), make_bound<double>(hi, hi_val, false), dst->n);
     else
-        LAUNCH(ctx, k_project_variables<float>, grid, (float*)dst->data, (const float*)src->data,
+        LAUNCH(ctx, OPKB_K_BOUNDS, k_project_variables<float>, grid, (float*)dst->data, (const float*)src->data,
                make_bound<float>(lo, lo_val, true), make_bound<float>(hi, hi_val, false), dst->n);
     return 0;
 }
@@ -679,11 +757,11 @@ extern "C" int opkb_project_direction(opkb_context* ctx, opkb_vector* dst, const
         return opkb_set_error(OPKB_EBOUNDS, "invalid bounds");
     int grid = opkb_grid_for(ctx, dst->n / (dst->eltype == OPKB_DOUBLE ? 2 : 4), 8);
     if (dst->eltype == OPKB_DOUBLE)
-        LAUNCH(ctx, k_project_direction<double>, grid, (double*)dst->data, (const double*)x->data,
+        LAUNCH(ctx, OPKB_K_BOUNDS, k_project_direction<double>, grid, (double*)dst->data, (const double*)x->data,
                make_bound<double>(lo, lo_val, true), make_bound<double>(hi, hi_val, false), orient,
                (const double*)d->data, dst->n);
     else
-        LAUNCH(ctx, k_project_direction<float>, grid, (float*)dst->data, (const float*)x->data,
+        LAUNCH(ctx, OPKB_K_BOUNDS, k_project_direction<float>, grid, (float*)dst->data, (const float*)x->data,
                make_bound<float>(lo, lo_val, true), make_bound<float>(hi, hi_val, false), orient,
                (const float*)d->data, dst->n);
     return 0;
@@ -731,11 +809,11 @@ extern "C" int opkb_step_limits(opkb_context* ctx, const opkb_vector* x, const o
     }
     int grid = opkb_grid_for(ctx, x->n / (x->eltype == OPKB_DOUBLE ? 2 : 4), 4);
     if (x->eltype == OPKB_DOUBLE)
-        LAUNCH(ctx, k_step_limits<double>, grid, (const double*)x->data,
+        LAUNCH(ctx, OPKB_K_BOUNDS, k_step_limits<double>, grid, (const double*)x->data,
                make_bound<double>(lo, lo_val, true), make_bound<double>(hi, hi_val, false),
                (double)(orient > 0 ? 1 : -1), (const double*)d->data, x->n, scratch(ctx));
     else
-        LAUNCH(ctx, k_step_limits<float>, grid, (const float*)x->data,
+        LAUNCH(ctx, OPKB_K_BOUNDS, k_step_limits<float>, grid, (const float*)x->data,
                make_bound<float>(lo, lo_val, true), make_bound<float>(hi, hi_val, false),
                (float)(orient > 0 ? 1 : -1), (const float*)d->data, x->n, scratch(ctx));
     int kinds[2] = {OPKB_RMIN, OPKB_RMAX};
@@ -772,9 +850,9 @@ extern "C" int opkb_free_variables(opkb_context* ctx, const opkb_vector* gp, int
     if (mask_bytes && gp->n > 0) OPKB_CUDA(cudaMalloc(&dmask, (size_t)gp->n));
     int grid = opkb_grid_for(ctx, gp->n, 4);
     if (gp->eltype == OPKB_DOUBLE)
-        LAUNCH(ctx, k_free_variables<double>, grid, (const double*)gp->data, gp->n, dmask, scratch(ctx));
+        LAUNCH(ctx, OPKB_K_BOUNDS, k_free_variables<double>, grid, (const double*)gp->data, gp->n, dmask, scratch(ctx));
     else
-        LAUNCH(ctx, k_free_variables<float>, grid, (const float*)gp->data, gp->n, dmask, scratch(ctx));
+        LAUNCH(ctx, OPKB_K_BOUNDS, k_free_variables<float>, grid, (const float*)gp->data, gp->n, dmask, scratch(ctx));
     double c = 0;
     int rc = opkb_finish_reduction(ctx, 1, NULL, &c);
     if (rc == 0) {
@@ -829,10 +907,10 @@ extern "C" int opkb_rosenbrock_fg(opkb_context* ctx, const opkb_vector* x, opkb_
     if (x->n % 2) return opkb_set_error(OPKB_EINVAL, "Rosenbrock needs an even number of variables");
     int grid = opkb_grid_for(ctx, x->n / (x->eltype == OPKB_DOUBLE ? 2 : 4), 4);
     if (x->eltype == OPKB_DOUBLE)
-        LAUNCH(ctx, (k_objective<double, OPKB_OBJ_ROSENBROCK>), grid, (const double*)x->data,
+        LAUNCH(ctx, OPKB_K_OBJECTIVE, (k_objective<double, OPKB_OBJ_ROSENBROCK>), grid, (const double*)x->data,
                (double*)g->data, (const double*)NULL, (const double*)NULL, x->n, scratch(ctx));
     else
-        LAUNCH(ctx, (k_objective<float, OPKB_OBJ_ROSENBROCK>), grid, (const float*)x->data,
+        LAUNCH(ctx, OPKB_K_OBJECTIVE, (k_objective<float, OPKB_OBJ_ROSENBROCK>), grid, (const float*)x->data,
                (float*)g->data, (const float*)NULL, (const float*)NULL, x->n, scratch(ctx));
     double out[2];
     int rc = opkb_finish_reduction(ctx, 2, NULL, out);
@@ -850,10 +928,10 @@ extern "C" int opkb_quadratic_fg(opkb_context* ctx, const opkb_vector* a, const 
     if (!f) return opkb_set_error(OPKB_EINVAL, "NULL result");
     int grid = opkb_grid_for(ctx, x->n / (x->eltype == OPKB_DOUBLE ? 2 : 4), 4);
     if (x->eltype == OPKB_DOUBLE)
-        LAUNCH(ctx, (k_objective<double, OPKB_OBJ_QUADRATIC>), grid, (const double*)x->data,
+        LAUNCH(ctx, OPKB_K_OBJECTIVE, (k_objective<double, OPKB_OBJ_QUADRATIC>), grid, (const double*)x->data,
                (double*)g->data, (const double*)a->data, (const double*)c->data, x->n, scratch(ctx));
     else
-        LAUNCH(ctx, (k_objective<float, OPKB_OBJ_QUADRATIC>), grid, (const float*)x->data,
+        LAUNCH(ctx, OPKB_K_OBJECTIVE, (k_objective<float, OPKB_OBJ_QUADRATIC>), grid, (const float*)x->data,
                (float*)g->data, (const float*)a->data, (const float*)c->data, x->n, scratch(ctx));
     double out[2];
     int rc = opkb_finish_reduction(ctx, 2, NULL, out);

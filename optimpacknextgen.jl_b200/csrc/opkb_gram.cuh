@@ -218,7 +218,9 @@ static int gram_launch(opkb_context* ctx, const GramArgs<T>& A, int nroles, int*
     rs.part = ctx->d_part;
     rs.ticket = ctx->d_ticket;
     rs.res = ctx->d_res;
+    opkb_prof_begin(ctx, OPKB_K_GRAM);
     kern<<<(int)grid, block, smem, ctx->stream>>>(A, rs);
+    opkb_prof_end(ctx);
     ctx->launches += 1;
     OPKB_CUDA(cudaGetLastError());
     *nslot_out = nroles * (2 * BS) * (BS + 1);

@@ -16,6 +16,14 @@
 #define OPKB_NRED_MAX 1024      // scalars one launch may reduce
 #define OPKB_MEM_MAX 20         // pairs the fused Gram path supports
 
+// kernel classes of the per-kernel profile (opkb_profile_*)
+enum { OPKB_K_OTHER = 0, OPKB_K_TRIAL = 1, OPKB_K_GRAM = 2, OPKB_K_DIRECTION = 3, OPKB_K_SPG = 4,
+       OPKB_K_REDUCE = 5, OPKB_K_ELEMENTWISE = 6, OPKB_K_BOUNDS = 7, OPKB_K_OBJECTIVE = 8,
+       OPKB_K_NCLASS = 9 };
+#define OPKB_PROF_RING 4096
+
+struct opkb_prof_rec { cudaEvent_t a, b; int cls; };
+
 // reduction kinds of one scalar slot
 enum { OPKB_RSUM = 0, OPKB_RMAX = 1, OPKB_RMIN = 2 };
 
@@ -34,7 +42,15 @@ struct opkb_context_ {
     int64_t launches;
     void* flush_buf;
     size_t flush_bytes;
+    // optional per-kernel CUDA-event profile (bench.py roofline)
+    int prof_on, prof_n;
+    opkb_prof_rec* prof;
+    double prof_ms[OPKB_K_NCLASS];
+    int64_t prof_cnt[OPKB_K_NCLASS];
 };
+
+void opkb_prof_begin(opkb_context* ctx, int cls);
+void opkb_prof_end(opkb_context* ctx);
 
 struct opkb_vector_ {
     opkb_context* ctx;

@@ -242,7 +242,9 @@ static int spg_run(opkb_spg* ws, int mode, double lambda, double stp, double eta
     rs.res = ctx->d_res;
 #define SPG_LAUNCH(OBJ, MODE)                                                     \
     do {                                                                          \
+        opkb_prof_begin(ctx, OPKB_K_SPG);                                         \
         k_spg<T, OBJ, MODE><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);         \
+        opkb_prof_end(ctx);                                                       \
         ctx->launches += 1;                                                       \
         OPKB_CUDA(cudaGetLastError());                                            \
     } while (0)

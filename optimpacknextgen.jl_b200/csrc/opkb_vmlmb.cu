@@ -30,9 +30,11 @@ struct opkb_vmlmb_ {
     opkb_vector* Y[OPKB_MEM_MAX];
 };
 
-#define LAUNCHB(ctx, kernel, grid, block, smem, ...)                         \
+#define LAUNCHB(ctx, cls, kernel, grid, block, smem, ...)                    \
     do {                                                                     \
+        opkb_prof_begin((ctx), (cls));                                       \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);     \
+        opkb_prof_end((ctx));                                                \
         (ctx)->launches += 1;                                                \
         OPKB_CUDA(cudaGetLastError());                                       \
     } while (0)
@@ -304,13 +306,13 @@ static int trial_launch(opkb_vmlmb* ws, int mark, double stp, int initial, int s
     int grid = opkb_grid_for(ctx, ws->n / VecOf<T>::N, 4);
     ReduceScratch rs = scratch(ctx);
     if (stage == 1)
-        LAUNCHB(ctx, (k_trial<T, OPKB_OBJ_USER, 1>), grid, OPKB_BLOCK, 0, A, rs);
+        LAUNCHB(ctx, OPKB_K_TRIAL, (k_trial<T, OPKB_OBJ_USER, 1>), grid, OPKB_BLOCK, 0, A, rs);
     else if (stage == 2)
-        LAUNCHB(ctx, (k_trial<T, OPKB_OBJ_USER, 2>), grid, OPKB_BLOCK, 0, A, rs);
+        LAUNCHB(ctx, OPKB_K_TRIAL, (k_trial<T, OPKB_OBJ_USER, 2>), grid, OPKB_BLOCK, 0, A, rs);
     else if (ws->obj == OPKB_OBJ_ROSENBROCK)
-        LAUNCHB(ctx, (k_trial<T, OPKB_OBJ_ROSENBROCK, 0>), grid, OPKB_BLOCK, 0, A, rs);
+        LAUNCHB(ctx, OPKB_K_TRIAL, (k_trial<T, OPKB_OBJ_ROSENBROCK, 0>), grid, OPKB_BLOCK, 0, A, rs);
     else
-        LAUNCHB(ctx, (k_trial<T, OPKB_OBJ_QUADRATIC, 0>), grid, OPKB_BLOCK, 0, A, rs);
+        LAUNCHB(ctx, OPKB_K_TRIAL, (k_trial<T, OPKB_OBJ_QUADRATIC, 0>), grid, OPKB_BLOCK, 0, A, rs);
     return 0;
 }
 
@@ -568,15 +570,15 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
     ReduceScratch rs = scratch(ctx);
     int grid = opkb_grid_for(ctx, ws->n / VecOf<T>::N, 2);
     if (A.m <= 4)
-        LAUNCHB(ctx, (k_direction<T, 4>), grid, OPKB_BLOCK, 0, A, rs);
+        LAUNCHB(ctx, OPKB_K_DIRECTION, (k_direction<T, 4>), grid, OPKB_BLOCK, 0, A, rs);
     else if (A.m <= 8)
-        LAUNCHB(ctx, (k_direction<T, 8>), grid, OPKB_BLOCK, 0, A, rs);
+        LAUNCHB(ctx, OPKB_K_DIRECTION, (k_direction<T, 8>), grid, OPKB_BLOCK, 0, A, rs);
     else if (A.m <= 12)
-        LAUNCHB(ctx, (k_direction<T, 12>), grid, OPKB_BLOCK, 0, A, rs);
+        LAUNCHB(ctx, OPKB_K_DIRECTION, (k_direction<T, 12>), grid, OPKB_BLOCK, 0, A, rs);
     else if (A.m <= 16)
-        LAUNCHB(ctx, (k_direction<T, 16>), grid, OPKB_BLOCK, 0, A, rs);
+        LAUNCHB(ctx, OPKB_K_DIRECTION, (k_direction<T, 16>), grid, OPKB_BLOCK, 0, A, rs);
     else
-        LAUNCHB(ctx, (k_direction<T, OPKB_MEM_MAX>), grid, OPKB_BLOCK, 0, A, rs);
+        LAUNCHB(ctx, OPKB_K_DIRECTION, (k_direction<T, OPKB_MEM_MAX>), grid, OPKB_BLOCK, 0, A, rs);
     int kinds[4] = {OPKB_RSUM, OPKB_RSUM, OPKB_RMIN, OPKB_RMAX};
     int rc = opkb_finish_reduction(ctx, 4, kinds, out);
     if (rc) return rc;

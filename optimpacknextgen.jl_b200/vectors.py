@@ -71,6 +71,24 @@ class Context:
         check(_lib.lib().opkb_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
+    KERNEL_CLASSES = ("other", "trial", "gram", "direction", "spg", "reduce", "elementwise",
+                      "bounds", "objective")
+
+    def profile(self, on: bool) -> None:
+        check(_lib.lib().opkb_profile_enable(self._h, int(bool(on))))
+        if on:
+            check(_lib.lib().opkb_profile_reset(self._h))
+
+    def profile_report(self) -> dict:
+        """{kernel class: (total ms, launches)} since the profile was enabled."""
+        out = {}
+        for k, name in enumerate(self.KERNEL_CLASSES):
+            ms, cnt = f64(), i64()
+            check(_lib.lib().opkb_profile_get(self._h, k, C.byref(ms), C.byref(cnt)))
+            if cnt.value:
+                out[name] = (ms.value, cnt.value)
+        return out
+
     def flush_l2(self) -> None:
         check(_lib.lib().opkb_flush_l2(self._h))
 

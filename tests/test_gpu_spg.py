@@ -71,7 +71,7 @@ def test_spg_converges_like_reference_test(opk, oracle, mode):
     ws = opk.Info()
     x = opk.spg(opk.Rosenbrock(), opk.BoxProjection(0.0, math.inf), x0, 10, ws=ws, mode=mode)
     assert np.abs(x - 1).max() < 1e-3
-    assert (ws.iter, ws.fcnt, ws.pcnt, ws.status) == (64, 82, 130, opk.SPGModule.INFNORM_CONVERGENCE)
+    assert (ws.iter, ws.fcnt, ws.pcnt, ws.status) == (64, 82, 130, opk.INFNORM_CONVERGENCE)
     assert opk.getreason(ws) == "Convergence with projected gradient infinite-norm"
 
 
@@ -91,8 +91,8 @@ def test_spg_user_projection_and_objective(opk):
     x = opk.spg(fg, nonnegative, np.full(n, 3.0), 10)
     assert np.abs(x - np.clip(np.linspace(-1, 2, n), 0, None)).max() < 1e-5
     ws = opk.Info()
-    opk.spg(fg, nonnegative, np.full(n, 3.0), 10, maxfc=3, ws=ws)
-    assert ws.status == opk.SPGModule.TOO_MANY_EVALUATIONS and ws.fcnt == 3
+    opk.spg(fg, nonnegative, np.full(n, 3.0), 10, maxfc=2, eps1=0, eps2=0, ws=ws)
+    assert ws.status == opk.TOO_MANY_EVALUATIONS and ws.fcnt == 2
 
 
 def test_spg_golden(opk):

@@ -182,8 +182,9 @@ def test_linesearch_options_and_limits(opk, oracle):
     assert (s.eval, s.iter, s.reason) == (ro["eval"], ro["iter"], ro["reason"])
     assert relerr(s.result(), xo) < 1e-12
     with pytest.raises(ValueError):
-        opk.vmlmb(opk.Rosenbrock(), pb["x0"], mem=64)  # fused path: mem <= 20
-    assert np.abs(opk.vmlmb(opk.Rosenbrock(), pb["x0"], mem=20, mode="primitive") - 1).max() < 1e-3
+        opk.vmlmb(opk.Rosenbrock(), opk.Rosenbrock.x0(100), mem=64)  # fused path: mem <= 20
+    x = opk.vmlmb(opk.Rosenbrock(), opk.Rosenbrock.x0(100), mem=64, mode="primitive")
+    assert np.abs(x - 1).max() < 1e-3
 
 
 def test_phase_kernels_single_step(opk, oracle):
