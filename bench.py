@@ -57,6 +57,7 @@ def config(args, n):
         "n": n, "mem": args.mem, "eltype": "Float64", "kappa": KAPPA,
         "sharding": "contiguous 1-D blocks, %d rank(s), one packed all-gather of partials per phase" % args.gpus,
         "l2": "no flush needed: every kernel streams >= 18 GiB per rank at N=1 (>> 126 MB L2)",
+        "priming": "mem+1 untimed iterations before the warm-up so that all m (s,y) pairs exist",
     }
 
 
@@ -143,6 +144,11 @@ class ClockSampler:
     def summary(self, t0, t1):
         if self.proc is not None:
             self.proc.terminate()
+            try:
+                self.proc.wait(timeout=3)
+            except Exception:
+                self.proc.kill()
+            self.t.join(timeout=3)   # no daemon thread may outlive the interpreter
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for t, line in self.rows:
@@ -229,6 +235,7 @@ def ours(args):
     kw = dict(lower=lo, upper=hi, mem=m, xtol=(0, 0), ftol=(0, 0), gtol=(0, 0), nglobal=n, ctx=ctx)
 
     solver = opk.VMLMB(obj, x0, **kw)
+    solver.iterate(m + 1)                               # priming: all m pairs exist (steady state)
     solver.iterate(W)                                   # warm-up (untimed)
     ctx.profile(True)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -320,6 +327,11 @@ def ours(args):
                       % (r["cores"], args.cpu_steps, args.cpu_log2n, r["seconds"], args.log2n)}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    # explicit teardown, in dependency order
+    obj = lo = hi = x0 = s2 = host = out_t = None
+    import gc
+    gc.collect()
+    ctx.synchronize()
     if world > 1:
         dist.destroy_process_group()
 

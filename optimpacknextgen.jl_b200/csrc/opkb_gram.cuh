@@ -227,6 +227,33 @@ static int gram_launch(opkb_context* ctx, const GramArgs<T>& A, int nroles, int*
     return 0;
 }
 
+// scatter the role tiles into G[2m][m+1] (row 2q: s_q, 2q+1: y_q; col 0: v0, 1+q: y_q)
+static void gram_scatter(const double* res, int m, int nb, int bs, double* G)
+{
+    const int RT = 2 * bs, CT = bs + 1, W = m + 1;
+    for (int i = 0; i < 2 * m * W; ++i) G[i] = 0.0;
+    int role = 0;
+    for (int bi = 0; bi < nb; ++bi) {
+        for (int bj = bi; bj < nb; ++bj, ++role) {
+            for (int r = 0; r < RT; ++r) {
+                const int qrow = bi * bs + r / 2;
+                if (qrow >= m) continue;
+                for (int c = 0; c < CT; ++c) {
+                    int col;
+                    if (bi == bj) {
+                        col = (c == 0) ? 0 : 1 + bi * bs + (c - 1);
+                    } else {
+                        if (c >= bs) continue;
+                        col = 1 + bj * bs + c;
+                    }
+                    if (col > m) continue;
+                    G[(2 * qrow + (r & 1)) * W + col] = res[role * RT * CT + r * CT + c];
+                }
+            }
+        }
+    }
+}
+
 template <typename T>
 static int gram_run(opkb_context* ctx, int64_t n, int m, const void* const* Sp, const void* const* Yp,
                     const void* v0, const void* x, const void* gcur, int masked, double* G)
@@ -262,28 +289,6 @@ static int gram_run(opkb_context* ctx, int64_t n, int m, const void* const* Sp, 
     static thread_local double res[OPKB_NRED_MAX];
     rc = opkb_finish_reduction(ctx, nslot, NULL, res);
     if (rc) return rc;
-    // scatter the role tiles into G[2m][m+1] (row 2q: s_q, 2q+1: y_q; col 0: v0, 1+q: y_q)
-    const int RT = 2 * bs, CT = bs + 1, W = m + 1;
-    for (int i = 0; i < 2 * m * W; ++i) G[i] = 0.0;
-    int role = 0;
-    for (int bi = 0; bi < nb; ++bi) {
-        for (int bj = bi; bj < nb; ++bj, ++role) {
-            for (int r = 0; r < RT; ++r) {
-                const int qrow = bi * bs + r / 2;
-                if (qrow >= m) continue;
-                for (int c = 0; c < CT; ++c) {
-                    int col;
-                    if (bi == bj) {
-                        col = (c == 0) ? 0 : 1 + bi * bs + (c - 1);
-                    } else {
-                        if (c >= bs) continue;
-                        col = 1 + bj * bs + c;
-                    }
-                    if (col > m) continue;
-                    G[(2 * qrow + (r & 1)) * W + col] = res[role * RT * CT + r * CT + c];
-                }
-            }
-        }
-    }
+    gram_scatter(res, m, nb, bs, G);
     return 0;
 }

@@ -375,6 +375,8 @@ extern "C" int opkb_vmlmb_trial_end(opkb_vmlmb* ws, int mark, double f, int init
 // ---------------------------------------------------------------------------
 // P3: Gram sweep
 #include "opkb_gram.cuh"
+#include "opkb_gram2.cuh"
+#include <stdlib.h>
 
 extern "C" int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots, double* G)
 {
@@ -395,10 +397,18 @@ extern "C" int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots
     // p for BLMVM (src/quasinewton.jl:513)
     const void* v0 = (ws->method == 2 ? ws->p->data : ws->g->data);
     const void* gcur = (ws->method == 1 ? ws->p->data : ws->g->data);
+    // OPKB_GRAM_V1=1 selects the first, non-pipelined kernel (A/B measurements only)
+    static const int use_v1 = (getenv("OPKB_GRAM_V1") && getenv("OPKB_GRAM_V1")[0] == '1');
+    if (use_v1) {
+        if (ws->eltype == OPKB_DOUBLE)
+            return gram_run<double>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur,
+                                    ws->method == 2, G);
+        return gram_run<float>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur, ws->method == 2, G);
+    }
     if (ws->eltype == OPKB_DOUBLE)
-        return gram_run<double>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur,
-                                ws->method == 2, G);
-    return gram_run<float>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur, ws->method == 2, G);
+        return gram2_run<double>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur,
+                                 ws->method == 2, G);
+    return gram2_run<float>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur, ws->method == 2, G);
 }
 
 // ---------------------------------------------------------------------------

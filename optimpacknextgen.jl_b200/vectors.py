@@ -190,7 +190,8 @@ class Vector:
         return self
 
     def free(self) -> None:
-        if self._own and self._h:
+        # never call into the library for a vector whose context is gone
+        if self._own and self._h and self.ctx is not None and self.ctx.handle:
             _lib.lib().opkb_vector_destroy(self._h)
         self._h = vp()
 
