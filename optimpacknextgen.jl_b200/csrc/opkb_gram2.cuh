@@ -12,11 +12,12 @@
 // memory (Float32 is widened when read), the free-set mask is p != 0 read from
 // the staged v0 row.
 #pragma once
+#include <stdlib.h>
 
 #define GRAM2_MAXSTAGE 8
 
 template <typename T> struct Gram2Args {
-    const T* rows[2 * OPKB_MEM_MAX + 3];  // 0: v0; 1+2q: S_q; 2+2q: Y_q (q oldest..newest); then x, gcur
+    const T* rows[2 * OPKB_MEM_MAX + 3];  // 0: v0; 1: x; 2: g|p; 3+2q: S_q; 4+2q: Y_q (q oldest..newest)
     T* Snew;
     T* Ynew;
     int64_t n;
@@ -78,8 +79,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <typename T, int BS>
-__global__ void __launch_bounds__(352, 1) k_gram2(Gram2Args<T> A, ReduceScratch rs)
+// Stage layout (rows of TILE elements of T): 0: v0, 1: x, 2: g|p, then the pairs
+// 3+2q: s_q, 4+2q: y_q for q = 0 (oldest) .. nb*BS-1 (rows of pairs q >= m are
+// zero and never overwritten), then 2 pad rows.  With TILE a compile-time
+// constant every shared-memory read of the inner loop is `LDS [base + imm]`.
+//
+// MAXT: 256 threads (<= 7 consumer warps + producer: 2 warps per SM sub-partition,
+// so up to 255 registers per thread and no spills) or 352 (3 warps per
+// sub-partition, 168 registers: the 10-role case m >= 16)
+template <typename T, int BS, int TILE, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch rs)
 {
     constexpr int RT = 2 * BS, CT = BS + 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -87,16 +96,15 @@ __global__ void __launch_bounds__(352, 1) k_gram2(Gram2Args<T> A, ReduceScratch 
     __shared__ __align__(8) uint64_t empty_bar[GRAM2_MAXSTAGE];
     __shared__ unsigned int s_last;
 
-    const int nb = A.nb, m = A.m, k = A.kshare, TILE = A.tile, NSTAGE = A.nstage;
+    const int nb = A.nb, m = A.m, k = A.kshare, NSTAGE = A.nstage;
     const int nroles = nb * (nb + 1) / 2;
     const int cwarps = nroles * k;            // consumer warps; warp `cwarps` is the producer
     const int cthreads = cwarps * 32;
     const int NRL = 2 * m + 3;                // rows loaded per stage
-    const int zrow = NRL;                     // an all-zero row per stage (pairs that do not exist)
-    const int srows = NRL + 1;
+    const int srows = 3 + 2 * nb * BS + 2;    // rows per stage
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     T* const stage0 = reinterpret_cast<T*>(smem_raw);
-    const size_t stage_elems = (size_t)srows * TILE;
+    const int stage_elems = srows * TILE;
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
@@ -105,13 +113,14 @@ __global__ void __launch_bounds__(352, 1) k_gram2(Gram2Args<T> A, ReduceScratch 
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // rows the bulk copies never write: zero once
     for (int s = 0; s < NSTAGE; ++s)
-        for (int e = tid; e < TILE; e += blockDim.x) stage0[s * stage_elems + (size_t)zrow * TILE + e] = T(0);
+        for (int i = NRL * TILE + tid; i < stage_elems; i += blockDim.x) stage0[s * stage_elems + i] = T(0);
     fence_proxy_async();
     __syncthreads();
 
     const int64_t ntiles = (A.n + TILE - 1) / TILE;
-    const uint32_t rowbytes = (uint32_t)(TILE * sizeof(T));
+    constexpr uint32_t rowbytes = (uint32_t)(TILE * sizeof(T));
 
     double acc[RT][CT];
 #pragma unroll
@@ -121,21 +130,24 @@ __global__ void __launch_bounds__(352, 1) k_gram2(Gram2Args<T> A, ReduceScratch 
 
     if (warp == cwarps) {
         // ------------------------------ producer ---------------------------------
-        if (lane == 0) {
-            int it = 0;
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const int s = it % NSTAGE;
-                const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
+        // lane 0 waits for the stage and arms its barrier, then every lane issues
+        // the bulk copies of its rows (row r -> lane r mod 32)
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int s = it % NSTAGE;
+            const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
+            const int64_t base = tile * TILE;
+            uint32_t bytes = rowbytes;
+            if (base + TILE > A.n) bytes = (uint32_t)(((A.n - base) * sizeof(T)) & ~(size_t)15);
+            if (lane == 0) {
                 mbar_wait(&empty_bar[s], ph ^ 1u);
-                const int64_t base = tile * TILE;
-                uint32_t bytes = rowbytes;
-                if (base + TILE > A.n) bytes = (uint32_t)(((A.n - base) * sizeof(T)) & ~(size_t)15);
                 mbar_expect_tx(&full_bar[s], bytes * (uint32_t)NRL);
-                if (bytes > 0) {
-                    T* dst = stage0 + s * stage_elems;
-                    for (int r = 0; r < NRL; ++r)
-                        bulk_g2s(dst + (size_t)r * TILE, A.rows[r] + base, bytes, &full_bar[s]);
-                }
+            }
+            __syncwarp();
+            if (bytes > 0) {
+                T* dst = stage0 + s * stage_elems;
+                for (int r = lane; r < NRL; r += 32)
+                    bulk_g2s(dst + r * TILE, A.rows[r] + base, bytes, &full_bar[s]);
             }
         }
     } else if (warp < cwarps) {
@@ -150,24 +162,26 @@ __global__ void __launch_bounds__(352, 1) k_gram2(Gram2Args<T> A, ReduceScratch 
                 r -= cnt;
             }
         }
-        // row / column -> staged row index (zrow for pairs beyond m)
-        int rowoff[RT], coloff[CT];   // element offsets of the staged rows inside a stage
-#pragma unroll
-        for (int r = 0; r < RT; ++r) {
-            const int q = bi * BS + (r >> 1);
-            rowoff[r] = ((q < m) ? 1 + 2 * q + (r & 1) : zrow) * TILE;
+        const bool diag = (bi == bj);
+        // element offsets inside a stage of: the first row of the register tile,
+        // its column 0 and its column 1 (columns c >= 1 are 2 rows apart)
+        const int rowbase = (3 + 2 * bi * BS) * TILE;
+        const int col0 = diag ? 0 : (4 + 2 * bj * BS) * TILE;
+        const int col1 = diag ? (4 + 2 * bi * BS) * TILE : (6 + 2 * bj * BS) * TILE;
+        // The newest slot still holds (x0, g0): its pair (x0 - x, g0 - g) is formed
+        // on the fly (vupdate!(S[mark], -1, x); vupdate!(Y[mark], -1, g|p),
+        // src/quasinewton.jl:512-513); tile coordinates of its rows and column:
+        const int qn = m - 1;
+        int rnew = -1, cnew = -1;
+        if (qn >= bi * BS && qn < (bi + 1) * BS) rnew = 2 * (qn - bi * BS);
+        if (diag) {
+            if (rnew >= 0) cnew = qn - bi * BS + 1;
+        } else if (qn >= bj * BS && qn < (bj + 1) * BS) {
+            cnew = qn - bj * BS;
         }
-#pragma unroll
-        for (int c = 0; c < CT; ++c) {
-            if (bi == bj) {
-                const int q = bi * BS + c - 1;
-                coloff[c] = ((c == 0) ? 0 : ((q < m) ? 2 + 2 * q : zrow)) * TILE;
-            } else {
-                const int q = bj * BS + c;
-                coloff[c] = ((c < BS && q < m) ? 2 + 2 * q : zrow) * TILE;
-            }
-        }
-        const int rs_new = 1 + 2 * (m - 1), ry_new = 2 + 2 * (m - 1), rx = 2 * m + 1, rg = 2 * m + 2;
+        // the last diagonal role owns the write-back of the new pair to HBM
+        const bool writer = (bi == nb - 1 && bj == nb - 1);
+        const bool masked = A.masked != 0;
 
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -176,48 +190,59 @@ __global__ void __launch_bounds__(352, 1) k_gram2(Gram2Args<T> A, ReduceScratch 
             T* st = stage0 + s * stage_elems;
             const int64_t base = tile * TILE;
             mbar_wait(&full_bar[s], ph);
-            if (base + TILE > A.n) {
-                // last, partial tile: elements the 16-byte granular bulk copy left out, zero padding
+            const bool partial = (base + TILE > A.n);
+            if (partial) {
+                // last tile: elements the 16-byte granular bulk copy left out, zero padding
                 const int valid = (int)(A.n - base);
                 const int copied = (int)((((size_t)valid * sizeof(T)) & ~(size_t)15) / sizeof(T));
                 for (int idx = tid; idx < NRL * TILE; idx += cthreads) {
                     const int r = idx / TILE, e = idx - r * TILE;
-                    if (e >= copied) st[(size_t)r * TILE + e] = (e < valid) ? A.rows[r][base + e] : T(0);
+                    if (e >= copied) st[r * TILE + e] = (e < valid) ? A.rows[r][base + e] : T(0);
                 }
                 named_bar_sync(1, cthreads);
             }
-            // vupdate!(S[mark], -1, x); vupdate!(Y[mark], -1, g|p)  (src/quasinewton.jl:512-513)
-            for (int e = tid; e < TILE; e += cthreads) {
-                if (base + e < A.n) {
-                    const T sn = st[(size_t)rs_new * TILE + e] - st[(size_t)rx * TILE + e];
-                    const T yn = st[(size_t)ry_new * TILE + e] - st[(size_t)rg * TILE + e];
-                    st[(size_t)rs_new * TILE + e] = sn;
-                    st[(size_t)ry_new * TILE + e] = yn;
-                    A.Snew[base + e] = sn;
-                    A.Ynew[base + e] = yn;
-                }
-            }
-            named_bar_sync(1, cthreads);
-            // accumulate this role's register tile
-#pragma unroll 2
             for (int e = sub * 32 + lane; e < TILE; e += 32 * k) {
+                const T* rp = st + rowbase + e;
+                const T* c0 = st + col0 + e;
+                const T* c1 = st + col1 + e;
+                T tv[RT], tc[CT];
+#pragma unroll
+                for (int r = 0; r < RT; ++r) tv[r] = rp[r * TILE];
+                tc[0] = c0[0];
+#pragma unroll
+                for (int c = 1; c < CT; ++c) tc[c] = c1[(c - 1) * 2 * TILE];
+                const T p0 = st[e], xs = st[TILE + e], gs = st[2 * TILE + e];
+                if (rnew >= 0) {
+#pragma unroll
+                    for (int r = 0; r < RT; r += 2) {
+                        if (r == rnew) {
+                            tv[r] = tv[r] - xs;          // s_new = x0 - x   (in the element type)
+                            tv[r + 1] = tv[r + 1] - gs;  // y_new = g0 - g
+                            if (writer && base + e < A.n) {
+                                A.Snew[base + e] = tv[r];
+                                A.Ynew[base + e] = tv[r + 1];
+                            }
+                        }
+                    }
+                }
+                if (cnew >= 0) {
+#pragma unroll
+                    for (int c = 0; c < CT; ++c)
+                        if (c == cnew) tc[c] = tc[c] - gs;
+                }
                 double rv[RT], cv[CT];
 #pragma unroll
-                for (int r = 0; r < RT; ++r) rv[r] = (double)st[rowoff[r] + e];
+                for (int r = 0; r < RT; ++r) rv[r] = (double)tv[r];
+                const bool fr = !masked || (p0 != T(0));  // free variable: p[i] != 0 (row 0 is v0 = p)
 #pragma unroll
-                for (int c = 0; c < CT; ++c) cv[c] = (double)st[coloff[c] + e];
-                if (A.masked) {
-                    const bool fr = (st[e] != T(0));  // free variable: p[i] != 0 (row 0 is v0 = p)
-#pragma unroll
-                    for (int c = 0; c < CT; ++c) cv[c] = fr ? cv[c] : 0.0;
-                }
+                for (int c = 0; c < CT; ++c) cv[c] = fr ? (double)tc[c] : 0.0;
 #pragma unroll
                 for (int r = 0; r < RT; ++r)
 #pragma unroll
                     for (int c = 0; c < CT; ++c) acc[r][c] = fma(rv[r], cv[c], acc[r][c]);
             }
-            // release the stage: generic-proxy writes above must be ordered before the next bulk copy
-            fence_proxy_async();
+            // release the stage
+            if (partial) fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
         }
@@ -262,28 +287,27 @@ __global__ void __launch_bounds__(352, 1) k_gram2(Gram2Args<T> A, ReduceScratch 
     if (tid == 0) *rs.ticket = 0u;
 }
 
-template <typename T, int BS>
+template <typename T, int BS, int TILE, int MAXT>
 static int gram2_launch(opkb_context* ctx, Gram2Args<T>& A, int nroles, int* nslot_out)
 {
     const int warps = nroles * A.kshare + 1;
     const int block = warps * 32;
-    // tile / ring geometry: >= 3 stages within ~200 KB of shared memory
-    const int srows = 2 * A.m + 4;
+    const int srows = 3 + 2 * A.nb * BS + 2;
     const size_t budget = 200 * 1024;
-    int tile = 512;
-    while (tile > 64 && (size_t)srows * tile * sizeof(T) * 3 > budget) tile >>= 1;
-    size_t stage_bytes = (size_t)srows * tile * sizeof(T);
+    const size_t stage_bytes = (size_t)srows * TILE * sizeof(T);
     int nstage = (int)(budget / stage_bytes);
+    if (const char* e = getenv("OPKB_GRAM_NSTAGE")) nstage = atoi(e);   // tuning knob
     if (nstage > GRAM2_MAXSTAGE) nstage = GRAM2_MAXSTAGE;
     if (nstage < 2) return opkb_set_error(OPKB_EINVAL, "Gram ring does not fit in shared memory");
     size_t smem = stage_bytes * nstage;
     const size_t red_bytes = (size_t)warps * (2 * BS) * (BS + 1) * sizeof(double);
     if (smem < red_bytes) smem = red_bytes;
-    A.tile = tile;
+    A.tile = TILE;
     A.nstage = nstage;
-    auto kern = k_gram2<T, BS>;
+    auto kern = k_gram2<T, BS, TILE, MAXT>;
+    if (block > MAXT) return opkb_set_error(OPKB_EINVAL, "Gram launch: %d threads > %d", block, MAXT);
     OPKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t ntiles = (A.n + tile - 1) / tile;
+    int64_t ntiles = (A.n + TILE - 1) / TILE;
     int64_t grid = ctx->sm_count;   // one persistent CTA per SM
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
@@ -295,9 +319,31 @@ static int gram2_launch(opkb_context* ctx, Gram2Args<T>& A, int nroles, int* nsl
     kern<<<(int)grid, block, smem, ctx->stream>>>(A, rs);
     opkb_prof_end(ctx);
     ctx->launches += 1;
-    OPKB_CUDA(cudaGetLastError());
+    {
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) {
+            cudaFuncAttributes fa;
+            memset(&fa, 0, sizeof(fa));
+            cudaFuncGetAttributes(&fa, kern);
+            return opkb_set_error(OPKB_ECUDA,
+                                  "k_gram2 launch failed: %s (grid %d, block %d, smem %zu, regs %d, "
+                                  "maxThreadsPerBlock %d, m %d, BS %d, tile %d, nstage %d)",
+                                  cudaGetErrorString(err), (int)grid, block, smem, fa.numRegs,
+                                  fa.maxThreadsPerBlock, A.m, BS, TILE, nstage);
+        }
+    }
     *nslot_out = nroles * (2 * BS) * (BS + 1);
     return 0;
+}
+
+// rows of 4 KB for up to 10 pairs (nb <= 2), 2 KB beyond
+template <typename T, int BS>
+static int gram2_dispatch(opkb_context* ctx, Gram2Args<T>& A, int nroles, int* nslot)
+{
+    constexpr int BIG = 4096 / (int)sizeof(T), SMALL = 2048 / (int)sizeof(T);
+    if (A.nb <= 2) return gram2_launch<T, BS, BIG, 256>(ctx, A, nroles, nslot);
+    if (nroles * A.kshare + 1 <= 8) return gram2_launch<T, BS, SMALL, 256>(ctx, A, nroles, nslot);
+    return gram2_launch<T, BS, SMALL, 352>(ctx, A, nroles, nslot);
 }
 
 template <typename T>
@@ -307,12 +353,12 @@ static int gram2_run(opkb_context* ctx, int64_t n, int m, const void* const* Sp,
     Gram2Args<T> A;
     memset(&A, 0, sizeof(A));
     A.rows[0] = (const T*)v0;
+    A.rows[1] = (const T*)x;
+    A.rows[2] = (const T*)gcur;
     for (int j = 0; j < m; ++j) {
-        A.rows[1 + 2 * j] = (const T*)Sp[j];
-        A.rows[2 + 2 * j] = (const T*)Yp[j];
+        A.rows[3 + 2 * j] = (const T*)Sp[j];
+        A.rows[4 + 2 * j] = (const T*)Yp[j];
     }
-    A.rows[2 * m + 1] = (const T*)x;
-    A.rows[2 * m + 2] = (const T*)gcur;
     A.Snew = (T*)Sp[m - 1];
     A.Ynew = (T*)Yp[m - 1];
     A.n = n;
@@ -322,15 +368,15 @@ static int gram2_run(opkb_context* ctx, int64_t n, int m, const void* const* Sp,
     const int bs = (m + nb - 1) / nb;
     const int nroles = nb * (nb + 1) / 2;
     A.nb = nb;
-    // consumer warps per role: 1 role: 8; 3 roles: 3 each; 6 or 10 roles: 1 each
-    A.kshare = (nroles == 1) ? 8 : ((nroles == 3) ? 3 : 1);
+    // consumer warps per role: 1 role: 7; 3 roles: 2 each; 6 or 10 roles: 1 each
+    A.kshare = (nroles == 1) ? 7 : ((nroles == 3) ? 2 : 1);
     int nslot = 0, rc = 0;
     switch (bs) {
-    case 1: rc = gram2_launch<T, 1>(ctx, A, nroles, &nslot); break;
-    case 2: rc = gram2_launch<T, 2>(ctx, A, nroles, &nslot); break;
-    case 3: rc = gram2_launch<T, 3>(ctx, A, nroles, &nslot); break;
-    case 4: rc = gram2_launch<T, 4>(ctx, A, nroles, &nslot); break;
-    default: rc = gram2_launch<T, 5>(ctx, A, nroles, &nslot); break;
+    case 1: rc = gram2_dispatch<T, 1>(ctx, A, nroles, &nslot); break;
+    case 2: rc = gram2_dispatch<T, 2>(ctx, A, nroles, &nslot); break;
+    case 3: rc = gram2_dispatch<T, 3>(ctx, A, nroles, &nslot); break;
+    case 4: rc = gram2_dispatch<T, 4>(ctx, A, nroles, &nslot); break;
+    default: rc = gram2_dispatch<T, 5>(ctx, A, nroles, &nslot); break;
     }
     if (rc) return rc;
     static thread_local double res[OPKB_NRED_MAX];
