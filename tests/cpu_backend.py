@@ -165,3 +165,99 @@ class NumpyGramOps(NumpyOps):
         if s.method > 0:
             O.project_direction(self.d, self.x, lo, hi, -1, self.d)
         return True, -O.vdot(self.g, self.d), O.vnorm2(self.d)
+
+
+class ShardedNumpyOps(NumpyOps):
+    """The N > 1 data path on CPU: every rank holds a contiguous shard, each
+    reduction produces per-rank partials that are all-gathered (gloo) and
+    combined in fixed rank order by opkb200.dist.combine_partials -- the same
+    scheme libopkb200 uses over NCCL (opkb_finish_reduction)."""
+
+    def __init__(self, solver, x0, obj):
+        super().__init__(solver, x0, obj)
+        self.alpha = [0.0] * solver.mem
+        self.rho = [0.0] * solver.mem
+
+    def _allreduce(self, vals, kinds=None):
+        import torch
+        import torch.distributed as dist
+        from opkb200.dist import combine_partials
+        t = torch.tensor(vals, dtype=torch.float64)
+        out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+        dist.all_gather(out, t)
+        return combine_partials([o.tolist() for o in out], kinds)
+
+    def _dot(self, x, y, sel=None):
+        part = O.vdot(x, y) if sel is None else O.vdot_sel(sel, x, y)
+        return self._allreduce([part])[0]
+
+    def evaluate(self, mark, stp, initial):
+        f = super().evaluate(mark, stp, initial)
+        return self._allreduce([f])[0]
+
+    def gnorm(self):
+        v = self.p if self.s.method > 0 else self.g
+        return math.sqrt(self._dot(v, v))
+
+    def gd_search(self, stp):
+        if self.s.method > 0:
+            return self._dot(self.g, self.sv) / stp
+        return -self._dot(self.g, self.d)
+
+    def xnorm(self):
+        return math.sqrt(self._dot(self.x, self.x))
+
+    def snorm(self):
+        return math.sqrt(self._dot(self.sv, self.sv))
+
+    def new_direction(self):
+        s = self.s
+        mark, mem = s.mark, s.mem
+        lo, hi = self._b()
+        S, Y, rho, alpha = self.S, self.Y, self.rho, self.alpha
+        O.vupdate(S[mark], -1, self.x)
+        O.vupdate(Y[mark], -1, self.p if s.method == 1 else self.g)
+        if s.method < 2:
+            rho[mark] = self._dot(Y[mark], S[mark])
+            if rho[mark] > 0:
+                s.gamma = rho[mark] / self._dot(Y[mark], Y[mark])
+        s.m = min(s.m + 1, mem)
+        v = self.d
+        v[:] = self.p if s.method == 2 else self.g
+        sel = O.get_free_variables(self.p) if s.method == 2 else None
+        gamma = 0.0 if s.method == 2 else s.gamma
+        modif = False
+        k = mark + 1
+        for _ in range(s.m):                     # apply_lbfgs!, src/quasinewton.jl:716-779
+            k = k - 1 if k > 0 else mem - 1
+            if s.method == 2:
+                rho[k] = self._dot(Y[k], S[k], sel)
+            if rho[k] > 0:
+                alpha[k] = self._dot(S[k], v, sel) / rho[k]
+                if sel is None:
+                    O.vupdate(v, -alpha[k], Y[k])
+                else:
+                    O.vupdate_sel(v, sel, -alpha[k], Y[k])
+                modif = True
+                if s.method == 2 and gamma == 0:
+                    gamma = rho[k] / self._dot(Y[k], Y[k], sel)
+        change = modif and gamma != 0
+        if change:
+            O.vscale(v, gamma)
+            for _ in range(s.m):
+                if rho[k] > 0:
+                    beta = self._dot(Y[k], v, sel) / rho[k]
+                    if sel is None:
+                        O.vupdate(v, alpha[k] - beta, S[k])
+                    else:
+                        O.vupdate_sel(v, sel, alpha[k] - beta, S[k])
+                k = k + 1 if k < mem - 1 else 0
+        if not change:
+            return False, 0.0, 0.0
+        if s.method > 0:
+            O.project_direction(self.d, self.x, lo, hi, -1, self.d)
+        return True, -self._dot(self.g, self.d), math.sqrt(self._dot(self.d, self.d))
+
+    def begin_search(self, mark):
+        smin, smax = super().begin_search(mark)
+        return tuple(self._allreduce([smin, smax], [2, 1]))

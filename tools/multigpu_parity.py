@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check (run under torchrun on N GPUs of one box):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29511 tools/multigpu_parity.py
+
+Every rank holds a contiguous shard on its own GPU; the reductions are combined
+by one packed NCCL all-gather per phase inside libopkb200.  Rank 0 compares the
+gathered iterates with the single-process CPU oracle (first 20 iterations within
+1e-10, identical decisions on every rank)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    import opk_oracle as O
+    import opkb200 as opk
+    from helpers import gpu_bounds, problem
+    from opkb200.dist import init_context, shard_range
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = init_context(local)
+    assert ctx.nranks == world and ctx.rank == rank
+    ok = True
+    for kind, n, dtype, kw in (("quad_box", 200001, np.float64, dict(mem=10)),
+                               ("rosen_box", 100000, np.float64, dict(mem=7)),
+                               ("rosen_unc", 100000, np.float64, dict()),
+                               ("rosen_box", 100000, np.float32, dict(mem=7)),
+                               ("quad_box", 200001, np.float64, dict(mem=10, mode="primitive"))):
+        pb = problem(kind, n, dtype)
+        first, cnt = shard_range(n, rank, world)
+        sl = slice(first, first + cnt)
+        lo, hi = gpu_bounds(pb)
+        lo = lo[sl] if isinstance(lo, np.ndarray) else lo
+        hi = hi[sl] if isinstance(hi, np.ndarray) else hi
+        obj = pb["gpu_obj"]
+        if isinstance(obj, opk.Quadratic):
+            obj = opk.Quadratic(obj.a[sl].copy(), obj.c[sl].copy())
+        trace = []
+        s = opk.VMLMB(obj, pb["x0"][sl].copy(), lower=lo, upper=hi, maxiter=25, nglobal=n, ctx=ctx,
+                      observer=lambda s: trace.append((s.iter, s.eval, s.f, s.gnorm, s.stp)), **kw)
+        s.solve()
+        xloc = s.result()
+        s.close()
+        # identical decisions on all ranks
+        t = torch.tensor([v for row in trace for v in row], dtype=torch.float64, device="cuda")
+        tmax, tmin = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        same = bool(torch.equal(tmax, tmin))
+        # gather x on rank 0
+        per = shard_range(n, 0, world)[1]
+        buf = torch.zeros(per, dtype=torch.float64, device="cuda")
+        buf[:cnt] = torch.from_numpy(xloc.astype(np.float64)).cuda()
+        bufs = [torch.zeros_like(buf) for _ in range(world)]
+        dist.all_gather(bufs, buf)
+        if rank == 0:
+            x = np.concatenate([b.cpu().numpy()[:shard_range(n, r, world)[1]] for r, b in enumerate(bufs)])
+            okw = {k: v for k, v in kw.items() if k != "mode"}
+            xo, ro, tro = O.vmlmb(pb["oracle_obj"], pb["x0"], pb["lower"], pb["upper"], trace=True,
+                                  maxiter=25, **okw)
+            rtol = 1e-10 if dtype == np.float64 else 1e-4
+            worst = 0.0
+            for g, w in zip(trace, tro):
+                if w["iter"] > 20:
+                    break
+                assert (g[0], g[1]) == (w["iter"], w["eval"]), (g, w["iter"], w["eval"])
+                worst = max(worst, abs(g[2] - w["f"]) / abs(w["f"]), abs(g[3] - w["gnorm"]) / w["gnorm"])
+            ex = np.linalg.norm(x - xo) / np.linalg.norm(xo)
+            good = same and worst <= rtol and ex <= 10 * rtol
+            ok = ok and good
+            print(f"[{world} GPUs] {kind} n={n} {np.dtype(dtype).name} {kw}: same_decisions={same} "
+                  f"worst_rel(f,|g|)={worst:.2e} rel(x)={ex:.2e} {'OK' if good else 'FAIL'}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0 and not ok:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
