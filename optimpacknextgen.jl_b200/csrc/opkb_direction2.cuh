@@ -1,0 +1,144 @@
+// opkb_direction2.cuh -- P4 "direction", pipelined version (m >= 1 pairs).
+//
+// Same arithmetic as k_direction (opkb_vmlmb.cu): d = H*v0 from the host-solved
+// two-loop coefficients with the reference's rounding sequence, projection,
+// g.d, |d|^2, step limits, save (x, g|p) for the next line search.  Other data
+// movement: one persistent CTA per SM; a producer warp streams rows of the
+// 2m+3..2m+6 input vectors into a shared-memory ring with bulk asynchronous
+// copies (cp.async.bulk, mbarrier completion) so that the 25+ concurrent input
+// streams reach HBM as multi-KB bursts with >= 100 KB per SM in flight; the
+// consumer warps do the element-wise work out of shared memory (128-bit LDS)
+// and write d, S[mark'], Y[mark'] with 128-bit stores.  Only whole tiles are
+// processed here; the caller runs the register kernel on the tail.
+#pragma once
+
+#define DIR2_MAXSTAGE 8
+#define DIR2_THREADS 288   // 8 consumer warps + 1 producer warp
+
+template <typename T> struct Dir2Args {
+    const T* rows[2 * OPKB_MEM_MAX + 6];  // v0, x, g, [lo], [hi], [ysrc], then (y_j, s_j) oldest..newest
+    T ma[OPKB_MEM_MAX];                   // -alpha_j
+    T cc[OPKB_MEM_MAX];                   // alpha_j - beta_j
+    unsigned use;
+    int m, nrows;
+    int r_lo, r_hi, r_ysrc;               // row index or -1 (scalar bound / ysrc == g)
+    T gamma, lo_val, hi_val;
+    int has_lo, has_hi, masked, bounded;
+    T* d;
+    T* Snext;
+    T* Ynext;
+    int64_t n;                            // multiple of `tile`
+    int tile, nstage;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, ReduceScratch rs)
+{
+    constexpr int VEC = VecOf<T>::N;
+    constexpr int CWARPS = DIR2_THREADS / 32 - 1;
+    constexpr int CTHREADS = CWARPS * 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[DIR2_MAXSTAGE];
+    __shared__ __align__(8) uint64_t empty_bar[DIR2_MAXSTAGE];
+
+    const int TILE = A.tile, NSTAGE = A.nstage, NR = A.nrows, m = A.m;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    T* const stage0 = reinterpret_cast<T*>(smem_raw);
+    const int stage_elems = NR * TILE;
+    const uint32_t rowbytes = (uint32_t)(TILE * sizeof(T));
+    const int64_t ntiles = A.n / TILE;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], CWARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // acc: 0 g.d; 1 |d|^2; 2 smin; 3 smax
+    T smin = T(INFINITY), smax = T(0);
+    double acc[4] = {0, 0, 0, 0};
+
+    if (warp == CWARPS) {
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int s = it % NSTAGE;
+            const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
+            if (lane == 0) {
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                mbar_expect_tx(&full_bar[s], rowbytes * (uint32_t)NR);
+            }
+            __syncwarp();
+            T* dst = stage0 + s * stage_elems;
+            const int64_t base = tile * TILE;
+            for (int r = lane; r < NR; r += 32)
+                bulk_g2s(dst + r * TILE, A.rows[r] + base, rowbytes, &full_bar[s]);
+        }
+    } else {
+        const int prow = 3 + (A.r_lo >= 0) + (A.r_hi >= 0) + (A.r_ysrc >= 0);  // first pair row
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int s = it % NSTAGE;
+            const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
+            const T* st = stage0 + s * stage_elems;
+            const int64_t base = tile * TILE;
+            mbar_wait(&full_bar[s], ph);
+            for (int e = tid * VEC; e < TILE; e += CTHREADS * VEC) {
+                Pack<T> pv = ld_pack<T>(st, e / VEC);
+                Pack<T> px = ld_pack<T>(st + TILE, e / VEC);
+                Pack<T> pg = ld_pack<T>(st + 2 * TILE, e / VEC);
+                Pack<T> pl = (A.r_lo >= 0) ? ld_pack<T>(st + A.r_lo * TILE, e / VEC) : splat_pack<T>(A.lo_val);
+                Pack<T> ph_ = (A.r_hi >= 0) ? ld_pack<T>(st + A.r_hi * TILE, e / VEC) : splat_pack<T>(A.hi_val);
+                Pack<T> pys = (A.r_ysrc >= 0) ? ld_pack<T>(st + A.r_ysrc * TILE, e / VEC) : pg;
+                Pack<T> v = pv;
+                bool upd[VEC];
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) upd[q] = !A.masked || (pv.v[q] != T(0));
+                // apply_lbfgs! :716-745 / :747-779, rounding sequence of the reference
+                for (int j = m - 1; j >= 0; --j) {
+                    if ((A.use >> j) & 1u) {
+                        const Pack<T> y = ld_pack<T>(st + (prow + 2 * j) * TILE, e / VEC);
+                        const T a = A.ma[j];
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q)
+                            if (upd[q]) v.v[q] = v.v[q] + a * y.v[q];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) v.v[q] = A.gamma * v.v[q];
+                for (int j = 0; j < m; ++j) {
+                    if ((A.use >> j) & 1u) {
+                        const Pack<T> sv = ld_pack<T>(st + (prow + 2 * j + 1) * TILE, e / VEC);
+                        const T c = A.cc[j];
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q)
+                            if (upd[q]) v.v[q] = v.v[q] + c * sv.v[q];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    T di = v.v[q];
+                    if (A.bounded)  // project_direction!(d, x, lo, hi, -, d) :535
+                        di = projdir(px.v[q], pl.v[q], ph_.v[q], A.has_lo, A.has_hi, -1, di);
+                    v.v[q] = di;
+                    acc[0] = dacc(pg.v[q], di, acc[0]);   // vdot(g, d) :537
+                    acc[1] = dacc(di, di, acc[1]);        // vnorm2(d) :629
+                    if (A.bounded)                        // step_limits(x, lo, hi, -1, d) :577
+                        step_limit_update(px.v[q], pl.v[q], ph_.v[q], A.has_lo, A.has_hi, -di, smin, smax);
+                }
+                const int64_t iv = (base + e) / VEC;
+                st_pack<T>(A.d, iv, v);
+                st_pack<T>(A.Snext, iv, px);    // vcopy!(S[mark], x) :562
+                st_pack<T>(A.Ynext, iv, pys);   // vcopy!(Y[mark], g|p) :563
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
+    }
+    acc[2] = (double)smin;
+    acc[3] = (double)smax;
+    __syncthreads();
+    block_reduce_publish<4, 8u, 4u>(acc, rs);  // slot 2: min, slot 3: max
+}

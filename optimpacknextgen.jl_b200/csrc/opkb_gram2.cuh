@@ -24,61 +24,6 @@ template <typename T> struct Gram2Args {
     int m, nb, kshare, masked, tile, nstage;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-
-__device__ __forceinline__ void fence_proxy_async()
-{
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
 // Stage layout (rows of TILE elements of T): 0: v0, 1: x, 2: g|p, then the pairs
 // 3+2q: s_q, 4+2q: y_q for q = 0 (oldest) .. nb*BS-1 (rows of pairs q >= m are
 // zero and never overwritten), then 2 pad rows.  With TILE a compile-time
@@ -94,6 +39,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[GRAM2_MAXSTAGE];
     __shared__ __align__(8) uint64_t empty_bar[GRAM2_MAXSTAGE];
+    __shared__ __align__(8) uint64_t pair_bar[GRAM2_MAXSTAGE];
     __shared__ unsigned int s_last;
 
     const int nb = A.nb, m = A.m, k = A.kshare, NSTAGE = A.nstage;
@@ -110,6 +56,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], cwarps);
+            mbar_init(&pair_bar[s], k);   // the k warps of the writer role
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -168,19 +115,15 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
         const int rowbase = (3 + 2 * bi * BS) * TILE;
         const int col0 = diag ? 0 : (4 + 2 * bj * BS) * TILE;
         const int col1 = diag ? (4 + 2 * bi * BS) * TILE : (6 + 2 * bj * BS) * TILE;
-        // The newest slot still holds (x0, g0): its pair (x0 - x, g0 - g) is formed
-        // on the fly (vupdate!(S[mark], -1, x); vupdate!(Y[mark], -1, g|p),
-        // src/quasinewton.jl:512-513); tile coordinates of its rows and column:
+        // The newest slot still holds (x0, g0).  The warps of the last diagonal
+        // role (the "writer") turn it in place, in the stage, into the pair
+        // (x0 - x, g0 - g) -- vupdate!(S[mark], -1, x); vupdate!(Y[mark], -1, g|p),
+        // src/quasinewton.jl:512-513 -- write it back to HBM once, and signal
+        // pair_bar; only the roles that read the newest pair wait for it.
         const int qn = m - 1;
-        int rnew = -1, cnew = -1;
-        if (qn >= bi * BS && qn < (bi + 1) * BS) rnew = 2 * (qn - bi * BS);
-        if (diag) {
-            if (rnew >= 0) cnew = qn - bi * BS + 1;
-        } else if (qn >= bj * BS && qn < (bj + 1) * BS) {
-            cnew = qn - bj * BS;
-        }
-        // the last diagonal role owns the write-back of the new pair to HBM
         const bool writer = (bi == nb - 1 && bj == nb - 1);
+        const bool needs_pair = !writer && (bj == nb - 1);   // its columns include y_new
+        const int snew = (3 + 2 * qn) * TILE, ynew = (4 + 2 * qn) * TILE;
         const bool masked = A.masked != 0;
 
         int it = 0;
@@ -201,48 +144,43 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
                 }
                 named_bar_sync(1, cthreads);
             }
+            if (writer) {
+                for (int e = sub * 32 + lane; e < TILE; e += 32 * k) {
+                    const T sn = st[snew + e] - st[TILE + e];       // s_new = x0 - x (element type)
+                    const T yn = st[ynew + e] - st[2 * TILE + e];   // y_new = g0 - g
+                    st[snew + e] = sn;
+                    st[ynew + e] = yn;
+                    if (base + e < A.n) {
+                        A.Snew[base + e] = sn;
+                        A.Ynew[base + e] = yn;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&pair_bar[s]);
+                mbar_wait(&pair_bar[s], ph);   // the other warps of this role
+            } else if (needs_pair) {
+                mbar_wait(&pair_bar[s], ph);
+            }
+#pragma unroll 2
             for (int e = sub * 32 + lane; e < TILE; e += 32 * k) {
                 const T* rp = st + rowbase + e;
                 const T* c0 = st + col0 + e;
                 const T* c1 = st + col1 + e;
-                T tv[RT], tc[CT];
-#pragma unroll
-                for (int r = 0; r < RT; ++r) tv[r] = rp[r * TILE];
-                tc[0] = c0[0];
-#pragma unroll
-                for (int c = 1; c < CT; ++c) tc[c] = c1[(c - 1) * 2 * TILE];
-                const T p0 = st[e], xs = st[TILE + e], gs = st[2 * TILE + e];
-                if (rnew >= 0) {
-#pragma unroll
-                    for (int r = 0; r < RT; r += 2) {
-                        if (r == rnew) {
-                            tv[r] = tv[r] - xs;          // s_new = x0 - x   (in the element type)
-                            tv[r + 1] = tv[r + 1] - gs;  // y_new = g0 - g
-                            if (writer && base + e < A.n) {
-                                A.Snew[base + e] = tv[r];
-                                A.Ynew[base + e] = tv[r + 1];
-                            }
-                        }
-                    }
-                }
-                if (cnew >= 0) {
-#pragma unroll
-                    for (int c = 0; c < CT; ++c)
-                        if (c == cnew) tc[c] = tc[c] - gs;
-                }
                 double rv[RT], cv[CT];
 #pragma unroll
-                for (int r = 0; r < RT; ++r) rv[r] = (double)tv[r];
-                const bool fr = !masked || (p0 != T(0));  // free variable: p[i] != 0 (row 0 is v0 = p)
+                for (int r = 0; r < RT; ++r) rv[r] = (double)rp[r * TILE];
+                const bool fr = !masked || (st[e] != T(0));  // free variable: p[i] != 0 (row 0 is v0 = p)
+                cv[0] = fr ? (double)c0[0] : 0.0;
 #pragma unroll
-                for (int c = 0; c < CT; ++c) cv[c] = fr ? (double)tc[c] : 0.0;
+                for (int c = 1; c < CT; ++c) cv[c] = fr ? (double)c1[(c - 1) * 2 * TILE] : 0.0;
 #pragma unroll
                 for (int r = 0; r < RT; ++r)
 #pragma unroll
                     for (int c = 0; c < CT; ++c) acc[r][c] = fma(rv[r], cv[c], acc[r][c]);
             }
-            // release the stage
-            if (partial) fence_proxy_async();
+            // release the stage (the writer's generic-proxy stores into it must be
+            // ordered before the next bulk copy)
+            if (partial || writer) fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
         }
@@ -336,14 +274,20 @@ static int gram2_launch(opkb_context* ctx, Gram2Args<T>& A, int nroles, int* nsl
     return 0;
 }
 
-// rows of 4 KB for up to 10 pairs (nb <= 2), 2 KB beyond
+// row size of a stage: 4 KB rows for up to 10 pairs (nb <= 2), 2 KB beyond;
+// OPKB_GRAM_ROWB = 2048 | 3072 | 4096 overrides (tuning knob)
 template <typename T, int BS>
 static int gram2_dispatch(opkb_context* ctx, Gram2Args<T>& A, int nroles, int* nslot)
 {
-    constexpr int BIG = 4096 / (int)sizeof(T), SMALL = 2048 / (int)sizeof(T);
-    if (A.nb <= 2) return gram2_launch<T, BS, BIG, 256>(ctx, A, nroles, nslot);
-    if (nroles * A.kshare + 1 <= 8) return gram2_launch<T, BS, SMALL, 256>(ctx, A, nroles, nslot);
-    return gram2_launch<T, BS, SMALL, 352>(ctx, A, nroles, nslot);
+    constexpr int R4 = 4096 / (int)sizeof(T), R3 = 3072 / (int)sizeof(T), R2 = 2048 / (int)sizeof(T);
+    int rowb = (A.nb <= 2) ? 4096 : 2048;
+    if (const char* e = getenv("OPKB_GRAM_ROWB")) rowb = atoi(e);
+    const bool small_block = (nroles * A.kshare + 1 <= 8);
+    if (!small_block && rowb == 4096) return gram2_launch<T, BS, R4, 352>(ctx, A, nroles, nslot);
+    if (!small_block) return gram2_launch<T, BS, R2, 352>(ctx, A, nroles, nslot);
+    if (rowb == 4096) return gram2_launch<T, BS, R4, 256>(ctx, A, nroles, nslot);
+    if (rowb == 3072) return gram2_launch<T, BS, R3, 256>(ctx, A, nroles, nslot);
+    return gram2_launch<T, BS, R2, 256>(ctx, A, nroles, nslot);
 }
 
 template <typename T>
@@ -370,6 +314,10 @@ static int gram2_run(opkb_context* ctx, int64_t n, int m, const void* const* Sp,
     A.nb = nb;
     // consumer warps per role: 1 role: 7; 3 roles: 2 each; 6 or 10 roles: 1 each
     A.kshare = (nroles == 1) ? 7 : ((nroles == 3) ? 2 : 1);
+    if (const char* e = getenv("OPKB_GRAM_KSHARE")) {   // tuning knob
+        const int kk = atoi(e);
+        if (kk >= 1 && (nroles * kk + 1) * 32 <= 352) A.kshare = kk;
+    }
     int nslot = 0, rc = 0;
     switch (bs) {
     case 1: rc = gram2_dispatch<T, 1>(ctx, A, nroles, &nslot); break;

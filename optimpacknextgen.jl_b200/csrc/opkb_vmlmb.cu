@@ -376,6 +376,7 @@ extern "C" int opkb_vmlmb_trial_end(opkb_vmlmb* ws, int mark, double f, int init
 // P3: Gram sweep
 #include "opkb_gram.cuh"
 #include "opkb_gram2.cuh"
+#include "opkb_direction2.cuh"
 #include <stdlib.h>
 
 extern "C" int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots, double* G)
@@ -577,21 +578,115 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
     A.masked = (ws->method == 2);
     A.bounded = (ws->method > 0);
     A.steepest = steepest;
-    ReduceScratch rs = scratch(ctx);
-    int grid = opkb_grid_for(ctx, ws->n / VecOf<T>::N, 2);
-    if (A.m <= 4)
-        LAUNCHB(ctx, OPKB_K_DIRECTION, (k_direction<T, 4>), grid, OPKB_BLOCK, 0, A, rs);
-    else if (A.m <= 8)
-        LAUNCHB(ctx, OPKB_K_DIRECTION, (k_direction<T, 8>), grid, OPKB_BLOCK, 0, A, rs);
-    else if (A.m <= 12)
-        LAUNCHB(ctx, OPKB_K_DIRECTION, (k_direction<T, 12>), grid, OPKB_BLOCK, 0, A, rs);
-    else if (A.m <= 16)
-        LAUNCHB(ctx, OPKB_K_DIRECTION, (k_direction<T, 16>), grid, OPKB_BLOCK, 0, A, rs);
-    else
-        LAUNCHB(ctx, OPKB_K_DIRECTION, (k_direction<T, OPKB_MEM_MAX>), grid, OPKB_BLOCK, 0, A, rs);
     int kinds[4] = {OPKB_RSUM, OPKB_RSUM, OPKB_RMIN, OPKB_RMAX};
-    int rc = opkb_finish_reduction(ctx, 4, kinds, out);
-    if (rc) return rc;
+    double part[2][4] = {{0, 0, INFINITY, 0}, {0, 0, INFINITY, 0}};
+    int nparts = 0;
+    int64_t done = 0;
+
+    // ---- whole tiles through the bulk-async ring (m >= 1 pairs) ---------------------
+    static const int force_v1 = (getenv("OPKB_DIR_V1") && getenv("OPKB_DIR_V1")[0] == '1');
+    if (!steepest && A.m >= 1 && !force_v1) {
+        Dir2Args<T> B;
+        memset(&B, 0, sizeof(B));
+        int nr = 0;
+        B.rows[nr++] = A.v0;
+        B.rows[nr++] = A.x;
+        B.rows[nr++] = A.g;
+        B.r_lo = B.r_hi = B.r_ysrc = -1;
+        if (A.bounded && A.lo.arr) { B.r_lo = nr; B.rows[nr++] = A.lo.arr; }
+        if (A.bounded && A.hi.arr) { B.r_hi = nr; B.rows[nr++] = A.hi.arr; }
+        if (A.ysrc != A.g) { B.r_ysrc = nr; B.rows[nr++] = A.ysrc; }
+        for (int j = 0; j < A.m; ++j) {
+            B.rows[nr++] = A.Y[j];
+            B.rows[nr++] = A.S[j];
+            B.ma[j] = A.ma[j];
+            B.cc[j] = A.cc[j];
+        }
+        B.use = A.use;
+        B.m = A.m;
+        B.nrows = nr;
+        B.gamma = A.gamma;
+        B.lo_val = A.lo.val;
+        B.hi_val = A.hi.val;
+        B.has_lo = A.lo.has;
+        B.has_hi = A.hi.has;
+        B.masked = A.masked;
+        B.bounded = A.bounded;
+        B.d = A.d;
+        B.Snext = A.Snext;
+        B.Ynext = A.Ynext;
+        // ring geometry: 4 KB rows when two stages fit in ~200 KB, else 2 KB rows
+        const size_t budget = 200 * 1024;
+        int tile = (int)(4096 / sizeof(T));
+        if ((size_t)nr * tile * sizeof(T) * 2 > budget) tile = (int)(2048 / sizeof(T));
+        if (const char* e = getenv("OPKB_DIR_TILE")) tile = atoi(e);
+        size_t stage_bytes = (size_t)nr * tile * sizeof(T);
+        int nstage = (int)(budget / stage_bytes);
+        if (const char* e = getenv("OPKB_DIR_NSTAGE")) nstage = atoi(e);
+        if (nstage > DIR2_MAXSTAGE) nstage = DIR2_MAXSTAGE;
+        const int64_t ntiles = ws->n / tile;
+        if (nstage >= 2 && ntiles >= 1) {
+            B.tile = tile;
+            B.nstage = nstage;
+            B.n = ntiles * tile;
+            const size_t smem = stage_bytes * nstage;
+            auto kern = k_direction2<T>;
+            OPKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int64_t grid = ctx->sm_count;
+            if (grid > ntiles) grid = ntiles;
+            opkb_prof_begin(ctx, OPKB_K_DIRECTION);
+            kern<<<(int)grid, DIR2_THREADS, smem, ctx->stream>>>(B, scratch(ctx));
+            opkb_prof_end(ctx);
+            ctx->launches += 1;
+            OPKB_CUDA(cudaGetLastError());
+            int rc = opkb_finish_reduction(ctx, 4, kinds, part[nparts++]);
+            if (rc) return rc;
+            done = B.n;
+        }
+    }
+
+    // ---- the rest (tail of the ring path, or everything) with the register kernel -----
+    if (done < ws->n) {
+        const int64_t off = done;
+        for (int j = 0; j < A.m; ++j) {
+            A.S[j] += off;
+            A.Y[j] += off;
+        }
+        A.v0 += off;
+        A.x += off;
+        A.g += off;
+        A.ysrc += off;
+        A.d += off;
+        A.Snext += off;
+        A.Ynext += off;
+        if (A.lo.arr) A.lo.arr += off;
+        if (A.hi.arr) A.hi.arr += off;
+        A.n = ws->n - off;
+        ReduceScratch rs = scratch(ctx);
+        int grid = opkb_grid_for(ctx, A.n / VecOf<T>::N, 2);
+        if (A.m <= 4)
+            LAUNCHB(ctx, OPKB_K_DIRECTION, (k_direction<T, 4>), grid, OPKB_BLOCK, 0, A, rs);
+        else if (A.m <= 8)
+            LAUNCHB(ctx, OPKB_K_DIRECTION, (k_direction<T, 8>), grid, OPKB_BLOCK, 0, A, rs);
+        else if (A.m <= 12)
+            LAUNCHB(ctx, OPKB_K_DIRECTION, (k_direction<T, 12>), grid, OPKB_BLOCK, 0, A, rs);
+        else if (A.m <= 16)
+            LAUNCHB(ctx, OPKB_K_DIRECTION, (k_direction<T, 16>), grid, OPKB_BLOCK, 0, A, rs);
+        else
+            LAUNCHB(ctx, OPKB_K_DIRECTION, (k_direction<T, OPKB_MEM_MAX>), grid, OPKB_BLOCK, 0, A, rs);
+        int rc = opkb_finish_reduction(ctx, 4, kinds, part[nparts++]);
+        if (rc) return rc;
+    }
+    out[0] = part[0][0];
+    out[1] = part[0][1];
+    out[2] = part[0][2];
+    out[3] = part[0][3];
+    if (nparts == 2) {  // fixed order: ring part, then tail
+        out[0] = out[0] + part[1][0];
+        out[1] = out[1] + part[1][1];
+        out[2] = (part[1][2] < out[2]) ? part[1][2] : out[2];
+        out[3] = (part[1][3] > out[3]) ? part[1][3] : out[3];
+    }
     if (!A.bounded) {  // no step limits for L-BFGS (:581-584)
         out[2] = INFINITY;
         out[3] = INFINITY;
