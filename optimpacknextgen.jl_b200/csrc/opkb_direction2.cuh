@@ -130,8 +130,10 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
                 }
                 const int64_t iv = (base + e) / VEC;
                 st_pack<T>(A.d, iv, v);
-                st_pack<T>(A.Snext, iv, px);    // vcopy!(S[mark], x) :562
-                st_pack<T>(A.Ynext, iv, pys);   // vcopy!(Y[mark], g|p) :563
+                if (A.Snext) {                      // (the workspace path aliases instead)
+                    st_pack<T>(A.Snext, iv, px);    // vcopy!(S[mark], x) :562
+                    st_pack<T>(A.Ynext, iv, pys);   // vcopy!(Y[mark], g|p) :563
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);

@@ -28,7 +28,35 @@ struct opkb_vmlmb_ {
     opkb_vector *x, *g, *p, *d;
     opkb_vector* S[OPKB_MEM_MAX];
     opkb_vector* Y[OPKB_MEM_MAX];
+    // The saves vcopy!(S[mark], x); vcopy!(Y[mark], g|p) (src/quasinewton.jl:562-563)
+    // are done by aliasing: after a direction phase S[mark'] / Y[mark'] share the
+    // buffers of x / g|p, and the buffers of the recycled slot become the targets
+    // of the next trial point (no copy, no HBM traffic).
+    void* spare_x;
+    void* spare_y;
+    int aliased_slot;      // -1: no aliasing active
 };
+
+// x (and g|p) get their own buffers back before they are written again
+static void vmlmb_unalias(opkb_vmlmb* ws)
+{
+    if (ws->aliased_slot < 0) return;
+    ws->x->data = ws->spare_x;
+    (ws->method == 1 ? ws->p : ws->g)->data = ws->spare_y;
+    ws->aliased_slot = -1;
+}
+
+static void vmlmb_alias(opkb_vmlmb* ws, int slot)
+{
+    if (ws->aliased_slot == slot) return;   // second direction of the same iteration (:542-556)
+    vmlmb_unalias(ws);
+    opkb_vector* ysrc = (ws->method == 1 ? ws->p : ws->g);
+    ws->spare_x = ws->S[slot]->data;
+    ws->spare_y = ws->Y[slot]->data;
+    ws->S[slot]->data = ws->x->data;
+    ws->Y[slot]->data = ysrc->data;
+    ws->aliased_slot = slot;
+}
 
 #define LAUNCHB(ctx, cls, kernel, grid, block, smem, ...)                    \
     do {                                                                     \
@@ -85,6 +113,7 @@ extern "C" int opkb_vmlmb_create(opkb_context* ctx, int eltype, int64_t n, int m
     ws->hi = hi;
     ws->hi_val = hi_val;
     ws->obj = OPKB_OBJ_USER;
+    ws->aliased_slot = -1;
     int rc = 0;
     rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->x);
     rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->g);
@@ -105,6 +134,7 @@ extern "C" int opkb_vmlmb_create(opkb_context* ctx, int eltype, int64_t n, int m
 extern "C" int opkb_vmlmb_destroy(opkb_vmlmb* ws)
 {
     if (!ws) return 0;
+    if (ws->x && ws->g) vmlmb_unalias(ws);
     opkb_vector_destroy(ws->x);
     opkb_vector_destroy(ws->g);
     opkb_vector_destroy(ws->p);
@@ -289,6 +319,7 @@ template <typename T>
 static int trial_launch(opkb_vmlmb* ws, int mark, double stp, int initial, int stage)
 {
     opkb_context* ctx = ws->ctx;
+    if (stage != 2) vmlmb_unalias(ws);   // x, g|p are about to be overwritten
     TrialArgs<T> A;
     A.x0 = (const T*)ws->S[mark]->data;
     A.d = (const T*)ws->d->data;
@@ -513,8 +544,10 @@ __global__ void __launch_bounds__(OPKB_BLOCK) k_direction(DirArgs<T> A, ReduceSc
                 step_limit_update(px.v[e], pl.v[e], ph.v[e], A.lo.has, A.hi.has, -di, smin, smax);
         }
         st_pack<T>(A.d, iv, pd);
-        st_pack<T>(A.Snext, iv, px);    // vcopy!(S[mark], x) :562
-        st_pack<T>(A.Ynext, iv, pys);   // vcopy!(Y[mark], g|p) :563
+        if (A.Snext) {                      // (the workspace path aliases instead of copying)
+            st_pack<T>(A.Snext, iv, px);    // vcopy!(S[mark], x) :562
+            st_pack<T>(A.Ynext, iv, pys);   // vcopy!(Y[mark], g|p) :563
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (int64_t i = nvec * VEC; i < A.n; ++i) {
@@ -536,8 +569,10 @@ __global__ void __launch_bounds__(OPKB_BLOCK) k_direction(DirArgs<T> A, ReduceSc
             acc[1] = dacc(di, di, acc[1]);
             if (A.bounded) step_limit_update(xi, lo, hi, A.lo.has, A.hi.has, -di, smin, smax);
             A.d[i] = di;
-            A.Snext[i] = xi;
-            A.Ynext[i] = ys;
+            if (A.Snext) {
+                A.Snext[i] = xi;
+                A.Ynext[i] = ys;
+            }
         }
     }
     acc[2] = (double)smin;
@@ -570,8 +605,8 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
     A.g = (const T*)ws->g->data;
     A.ysrc = (const T*)(ws->method == 1 ? ws->p->data : ws->g->data);
     A.d = (T*)ws->d->data;
-    A.Snext = (T*)ws->S[mark_next]->data;
-    A.Ynext = (T*)ws->Y[mark_next]->data;
+    A.Snext = NULL;   // saved by aliasing after the launch (vmlmb_alias)
+    A.Ynext = NULL;
     A.lo = make_bound<T>(ws->lo, ws->lo_val, true);
     A.hi = make_bound<T>(ws->hi, ws->hi_val, false);
     A.n = ws->n;
@@ -657,8 +692,6 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         A.g += off;
         A.ysrc += off;
         A.d += off;
-        A.Snext += off;
-        A.Ynext += off;
         if (A.lo.arr) A.lo.arr += off;
         if (A.hi.arr) A.hi.arr += off;
         A.n = ws->n - off;
@@ -694,6 +727,8 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         out[2] = INFINITY;
         out[3] = INFINITY;
     }
+    // vcopy!(S[mark], x); vcopy!(Y[mark], g|p) :562-563, without a copy
+    vmlmb_alias(ws, mark_next);
     return 0;
 }
 
