@@ -16,7 +16,8 @@
 #define DIR2_THREADS 288   // 8 consumer warps + 1 producer warp
 
 template <typename T> struct Dir2Args {
-    const T* rows[2 * OPKB_MEM_MAX + 6];  // v0, x, g, [lo], [hi], [ysrc], then (y_j, s_j) oldest..newest
+    const T* rows[2 * OPKB_MEM_MAX + 6];  // v0 | -, x, g, [lo], [hi], [ysrc], then (y_j, s_j) oldest..newest
+    int v0_from_g;                        // VMLMB: v0 = p is recomputed from (x, g, lo, hi), row 0 unused
     T ma[OPKB_MEM_MAX];                   // -alpha_j
     T cc[OPKB_MEM_MAX];                   // alpha_j - beta_j
     unsigned use;
@@ -68,12 +69,12 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
             const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
             if (lane == 0) {
                 mbar_wait(&empty_bar[s], ph ^ 1u);
-                mbar_expect_tx(&full_bar[s], rowbytes * (uint32_t)NR);
+                mbar_expect_tx(&full_bar[s], rowbytes * (uint32_t)(NR - A.v0_from_g));
             }
             __syncwarp();
             T* dst = stage0 + s * stage_elems;
             const int64_t base = tile * TILE;
-            for (int r = lane; r < NR; r += 32)
+            for (int r = lane + A.v0_from_g; r < NR; r += 32)
                 bulk_g2s(dst + r * TILE, A.rows[r] + base, rowbytes, &full_bar[s]);
         }
     } else {
@@ -86,12 +87,21 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
             const int64_t base = tile * TILE;
             mbar_wait(&full_bar[s], ph);
             for (int e = tid * VEC; e < TILE; e += CTHREADS * VEC) {
-                Pack<T> pv = ld_pack<T>(st, e / VEC);
                 Pack<T> px = ld_pack<T>(st + TILE, e / VEC);
                 Pack<T> pg = ld_pack<T>(st + 2 * TILE, e / VEC);
                 Pack<T> pl = (A.r_lo >= 0) ? ld_pack<T>(st + A.r_lo * TILE, e / VEC) : splat_pack<T>(A.lo_val);
                 Pack<T> ph_ = (A.r_hi >= 0) ? ld_pack<T>(st + A.r_hi * TILE, e / VEC) : splat_pack<T>(A.hi_val);
                 Pack<T> pys = (A.r_ysrc >= 0) ? ld_pack<T>(st + A.r_ysrc * TILE, e / VEC) : pg;
+                Pack<T> pv;
+                if (A.v0_from_g) {
+                    // p = project_direction!(p, x, lo, hi, -, g) (src/quasinewton.jl:396),
+                    // bit-identical to the stored vector, without reading it
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q)
+                        pv.v[q] = projdir(px.v[q], pl.v[q], ph_.v[q], A.has_lo, A.has_hi, -1, pg.v[q]);
+                } else {
+                    pv = ld_pack<T>(st, e / VEC);
+                }
                 Pack<T> v = pv;
                 bool upd[VEC];
 #pragma unroll

@@ -1,20 +1,59 @@
-// opkb_gram2.cuh -- P3, the tall-skinny Gram sweep, pipelined version.
+// opkb_gram2.cuh -- P3: the tall-skinny Gram sweep of the L-BFGS two-loop
+// recursion (north_star: "the m dot products batched as one S^T.g / Y^T.g
+// sweep").  One pass over S[1..m], Y[1..m], v0 (and x, g for the in-place pair
+// update of the newest slot) yields every inner product apply_lbfgs!
+// (src/quasinewton.jl:716-779) needs:
+//     s_a.v0, y_a.v0, s_a.y_b, y_a.y_b   for age(b) >= age(a),
+// restricted to the free set {i : p[i] != 0} for VMLMB (:758-771).
 //
-// Same mathematics and role decomposition as opkb_gram.cuh (see there), other
-// data movement: one persistent CTA per SM; a producer warp streams raw tiles of
-// the 2m+3 vectors (v0, s_q, y_q, x, g) into a ring of NSTAGE shared-memory
+// Decomposition.  The pairs are split in NB blocks of BS <= 5 pairs; warp
+// "roles" own one register tile each: rows {s_q, y_q : q in block bi} (2*BS
+// rows) times columns {v0, y_q : q in block bi} (diagonal role) or
+// {y_q : q in block bj > bi}.  Only the NB(NB+1)/2 upper-triangular roles exist
+// (age(col) >= age(row)).  Each lane owns the elements e = lane (mod 32) of a
+// tile, so shared-memory reads are conflict free, and keeps 2*BS*(BS+1) double
+// accumulators for the whole sweep (exact products: Float32 is widened when
+// read).  Partials go through the same deterministic CTA -> last-CTA scheme as
+// every other reduction of the library.
+//
+// Data movement.  One persistent CTA per SM; a producer warp streams raw tiles
+// of the 2m+3 vectors (v0, x, g, s_q, y_q) into a ring of NSTAGE shared-memory
 // stages with bulk asynchronous copies (cp.async.bulk -> UBLKCP, completion on
-// an mbarrier), so that several stages (>= 100 KB per SM) are always in flight;
-// the consumer warps (one register tile of the Gram block each) wait on the
-// "full" barrier of a stage, turn the newest slot into the pair (x0 - x, g0 - g)
-// in place (written back to HBM once), accumulate, and release the stage
-// through its "empty" barrier.  Tiles stay in the element type in shared
-// memory (Float32 is widened when read), the free-set mask is p != 0 read from
-// the staged v0 row.
+// an mbarrier), so that ~100 KB per SM are always in flight; the consumer warps
+// wait on the "full" barrier of a stage, accumulate, and release the stage
+// through its "empty" barrier.  The free-set mask is p != 0 read from the staged
+// v0 row.
 #pragma once
 #include <stdlib.h>
 
 #define GRAM2_MAXSTAGE 8
+
+// scatter the role tiles into G[2m][m+1] (row 2q: s_q, 2q+1: y_q; col 0: v0, 1+q: y_q)
+static void gram_scatter(const double* res, int m, int nb, int bs, double* G)
+{
+    const int RT = 2 * bs, CT = bs + 1, W = m + 1;
+    for (int i = 0; i < 2 * m * W; ++i) G[i] = 0.0;
+    int role = 0;
+    for (int bi = 0; bi < nb; ++bi) {
+        for (int bj = bi; bj < nb; ++bj, ++role) {
+            for (int r = 0; r < RT; ++r) {
+                const int qrow = bi * bs + r / 2;
+                if (qrow >= m) continue;
+                for (int c = 0; c < CT; ++c) {
+                    int col;
+                    if (bi == bj) {
+                        col = (c == 0) ? 0 : 1 + bi * bs + (c - 1);
+                    } else {
+                        if (c >= bs) continue;
+                        col = 1 + bj * bs + c;
+                    }
+                    if (col > m) continue;
+                    G[(2 * qrow + (r & 1)) * W + col] = res[role * RT * CT + r * CT + c];
+                }
+            }
+        }
+    }
+}
 
 template <typename T> struct Gram2Args {
     const T* rows[2 * OPKB_MEM_MAX + 3];  // 0: v0; 1: x; 2: g|p; 3+2q: S_q; 4+2q: Y_q (q oldest..newest)

@@ -3,7 +3,7 @@
 // HBM once per phase:
 //   P1 trial      : x = prj(x0 - stp d); f, g = fg(x); p = projdir(g); 6 reductions
 //   P3 gram       : in-place pair update + all inner products of the two-loop
-//                   recursion in one tall-skinny sweep (opkb_gram.cuh)
+//                   recursion in one tall-skinny sweep (opkb_gram2.cuh)
 //   P4 direction  : d = H v0 from the host-solved coefficients, projection,
 //                   g.d, |d|^2, step limits, save (x, g) for the next search
 //   P4' steepest, P0 revert
@@ -405,7 +405,6 @@ extern "C" int opkb_vmlmb_trial_end(opkb_vmlmb* ws, int mark, double f, int init
 
 // ---------------------------------------------------------------------------
 // P3: Gram sweep
-#include "opkb_gram.cuh"
 #include "opkb_gram2.cuh"
 #include "opkb_direction2.cuh"
 #include <stdlib.h>
@@ -429,14 +428,6 @@ extern "C" int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots
     // p for BLMVM (src/quasinewton.jl:513)
     const void* v0 = (ws->method == 2 ? ws->p->data : ws->g->data);
     const void* gcur = (ws->method == 1 ? ws->p->data : ws->g->data);
-    // OPKB_GRAM_V1=1 selects the first, non-pipelined kernel (A/B measurements only)
-    static const int use_v1 = (getenv("OPKB_GRAM_V1") && getenv("OPKB_GRAM_V1")[0] == '1');
-    if (use_v1) {
-        if (ws->eltype == OPKB_DOUBLE)
-            return gram_run<double>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur,
-                                    ws->method == 2, G);
-        return gram_run<float>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur, ws->method == 2, G);
-    }
     if (ws->eltype == OPKB_DOUBLE)
         return gram2_run<double>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur,
                                  ws->method == 2, G);
@@ -619,12 +610,12 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
     int64_t done = 0;
 
     // ---- whole tiles through the bulk-async ring (m >= 1 pairs) ---------------------
-    static const int force_v1 = (getenv("OPKB_DIR_V1") && getenv("OPKB_DIR_V1")[0] == '1');
-    if (!steepest && A.m >= 1 && !force_v1) {
+    if (!steepest && A.m >= 1) {
         Dir2Args<T> B;
         memset(&B, 0, sizeof(B));
         int nr = 0;
         B.rows[nr++] = A.v0;
+        B.v0_from_g = (ws->method == 2);   // v0 = p: recomputed in the kernel, not read
         B.rows[nr++] = A.x;
         B.rows[nr++] = A.g;
         B.r_lo = B.r_hi = B.r_ysrc = -1;

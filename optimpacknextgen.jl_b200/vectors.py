@@ -328,9 +328,20 @@ def step_limits(x: Vector, lo, hi, orient, d: Vector):
     return smin.value, smax.value
 
 
-def get_free_variables(gp: Vector, want_mask: bool = False):
-    """The free set of the reference's `get_free_variables!(sel, gp)` as a mask
-    (no index list is materialised): returns the count, or (count, bool mask)."""
+def get_free_variables(*args, want_mask: bool = False):
+    """`get_free_variables(gp)` (src/bounds.jl:701-714) or
+    `get_free_variables(x, lo, hi, orient, d)` (:716-844): the free set as a mask
+    (no index list is materialised).  Returns the count, or (count, bool mask)."""
+    if len(args) == 5:
+        x, lo, hi, orient, d = args
+        if (lo is None or (not isinstance(lo, Vector) and float(lo) == -math.inf)) and \
+                (hi is None or (not isinstance(hi, Vector) and float(hi) == math.inf)):
+            # no bounds: the reference lists every variable (:762-767)
+            return (x.n, np.ones(x.n, dtype=bool)) if want_mask else x.n
+        # can_change(x, lo, hi, o, d) <=> projdir(x, lo, hi, o, d) != 0 (:306-311, :638-648)
+        gp = project_direction_(x.similar(), x, lo, hi, orient, d)
+    else:
+        (gp,) = args
     cnt = i64()
     mask = np.empty(gp.n, dtype=np.uint8) if want_mask else None
     check(_lib.lib().opkb_free_variables(gp.ctx.handle, gp.handle, C.byref(cnt),

@@ -158,6 +158,9 @@ typedef struct {
                           const T* hi, double hi_val, int orient, const T* d,  \
                           double* smin, double* smax);                         \
     int64_t P##get_free_variables(int64_t n, int64_t* sel, const T* gp);       \
+    int64_t P##get_free_variables_dir(int64_t n, int64_t* sel, const T* x,     \
+                                      const T* lo, double lo_val, const T* hi, \
+                                      double hi_val, int orient, const T* d);  \
     /* apply_lbfgs! (src/quasinewton.jl:703-779); slots are 0-based here */    \
     int    P##apply_lbfgs(int64_t n, int64_t mem, T* const* S, T* const* Y,    \
                           const double* rho, double gamma, const T* diag,      \

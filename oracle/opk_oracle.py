@@ -116,6 +116,7 @@ def lib():
             sig("project_direction", C.c_int, i64, P, P, P, f64, P, f64, C.c_int, P)
             sig("step_limits", C.c_int, i64, P, P, f64, P, f64, C.c_int, P, Pd, Pd)
             sig("get_free_variables", i64, i64, Pi, P)
+            sig("get_free_variables_dir", i64, i64, Pi, P, P, f64, P, f64, C.c_int, P)
             sig("apply_lbfgs", C.c_int, i64, i64, PP, PP, Pd, f64, P, i64, i64, P, Pd)
             sig("apply_lbfgs_sel", C.c_int, i64, i64, PP, PP, Pd, i64, i64, P, Pd, i64, Pi)
             sig("rosenbrock_fg", f64, C.c_void_p, i64, P, P)
@@ -262,6 +263,18 @@ def get_free_variables(gp):
     fn, ct = _fn(gp, "get_free_variables")
     sel = np.empty(gp.size, dtype=np.int64)
     j = fn(gp.size, sel.ctypes.data_as(C.POINTER(i64)), _ptr(gp, ct))
+    return sel[:j].copy()
+
+
+def get_free_variables_dir(x, lo, hi, orient, d):
+    fn, ct = _fn(x, "get_free_variables_dir")
+    lp, lv, k1 = _bound(lo, x.dtype, ct, -math.inf)
+    hp, hv, k2 = _bound(hi, x.dtype, ct, math.inf)
+    sel = np.empty(x.size, dtype=np.int64)
+    j = fn(x.size, sel.ctypes.data_as(C.POINTER(i64)), _ptr(x, ct), lp, lv, hp, hv, int(orient),
+           _ptr(d, ct))
+    if j < 0:
+        raise ValueError("invalid orientation" if j == -1 else "invalid bounds")
     return sel[:j].copy()
 
 

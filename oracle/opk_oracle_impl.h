@@ -334,6 +334,35 @@ int64_t FN(get_free_variables)(int64_t n, int64_t* sel, const REAL* gp)
     return j;
 }
 
+int64_t FN(get_free_variables_dir)(int64_t n, int64_t* sel, const REAL* x,
+                                   const REAL* lo, double lo_val,
+                                   const REAL* hi, double hi_val, int orient,
+                                   const REAL* d)
+{
+    /* get_free_variables!(sel, x, lo, hi, orient, d): src/bounds.jl:716-844,
+     * can_change :638-648 (0-based indices); -1 / -2 on invalid arguments */
+    const REAL slo = (REAL)lo_val, shi = (REAL)hi_val;
+    if (orient == 0) return -1;
+    if (!lo && !hi && !(slo <= shi)) return -2; /* :735 */
+    const int has_lo = (lo != NULL) || (slo > -REAL_INF);
+    const int has_hi = (hi != NULL) || (shi < REAL_INF);
+    int64_t j = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        REAL l = (lo ? lo[i] : slo), h = (hi ? hi[i] : shi);
+        REAL di = d[i], xi = x[i];
+        int neg = (orient > 0 ? di < 0 : di > 0);
+        int pos = (orient > 0 ? di > 0 : di < 0);
+        int ok;
+        if (!has_lo && !has_hi)
+            ok = (di != 0); /* is_non_zero :638-639; the scalar/scalar method lists all (:763-766) */
+        else
+            ok = (neg & (!has_lo | (xi > l))) | (pos & (!has_hi | (xi < h)));
+        if (!lo && !hi && !has_lo && !has_hi) ok = 1; /* :762-767: sel = 1:n */
+        if (ok) sel[j++] = i;
+    }
+    return j;
+}
+
 /* ---- apply_lbfgs! (src/quasinewton.jl:703-779) --------------------------- */
 
 int FN(apply_lbfgs)(int64_t n, int64_t mem, REAL* const* S, REAL* const* Y,

@@ -110,6 +110,10 @@ def test_bounds_bit_exact(opk, ctx, oracle, dtype, n, kinds):
         got = opk.project_direction_(ctx.vector(n, dtype), vxp, vlo, vhi, orient, vd).download()
         assert np.array_equal(got, oracle.project_direction(np.empty_like(x), xp, lo, hi, orient, d))
         assert opk.step_limits(vxp, vlo, vhi, orient, vd) == oracle.step_limits(xp, lo, hi, orient, d)
+        # get_free_variables(x, lo, hi, orient, d), src/bounds.jl:716-844
+        cnt, mask = opk.get_free_variables(vxp, vlo, vhi, orient, vd, want_mask=True)
+        sel = oracle.get_free_variables_dir(xp, lo, hi, orient, d)
+        assert cnt == sel.size and np.array_equal(np.flatnonzero(mask), sel)
 
 
 def test_bounds_errors_and_nan(opk, ctx, oracle):
@@ -159,3 +163,38 @@ def test_fill_random_matches_host(opk, ctx):
     v = ctx.vector(n).fill_random(3, first, 1.0, 1e4, log_scale=True)
     want = 1e4 ** opk.uniform(3, first, n)
     assert np.allclose(v.download(), want, rtol=1e-12)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_apply_lbfgs_variants(opk, ctx, oracle, dtype):
+    """apply_lbfgs! with gamma*I, a diagonal H0 (vproduct!, src/quasinewton.jl:710-714)
+    and on a free set (:747-779), one kernel per reference call, vs the oracle."""
+    rng = np.random.default_rng(11)
+    n, mem, m, mark = 3001, 6, 5, 2
+    S = [rng.standard_normal(n).astype(dtype) for _ in range(mem)]
+    Y = [(1.3 * S[k] + 0.4 * rng.standard_normal(n)).astype(dtype) for k in range(mem)]
+    Y[4] = (-Y[4]).astype(dtype)                       # a pair with rho <= 0 is skipped
+    v0 = rng.standard_normal(n).astype(dtype)
+    diag = rng.uniform(0.5, 2.0, n).astype(dtype)
+    rho = np.array([oracle.vdot(Y[k], S[k]) for k in range(mem)])
+    dS, dY = [ctx.from_numpy(a) for a in S], [ctx.from_numpy(a) for a in Y]
+    tol = 1e-12 if dtype == np.float64 else 2e-5
+    for H0, dH0 in ((0.7, 0.7), (diag, ctx.from_numpy(diag))):
+        want = v0.copy()
+        modif, _ = oracle.apply_lbfgs(S, Y, rho, H0 if np.isscalar(H0) else 1.0, m, mark, want,
+                                      diag=None if np.isscalar(H0) else H0)
+        got = ctx.from_numpy(v0)
+        alpha = [0.0] * mem
+        assert opk.apply_lbfgs_(dS, dY, list(rho), dH0, m, mark, got, alpha) == modif
+        assert np.linalg.norm(got.download() - want) <= tol * np.linalg.norm(want)
+    w = v0.copy()
+    w[rng.random(n) < 0.4] = 0
+    sel = np.flatnonzero(w != 0)
+    want = w.copy()
+    rho2 = np.zeros(mem)
+    modif, _ = oracle.apply_lbfgs_sel(S, Y, rho2, m, mark, want, sel)
+    got = ctx.from_numpy(w)
+    rho3 = [0.0] * mem
+    assert opk.apply_lbfgs_masked_(dS, dY, rho3, m, mark, got, [0.0] * mem, ctx.from_numpy(w)) == modif
+    assert np.linalg.norm(got.download() - want) <= tol * np.linalg.norm(want)
+    assert np.allclose(rho3, rho2, rtol=1e-12, atol=1e-9)

@@ -161,6 +161,12 @@ def test_bounds_semantics(oracle, dtype):
     # get_free_variables (src/bounds.jl:701-714), 0-based here
     gp = np.array([0, 1, -0.0, 2, nan], dtype=T)
     assert oracle.get_free_variables(gp).tolist() == [1, 3, 4]
+    # get_free_variables(x, lo, hi, orient, d) (src/bounds.jl:716-844) == projdir != 0
+    x = np.array([0, 0, 1, 1, 0.5, 0.5], dtype=T)
+    d = np.array([1, -1, 1, -1, 0, -1], dtype=T)
+    assert oracle.get_free_variables_dir(x, 0.0, 1.0, -1, d).tolist() == [1, 2, 5]
+    assert oracle.get_free_variables_dir(x, None, None, -1, d).tolist() == [0, 1, 2, 3, 4, 5]
+    assert oracle.get_free_variables_dir(x, 0.0, None, +1, d).tolist() == [0, 2, 3, 5]
     # empty input
     e = np.empty(0, dtype=T)
     assert oracle.vdot(e, e) == 0.0 and oracle.get_free_variables(e).size == 0
