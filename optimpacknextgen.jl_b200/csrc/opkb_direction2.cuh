@@ -8,8 +8,9 @@
 // copies (cp.async.bulk, mbarrier completion) so that the 25+ concurrent input
 // streams reach HBM as multi-KB bursts with >= 100 KB per SM in flight; the
 // consumer warps do the element-wise work out of shared memory (128-bit LDS)
-// and write d, S[mark'], Y[mark'] with 128-bit stores.  Only whole tiles are
-// processed here; the caller runs the register kernel on the tail.
+// and write d with 128-bit stores.  The last, partial tile is copied with
+// 16-byte granularity, completed and zero-padded by the consumers, and its
+// results are stored element by element.
 #pragma once
 
 #define DIR2_MAXSTAGE 8
@@ -28,7 +29,7 @@ template <typename T> struct Dir2Args {
     T* d;
     T* Snext;
     T* Ynext;
-    int64_t n;                            // multiple of `tile`
+    int64_t n;
     int tile, nstage;
 };
 
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
     T* const stage0 = reinterpret_cast<T*>(smem_raw);
     const int stage_elems = NR * TILE;
     const uint32_t rowbytes = (uint32_t)(TILE * sizeof(T));
-    const int64_t ntiles = A.n / TILE;
+    const int64_t ntiles = (A.n + TILE - 1) / TILE;
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
@@ -67,15 +68,19 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int s = it % NSTAGE;
             const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
+            const int64_t base = tile * TILE;
+            uint32_t bytes = rowbytes;
+            if (base + TILE > A.n) bytes = (uint32_t)(((A.n - base) * sizeof(T)) & ~(size_t)15);
             if (lane == 0) {
                 mbar_wait(&empty_bar[s], ph ^ 1u);
-                mbar_expect_tx(&full_bar[s], rowbytes * (uint32_t)(NR - A.v0_from_g));
+                mbar_expect_tx(&full_bar[s], bytes * (uint32_t)(NR - A.v0_from_g));
             }
             __syncwarp();
             T* dst = stage0 + s * stage_elems;
-            const int64_t base = tile * TILE;
-            for (int r = lane + A.v0_from_g; r < NR; r += 32)
-                bulk_g2s(dst + r * TILE, A.rows[r] + base, rowbytes, &full_bar[s]);
+            if (bytes > 0) {
+                for (int r = lane + A.v0_from_g; r < NR; r += 32)
+                    bulk_g2s(dst + r * TILE, A.rows[r] + base, bytes, &full_bar[s]);
+            }
         }
     } else {
         const int prow = 3 + (A.r_lo >= 0) + (A.r_hi >= 0) + (A.r_ysrc >= 0);  // first pair row
@@ -83,10 +88,23 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int s = it % NSTAGE;
             const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
-            const T* st = stage0 + s * stage_elems;
+            T* st = stage0 + s * stage_elems;
             const int64_t base = tile * TILE;
             mbar_wait(&full_bar[s], ph);
+            const bool partial = (base + TILE > A.n);
+            if (partial) {
+                // elements the 16-byte granular bulk copy left out, zero padding
+                const int valid = (int)(A.n - base);
+                const int copied = (int)((((size_t)valid * sizeof(T)) & ~(size_t)15) / sizeof(T));
+                for (int idx = tid; idx < NR * TILE; idx += CTHREADS) {
+                    const int r = idx / TILE, e = idx - r * TILE;
+                    if (e >= copied && r >= A.v0_from_g)
+                        st[r * TILE + e] = (e < valid) ? A.rows[r][base + e] : T(0);
+                }
+                named_bar_sync(1, CTHREADS);
+            }
             for (int e = tid * VEC; e < TILE; e += CTHREADS * VEC) {
+                if (partial && base + e >= A.n) break;
                 Pack<T> px = ld_pack<T>(st + TILE, e / VEC);
                 Pack<T> pg = ld_pack<T>(st + 2 * TILE, e / VEC);
                 Pack<T> pl = (A.r_lo >= 0) ? ld_pack<T>(st + A.r_lo * TILE, e / VEC) : splat_pack<T>(A.lo_val);
@@ -138,13 +156,24 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
                     if (A.bounded)                        // step_limits(x, lo, hi, -1, d) :577
                         step_limit_update(px.v[q], pl.v[q], ph_.v[q], A.has_lo, A.has_hi, -di, smin, smax);
                 }
-                const int64_t iv = (base + e) / VEC;
-                st_pack<T>(A.d, iv, v);
-                if (A.Snext) {                      // (the workspace path aliases instead)
-                    st_pack<T>(A.Snext, iv, px);    // vcopy!(S[mark], x) :562
-                    st_pack<T>(A.Ynext, iv, pys);   // vcopy!(Y[mark], g|p) :563
+                if (!partial || base + e + VEC <= A.n) {
+                    const int64_t iv = (base + e) / VEC;
+                    st_pack<T>(A.d, iv, v);
+                    if (A.Snext) {                      // (the workspace path aliases instead)
+                        st_pack<T>(A.Snext, iv, px);    // vcopy!(S[mark], x) :562
+                        st_pack<T>(A.Ynext, iv, pys);   // vcopy!(Y[mark], g|p) :563
+                    }
+                } else {
+                    for (int q = 0; q < VEC && base + e + q < A.n; ++q) {
+                        A.d[base + e + q] = v.v[q];
+                        if (A.Snext) {
+                            A.Snext[base + e + q] = px.v[q];
+                            A.Ynext[base + e + q] = pys.v[q];
+                        }
+                    }
                 }
             }
+            if (partial) fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
         }

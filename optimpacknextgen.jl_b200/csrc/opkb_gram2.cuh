@@ -194,28 +194,64 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
                         A.Ynew[base + e] = yn;
                     }
                 }
+                // a writer warp only reads back the elements it has just updated (same
+                // element partition in the loop below): no wait on the other writers
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&pair_bar[s]);
-                mbar_wait(&pair_bar[s], ph);   // the other warps of this role
             } else if (needs_pair) {
                 mbar_wait(&pair_bar[s], ph);
             }
+            if constexpr (sizeof(T) == 8) {
 #pragma unroll 2
-            for (int e = sub * 32 + lane; e < TILE; e += 32 * k) {
-                const T* rp = st + rowbase + e;
-                const T* c0 = st + col0 + e;
-                const T* c1 = st + col1 + e;
-                double rv[RT], cv[CT];
+                for (int e = sub * 32 + lane; e < TILE; e += 32 * k) {
+                    const T* rp = st + rowbase + e;
+                    const T* c0 = st + col0 + e;
+                    const T* c1 = st + col1 + e;
+                    double rv[RT], cv[CT];
 #pragma unroll
-                for (int r = 0; r < RT; ++r) rv[r] = (double)rp[r * TILE];
-                const bool fr = !masked || (st[e] != T(0));  // free variable: p[i] != 0 (row 0 is v0 = p)
-                cv[0] = fr ? (double)c0[0] : 0.0;
+                    for (int r = 0; r < RT; ++r) rv[r] = rp[r * TILE];
+                    const bool fr = !masked || (st[e] != T(0));  // free variable: p[i] != 0 (row 0 = p)
+                    cv[0] = fr ? c0[0] : 0.0;
 #pragma unroll
-                for (int c = 1; c < CT; ++c) cv[c] = fr ? (double)c1[(c - 1) * 2 * TILE] : 0.0;
+                    for (int c = 1; c < CT; ++c) cv[c] = fr ? c1[(c - 1) * 2 * TILE] : 0.0;
+#pragma unroll
+                    for (int r = 0; r < RT; ++r)
+#pragma unroll
+                        for (int c = 0; c < CT; ++c) acc[r][c] = fma(rv[r], cv[c], acc[r][c]);
+                }
+            } else {
+                // Float32: widening every operand to Float64 is conversion-bound (the
+                // F2F pipe is 1/4 of the FP64 rate), so the products of ONE stage
+                // (<= 32 per lane) are accumulated with FFMA and each stage sum is
+                // then added to the Float64 accumulators.
+                float af[RT][CT];
 #pragma unroll
                 for (int r = 0; r < RT; ++r)
 #pragma unroll
-                    for (int c = 0; c < CT; ++c) acc[r][c] = fma(rv[r], cv[c], acc[r][c]);
+                    for (int c = 0; c < CT; ++c) af[r][c] = 0.0f;
+#pragma unroll 2
+                for (int e = sub * 32 + lane; e < TILE; e += 32 * k) {
+                    const T* rp = st + rowbase + e;
+                    const T* c0 = st + col0 + e;
+                    const T* c1 = st + col1 + e;
+                    float rv[RT], cv[CT];
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) rv[r] = rp[r * TILE];
+                    // branch-free mask: all-ones / all-zeros bit pattern ANDed with the column
+                    const int fm = (!masked || (st[e] != T(0))) ? -1 : 0;
+                    cv[0] = __int_as_float(__float_as_int((float)c0[0]) & fm);
+#pragma unroll
+                    for (int c = 1; c < CT; ++c)
+                        cv[c] = __int_as_float(__float_as_int((float)c1[(c - 1) * 2 * TILE]) & fm);
+#pragma unroll
+                    for (int r = 0; r < RT; ++r)
+#pragma unroll
+                        for (int c = 0; c < CT; ++c) af[r][c] = fmaf(rv[r], cv[c], af[r][c]);
+                }
+#pragma unroll
+                for (int r = 0; r < RT; ++r)
+#pragma unroll
+                    for (int c = 0; c < CT; ++c) acc[r][c] += (double)af[r][c];
             }
             // release the stage (the writer's generic-proxy stores into it must be
             // ordered before the next bulk copy)

@@ -650,11 +650,11 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         int nstage = (int)(budget / stage_bytes);
         if (const char* e = getenv("OPKB_DIR_NSTAGE")) nstage = atoi(e);
         if (nstage > DIR2_MAXSTAGE) nstage = DIR2_MAXSTAGE;
-        const int64_t ntiles = ws->n / tile;
+        const int64_t ntiles = (ws->n + tile - 1) / tile;
         if (nstage >= 2 && ntiles >= 1) {
             B.tile = tile;
             B.nstage = nstage;
-            B.n = ntiles * tile;
+            B.n = ws->n;
             const size_t smem = stage_bytes * nstage;
             auto kern = k_direction2<T>;
             OPKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -39,16 +39,21 @@ def run_vmlmb(ctx, name, obj, x0, lo, hi, mem, n, nglobal, K, es, walg, twoloop=
     s = opk.VMLMB(obj, x0, **kw)
     s.iterate((mem + 1 if prime is None else prime) + 3)
     ctx.synchronize()
+    ctx.profile(True)
     e0, i0, l0 = s.eval, s.iter, ctx.launch_count
     ctx.timer_start()
     alive = s.iterate(K)
     ms = ctx.timer_stop()
+    prof = ctx.profile_report()
+    ctx.profile(False)
     it = s.iter - i0
     out = {"config": name, "n": nglobal, "iterations": it, "ms_per_iteration": ms / max(it, 1),
            "iterations_per_s": it / (ms * 1e-3), "evals_per_iteration": (s.eval - e0) / max(it, 1),
            "launches_per_iteration": (ctx.launch_count - l0) / max(it, 1),
            "alg_GBps_per_gpu": walg * es * n / (ms * 1e-3 / max(it, 1)) / 1e9,
-           "twoloop": s.twoloop, "stopped_early": (not alive), "f": s.f}
+           "twoloop": s.twoloop, "stopped_early": (not alive), "f": s.f,
+           "kernels_ms_per_iteration": {k: round(v[0] / max(it, 1), 4) for k, v in prof.items()},
+           "kernel_launches_per_iteration": {k: round(v[1] / max(it, 1), 2) for k, v in prof.items()}}
     out["frac_of_measured_peak"] = out["alg_GBps_per_gpu"] / PEAK
     s.close()
     return out
