@@ -204,10 +204,27 @@ int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots, double* G
  * exactly is skipped (rho <= 0).  out[0..3] = { g.d, |d|^2, smin, smax }. */
 int opkb_vmlmb_direction(opkb_vmlmb* ws, int m, const int* slots, const double* alpha,
                          const double* c, double gamma, int mark_next, double out[4]);
-/* P4 tail alone, for a direction the caller has already written in d (the
- * sequential two-loop recursion made of Tier-1 calls): :535, :537, :629,
- * :562-563, :577.  Same outputs. */
-int opkb_vmlmb_finish_direction(opkb_vmlmb* ws, int mark_next, double out[4]);
+/* Sequential two-loop recursion, fused step by step (parity-grade: the
+ * intermediate vector is rounded in the element type after every vupdate!, as
+ * the reference does).  v is the workspace vector d.
+ * pair_update = :512-518: S[mark] -= x; Y[mark] -= g (p for BLMVM);
+ *   out = { <y, s>, <y, y> } (unrestricted: rho and gamma of L-BFGS / BLMVM).
+ * twoloop_step = one iteration of the loops :725-741 / :756-775:
+ *   [v += a*u on the free set]  u = S[u_slot] if u_which == 'S', Y[u_slot] if 'Y', nothing if 0
+ *   [v *= gamma]                if has_scale (:707, :768)
+ *   out[0] = <z, v>, z = S|Y[z_slot];  if want_rho: out[1] = <Y[z_slot], S[z_slot]>,
+ *   out[2] = <Y[z_slot], Y[z_slot]>, all on the free set {p != 0} for VMLMB.
+ *   `first` != 0: v is read from p (g for L-BFGS / BLMVM): the copy of :525/:528
+ *   is fused into the first step that writes v.
+ * finish_direction = P4 tail for a direction held in d, after the pending last
+ *   axpy d += a*u (u_which = 0: none): :535, :537, :629, :562-563, :577; same
+ *   outputs as opkb_vmlmb_direction. */
+int opkb_vmlmb_pair_update(opkb_vmlmb* ws, int mark, double out[2]);
+int opkb_vmlmb_twoloop_step(opkb_vmlmb* ws, int first, int u_which, int u_slot, double a,
+                            int has_scale, double gamma, int z_which, int z_slot,
+                            int want_rho, double out[3]);
+int opkb_vmlmb_finish_direction(opkb_vmlmb* ws, int mark_next, int u_which, int u_slot,
+                                double a, double out[4]);
 /* P4' "steepest descent" = :554, :562-563, :577: d = p (g for L-BFGS). */
 int opkb_vmlmb_steepest(opkb_vmlmb* ws, int mark_next, double out[4]);
 /* P0 "revert to best" = :490-492: x = project(S[mark] - stp*d). */

@@ -87,7 +87,10 @@ _SIGNATURES = {
     "opkb_vmlmb_trial_end": (C.c_int, [vp, C.c_int, f64, C.c_int, Pd]),
     "opkb_vmlmb_gram": (C.c_int, [vp, C.c_int, C.c_int, Pi, Pd]),
     "opkb_vmlmb_direction": (C.c_int, [vp, C.c_int, Pi, Pd, Pd, f64, C.c_int, Pd]),
-    "opkb_vmlmb_finish_direction": (C.c_int, [vp, C.c_int, Pd]),
+    "opkb_vmlmb_pair_update": (C.c_int, [vp, C.c_int, Pd]),
+    "opkb_vmlmb_twoloop_step": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, f64, C.c_int, f64, C.c_int,
+                                          C.c_int, C.c_int, Pd]),
+    "opkb_vmlmb_finish_direction": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, f64, Pd]),
     "opkb_vmlmb_steepest": (C.c_int, [vp, C.c_int, Pd]),
     "opkb_vmlmb_revert": (C.c_int, [vp, C.c_int, f64]),
     "opkb_spg_create": (C.c_int, [vp, C.c_int, i64, vp, f64, vp, f64, C.POINTER(vp)]),

@@ -455,6 +455,9 @@ template <typename T> struct DirArgs {
     int64_t n;
     int masked, bounded;
     int steepest;         // 0: two-loop assembly; 1: d = p|g (:554); 2: d given, finish only
+    const T* pu;          // finish only: pending last axpy d += pa*pu on the free set {pw != 0}
+    const T* pw;
+    T pa;
 };
 
 template <typename T>
@@ -498,6 +501,14 @@ __global__ void __launch_bounds__(OPKB_BLOCK) k_direction(DirArgs<T> A, ReduceSc
         }
         if (A.steepest) {
             pd = pv;
+            if (A.pu) {  // the last vupdate! of the sequential two-loop recursion (:738, :772)
+                const Pack<T> u = ld_pack<T>(A.pu, iv);
+                Pack<T> w = u;
+                if (A.pw) w = ld_pack<T>(A.pw, iv);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e)
+                    if (!A.pw || w.v[e] != T(0)) pd.v[e] = pd.v[e] + A.pa * u.v[e];
+            }
         } else {
             Pack<T> py[MB], ps[MB];
 #pragma unroll
@@ -548,6 +559,7 @@ __global__ void __launch_bounds__(OPKB_BLOCK) k_direction(DirArgs<T> A, ReduceSc
             T di;
             if (A.steepest) {
                 di = v0;
+                if (A.pu && (!A.pw || A.pw[i] != T(0))) di = di + A.pa * A.pu[i];
             } else {
                 for (int j = 0; j < A.m; ++j) {
                     yv[j] = A.Y[j][i];
@@ -573,7 +585,8 @@ __global__ void __launch_bounds__(OPKB_BLOCK) k_direction(DirArgs<T> A, ReduceSc
 
 template <typename T>
 static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* alpha,
-                         const double* c, double gamma, int mark_next, int steepest, double out[4])
+                         const double* c, double gamma, int mark_next, int steepest, double out[4],
+                         const opkb_vector* pend_u = NULL, double pend_a = 0.0)
 {
     opkb_context* ctx = ws->ctx;
     DirArgs<T> A;
@@ -604,6 +617,11 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
     A.masked = (ws->method == 2);
     A.bounded = (ws->method > 0);
     A.steepest = steepest;
+    if (pend_u) {
+        A.pu = (const T*)pend_u->data;
+        A.pa = (T)pend_a;
+        A.pw = (ws->method == 2) ? (const T*)ws->p->data : NULL;
+    }
     int kinds[4] = {OPKB_RSUM, OPKB_RSUM, OPKB_RMIN, OPKB_RMAX};
     double part[2][4] = {{0, 0, INFINITY, 0}, {0, 0, INFINITY, 0}};
     int nparts = 0;
@@ -683,6 +701,8 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         A.g += off;
         A.ysrc += off;
         A.d += off;
+        if (A.pu) A.pu += off;
+        if (A.pw) A.pw += off;
         if (A.lo.arr) A.lo.arr += off;
         if (A.hi.arr) A.hi.arr += off;
         A.n = ws->n - off;
@@ -747,14 +767,196 @@ extern "C" int opkb_vmlmb_steepest(opkb_vmlmb* ws, int mark_next, double out[4])
                : direction_run<float>(ws, 0, NULL, NULL, NULL, 1.0, mark_next, 1, out);
 }
 
-extern "C" int opkb_vmlmb_finish_direction(opkb_vmlmb* ws, int mark_next, double out[4])
+static opkb_vector* pair_vector(opkb_vmlmb* ws, int which, int slot)
+{
+    if (slot < 0 || slot >= ws->mem) return NULL;
+    if (which == 'S') return ws->S[slot];
+    if (which == 'Y') return ws->Y[slot];
+    return NULL;
+}
+
+extern "C" int opkb_vmlmb_finish_direction(opkb_vmlmb* ws, int mark_next, int u_which, int u_slot,
+                                           double a, double out[4])
 {
     int rc = check_mark(ws, mark_next);
     if (rc) return rc;
     if (!out) return opkb_set_error(OPKB_EINVAL, "NULL result");
+    const opkb_vector* u = NULL;
+    if (u_which) {
+        u = pair_vector(ws, u_which, u_slot);
+        if (!u) return opkb_set_error(OPKB_EINVAL, "invalid pending vector");
+    }
     return (ws->eltype == OPKB_DOUBLE)
-               ? direction_run<double>(ws, 0, NULL, NULL, NULL, 1.0, mark_next, 2, out)
-               : direction_run<float>(ws, 0, NULL, NULL, NULL, 1.0, mark_next, 2, out);
+               ? direction_run<double>(ws, 0, NULL, NULL, NULL, 1.0, mark_next, 2, out, u, a)
+               : direction_run<float>(ws, 0, NULL, NULL, NULL, 1.0, mark_next, 2, out, u, a);
+}
+
+// ---------------------------------------------------------------------------
+// Sequential two-loop recursion, fused step by step (parity-grade: the
+// intermediate vector is rounded in the element type after every vupdate!,
+// exactly as the reference does; used for Float32).
+template <typename T> struct StepArgs {
+    const T* vsrc;
+    T* vdst;          // NULL: v is not modified by this step
+    const T* u;       // pending axpy vector or NULL
+    const T* z;       // out[0] = <z, v>
+    const T* z2;      // out[1] = <z2, z3>, out[2] = <z2, z2>, or NULL
+    const T* z3;
+    const T* w;       // free set {w != 0} or NULL
+    T a, gamma;
+    int has_scale;
+    int64_t n;
+};
+
+template <typename T>
+__device__ __forceinline__ T step_elem(const StepArgs<T>& A, T v, T u, bool fr)
+{
+    if (A.u && fr) v = v + A.a * u;     // vupdate!(v, [sel,] a, u) :729, :738, :761, :772
+    if (A.has_scale) v = A.gamma * v;   // vscale!(v, gamma) :707, :768 (all elements)
+    return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(OPKB_BLOCK) k_twoloop_step(StepArgs<T> A, ReduceScratch rs)
+{
+    constexpr int VEC = VecOf<T>::N;
+    const int64_t nvec = A.n / VEC;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double acc[3] = {0, 0, 0};
+    for (int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += stride) {
+        Pack<T> v = ld_pack<T>(A.vsrc, iv), z = ld_pack<T>(A.z, iv), u = v, w = v, z2 = v, z3 = v;
+        if (A.u) u = ld_pack<T>(A.u, iv);
+        if (A.w) w = ld_pack<T>(A.w, iv);
+        if (A.z2) {
+            z2 = ld_pack<T>(A.z2, iv);
+            z3 = ld_pack<T>(A.z3, iv);
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const bool fr = !A.w || (w.v[e] != T(0));
+            v.v[e] = step_elem(A, v.v[e], u.v[e], fr);
+            if (fr) {
+                acc[0] = dacc(z.v[e], v.v[e], acc[0]);
+                if (A.z2) {
+                    acc[1] = dacc(z2.v[e], z3.v[e], acc[1]);
+                    acc[2] = dacc(z2.v[e], z2.v[e], acc[2]);
+                }
+            }
+        }
+        if (A.vdst) st_pack<T>(A.vdst, iv, v);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int64_t i = nvec * VEC; i < A.n; ++i) {
+            const bool fr = !A.w || (A.w[i] != T(0));
+            T v = step_elem(A, A.vsrc[i], A.u ? A.u[i] : T(0), fr);
+            if (fr) {
+                acc[0] = dacc(A.z[i], v, acc[0]);
+                if (A.z2) {
+                    acc[1] = dacc(A.z2[i], A.z3[i], acc[1]);
+                    acc[2] = dacc(A.z2[i], A.z2[i], acc[2]);
+                }
+            }
+            if (A.vdst) A.vdst[i] = v;
+        }
+    }
+    block_reduce_publish<3, 0u, 0u>(acc, rs);
+}
+
+template <typename T>
+static int step_run(opkb_vmlmb* ws, int first, const opkb_vector* u, double a, int has_scale,
+                    double gamma, const opkb_vector* z, const opkb_vector* z2, const opkb_vector* z3,
+                    double out[3])
+{
+    opkb_context* ctx = ws->ctx;
+    StepArgs<T> A;
+    memset(&A, 0, sizeof(A));
+    const opkb_vector* src = first ? (ws->method == 2 ? ws->p : ws->g) : ws->d;   // vcopy!(d, p|g) :525/:528
+    A.vsrc = (const T*)src->data;
+    A.vdst = (u || has_scale || first) ? (T*)ws->d->data : NULL;
+    if (first && !u && !has_scale) A.vdst = NULL;   // nothing to write yet: d stays "= p|g" virtually
+    A.u = u ? (const T*)u->data : NULL;
+    A.z = (const T*)z->data;
+    A.z2 = z2 ? (const T*)z2->data : NULL;
+    A.z3 = z3 ? (const T*)z3->data : NULL;
+    A.w = (ws->method == 2) ? (const T*)ws->p->data : NULL;
+    A.a = (T)a;
+    A.gamma = (T)gamma;
+    A.has_scale = has_scale;
+    A.n = ws->n;
+    int grid = opkb_grid_for(ctx, ws->n / VecOf<T>::N, 4);
+    LAUNCHB(ctx, OPKB_K_REDUCE, (k_twoloop_step<T>), grid, OPKB_BLOCK, 0, A, scratch(ctx));
+    return opkb_finish_reduction(ctx, 3, NULL, out);
+}
+
+extern "C" int opkb_vmlmb_twoloop_step(opkb_vmlmb* ws, int first, int u_which, int u_slot, double a,
+                                       int has_scale, double gamma, int z_which, int z_slot,
+                                       int want_rho, double out[3])
+{
+    if (!ws || !out) return opkb_set_error(OPKB_EINVAL, "NULL argument");
+    const opkb_vector* u = NULL;
+    if (u_which) {
+        u = pair_vector(ws, u_which, u_slot);
+        if (!u) return opkb_set_error(OPKB_EINVAL, "invalid pending vector");
+    }
+    const opkb_vector* z = pair_vector(ws, z_which, z_slot);
+    if (!z) return opkb_set_error(OPKB_EINVAL, "invalid dot vector");
+    const opkb_vector* z2 = want_rho ? ws->Y[z_slot] : NULL;
+    const opkb_vector* z3 = want_rho ? ws->S[z_slot] : NULL;
+    return (ws->eltype == OPKB_DOUBLE)
+               ? step_run<double>(ws, first, u, a, has_scale, gamma, z, z2, z3, out)
+               : step_run<float>(ws, first, u, a, has_scale, gamma, z, z2, z3, out);
+}
+
+// :512-518 fused: S[mark] -= x; Y[mark] -= g|p; out = { <y, s>, <y, y> } (unrestricted)
+template <typename T>
+__global__ void __launch_bounds__(OPKB_BLOCK)
+k_pair_update(T* s, T* y, const T* x, const T* g, int64_t n, ReduceScratch rs)
+{
+    constexpr int VEC = VecOf<T>::N;
+    const int64_t nvec = n / VEC;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double acc[2] = {0, 0};
+    for (int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += stride) {
+        Pack<T> ps = ld_pack<T>(s, iv), py = ld_pack<T>(y, iv), px = ld_pack<T>(x, iv), pg = ld_pack<T>(g, iv);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            ps.v[e] = ps.v[e] - px.v[e];   // vupdate!(S[mark], -1, x) :512
+            py.v[e] = py.v[e] - pg.v[e];   // vupdate!(Y[mark], -1, g|p) :513
+            acc[0] = dacc(py.v[e], ps.v[e], acc[0]);
+            acc[1] = dacc(py.v[e], py.v[e], acc[1]);
+        }
+        st_pack<T>(s, iv, ps);
+        st_pack<T>(y, iv, py);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int64_t i = nvec * VEC; i < n; ++i) {
+            T sv = s[i] - x[i], yv = y[i] - g[i];
+            s[i] = sv;
+            y[i] = yv;
+            acc[0] = dacc(yv, sv, acc[0]);
+            acc[1] = dacc(yv, yv, acc[1]);
+        }
+    }
+    block_reduce_publish<2, 0u, 0u>(acc, rs);
+}
+
+extern "C" int opkb_vmlmb_pair_update(opkb_vmlmb* ws, int mark, double out[2])
+{
+    int rc = check_mark(ws, mark);
+    if (rc) return rc;
+    if (!out) return opkb_set_error(OPKB_EINVAL, "NULL result");
+    opkb_context* ctx = ws->ctx;
+    const opkb_vector* gs = (ws->method == 1 ? ws->p : ws->g);
+    int grid = opkb_grid_for(ctx, ws->n / (ws->eltype == OPKB_DOUBLE ? 2 : 4), 4);
+    if (ws->eltype == OPKB_DOUBLE)
+        LAUNCHB(ctx, OPKB_K_ELEMENTWISE, k_pair_update<double>, grid, OPKB_BLOCK, 0,
+                (double*)ws->S[mark]->data, (double*)ws->Y[mark]->data, (const double*)ws->x->data,
+                (const double*)gs->data, ws->n, scratch(ctx));
+    else
+        LAUNCHB(ctx, OPKB_K_ELEMENTWISE, k_pair_update<float>, grid, OPKB_BLOCK, 0,
+                (float*)ws->S[mark]->data, (float*)ws->Y[mark]->data, (const float*)ws->x->data,
+                (const float*)gs->data, ws->n, scratch(ctx));
+    return opkb_finish_reduction(ctx, 2, NULL, out);
 }
 
 // ---------------------------------------------------------------------------

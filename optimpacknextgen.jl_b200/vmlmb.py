@@ -241,11 +241,13 @@ class _FusedOps:
         self.r = [0.0] * 8
         self._out8 = (f64 * 8)()
         self._out4 = (f64 * 4)()
+        self._out3 = (f64 * 3)()
+        self._out2 = (f64 * 2)()
+        self._alpha = [0.0] * solver.mem
         self._limits = (math.inf, math.inf)
         self._saved_for = -1
         self._need_steepest = False
         self.rho = [0.0] * solver.mem    # per slot, for L-BFGS / BLMVM (:515)
-        self._S = self._Y = self._alpha = None
         self.g = self._vec("g")
         self.p = self._vec("p") if solver.method > 0 else None
         self.d = self._vec("d")
@@ -342,33 +344,65 @@ class _FusedOps:
 
     def _new_direction_sequential(self):
         """Parity-grade variant: the reference's sequential two-loop recursion
-        (one kernel per vdot / vupdate!, same roundings of the intermediate v in
-        the element type), between the fused P1 and the fused tail of P4."""
+        (apply_lbfgs!, :716-779) with the same roundings of the intermediate
+        vector in the element type, one fused kernel per loop iteration: the
+        pending vupdate! of the previous iteration, the vscale! between the
+        loops and the dot products of the current pair share one pass."""
         s = self.s
-        mark = s.mark
-        if self._S is None:
-            self._S = [self._vec("S", k) for k in range(s.mem)]
-            self._Y = [self._vec("Y", k) for k in range(s.mem)]
-            self._alpha = [0.0] * s.mem
-        S, Y = self._S, self._Y
-        vupdate_(S[mark], -1, self.x)                                    # :512
-        vupdate_(Y[mark], -1, self.p if s.method == 1 else self.g)       # :513
-        if s.method < 2:
-            self.rho[mark] = vdot(Y[mark], S[mark])                      # :515
-            if self.rho[mark] > 0:
-                s.gamma = self.rho[mark] / vdot(Y[mark], Y[mark])        # :518
-        s.m = min(s.m + 1, s.mem)
-        if s.method < 2:
-            vcopy_(self.d, self.g)
-            change = apply_lbfgs_(S, Y, self.rho, s.gamma, s.m, mark, self.d, self._alpha)
-        else:
-            vcopy_(self.d, self.p)
-            change = apply_lbfgs_masked_(S, Y, self.rho, s.m, mark, self.d, self._alpha, self.p)
+        L, ws = self.L, self.ws
+        mark, mem, method = s.mark, s.mem, s.method
+        out2, out3 = self._out2, self._out3
+        check(L.opkb_vmlmb_pair_update(ws, mark, out2))                  # :512-513
+        rho, alpha = self.rho, self._alpha
+        if method < 2:
+            rho[mark] = out2[0]                                          # :515
+            if rho[mark] > 0:
+                s.gamma = rho[mark] / out2[1]                            # :518
+        s.m = min(s.m + 1, mem)                                          # :521
+        m = s.m
+        S, Y = ord("S"), ord("Y")
+        first = 1            # d not written yet: v is still p (g for L-BFGS / BLMVM), :525/:528
+        pend = (0, 0, 0.0)   # pending vupdate!: (which, slot, coefficient)
+        gamma = 0.0
+        modif = False
+        k = mark + 1
+        for _ in range(m):                                               # :725-732 / :756-766
+            k = k - 1 if k > 0 else mem - 1
+            if method < 2 and not rho[k] > 0:
+                continue
+            check(L.opkb_vmlmb_twoloop_step(ws, first, pend[0], pend[1], pend[2], 0, 1.0, S, k,
+                                            int(method == 2), out3))
+            if pend[0]:
+                first = 0
+            pend = (0, 0, 0.0)
+            if method == 2:
+                rho[k] = out3[1]                                         # :758
+            if rho[k] > 0:
+                alpha[k] = out3[0] / rho[k]                              # :728 / :760
+                pend = (Y, k, -alpha[k])                                 # :729 / :761
+                modif = True
+                if method == 2 and gamma == 0:
+                    gamma = rho[k] / out3[2]                             # :762-764
         self._saved_for = -1
+        if method < 2:
+            gamma = s.gamma
+            change = modif
+        else:
+            change = gamma != 0
         if not change:
             return False, 0.0, 0.0
-        mark_next = mark + 1 if mark < s.mem - 1 else 0
-        check(self.L.opkb_vmlmb_finish_direction(self.ws, mark_next, self._out4))
+        scale = 1                                                        # vscale!(v, gamma) :734 / :768
+        for _ in range(m):                                               # :735-741 / :769-775
+            if rho[k] > 0:
+                check(L.opkb_vmlmb_twoloop_step(ws, first, pend[0], pend[1], pend[2], scale, gamma,
+                                                Y, k, 0, out3))
+                first, scale = 0, 0
+                beta = out3[0] / rho[k]                                  # :737 / :771
+                pend = (S, k, alpha[k] - beta)                           # :738 / :772
+            k = k + 1 if k < mem - 1 else 0
+        mark_next = mark + 1 if mark < mem - 1 else 0
+        # last vupdate! + :535, :537, :629, :562-563, :577
+        check(L.opkb_vmlmb_finish_direction(ws, mark_next, pend[0], pend[1], pend[2], self._out4))
         self._limits = (self._out4[2], self._out4[3])
         self._saved_for = mark_next
         self._need_steepest = False

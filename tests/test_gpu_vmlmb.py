@@ -81,6 +81,16 @@ def test_trajectory_fused(opk, oracle, kind, n, dtype, kw):
     compare_traces(trg, tro, 20, rtol)
 
 
+@pytest.mark.parametrize("kind,n,dtype,kw", [c for c in CASES if c[2] == np.float64])
+def test_trajectory_fused_sequential_float64(opk, oracle, kind, n, dtype, kw):
+    """The fused step-by-step two-loop recursion (default for Float32) in Float64."""
+    pb = problem(kind, n, dtype)
+    kw = dict(kw, maxiter=25)
+    xo, ro, tro = run_oracle(oracle, pb, **kw)
+    xg, rg, trg = run_gpu(opk, pb, "fused", twoloop="sequential", **kw)
+    compare_traces(trg, tro, 20, F64_RTOL)
+
+
 @pytest.mark.parametrize("kind,n,dtype,kw", [c for c in CASES if c[2] == np.float32])
 def test_trajectory_fused_gram_float32(opk, oracle, kind, n, dtype, kw):
     """Float32 with the Gram-form two-loop (opt-in): the quadratic stays within
