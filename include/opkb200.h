@@ -204,6 +204,19 @@ int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots, double* G
  * exactly is skipped (rho <= 0).  out[0..3] = { g.d, |d|^2, smin, smax }. */
 int opkb_vmlmb_direction(opkb_vmlmb* ws, int m, const int* slots, const double* alpha,
                          const double* c, double gamma, int mark_next, double out[4]);
+/* P4 + P1 in ONE pass: as opkb_vmlmb_direction, and when the workspace has a
+ * built-in objective (and the method is not BLMVM) the first trial point of the
+ * next line search, x' = project(x - 1*d) -- the step the driver takes after a
+ * successful update, :567 -- is evaluated speculatively in the same kernel:
+ * trial[0..6] as out[] of opkb_vmlmb_trial, trial[7] = 1 (0: nothing was fused,
+ * call opkb_vmlmb_trial as usual).  The caller uses trial[] iff the direction
+ * is accepted and min(1, smax) == 1; if the direction is rejected it must call
+ * opkb_vmlmb_discard_trial before the steepest-descent phase; a different first
+ * step needs no repair (opkb_vmlmb_trial simply overwrites x, g, p). */
+int opkb_vmlmb_direction_trial(opkb_vmlmb* ws, int m, const int* slots, const double* alpha,
+                               const double* c, double gamma, int mark_next, double out[4],
+                               double trial[8]);
+int opkb_vmlmb_discard_trial(opkb_vmlmb* ws, int mark_next);
 /* Sequential two-loop recursion, fused step by step (parity-grade: the
  * intermediate vector is rounded in the element type after every vupdate!, as
  * the reference does).  v is the workspace vector d.

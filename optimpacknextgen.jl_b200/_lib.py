@@ -87,6 +87,8 @@ _SIGNATURES = {
     "opkb_vmlmb_trial_end": (C.c_int, [vp, C.c_int, f64, C.c_int, Pd]),
     "opkb_vmlmb_gram": (C.c_int, [vp, C.c_int, C.c_int, Pi, Pd]),
     "opkb_vmlmb_direction": (C.c_int, [vp, C.c_int, Pi, Pd, Pd, f64, C.c_int, Pd]),
+    "opkb_vmlmb_direction_trial": (C.c_int, [vp, C.c_int, Pi, Pd, Pd, f64, C.c_int, Pd, Pd]),
+    "opkb_vmlmb_discard_trial": (C.c_int, [vp, C.c_int]),
     "opkb_vmlmb_pair_update": (C.c_int, [vp, C.c_int, Pd]),
     "opkb_vmlmb_twoloop_step": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, f64, C.c_int, f64, C.c_int,
                                           C.c_int, C.c_int, Pd]),

@@ -17,7 +17,7 @@
 #define DIR2_THREADS 288   // 8 consumer warps + 1 producer warp
 
 template <typename T> struct Dir2Args {
-    const T* rows[2 * OPKB_MEM_MAX + 6];  // v0 | -, x, g, [lo], [hi], [ysrc], then (y_j, s_j) oldest..newest
+    const T* rows[2 * OPKB_MEM_MAX + 8];  // v0 | -, x, g, [lo], [hi], [ysrc], then (y_j, s_j) oldest..newest
     int v0_from_g;                        // VMLMB: v0 = p is recomputed from (x, g, lo, hi), row 0 unused
     T ma[OPKB_MEM_MAX];                   // -alpha_j
     T cc[OPKB_MEM_MAX];                   // alpha_j - beta_j
@@ -31,9 +31,18 @@ template <typename T> struct Dir2Args {
     T* Ynext;
     int64_t n;
     int tile, nstage;
+    // FUSE != 0: the first trial point of the next line search is evaluated in the
+    // same pass with the step the driver takes after a successful update, stp = 1
+    // (src/quasinewton.jl:567, :599, :386-399, :427-448); the host discards it if
+    // the direction is rejected or min(1, smax) < 1.
+    int r_a, r_c;                         // rows of the quadratic's a and c
+    T* xout;
+    T* gout;
+    T* pout;                              // NULL for L-BFGS
 };
 
-template <typename T>
+// FUSE: 0 direction only; OPKB_OBJ_ROSENBROCK / OPKB_OBJ_QUADRATIC: + speculative trial
+template <typename T, int FUSE>
 __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, ReduceScratch rs)
 {
     constexpr int VEC = VecOf<T>::N;
@@ -59,9 +68,13 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
     }
     __syncthreads();
 
-    // acc: 0 g.d; 1 |d|^2; 2 smin; 3 smax
+    // acc: 0 g.d; 1 |d|^2; 2 smin; 3 smax; with FUSE: 4,5 objective sums; 6 |p'|^2; 7 g'.s;
+    // 8 g'.d; 9 |x'|^2; 10 |s|^2; 11 number of free variables at x'
+    constexpr int NACC = FUSE ? 12 : 4;
     T smin = T(INFINITY), smax = T(0);
-    double acc[4] = {0, 0, 0, 0};
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
 
     if (warp == CWARPS) {
         int it = 0;
@@ -156,9 +169,55 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
                     if (A.bounded)                        // step_limits(x, lo, hi, -1, d) :577
                         step_limit_update(px.v[q], pl.v[q], ph_.v[q], A.has_lo, A.has_hi, -di, smin, smax);
                 }
+                Pack<T> xt, gt, pt;
+                if (FUSE) {
+                    // x' = project(x - 1*d) (:599, :386); f, g' = fg(x') (:391); p' (:396)
+                    Pack<T> pa, pc;
+                    if (FUSE == OPKB_OBJ_QUADRATIC) {
+                        pa = ld_pack<T>(st + A.r_a * TILE, e / VEC);
+                        pc = ld_pack<T>(st + A.r_c * TILE, e / VEC);
+                    }
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        T xi = px.v[q] + T(-1) * v.v[q];
+                        if (A.bounded) xi = fastclamp(xi, pl.v[q], ph_.v[q]);
+                        xt.v[q] = xi;
+                    }
+                    if (FUSE == OPKB_OBJ_ROSENBROCK) {
+#pragma unroll
+                        for (int q = 0; q < VEC; q += 2) {
+                            gt.v[q] = gt.v[q + 1] = T(0);
+                            if (!partial || base + e + q < A.n)   // zero padding is not a variable
+                                rosenbrock_pair(xt.v[q], xt.v[q + 1], gt.v[q], gt.v[q + 1], acc[4], acc[5]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q)
+                            quadratic_elem(xt.v[q], pa.v[q], pc.v[q], gt.v[q], acc[4]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        if (partial && base + e + q >= A.n) break;
+                        const T xi = xt.v[q], gi = gt.v[q];
+                        const T pi = A.bounded ? projdir(xi, pl.v[q], ph_.v[q], A.has_lo, A.has_hi, -1, gi) : gi;
+                        pt.v[q] = pi;
+                        const T si = xi - px.v[q];              // s = x' - x0 (:427)
+                        acc[6] = dacc(pi, pi, acc[6]);          // |p'|^2 (:399)
+                        acc[7] = dacc(gi, si, acc[7]);          // g'.s (:432)
+                        acc[8] = dacc(gi, v.v[q], acc[8]);      // g'.d (:434)
+                        acc[9] = dacc(xi, xi, acc[9]);          // |x'|^2 (:446)
+                        acc[10] = dacc(si, si, acc[10]);        // |s|^2 (:448)
+                        acc[11] += (pi != T(0)) ? 1.0 : 0.0;
+                    }
+                }
                 if (!partial || base + e + VEC <= A.n) {
                     const int64_t iv = (base + e) / VEC;
                     st_pack<T>(A.d, iv, v);
+                    if (FUSE) {
+                        st_pack<T>(A.xout, iv, xt);
+                        st_pack<T>(A.gout, iv, gt);
+                        if (A.pout) st_pack<T>(A.pout, iv, pt);
+                    }
                     if (A.Snext) {                      // (the workspace path aliases instead)
                         st_pack<T>(A.Snext, iv, px);    // vcopy!(S[mark], x) :562
                         st_pack<T>(A.Ynext, iv, pys);   // vcopy!(Y[mark], g|p) :563
@@ -166,6 +225,11 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
                 } else {
                     for (int q = 0; q < VEC && base + e + q < A.n; ++q) {
                         A.d[base + e + q] = v.v[q];
+                        if (FUSE) {
+                            A.xout[base + e + q] = xt.v[q];
+                            A.gout[base + e + q] = gt.v[q];
+                            if (A.pout) A.pout[base + e + q] = pt.v[q];
+                        }
                         if (A.Snext) {
                             A.Snext[base + e + q] = px.v[q];
                             A.Ynext[base + e + q] = pys.v[q];
@@ -181,5 +245,5 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
     acc[2] = (double)smin;
     acc[3] = (double)smax;
     __syncthreads();
-    block_reduce_publish<4, 8u, 4u>(acc, rs);  // slot 2: min, slot 3: max
+    block_reduce_publish<NACC, 8u, 4u>(acc, rs);  // slot 2: min, slot 3: max
 }

@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(OPKB_BLOCK) k_direction(DirArgs<T> A, ReduceSc
 template <typename T>
 static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* alpha,
                          const double* c, double gamma, int mark_next, int steepest, double out[4],
-                         const opkb_vector* pend_u = NULL, double pend_a = 0.0)
+                         const opkb_vector* pend_u = NULL, double pend_a = 0.0, double* out8 = NULL)
 {
     opkb_context* ctx = ws->ctx;
     DirArgs<T> A;
@@ -622,8 +622,14 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         A.pa = (T)pend_a;
         A.pw = (ws->method == 2) ? (const T*)ws->p->data : NULL;
     }
-    int kinds[4] = {OPKB_RSUM, OPKB_RSUM, OPKB_RMIN, OPKB_RMAX};
-    double part[2][4] = {{0, 0, INFINITY, 0}, {0, 0, INFINITY, 0}};
+    int kinds[12] = {OPKB_RSUM, OPKB_RSUM, OPKB_RMIN, OPKB_RMAX, OPKB_RSUM, OPKB_RSUM, OPKB_RSUM,
+                     OPKB_RSUM, OPKB_RSUM, OPKB_RSUM, OPKB_RSUM, OPKB_RSUM};
+    double part[2][12] = {{0, 0, INFINITY, 0}, {0, 0, INFINITY, 0}};
+    // speculative first trial of the next line search (stp = 1) in the same pass?
+    const int fuse = (out8 && !steepest && A.m >= 1 && ws->method != 1 &&
+                      (ws->obj == OPKB_OBJ_ROSENBROCK || ws->obj == OPKB_OBJ_QUADRATIC))
+                         ? ws->obj : 0;
+    if (out8) out8[7] = 0.0;
     int nparts = 0;
     int64_t done = 0;
 
@@ -640,6 +646,18 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         if (A.bounded && A.lo.arr) { B.r_lo = nr; B.rows[nr++] = A.lo.arr; }
         if (A.bounded && A.hi.arr) { B.r_hi = nr; B.rows[nr++] = A.hi.arr; }
         if (A.ysrc != A.g) { B.r_ysrc = nr; B.rows[nr++] = A.ysrc; }
+        if (fuse == OPKB_OBJ_QUADRATIC) {
+            B.r_a = nr;
+            B.rows[nr++] = (const T*)ws->qa->data;
+            B.r_c = nr;
+            B.rows[nr++] = (const T*)ws->qc->data;
+        }
+        if (fuse) {
+            // x', g' go to the buffers of the recycled slot, which become x and g
+            B.xout = (T*)ws->S[mark_next]->data;
+            B.gout = (T*)ws->Y[mark_next]->data;
+            B.pout = ws->p ? (T*)ws->p->data : NULL;
+        }
         for (int j = 0; j < A.m; ++j) {
             B.rows[nr++] = A.Y[j];
             B.rows[nr++] = A.S[j];
@@ -659,8 +677,8 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         B.d = A.d;
         B.Snext = A.Snext;
         B.Ynext = A.Ynext;
-        // ring geometry: 4 KB rows when two stages fit in ~200 KB, else 2 KB rows
-        const size_t budget = 200 * 1024;
+        // ring geometry: 4 KB rows when two stages fit in ~220 KB, else 2 KB rows
+        const size_t budget = 220 * 1024;
         int tile = (int)(4096 / sizeof(T));
         if ((size_t)nr * tile * sizeof(T) * 2 > budget) tile = (int)(2048 / sizeof(T));
         if (const char* e = getenv("OPKB_DIR_TILE")) tile = atoi(e);
@@ -674,7 +692,9 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
             B.nstage = nstage;
             B.n = ws->n;
             const size_t smem = stage_bytes * nstage;
-            auto kern = k_direction2<T>;
+            auto kern = (fuse == OPKB_OBJ_ROSENBROCK)  ? k_direction2<T, OPKB_OBJ_ROSENBROCK>
+                        : (fuse == OPKB_OBJ_QUADRATIC) ? k_direction2<T, OPKB_OBJ_QUADRATIC>
+                                                       : k_direction2<T, 0>;
             OPKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int64_t grid = ctx->sm_count;
             if (grid > ntiles) grid = ntiles;
@@ -683,9 +703,20 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
             opkb_prof_end(ctx);
             ctx->launches += 1;
             OPKB_CUDA(cudaGetLastError());
-            int rc = opkb_finish_reduction(ctx, 4, kinds, part[nparts++]);
+            int rc = opkb_finish_reduction(ctx, fuse ? 12 : 4, kinds, part[nparts++]);
             if (rc) return rc;
             done = B.n;
+            if (fuse) {
+                const double* r = part[0];
+                out8[0] = (fuse == OPKB_OBJ_ROSENBROCK) ? r[4] + r[5] : 0.5 * r[4];
+                out8[1] = r[6];
+                out8[2] = r[7];
+                out8[3] = r[8];
+                out8[4] = r[9];
+                out8[5] = r[10];
+                out8[6] = r[11];
+                out8[7] = 1.0;
+            }
         }
     }
 
@@ -738,6 +769,18 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         out[2] = INFINITY;
         out[3] = INFINITY;
     }
+    if (fuse) {
+        // S[mark'] <- x, Y[mark'] <- g (:562-563) and x, g <- the trial point just
+        // written into the recycled buffers: two pointer swaps
+        vmlmb_unalias(ws);
+        void* t = ws->S[mark_next]->data;
+        ws->S[mark_next]->data = ws->x->data;
+        ws->x->data = t;
+        t = ws->Y[mark_next]->data;
+        ws->Y[mark_next]->data = ws->g->data;
+        ws->g->data = t;
+        return 0;
+    }
     // vcopy!(S[mark], x); vcopy!(Y[mark], g|p) :562-563, without a copy
     vmlmb_alias(ws, mark_next);
     return 0;
@@ -755,6 +798,44 @@ extern "C" int opkb_vmlmb_direction(opkb_vmlmb* ws, int m, const int* slots, con
     return (ws->eltype == OPKB_DOUBLE)
                ? direction_run<double>(ws, m, slots, alpha, c, gamma, mark_next, 0, out)
                : direction_run<float>(ws, m, slots, alpha, c, gamma, mark_next, 0, out);
+}
+
+extern "C" int opkb_vmlmb_direction_trial(opkb_vmlmb* ws, int m, const int* slots, const double* alpha,
+                                          const double* c, double gamma, int mark_next, double out[4],
+                                          double trial[8])
+{
+    int rc = check_mark(ws, mark_next);
+    if (rc) return rc;
+    if (m < 1 || m > ws->mem || !slots || !alpha || !c || !out || !trial)
+        return opkb_set_error(OPKB_EINVAL, "invalid argument");
+    for (int j = 0; j < m; ++j)
+        if (slots[j] < 0 || slots[j] >= ws->mem) return opkb_set_error(OPKB_EINVAL, "slot out of range");
+    return (ws->eltype == OPKB_DOUBLE)
+               ? direction_run<double>(ws, m, slots, alpha, c, gamma, mark_next, 0, out, NULL, 0.0, trial)
+               : direction_run<float>(ws, m, slots, alpha, c, gamma, mark_next, 0, out, NULL, 0.0, trial);
+}
+
+extern "C" int opkb_vmlmb_discard_trial(opkb_vmlmb* ws, int mark_next)
+{
+    // undo the two pointer swaps of a fused trial that the host does not use
+    // because the direction was rejected (:542-546): x, g are the current
+    // iterate again, S[mark'], Y[mark'] alias them, p is recomputed (:396)
+    int rc = check_mark(ws, mark_next);
+    if (rc) return rc;
+    void* t = ws->S[mark_next]->data;
+    ws->S[mark_next]->data = ws->x->data;
+    ws->x->data = t;
+    t = ws->Y[mark_next]->data;
+    ws->Y[mark_next]->data = ws->g->data;
+    ws->g->data = t;
+    if (ws->p) {
+        rc = opkb_project_direction(ws->ctx, ws->p, ws->x, ws->lo, ws->lo_val, ws->hi, ws->hi_val,
+                                    OPKB_BACKWARD, ws->g);
+        if (rc) return rc;
+    }
+    ws->aliased_slot = -1;
+    vmlmb_alias(ws, mark_next);
+    return 0;
 }
 
 extern "C" int opkb_vmlmb_steepest(opkb_vmlmb* ws, int mark_next, double out[4])

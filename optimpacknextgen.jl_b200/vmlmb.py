@@ -245,6 +245,9 @@ class _FusedOps:
         self._out2 = (f64 * 2)()
         self._alpha = [0.0] * solver.mem
         self._limits = (math.inf, math.inf)
+        self._spec8 = (f64 * 8)()
+        self._spec = None        # results of a speculative first trial (stp = 1) fused into P4
+        self._spec_mark = -1
         self._saved_for = -1
         self._need_steepest = False
         self.rho = [0.0] * solver.mem    # per slot, for L-BFGS / BLMVM (:515)
@@ -261,6 +264,12 @@ class _FusedOps:
         return self._vec(which, slot)
 
     def evaluate(self, mark, stp, initial):
+        if self._spec is not None:
+            spec, self._spec = self._spec, None
+            if not initial and mark == self._spec_mark and stp == 1.0:
+                self.r = spec    # the trial point was evaluated by the direction kernel
+                return spec[0]
+            # another first step: the trial below simply overwrites x, g, p
         if self.builtin:
             check(self.L.opkb_vmlmb_trial(self.ws, mark, stp, int(initial), self._out8))
         else:
@@ -424,8 +433,16 @@ class _FusedOps:
         if not change:
             return False, 0.0, 0.0
         mark_next = mark + 1 if mark < s.mem - 1 else 0
-        check(self.L.opkb_vmlmb_direction(self.ws, m, cslots, (f64 * m)(*alpha), (f64 * m)(*c),
-                                          gamma, mark_next, self._out4))
+        if s.speculate and self.builtin and s.method != 1:
+            # P4 + P1: the first trial of the next search (stp = 1, :567) in the same pass
+            check(self.L.opkb_vmlmb_direction_trial(self.ws, m, cslots, (f64 * m)(*alpha),
+                                                    (f64 * m)(*c), gamma, mark_next, self._out4,
+                                                    self._spec8))
+            self._spec = list(self._spec8) if self._spec8[7] == 1.0 else None
+            self._spec_mark = mark_next
+        else:
+            check(self.L.opkb_vmlmb_direction(self.ws, m, cslots, (f64 * m)(*alpha), (f64 * m)(*c),
+                                              gamma, mark_next, self._out4))
         gd = -self._out4[0]
         dnorm = math.sqrt(self._out4[1])
         self._limits = (self._out4[2], self._out4[3])
@@ -434,6 +451,9 @@ class _FusedOps:
         return True, gd, dnorm
 
     def steepest(self):
+        if self._spec is not None:   # the direction was rejected: drop its speculative trial
+            check(self.L.opkb_vmlmb_discard_trial(self.ws, self._spec_mark))
+            self._spec = None
         self._need_steepest = True
 
     def begin_search(self, mark):
@@ -458,7 +478,7 @@ class VMLMB:
                  blmvm=False, fmin=-math.inf, maxiter=None, maxeval=None, xtol=(0.0, 1e-7),
                  ftol=(0.0, 1e-8), gtol=(0.0, 1e-6), epsilon=0.0, verb=0, printer=print_iteration,
                  output=None, lnsrch=None, ctx: Context = None, mode="fused", twoloop=None,
-                 observer=None, nglobal=None):
+                 speculate=True, observer=None, nglobal=None):
         if autodiff:
             raise NotImplementedError("autodiff is a host-side hook of the reference "
                                       "(src/autodiff.jl); pass fg(x, g) -> f")
@@ -555,6 +575,10 @@ class VMLMB:
         if twoloop not in ("gram", "sequential"):
             raise ValueError("twoloop must be 'gram' or 'sequential'")
         self.twoloop = twoloop
+        # With a built-in objective the fused path evaluates the first trial point
+        # of the next line search (stp = 1) inside the direction kernel; the result
+        # is used iff the driver indeed takes that step (same numbers either way).
+        self.speculate = bool(speculate)
 
         # device storage (:358-371) ----------------------------------------------
         self.mode = mode
@@ -767,6 +791,14 @@ class VMLMB:
     def solve(self):
         while self.step():
             pass
+        return self.x
+
+    def current(self):
+        """The current iterate (the last accepted point) as a device Vector, valid
+        between calls of `step()` / `iterate()`: during a line search `x` holds the
+        trial point and slot `mark` of S holds the iterate (:562)."""
+        if self.stage == 1 and not self.finished:
+            return self.ops.vector("S", self.mark)
         return self.x
 
     def result(self):
