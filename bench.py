@@ -267,7 +267,10 @@ def ours(args):
     # P4 is counted with 2m+6: the two saves of :562-563 are done by buffer aliasing
     # (no traffic at all), see DESIGN.md section 4.  The iteration figure keeps the
     # survey's yardstick W_alg = 4m+20.
-    passes = {"trial": 7, "gram": 2 * m + 5, "direction": 2 * m + 6}
+    # When the first trial of the next line search is fused into P4 (speculation, the
+    # default with a built-in objective) that kernel also writes x, g, p: 2m+9.
+    fused_trial = prof.get("trial", (0.0, 0))[1] < K / 2
+    passes = {"trial": 7, "gram": 2 * m + 5, "direction": 2 * m + (9 if fused_trial else 6)}
     kern = {}
     for name, npass in passes.items():
         if name in prof:
@@ -280,7 +283,7 @@ def ours(args):
     dom = max(kern, key=lambda k: kern[k]["avg_ms"] * kern[k]["launches"])
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": traffic_for(dom, nloc),
-                "peak_source": peak_src, "kernels": kern,
+                "peak_source": peak_src, "kernels": kern, "trial_fused_into_direction": fused_trial,
                 "iteration": {"alg_bytes": (4 * m + 20) * es * n, "evals_per_iter": evals / K,
                               "achieved_gbs": (4 * m + 20) * es * n / (ms * 1e-3 / K) / 1e9 / world,
                               "frac_per_gpu": (4 * m + 20) * es * n / (ms * 1e-3 / K) / 1e9 / world / peak}}

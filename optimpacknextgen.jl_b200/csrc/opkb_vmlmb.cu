@@ -646,12 +646,6 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         if (A.bounded && A.lo.arr) { B.r_lo = nr; B.rows[nr++] = A.lo.arr; }
         if (A.bounded && A.hi.arr) { B.r_hi = nr; B.rows[nr++] = A.hi.arr; }
         if (A.ysrc != A.g) { B.r_ysrc = nr; B.rows[nr++] = A.ysrc; }
-        if (fuse == OPKB_OBJ_QUADRATIC) {
-            B.r_a = nr;
-            B.rows[nr++] = (const T*)ws->qa->data;
-            B.r_c = nr;
-            B.rows[nr++] = (const T*)ws->qc->data;
-        }
         if (fuse) {
             // x', g' go to the buffers of the recycled slot, which become x and g
             B.xout = (T*)ws->S[mark_next]->data;
@@ -663,6 +657,12 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
             B.rows[nr++] = A.S[j];
             B.ma[j] = A.ma[j];
             B.cc[j] = A.cc[j];
+        }
+        if (fuse == OPKB_OBJ_QUADRATIC) {   // objective data: after the pair rows
+            B.r_a = nr;
+            B.rows[nr++] = (const T*)ws->qa->data;
+            B.r_c = nr;
+            B.rows[nr++] = (const T*)ws->qc->data;
         }
         B.use = A.use;
         B.m = A.m;
