@@ -116,8 +116,8 @@ def main():
             x0 = ctx.vector(nl, np.float64).fill(0.5)
             r = run_vmlmb(ctx, "C4 VMLMB quadratic box n=2^28 f64 m=10", obj, x0, lo, hi, 10, nl, n, 30,
                           8, 60)
-        elif c in ("C5", "C5s", "C5s-gram"):   # VMLMB bound-constrained Rosenbrock f32 m=7
-            n = (1 << 31) if c == "C5" else (1 << 28)
+        elif c in ("C5", "C5-gram", "C5s", "C5s-gram"):   # VMLMB bound-constrained Rosenbrock f32 m=7
+            n = (1 << 31) if c in ("C5", "C5-gram") else (1 << 28)
             first, nl = shard_range(n, rank, world)
             x0 = ctx.from_numpy(opk.Rosenbrock.x0(nl, np.float32, perturb_seed=7, first=first))
             lo, hi = rosen_bounds(ctx, nl, np.float32, first)
