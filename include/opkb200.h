@@ -243,6 +243,51 @@ int opkb_vmlmb_steepest(opkb_vmlmb* ws, int mark_next, double out[4]);
 /* P0 "revert to best" = :490-492: x = project(S[mark] - stp*d). */
 int opkb_vmlmb_revert(opkb_vmlmb* ws, int mark, double stp);
 
+/* ---- Tier 3: native reverse-communication driver of VMLMB ------
+ * The stage machine of `_vmlmb!` (src/quasinewton.jl:296-612), the line searches
+ * (src/linesearches.jl) and the two-loop solver in host C++ inside the library,
+ * over the fused phases above: one call per objective evaluation, as the
+ * reference's own C API does (`opk_iterate_vmlmb`, src/wrappers.jl:1831-1859;
+ * tasks as OPK_TASK_*, :758-765).  The Julia/Python hosts may keep their own
+ * driver loop (north_star) or use this one. */
+#define OPKB_TASK_ERROR      -1
+#define OPKB_TASK_START       0
+#define OPKB_TASK_COMPUTE_FG  1   /* evaluate f(x), write g (workspace vectors 'x', 'g') */
+#define OPKB_TASK_NEW_X       2   /* (reported through `new_x` of opkb_solver_status) */
+#define OPKB_TASK_FINAL_X     3   /* convergence: x holds the solution */
+#define OPKB_TASK_WARNING     4   /* stopped with a warning: x holds the best point */
+
+#define OPKB_LS_DEFAULT       0   /* More & Thuente without bounds, More & Toraldo with (:276-284) */
+#define OPKB_LS_ARMIJO        1
+#define OPKB_LS_MORE_TORALDO  2
+#define OPKB_LS_MORE_THUENTE  3
+
+typedef struct opkb_vmlmb_options {   /* keywords of vmlmb!, src/quasinewton.jl:227-242 */
+    int     blmvm;                    /* informative: the method is fixed by opkb_vmlmb_create */
+    double  fmin;
+    int64_t maxiter, maxeval;
+    double  xatol, xrtol, fatol, frtol, gatol, grtol, epsilon;
+    int     lnsrch;                   /* OPKB_LS_* */
+    double  ls_ftol, ls_gtol, ls_xtol, ls_gamma1, ls_gamma2;
+    int     ls_strict;
+    int     twoloop;                  /* -1 default (Gram for Float64, sequential for Float32), 0 Gram, 1 sequential */
+    int     speculate;                /* fuse the first trial of a line search into P4 (default 1) */
+} opkb_vmlmb_options;
+typedef struct opkb_solver_ opkb_solver;
+
+void opkb_vmlmb_default_options(opkb_vmlmb_options* opt);
+/* The workspace must hold the starting point in 'x' and have its objective set. */
+int  opkb_solver_create(opkb_vmlmb* ws, const opkb_vmlmb_options* opt, opkb_solver** solver);
+int  opkb_solver_destroy(opkb_solver* solver);
+/* reverse communication: start -> COMPUTE_FG; then iterate(f) after every evaluation */
+int  opkb_solver_start(opkb_solver* solver, int* task);
+int  opkb_solver_iterate(opkb_solver* solver, double f, int* task);
+/* built-in objective: run until `iter` has advanced by niter or termination */
+int  opkb_solver_run(opkb_solver* solver, int64_t niter, int* task);
+int  opkb_solver_status(const opkb_solver* solver, int64_t* iter, int64_t* eval, int64_t* rejects,
+                        double* f, double* gnorm, double* stp, int* stage, int* new_x);
+const char* opkb_solver_reason(const opkb_solver* solver);
+
 /* ---- Tier 2: fused passes of `_spg!` with the box projection (src/spg.jl:245-380) */
 /* The workspace owns four x buffers and two g buffers: x0/g0 (:322-323) and
  * xbest (:344) are kept by rotating buffers, never by copying; pg, d, s, y

@@ -16,7 +16,7 @@ from .linesearches import (LineSearch, ArmijoLineSearch, MoreToraldoLineSearch,
                            getstatus, usederivatives)
 from .linesearches import getreason as _ls_getreason
 from .objectives import Rosenbrock, Quadratic, splitmix64, uniform
-from .vmlmb import (VMLMB, vmlmb, vmlmb_, BoundedSet, EMULATE_BLMVM, apply_lbfgs_,
+from .vmlmb import (VMLMB, NativeVMLMB, vmlmb, vmlmb_, BoundedSet, EMULATE_BLMVM, apply_lbfgs_,
                     apply_lbfgs_masked_, sufficient_descent, print_iteration, verbose)
 from .spg import SPG, spg, spg_, Info, BoxProjection, default_printer
 from .spg import getreason as _spg_getreason

@@ -32,6 +32,17 @@ class OpkbError(RuntimeError):
         self.code = code
 
 
+class VmlmbOptions(C.Structure):
+    """opkb_vmlmb_options of include/opkb200.h"""
+    _fields_ = [("blmvm", C.c_int), ("fmin", f64), ("maxiter", i64), ("maxeval", i64),
+                ("xatol", f64), ("xrtol", f64), ("fatol", f64), ("frtol", f64), ("gatol", f64),
+                ("grtol", f64), ("epsilon", f64), ("lnsrch", C.c_int), ("ls_ftol", f64),
+                ("ls_gtol", f64), ("ls_xtol", f64), ("ls_gamma1", f64), ("ls_gamma2", f64),
+                ("ls_strict", C.c_int), ("twoloop", C.c_int), ("speculate", C.c_int)]
+
+
+TASK_ERROR, TASK_START, TASK_COMPUTE_FG, TASK_NEW_X, TASK_FINAL_X, TASK_WARNING = -1, 0, 1, 2, 3, 4
+
 # name -> (restype, argtypes); the list mirrors include/opkb200.h one for one
 _SIGNATURES = {
     "opkb_last_error": (C.c_char_p, []),
@@ -95,6 +106,15 @@ _SIGNATURES = {
     "opkb_vmlmb_finish_direction": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, f64, Pd]),
     "opkb_vmlmb_steepest": (C.c_int, [vp, C.c_int, Pd]),
     "opkb_vmlmb_revert": (C.c_int, [vp, C.c_int, f64]),
+    "opkb_vmlmb_default_options": (None, [C.POINTER(VmlmbOptions)]),
+    "opkb_solver_create": (C.c_int, [vp, C.POINTER(VmlmbOptions), C.POINTER(vp)]),
+    "opkb_solver_destroy": (C.c_int, [vp]),
+    "opkb_solver_start": (C.c_int, [vp, Pi]),
+    "opkb_solver_iterate": (C.c_int, [vp, f64, Pi]),
+    "opkb_solver_run": (C.c_int, [vp, i64, Pi]),
+    "opkb_solver_status": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), Pd, Pd, Pd,
+                                     Pi, Pi]),
+    "opkb_solver_reason": (C.c_char_p, [vp]),
     "opkb_spg_create": (C.c_int, [vp, C.c_int, i64, vp, f64, vp, f64, C.POINTER(vp)]),
     "opkb_spg_destroy": (C.c_int, [vp]),
     "opkb_spg_set_objective": (C.c_int, [vp, C.c_int, vp, vp]),

@@ -167,6 +167,16 @@ extern "C" int opkb_vmlmb_set_objective(opkb_vmlmb* ws, int kind, const opkb_vec
     return 0;
 }
 
+// used by the native driver (opkb_driver.cu)
+int opkb_vmlmb_info(const opkb_vmlmb* ws, int* mem, int* method, int* eltype, int* obj)
+{
+    *mem = ws->mem;
+    *method = ws->method;
+    *eltype = ws->eltype;
+    *obj = ws->obj;
+    return 0;
+}
+
 extern "C" opkb_vector* opkb_vmlmb_vector(opkb_vmlmb* ws, int which, int slot)
 {
     if (!ws) return NULL;

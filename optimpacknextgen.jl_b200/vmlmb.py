@@ -816,6 +816,98 @@ class VMLMB:
         return (p.download() if isinstance(p, Vector) else np.asarray(p)) != 0
 
 
+class NativeVMLMB(VMLMB):
+    """`vmlmb!` with the driver loop inside libopkb200 (`opkb_solver_*`, the
+    reverse-communication API in the style of the reference's own C FFI,
+    src/wrappers.jl:1831-1859): same keywords and results as `VMLMB`, one native
+    call per objective evaluation (a user `fg`) or per run (built-in objective)."""
+
+    def __init__(self, fg, x0, **kw):
+        from .linesearches import ArmijoLineSearch
+        ls = kw.get("lnsrch")
+        kw.pop("mode", None)
+        super().__init__(fg, x0, mode="fused", **kw)
+        L = _lib.lib()
+        opt = _lib.VmlmbOptions()
+        L.opkb_vmlmb_default_options(C.byref(opt))
+        opt.fmin = self.fmin
+        opt.maxiter, opt.maxeval = self.maxiter, self.maxeval
+        opt.xatol, opt.xrtol = self.xatol, self.xrtol
+        opt.fatol, opt.frtol = self.fatol, self.frtol
+        opt.gatol, opt.grtol = self.gatol, self.grtol
+        opt.epsilon = self.epsilon
+        opt.twoloop = 0 if self.twoloop == "gram" else 1
+        opt.speculate = int(self.speculate)
+        ls = self.lnsrch if ls is None else ls
+        if isinstance(ls, MoreThuenteLineSearch):
+            opt.lnsrch, opt.ls_ftol, opt.ls_gtol, opt.ls_xtol = 3, ls.ftol, ls.gtol, ls.xtol
+        elif isinstance(ls, MoreToraldoLineSearch):
+            opt.lnsrch, opt.ls_ftol, opt.ls_strict = 2, ls.ftol, int(ls.strict)
+            opt.ls_gamma1, opt.ls_gamma2 = ls.gamma1, ls.gamma2
+        elif isinstance(ls, ArmijoLineSearch):
+            opt.lnsrch, opt.ls_ftol = 1, ls.ftol
+        else:
+            raise TypeError("the native driver knows the three line searches of the reference")
+        self._solver = vp()
+        check(L.opkb_solver_create(self._ws, C.byref(opt), C.byref(self._solver)))
+        self._task = C.c_int(_lib.TASK_START)
+        self._g = self.ops.vector("g")
+        self._builtin = is_builtin(fg)
+
+    def close(self):
+        if getattr(self, "_solver", None):
+            _lib.lib().opkb_solver_destroy(self._solver)
+            self._solver = None
+        super().close()
+
+    def _refresh(self):
+        L = _lib.lib()
+        it, ev, rej = _lib.i64(), _lib.i64(), _lib.i64()
+        f, gn, stp = f64(), f64(), f64()
+        stage, newx = C.c_int(), C.c_int()
+        check(L.opkb_solver_status(self._solver, C.byref(it), C.byref(ev), C.byref(rej), C.byref(f),
+                                   C.byref(gn), C.byref(stp), C.byref(stage), C.byref(newx)))
+        self.iter, self.eval, self.rejects = it.value, ev.value, rej.value
+        self.f, self.gnorm, self.stp, self.stage = f.value, gn.value, stp.value, stage.value
+        self.reason = L.opkb_solver_reason(self._solver).decode()
+        self.finished = self._task.value in (_lib.TASK_FINAL_X, _lib.TASK_WARNING)
+        return bool(newx.value)
+
+    def step(self):
+        raise NotImplementedError("the native driver advances by iterations: use iterate()")
+
+    def iterate(self, niter: int = 1) -> bool:
+        L = _lib.lib()
+        if self.finished:
+            return False
+        if self._builtin:
+            check(L.opkb_solver_run(self._solver, int(min(niter, 2 ** 62)), C.byref(self._task)))
+            if self._refresh() and self.observer is not None:
+                self.observer(self)
+            return not self.finished
+        target = self.iter + niter
+        if self._task.value == _lib.TASK_START:
+            check(L.opkb_solver_start(self._solver, C.byref(self._task)))
+        while self._task.value == _lib.TASK_COMPUTE_FG and self.iter < target:
+            f = float(self.fg(self.x, self._g))
+            try:
+                check(L.opkb_solver_iterate(self._solver, f, C.byref(self._task)))
+            except _lib.OpkbError as e:
+                if "line search" in str(e):   # ArgumentError thrown by start!/cstep in the reference
+                    raise ValueError(str(e)) from e
+                raise
+            if self._refresh() and self.observer is not None:
+                self.observer(self)
+        return not self.finished
+
+    def solve(self):
+        while self.iterate(2 ** 62):
+            pass
+        if verbose(self.verb, 0):
+            self._finish()
+        return self.x
+
+
 def _builtin_as_callable(obj, ctx, n, dtype):
     """Stand-alone `fg!(x, g)` of a built-in objective (Tier 1), for mode='primitive'."""
     L = _lib.lib()
@@ -837,7 +929,10 @@ def _builtin_as_callable(obj, ctx, n, dtype):
 def vmlmb_(fg, x, **kwds):
     """`vmlmb!(fg!, x; kwds...) -> x` (src/quasinewton.jl:226): the best solution
     is stored in `x` (a device Vector or a writeable host array) and returned."""
-    solver = VMLMB(fg, x, **kwds)
+    driver = kwds.pop("driver", "python")
+    if driver not in ("python", "native"):
+        raise ValueError("driver must be 'python' or 'native'")
+    solver = (NativeVMLMB if driver == "native" else VMLMB)(fg, x, **kwds)
     solver.solve()
     if isinstance(x, Vector):
         if solver.x is not x:

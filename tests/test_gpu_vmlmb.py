@@ -303,3 +303,68 @@ def test_large_properties(opk, dtype, n, mem):
     rtol = 1e-9 if dtype == np.float64 else 1e-3
     for a, b in zip(runs[0], runs[2]):
         assert a[0] == b[0] and abs(a[1] - b[1]) <= rtol * abs(b[1])
+
+
+# ---------------------------------------------------------------------------
+# native reverse-communication driver (opkb_solver_*)
+@pytest.mark.parametrize("kind,n,dtype,kw", CASES)
+def test_native_driver_trajectory(opk, oracle, kind, n, dtype, kw):
+    """The driver loop inside libopkb200 gives the oracle's trajectory (same
+    gates as the Python twin); iterate(1) stops at every iteration boundary."""
+    pb = problem(kind, n, dtype)
+    kw = dict(kw, maxiter=25)
+    xo, ro, tro = run_oracle(oracle, pb, **kw)
+    lo, hi = gpu_bounds(pb)
+    s = opk.NativeVMLMB(pb["gpu_obj"], pb["x0"], lower=lo, upper=hi, **kw)
+    rtol = F64_RTOL if dtype == np.float64 else F32_RTOL
+    by_iter = {t["iter"]: t for t in tro}
+    seen = 0
+    while s.iterate(1):
+        w = by_iter.get(s.iter)
+        if w is None or s.iter > 20:
+            continue
+        assert abs(s.f - w["f"]) <= rtol * abs(w["f"]) + 1e-300, (s.iter, s.f, w["f"])
+        assert abs(s.gnorm - w["gnorm"]) <= rtol * abs(w["gnorm"]) + 1e-300
+        xcur = s.current().download()
+        assert relerr(xcur, w["x"]) <= rtol
+        seen += 1
+    assert seen >= 15
+    assert (s.iter, s.eval, s.rejects, s.reason) == (ro["iter"], ro["eval"], ro["rejects"], ro["reason"])
+    assert relerr(s.result(), xo) <= 10 * rtol
+    s.close()
+
+
+def test_native_driver_options_and_user_objective(opk, oracle):
+    pb = problem("rosen_lower0", 20, np.float64)
+    for kw in (dict(maxeval=7), dict(maxiter=3), dict(fmin=0.0), dict(epsilon=0.01), dict(gtol=(1e-3, 0.0)),
+               dict(xtol=(0.0, 1e-2)), dict(ftol=(1e-4, 0.0)), dict(fmin=300.0), dict(blmvm=True), dict(mem=3)):
+        xo, ro, _ = oracle.vmlmb("rosenbrock", pb["x0"], 0.0, None, **kw)
+        x = opk.Rosenbrock.x0(20)
+        s = opk.NativeVMLMB(opk.Rosenbrock(), x, lower=0.0, **kw)
+        s.solve()
+        assert (s.iter, s.eval, s.reason, s.stage) == (ro["iter"], ro["eval"], ro["reason"], ro["stage"]), kw
+        assert relerr(s.result(), xo) <= 1e-9
+        s.close()
+    for ls, code in ((opk.ArmijoLineSearch(ftol=1e-4), oracle.LS_ARMIJO),
+                     (opk.MoreThuenteLineSearch(ftol=1e-3, gtol=0.9, xtol=0.1), oracle.LS_MORE_THUENTE)):
+        okw = dict(lnsrch=code, ls_ftol=ls.ftol)
+        xo, ro, _ = oracle.vmlmb("rosenbrock", pb["x0"], 0.0, None, **okw)
+        x = opk.vmlmb(opk.Rosenbrock(), pb["x0"], lower=0.0, lnsrch=ls, driver="native")
+        assert relerr(x, xo) <= 1e-9
+    # reverse communication with a user objective on device vectors
+    ctx = opk.default_context()
+    n = 1000
+    t = ctx.from_numpy(np.linspace(-1, 2, n))
+    calls = []
+
+    def fg(x, g):
+        calls.append(1)
+        opk.vcombine_(g, 2, x, -2, t)
+        r = opk.vcombine_(x.similar(), 1, x, -1, t)
+        return opk.vdot(r, r)
+
+    x = opk.vmlmb(fg, np.zeros(n), lower=opk.BoundedSet(0.0, 1.0), driver="native")
+    assert np.abs(x - np.clip(np.linspace(-1, 2, n), 0, 1)).max() < 1e-5
+    ncalls = len(calls)
+    x2 = opk.vmlmb(fg, np.zeros(n), lower=opk.BoundedSet(0.0, 1.0))
+    assert np.array_equal(x, x2) and len(calls) == 2 * ncalls    # same path as the Python driver
