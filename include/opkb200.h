@@ -287,6 +287,8 @@ int  opkb_solver_run(opkb_solver* solver, int64_t niter, int* task);
 int  opkb_solver_status(const opkb_solver* solver, int64_t* iter, int64_t* eval, int64_t* rejects,
                         double* f, double* gnorm, double* stp, int* stage, int* new_x);
 const char* opkb_solver_reason(const opkb_solver* solver);
+/* slot of S, Y that holds (x0, g0) of the line search in progress: S[mark] is the current iterate */
+int  opkb_solver_mark(const opkb_solver* solver);
 
 /* ---- Tier 2: fused passes of `_spg!` with the box projection (src/spg.jl:245-380) */
 /* The workspace owns four x buffers and two g buffers: x0/g0 (:322-323) and

@@ -115,6 +115,7 @@ _SIGNATURES = {
     "opkb_solver_status": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), Pd, Pd, Pd,
                                      Pi, Pi]),
     "opkb_solver_reason": (C.c_char_p, [vp]),
+    "opkb_solver_mark": (C.c_int, [vp]),
     "opkb_spg_create": (C.c_int, [vp, C.c_int, i64, vp, f64, vp, f64, C.POINTER(vp)]),
     "opkb_spg_destroy": (C.c_int, [vp]),
     "opkb_spg_set_objective": (C.c_int, [vp, C.c_int, vp, vp]),

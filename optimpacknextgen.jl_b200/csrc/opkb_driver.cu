@@ -659,3 +659,4 @@ extern "C" int opkb_solver_status(const opkb_solver* s, int64_t* iter, int64_t* 
 }
 
 extern "C" const char* opkb_solver_reason(const opkb_solver* s) { return s ? s->reason : ""; }
+extern "C" int opkb_solver_mark(const opkb_solver* s) { return s ? s->mark : -1; }

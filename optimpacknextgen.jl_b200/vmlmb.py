@@ -870,6 +870,7 @@ class NativeVMLMB(VMLMB):
         self.iter, self.eval, self.rejects = it.value, ev.value, rej.value
         self.f, self.gnorm, self.stp, self.stage = f.value, gn.value, stp.value, stage.value
         self.reason = L.opkb_solver_reason(self._solver).decode()
+        self.mark = L.opkb_solver_mark(self._solver)
         self.finished = self._task.value in (_lib.TASK_FINAL_X, _lib.TASK_WARNING)
         return bool(newx.value)
 

@@ -32,11 +32,15 @@ def rosen_bounds(ctx, n, dtype, first):
     return ctx.vector(n, dtype).fill(0.0), ctx.from_numpy(hi)
 
 
+NATIVE = bool(int(os.environ.get("OPKB_BENCH_NATIVE", "0")))   # driver loop inside the library
+
+
 def run_vmlmb(ctx, name, obj, x0, lo, hi, mem, n, nglobal, K, es, walg, twoloop=None, prime=None):
     kw = dict(mem=mem, xtol=(0, 0), ftol=(0, 0), gtol=(0, 0), nglobal=nglobal, ctx=ctx, twoloop=twoloop)
     if lo is not None:
         kw.update(lower=lo, upper=hi)
-    s = opk.VMLMB(obj, x0, **kw)
+    s = (opk.NativeVMLMB if NATIVE else opk.VMLMB)(obj, x0, **kw)
+    name += " [native driver]" if NATIVE else ""
     s.iterate((mem + 1 if prime is None else prime) + 3)
     ctx.synchronize()
     ctx.profile(True)
