@@ -22,7 +22,7 @@
 #
 module OptimPackB200
 
-export DeviceVector, BoundedSet, Rosenbrock, Quadratic, vmlmb, vmlmb!, spg, spg!
+export DeviceVector, BoundedSet, Rosenbrock, Quadratic, vmlmb, vmlmb!, vmlmb_native!, spg, spg!
 
 using Libdl
 import LazyAlgebra
@@ -539,6 +539,70 @@ function vmlmb!(fg!, x::DeviceVector{T};
                     color = (stage > 3 ? :red : :green))
     end
     vcopy!(x, xw)
+    return x
+end
+
+# ---------------------------------------------------------------------------
+# (C) The same solver with the driver loop inside the library (opkb_solver_*):
+# reverse communication in the style of `opk_iterate_vmlmb`
+# (src/wrappers.jl:1831-1859) -- one ccall per objective evaluation, or a single
+# ccall for a built-in objective.
+struct NativeOptions          # opkb_vmlmb_options of include/opkb200.h (same layout)
+    blmvm::Cint
+    fmin::Cdouble
+    maxiter::Int64
+    maxeval::Int64
+    xatol::Cdouble; xrtol::Cdouble; fatol::Cdouble; frtol::Cdouble; gatol::Cdouble; grtol::Cdouble
+    epsilon::Cdouble
+    lnsrch::Cint              # 0 default, 1 Armijo, 2 More & Toraldo, 3 More & Thuente
+    ls_ftol::Cdouble; ls_gtol::Cdouble; ls_xtol::Cdouble; ls_gamma1::Cdouble; ls_gamma2::Cdouble
+    ls_strict::Cint
+    twoloop::Cint
+    speculate::Cint
+end
+
+const TASK_COMPUTE_FG = Cint(1)
+
+function vmlmb_native!(fg!, x::DeviceVector{T}; mem::Integer = min(5, length(x)),
+                       lower = -Inf, upper = +Inf, blmvm::Bool = false, fmin::Real = -Inf,
+                       maxiter::Integer = typemax(Int), maxeval::Integer = typemax(Int),
+                       xtol::NTuple{2,Real} = (0.0, 1e-7), ftol::NTuple{2,Real} = (0.0, 1e-8),
+                       gtol::NTuple{2,Real} = (0.0, 1e-6), epsilon::Real = 0.0,
+                       nglobal::Integer = length(x)) where {T}
+    ctx = x.ctx
+    lo = to_device(ctx, lower, T); hi = to_device(ctx, upper, T)
+    bounded = (lo isa DeviceVector || lo > -Inf) || (hi isa DeviceVector || hi < +Inf)
+    method = !bounded ? 0 : blmvm ? 1 : 2
+    ws = Workspace{T}(ctx, length(x), Int(min(mem, nglobal)), method, lo, hi)
+    kind, pa, pc = objective_code(fg!)
+    fg! isa Quadratic && push!(ws.keep, fg!)
+    check(ccall((:opkb_vmlmb_set_objective, libopkb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
+                ws.ptr, kind, pa, pc))
+    xw = wsvector(ws, 'x'); gw = wsvector(ws, 'g')
+    vcopy!(xw, x)
+    opt = Ref(NativeOptions(blmvm, fmin, maxiter, maxeval, xtol[1], xtol[2], ftol[1], ftol[2],
+                            gtol[1], gtol[2], epsilon, 0, 1e-3, 0.9, 0.1, 0.1, 0.5, 0, -1, 1))
+    sref = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:opkb_solver_create, libopkb200), Cint, (Ptr{Cvoid}, Ref{NativeOptions}, Ref{Ptr{Cvoid}}),
+                ws.ptr, opt, sref))
+    solver = sref[]
+    task = Ref{Cint}(0)
+    try
+        if kind != 0      # built-in objective: the whole run in one call
+            check(ccall((:opkb_solver_run, libopkb200), Cint, (Ptr{Cvoid}, Int64, Ref{Cint}),
+                        solver, typemax(Int64), task))
+        else              # reverse communication
+            check(ccall((:opkb_solver_start, libopkb200), Cint, (Ptr{Cvoid}, Ref{Cint}), solver, task))
+            while task[] == TASK_COMPUTE_FG
+                fx = Float(fg!(xw, gw))
+                check(ccall((:opkb_solver_iterate, libopkb200), Cint, (Ptr{Cvoid}, Cdouble, Ref{Cint}),
+                            solver, fx, task))
+            end
+        end
+        vcopy!(x, xw)
+    finally
+        ccall((:opkb_solver_destroy, libopkb200), Cint, (Ptr{Cvoid},), solver)
+    end
     return x
 end
 

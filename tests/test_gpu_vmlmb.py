@@ -368,3 +368,36 @@ def test_native_driver_options_and_user_objective(opk, oracle):
     ncalls = len(calls)
     x2 = opk.vmlmb(fg, np.zeros(n), lower=opk.BoundedSet(0.0, 1.0))
     assert np.array_equal(x, x2) and len(calls) == 2 * ncalls    # same path as the Python driver
+
+
+@pytest.mark.parametrize("driver", ["python", "native"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_large_memory_and_tiny_problems(opk, oracle, dtype, driver):
+    """mem = 18 reaches the 10-role Gram decomposition (4 blocks of pairs); n = 1, 2, 3
+    exercise the partial-tile paths of the ring kernels; mem = 1."""
+    cls = opk.NativeVMLMB if driver == "native" else opk.VMLMB
+    rtol = F64_RTOL if dtype == np.float64 else F32_RTOL
+    for kind, n, kw in (("quad_box", 3001, dict(mem=18, maxiter=25)),
+                        ("quad_box", 3001, dict(mem=18, maxiter=25, twoloop="sequential")),
+                        ("quad_box", 1, dict(mem=3, maxiter=10)),
+                        ("quad_box", 3, dict(mem=1, maxiter=10)),
+                        ("rosen_lower0", 2, dict(mem=2, maxiter=15)),
+                        ("rosen_box", 6, dict(mem=4, maxiter=20, twoloop="gram"))):
+        if dtype == np.float32 and kw.get("twoloop") == "gram":
+            continue
+        pb = problem(kind, n, dtype)
+        okw = {k: v for k, v in kw.items() if k != "twoloop"}
+        okw["mem"] = min(okw["mem"], n)
+        xo, ro, tro = run_oracle(oracle, pb, **okw)
+        lo, hi = gpu_bounds(pb)
+        if dtype == np.float32 and kw.get("mem") == 18 and "twoloop" not in kw:
+            kw = dict(kw, twoloop="gram")          # exercise the 10-role Float32 kernel too
+            rtol_case = 1e-3
+        else:
+            rtol_case = rtol
+        s = cls(pb["gpu_obj"], pb["x0"], lower=lo, upper=hi, **kw)
+        s.solve()
+        assert (s.iter, s.eval) == (ro["iter"], ro["eval"]), (kind, n, kw, s.iter, s.eval, ro["iter"], ro["eval"])
+        assert abs(s.f - ro["f"]) <= 100 * rtol_case * abs(ro["f"]) + 1e-20, (kind, n, kw, s.f, ro["f"])
+        assert relerr(s.result(), xo) <= 100 * rtol_case + 1e-300, (kind, n, kw)
+        s.close()
