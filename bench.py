@@ -281,7 +281,8 @@ def ours(args):
                           "alg_bytes_per_launch": npass * es * nloc, "achieved_gbs": ach,
                           "frac": ach / peak}
     dom = max(kern, key=lambda k: kern[k]["avg_ms"] * kern[k]["launches"])
-    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": kern[dom]["achieved_gbs"], "peak": peak,
+    names = {"trial": "k_trial", "gram": "k_gram2", "direction": "k_direction2"}
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": kern[dom]["achieved_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": traffic_for(dom, nloc),
                 "peak_source": peak_src, "kernels": kern, "trial_fused_into_direction": fused_trial,
                 "iteration": {"alg_bytes": (4 * m + 20) * es * n, "evals_per_iter": evals / K,

@@ -212,21 +212,6 @@ struct ReduceScratch {
     double* res;
 };
 
-template <int KIND>
-__device__ __forceinline__ double rcombine(double a, double b)
-{
-    if (KIND == OPKB_RSUM) return a + b;
-    if (KIND == OPKB_RMAX) return (b > a ? b : a);
-    return (b < a ? b : a);
-}
-
-template <int KIND> __device__ __forceinline__ double rneutral()
-{
-    if (KIND == OPKB_RSUM) return 0.0;
-    if (KIND == OPKB_RMAX) return -INFINITY;
-    return INFINITY;
-}
-
 __device__ __forceinline__ double rcombine_dyn(int kind, double a, double b)
 {
     if (kind == OPKB_RSUM) return a + b;

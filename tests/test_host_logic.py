@@ -51,6 +51,26 @@ def test_no_cpu_fallback():
             opk.vmlmb(opk.Rosenbrock(), np.zeros(4))
 
 
+def test_cabi_argument_validation_without_gpu():
+    """Status codes and opkb_last_error for invalid arguments (no CUDA call is reached)."""
+    import ctypes as C
+    from opkb200 import _lib
+    L = _lib.lib()
+    r = C.c_double()
+    assert L.opkb_vdot(None, None, None, C.byref(r)) == -1
+    assert b"NULL context" in L.opkb_last_error()
+    assert L.opkb_vector_create(None, 1, 10, C.byref(C.c_void_p())) == -1
+    assert L.opkb_vmlmb_create(None, 1, 10, 5, 2, None, 0.0, None, 1.0, C.byref(C.c_void_p())) == -1
+    assert L.opkb_vmlmb_trial(None, 0, 1.0, 0, (C.c_double * 8)()) == -1
+    assert L.opkb_spg_start(None, 1.0, (C.c_double * 8)()) == -1
+    assert L.opkb_solver_create(None, None, C.byref(C.c_void_p())) == -1
+    assert L.opkb_vector_length(None) == -1 and L.opkb_vector_destroy(None) == 0
+    opt = _lib.VmlmbOptions()
+    L.opkb_vmlmb_default_options(C.byref(opt))   # defaults of src/quasinewton.jl:227-242
+    assert (opt.xrtol, opt.frtol, opt.grtol, opt.epsilon) == (1e-7, 1e-8, 1e-6, 0.0)
+    assert opt.fmin == -math.inf and opt.maxiter == 2 ** 63 - 1 and opt.speculate == 1
+
+
 def test_product_does_not_import_the_oracle():
     pkg = os.path.join(ROOT, "optimpacknextgen.jl_b200")
     for dirpath, _, files in os.walk(pkg):

@@ -84,6 +84,33 @@ def main():
             ok = ok and good
             print(f"[{world} GPUs] {kind} n={n} {np.dtype(dtype).name} {kw}: same_decisions={same} "
                   f"worst_rel(f,|g|)={worst:.2e} rel(x)={ex:.2e} {'OK' if good else 'FAIL'}", flush=True)
+    # SPG: the same sharding, one packed all-gather per function evaluation
+    for kind, n, dtype, m in (("quad_box", 200001, np.float64, 10), ("rosen_box", 100000, np.float64, 10)):
+        pb = problem(kind, n, dtype)
+        first, cnt = shard_range(n, rank, world)
+        sl = slice(first, first + cnt)
+        obj = pb["gpu_obj"]
+        if isinstance(obj, opk.Quadratic):
+            obj = opk.Quadratic(obj.a[sl].copy(), obj.c[sl].copy())
+        ws = opk.Info()
+        s = opk.SPG(obj, opk.BoxProjection(pb["lower"][sl].copy(), pb["upper"][sl].copy()), pb["x0"][sl].copy(),
+                    m, maxit=25, ws=ws, ctx=ctx)
+        s.solve()
+        xloc = s.result()
+        s.close()
+        per = shard_range(n, 0, world)[1]
+        buf = torch.zeros(per, dtype=torch.float64, device="cuda")
+        buf[:cnt] = torch.from_numpy(xloc.astype(np.float64)).cuda()
+        bufs = [torch.zeros_like(buf) for _ in range(world)]
+        dist.all_gather(bufs, buf)
+        if rank == 0:
+            x = np.concatenate([b.cpu().numpy()[:shard_range(n, r, world)[1]] for r, b in enumerate(bufs)])
+            xo, io, _ = O.spg(pb["oracle_obj"], pb["x0"], m, pb["lower"], pb["upper"], maxit=25)
+            ex = np.linalg.norm(x - xo) / np.linalg.norm(xo)
+            good = (ws.iter, ws.fcnt, ws.status) == (io["iter"], io["fcnt"], io["status"]) and ex <= 1e-9
+            ok = ok and good
+            print(f"[{world} GPUs] SPG {kind} n={n}: iter/fcnt={ws.iter}/{ws.fcnt} rel(x)={ex:.2e} "
+                  f"{'OK' if good else 'FAIL'}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:
