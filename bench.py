@@ -69,7 +69,7 @@ def cpu_run(args, steps, warmup, log2n):
     import opk_oracle as O
     O.build()
     O.set_sum_mode(O.SUM_ACCURATE)
-    O.set_num_threads(0)
+    O.set_num_threads(int(os.environ.get("OPKB_CPU_THREADS", "0")))   # 0 = all host cores
     cores = O.max_threads()
     ns = 1 << log2n
     sys.path.insert(0, ROOT)

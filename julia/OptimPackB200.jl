@@ -282,7 +282,7 @@ mutable struct Workspace{T}
     method::Int
     keep::Vector{Any}      # bounds / objective data that must outlive the workspace
 end
-function Workspace{T}(ctx, n, mem, method, lo, hi) where {T}
+function make_workspace(::Type{T}, ctx::Context, n::Int, mem::Int, method::Int, lo, hi) where {T}
     (lp, lv), (hp, hv) = bound_args(lo, -Inf), bound_args(hi, +Inf)
     ref = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:opkb_vmlmb_create, libopkb200), Cint,
@@ -389,7 +389,7 @@ function vmlmb!(fg!, x::DeviceVector{T};
                        MoreToraldoLineSearch(Float; ftol=1e-3, gamma=(0.1,0.5))
     mem = Int(min(mem, nglobal))
     n = length(x)
-    ws = Workspace{T}(ctx, n, mem, method, lo, hi)
+    ws = make_workspace(T, ctx, n, mem, method, lo, hi)
     kind, pa, pc = objective_code(fg!)
     fg! isa Quadratic && push!(ws.keep, fg!)
     check(ccall((:opkb_vmlmb_set_objective, libopkb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
@@ -573,7 +573,7 @@ function vmlmb_native!(fg!, x::DeviceVector{T}; mem::Integer = min(5, length(x))
     lo = to_device(ctx, lower, T); hi = to_device(ctx, upper, T)
     bounded = (lo isa DeviceVector || lo > -Inf) || (hi isa DeviceVector || hi < +Inf)
     method = !bounded ? 0 : blmvm ? 1 : 2
-    ws = Workspace{T}(ctx, length(x), Int(min(mem, nglobal)), method, lo, hi)
+    ws = make_workspace(T, ctx, length(x), Int(min(mem, nglobal)), method, lo, hi)
     kind, pa, pc = objective_code(fg!)
     fg! isa Quadratic && push!(ws.keep, fg!)
     check(ccall((:opkb_vmlmb_set_objective, libopkb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
