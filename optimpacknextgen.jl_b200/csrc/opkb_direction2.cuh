@@ -41,8 +41,10 @@ template <typename T> struct Dir2Args {
     T* pout;                              // NULL for L-BFGS
 };
 
-// FUSE: 0 direction only; OPKB_OBJ_ROSENBROCK / OPKB_OBJ_QUADRATIC: + speculative trial
-template <typename T, int FUSE>
+// FUSE: 0 direction only; OPKB_OBJ_ROSENBROCK / OPKB_OBJ_QUADRATIC: + speculative trial.
+// MB >= m (unrolled pair loops, coefficients as constant-bank operands), TILE =
+// elements per staged row (compile time: every shared read is `LDS [base + imm]`).
+template <typename T, int FUSE, int MB, int TILE>
 __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, ReduceScratch rs)
 {
     constexpr int VEC = VecOf<T>::N;
@@ -52,12 +54,13 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
     __shared__ __align__(8) uint64_t full_bar[DIR2_MAXSTAGE];
     __shared__ __align__(8) uint64_t empty_bar[DIR2_MAXSTAGE];
 
-    const int TILE = A.tile, NSTAGE = A.nstage, NR = A.nrows, m = A.m;
+    const int NSTAGE = A.nstage, NR = A.nrows, m = A.m;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     T* const stage0 = reinterpret_cast<T*>(smem_raw);
     const int stage_elems = NR * TILE;
-    const uint32_t rowbytes = (uint32_t)(TILE * sizeof(T));
+    constexpr uint32_t rowbytes = (uint32_t)(TILE * sizeof(T));
     const int64_t ntiles = (A.n + TILE - 1) / TILE;
+    const bool all_used = (A.use == (m >= 32 ? 0xffffffffu : ((1u << m) - 1u)));
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
@@ -138,24 +141,53 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) upd[q] = !A.masked || (pv.v[q] != T(0));
                 // apply_lbfgs! :716-745 / :747-779, rounding sequence of the reference
-                for (int j = m - 1; j >= 0; --j) {
-                    if ((A.use >> j) & 1u) {
-                        const Pack<T> y = ld_pack<T>(st + (prow + 2 * j) * TILE, e / VEC);
-                        const T a = A.ma[j];
+                if (all_used) {
+                    // every pair takes part (the usual case): unrolled and branch-free.  The
+                    // chain also runs on the masked elements, whose result is then replaced
+                    // by what the reference gives them, gamma*v0 (they are never updated).
+                    const T* pb = st + prow * TILE + e;
 #pragma unroll
-                        for (int q = 0; q < VEC; ++q)
-                            if (upd[q]) v.v[q] = v.v[q] + a * y.v[q];
+                    for (int jj = 0; jj < MB; ++jj) {
+                        const int j = MB - 1 - jj;
+                        if (j < m) {
+                            const Pack<T> y = ld_pack<T>(pb + 2 * j * TILE, 0);
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + A.ma[j] * y.v[q];
+                        }
                     }
-                }
 #pragma unroll
-                for (int q = 0; q < VEC; ++q) v.v[q] = A.gamma * v.v[q];
-                for (int j = 0; j < m; ++j) {
-                    if ((A.use >> j) & 1u) {
-                        const Pack<T> sv = ld_pack<T>(st + (prow + 2 * j + 1) * TILE, e / VEC);
-                        const T c = A.cc[j];
+                    for (int q = 0; q < VEC; ++q) v.v[q] = A.gamma * v.v[q];
 #pragma unroll
-                        for (int q = 0; q < VEC; ++q)
-                            if (upd[q]) v.v[q] = v.v[q] + c * sv.v[q];
+                    for (int j = 0; j < MB; ++j) {
+                        if (j < m) {
+                            const Pack<T> sv = ld_pack<T>(pb + (2 * j + 1) * TILE, 0);
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + A.cc[j] * sv.v[q];
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q)
+                        if (!upd[q]) v.v[q] = A.gamma * pv.v[q];
+                } else {
+                    for (int j = m - 1; j >= 0; --j) {
+                        if ((A.use >> j) & 1u) {
+                            const Pack<T> y = ld_pack<T>(st + (prow + 2 * j) * TILE, e / VEC);
+                            const T a = A.ma[j];
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q)
+                                if (upd[q]) v.v[q] = v.v[q] + a * y.v[q];
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) v.v[q] = A.gamma * v.v[q];
+                    for (int j = 0; j < m; ++j) {
+                        if ((A.use >> j) & 1u) {
+                            const Pack<T> sv = ld_pack<T>(st + (prow + 2 * j + 1) * TILE, e / VEC);
+                            const T c = A.cc[j];
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q)
+                                if (upd[q]) v.v[q] = v.v[q] + c * sv.v[q];
+                        }
                     }
                 }
 #pragma unroll

@@ -690,8 +690,11 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         // ring geometry: 4 KB rows when two stages fit in ~220 KB, else 2 KB rows
         const size_t budget = 220 * 1024;
         int tile = (int)(4096 / sizeof(T));
-        if ((size_t)nr * tile * sizeof(T) * 2 > budget) tile = (int)(2048 / sizeof(T));
-        if (const char* e = getenv("OPKB_DIR_TILE")) tile = atoi(e);
+        if ((size_t)nr * tile * sizeof(T) * 2 > budget || A.m > 12) tile = (int)(2048 / sizeof(T));
+        if (const char* e = getenv("OPKB_DIR_ROWB")) {   // tuning knob: 2048 | 4096 bytes per row
+            const int rb = atoi(e);
+            if (rb == 2048 || (rb == 4096 && A.m <= 12)) tile = rb / (int)sizeof(T);
+        }
         size_t stage_bytes = (size_t)nr * tile * sizeof(T);
         int nstage = (int)(budget / stage_bytes);
         if (const char* e = getenv("OPKB_DIR_NSTAGE")) nstage = atoi(e);
@@ -702,9 +705,18 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
             B.nstage = nstage;
             B.n = ws->n;
             const size_t smem = stage_bytes * nstage;
-            auto kern = (fuse == OPKB_OBJ_ROSENBROCK)  ? k_direction2<T, OPKB_OBJ_ROSENBROCK>
-                        : (fuse == OPKB_OBJ_QUADRATIC) ? k_direction2<T, OPKB_OBJ_QUADRATIC>
-                                                       : k_direction2<T, 0>;
+            // (MB, TILE) instances: 4 KB rows with up to 8 / 12 pairs, 2 KB rows with up to 12 / 20
+            constexpr int TB = 4096 / (int)sizeof(T), TS = 2048 / (int)sizeof(T);
+            void (*kern)(Dir2Args<T>, ReduceScratch) = NULL;
+#define DIR2_PICK(F)                                                                 \
+    do {                                                                             \
+        if (tile == TB) kern = (A.m <= 8) ? k_direction2<T, F, 8, TB> : k_direction2<T, F, 12, TB>;   \
+        else kern = (A.m <= 12) ? k_direction2<T, F, 12, TS> : k_direction2<T, F, 20, TS>;            \
+    } while (0)
+            if (fuse == OPKB_OBJ_ROSENBROCK) DIR2_PICK(OPKB_OBJ_ROSENBROCK);
+            else if (fuse == OPKB_OBJ_QUADRATIC) DIR2_PICK(OPKB_OBJ_QUADRATIC);
+            else DIR2_PICK(0);
+#undef DIR2_PICK
             OPKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int64_t grid = ctx->sm_count;
             if (grid > ntiles) grid = ntiles;
