@@ -401,3 +401,78 @@ def test_large_memory_and_tiny_problems(opk, oracle, dtype, driver):
         assert abs(s.f - ro["f"]) <= 100 * rtol_case * abs(ro["f"]) + 1e-20, (kind, n, kw, s.f, ro["f"])
         assert relerr(s.result(), xo) <= 100 * rtol_case + 1e-300, (kind, n, kw)
         s.close()
+
+
+def _free_gib():
+    import torch
+    free, total = torch.cuda.mem_get_info()
+    return free / 2 ** 30
+
+
+@pytest.mark.parametrize("dtype,log2n,mem", [(np.float64, 28, 10), (np.float32, 28, 7)])
+def test_full_size_properties(opk, dtype, log2n, mem):
+    """BASELINE.json's full per-GPU sizes (C4: n = 2^28 Float64 m = 10; the C5 shard:
+    n = 2^28 Float32 m = 7), where the oracle is not run: size-independent properties --
+    feasibility of every iterate, monotone decrease (Armijo), bit reproducibility,
+    agreement of the fused path with the one-kernel-per-call path, and of the
+    native driver with the Python driver."""
+    n = 1 << log2n
+    need = (2 * mem + 12) * n * np.dtype(dtype).itemsize / 2 ** 30
+    if _free_gib() < need + 4:
+        pytest.skip("needs %.0f GiB of free device memory" % need)
+    ctx = opk.default_context()
+    obj = opk.Quadratic.synthetic_device(ctx, n, dtype, kappa=1e4)
+    lo = ctx.vector(n, dtype).fill(0.0)
+    hi = ctx.vector(n, dtype).fill(1.0)
+    x0 = ctx.vector(n, dtype).fill(0.5)
+    kw = dict(lower=lo, upper=hi, mem=mem, maxiter=12, xtol=(0, 0), ftol=(0, 0), gtol=(0, 0))
+    runs = {}
+    for name, cls, extra in (("fused", opk.VMLMB, {}), ("fused2", opk.VMLMB, {}),
+                             ("native", opk.NativeVMLMB, {}), ("primitive", opk.VMLMB, dict(mode="primitive"))):
+        fs = []
+        s = cls(obj, opk.vcopy(x0), observer=lambda s: fs.append((s.iter, s.eval, s.f, s.gnorm)), **kw, **extra)
+        s.solve()
+        x = s.x
+        assert opk.vnorminf(x) <= 1.0                                       # x <= hi
+        neg = opk.project_variables_(x.similar(), x, None, 0.0)             # min(x, 0)
+        assert opk.vnorminf(neg) == 0.0                                     # x >= lo
+        assert all(b[2] < a[2] for a, b in zip(fs, fs[1:]))                 # monotone (Armijo)
+        assert (s.iter, s.stage) == (12, 4)
+        runs[name] = fs
+        s.close()
+        del s, x, neg
+    assert runs["fused"] == runs["fused2"]                                  # bit reproducible
+    assert runs["native"][-1] == runs["fused"][-1]                          # same numbers, native loop
+    rtol = 1e-9 if dtype == np.float64 else 1e-3
+    for a, b in zip(runs["fused"], runs["primitive"]):
+        assert a[:2] == b[:2] and abs(a[2] - b[2]) <= rtol * abs(b[2]) and abs(a[3] - b[3]) <= rtol * abs(b[3])
+
+
+def test_full_size_spg(opk):
+    """C3: SPG on the box-constrained quadratic, n = 10^8 Float32: feasibility, the
+    nonmonotone Armijo condition (f <= max of the last m values), reproducibility,
+    fused == one-kernel-per-call."""
+    n, dtype, m = 10 ** 8, np.float32, 10
+    if _free_gib() < 12:
+        pytest.skip("needs 12 GiB of free device memory")
+    ctx = opk.default_context()
+    obj = opk.Quadratic.synthetic_device(ctx, n, dtype, kappa=1e3)
+    lo = ctx.vector(n, dtype).fill(0.0)
+    hi = ctx.vector(n, dtype).fill(1.0)
+    x0 = ctx.vector(n, dtype).fill(0.5)
+    runs = {}
+    for name, mode in (("fused", "fused"), ("fused2", "fused"), ("primitive", "primitive")):
+        fs = []
+        s = opk.SPG(obj, opk.BoxProjection(lo, hi), opk.vcopy(x0), m, maxit=15, eps1=0, eps2=0, mode=mode,
+                    observer=lambda s: fs.append((s.iter, s.fcnt, s.f, s.pgtwon, s.pginfn)))
+        s.solve()
+        x = s.solution()
+        assert opk.vnorminf(x) <= 1.0
+        assert opk.vnorminf(opk.project_variables_(x.similar(), x, None, 0.0)) == 0.0
+        for k in range(1, len(fs)):
+            assert fs[k][2] <= max(f[2] for f in fs[max(0, k - m):k])
+        runs[name] = fs
+        s.close()
+    assert runs["fused"] == runs["fused2"]
+    for a, b in zip(runs["fused"], runs["primitive"]):
+        assert a[:2] == b[:2] and abs(a[2] - b[2]) <= 1e-4 * abs(b[2])
