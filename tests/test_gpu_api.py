@@ -1,0 +1,102 @@
+"""API-surface behaviour of the host twin on the GPU: in-place variants, printing
+(`verb`, `printer`, `output`), BoundedSet, status objects -- the keyword contract
+of src/quasinewton.jl:226-242 and src/spg.jl:168-178."""
+import io
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def opk():
+    import opkb200
+    return opkb200
+
+
+def test_inplace_and_copy_semantics(opk):
+    ctx = opk.default_context()
+    x0 = opk.Rosenbrock.x0(20)
+    # vmlmb leaves x0 unchanged (src/quasinewton.jl:215); vmlmb! overwrites (:226)
+    x = opk.vmlmb(opk.Rosenbrock(), x0)
+    assert x is not x0 and x0[0] == -1.2 and np.abs(x - 1).max() < 1e-3
+    y = x0.copy()
+    out = opk.vmlmb_(opk.Rosenbrock(), y)
+    assert out is y and np.array_equal(y, x)
+    v = ctx.from_numpy(x0)
+    w = opk.vmlmb(opk.Rosenbrock(), v)
+    assert isinstance(w, opk.Vector) and w is not v and np.array_equal(v.download(), x0)
+    assert np.array_equal(w.download(), x)
+    out = opk.vmlmb_(opk.Rosenbrock(), v, mode="primitive")
+    assert out is v and np.abs(v.download() - 1).max() < 1e-3
+    # Float32 in, Float32 out; integers are promoted to Float64
+    assert opk.vmlmb(opk.Rosenbrock(), x0.astype(np.float32)).dtype == np.float32
+    assert opk.vmlmb(opk.Quadratic(np.ones(4), np.full(4, 2.0)), np.zeros(4, dtype=np.int64)).dtype == np.float64
+    # spg / spg!
+    z = opk.spg(opk.Rosenbrock(), opk.BoxProjection(0.0, math.inf), x0, 10)
+    assert x0[0] == -1.2 and np.abs(z - 1).max() < 1e-3
+    y = x0.copy()
+    assert opk.spg_(opk.Rosenbrock(), opk.BoxProjection(0.0, math.inf), y, 10) is y and np.array_equal(y, z)
+
+
+def test_printing_and_reasons(opk):
+    x0 = opk.Rosenbrock.x0(20)
+    buf = io.StringIO()
+    opk.vmlmb(opk.Rosenbrock(), x0, verb=10, output=buf)
+    lines = buf.getvalue().splitlines()
+    # header (2 lines) + iterations 0, 10, 20, 30 + the final iterate + the reason line
+    assert lines[0].startswith("# ITER   EVAL   REJECTS") and lines[1].startswith("#-----")
+    its = [int(l.split()[0]) for l in lines[2:-1]]
+    assert its[:4] == [0, 10, 20, 30] and lines[-1] == "# CONVERGENCE: gradient norm sufficiently small"
+    seen = []
+    opk.vmlmb(opk.Rosenbrock(), x0, verb=1, maxiter=3, output=io.StringIO(),
+              printer=lambda out, it, ev, rej, f, gn, stp: seen.append((it, ev)))
+    assert [s[0] for s in seen] == [0, 1, 2, 3]
+    buf = io.StringIO()
+    ws = opk.Info()
+    opk.spg(opk.Rosenbrock(), opk.BoxProjection(0.0, math.inf), x0, 10, verb=20, io=buf, ws=ws)
+    out = buf.getvalue().splitlines()
+    assert out[0].startswith("#  ITER   EVAL   PROJ") and out[-1].startswith("# SUCCESS: Convergence with projected")
+    assert ws.status == opk.INFNORM_CONVERGENCE and ws.f == ws.fbest
+    assert opk.getreason(ws) == "Convergence with projected gradient infinite-norm"
+
+
+def test_boundedset_and_bound_kinds(opk):
+    n = 1000
+    a, c = opk.Quadratic.synthetic(n, kappa=100.0)
+    want = np.clip(c, 0.2, 0.8)
+    kw = dict(mem=5, ftol=(0, 0), xtol=(0, 0), gtol=(0, 1e-10), maxiter=300)
+    ctx = opk.default_context()
+    lo_a, hi_a = np.full(n, 0.2), np.full(n, 0.8)
+    for lower, upper in ((0.2, 0.8), (lo_a, 0.8), (0.2, hi_a), (lo_a, hi_a),
+                         (ctx.from_numpy(lo_a), ctx.from_numpy(hi_a)), (opk.BoundedSet(0.2, hi_a), None)):
+        if upper is None:
+            x = opk.vmlmb(opk.Quadratic(a, c), np.full(n, 0.5), lower=lower, **kw)
+        else:
+            x = opk.vmlmb(opk.Quadratic(a, c), np.full(n, 0.5), lower=lower, upper=upper, **kw)
+        assert np.abs(x - want).max() < 1e-7
+    x = opk.vmlmb(opk.Quadratic(a, c), np.full(n, 0.5), lower=0.2, **kw)            # one-sided
+    assert np.abs(x - np.maximum(c, 0.2)).max() < 1e-7
+    x = opk.vmlmb(opk.Quadratic(a, c), np.full(n, 0.5), upper=hi_a, blmvm=True, **kw)
+    assert np.abs(x - np.minimum(c, 0.8)).max() < 1e-7
+    with pytest.raises(TypeError):
+        opk.vmlmb(opk.Quadratic(a, c), np.full(n, 0.5), lower=np.zeros(n - 1))     # "invalid lower bound type"
+    with pytest.raises(NotImplementedError):
+        opk.vmlmb(lambda x: 0.0, np.zeros(4), autodiff=True)
+
+
+def test_context_and_profile(opk):
+    ctx = opk.default_context()
+    assert ctx.sm_count == 148 and ctx.nranks == 1 and ctx.rank == 0 and ctx.device >= 0
+    n0 = ctx.launch_count
+    v = ctx.vector(1000).fill(2.0)
+    ctx.profile(True)
+    assert opk.vdot(v, v) == 4000.0 and opk.vnorm2(v) == math.sqrt(4000.0)
+    rep = ctx.profile_report()
+    ctx.profile(False)
+    assert rep["reduce"][1] == 2 and ctx.launch_count == n0 + 3
+    ctx.timer_start()
+    opk.vscale_(v, 0.5)
+    assert ctx.timer_stop() >= 0.0 and v.download()[0] == 1.0
