@@ -217,6 +217,21 @@ int opkb_vmlmb_direction_trial(opkb_vmlmb* ws, int m, const int* slots, const do
                                const double* c, double gamma, int mark_next, double out[4],
                                double trial[8]);
 int opkb_vmlmb_discard_trial(opkb_vmlmb* ws, int mark_next);
+/* Incremental Gram.  When opkb_vmlmb_direction_trial follows opkb_vmlmb_gram for
+ * the same pairs (m <= 12), the fused kernel also writes the pair the trial
+ * point would form, (x - x', g - g') (:512-513), to two spare buffers and reduces
+ * every inner product of the NEXT Gram block that involves it or the new v0;
+ * the products between old pairs are the previous block plus signed corrections
+ * over the variables that enter or leave the free set.  If the caller then takes
+ * the speculated point and calls opkb_vmlmb_gram for the foreseen pairs, the
+ * block is assembled on the host and the spare buffers are swapped in: no kernel
+ * launch, S and Y cross HBM once per iteration instead of twice.  Any other use
+ * of the workspace falls back to the sweep.  Same values up to the summation
+ * order.  OPKB_CARRY=0 in the environment disables it.  carry_stats: how many
+ * opkb_vmlmb_gram calls were served that way / fell back although armed. */
+int opkb_vmlmb_carry_stats(const opkb_vmlmb* ws, int64_t* hits, int64_t* misses);
+/* the Gram block the last opkb_vmlmb_gram call returned (*m = 0: none), for checks */
+int opkb_vmlmb_last_gram(const opkb_vmlmb* ws, int* m, int* slots, double* G);
 /* Sequential two-loop recursion, fused step by step (parity-grade: the
  * intermediate vector is rounded in the element type after every vupdate!, as
  * the reference does).  v is the workspace vector d.

@@ -14,7 +14,9 @@
 #pragma once
 
 #define DIR2_MAXSTAGE 8
-#define DIR2_THREADS 288   // 8 consumer warps + 1 producer warp
+// 8 consumer warps + 1 producer warp; the CARRY instances run 7 + 1 (two warps per
+// SM sub-partition: up to 255 registers per thread for the extra accumulators)
+#define DIR2_NTHREADS(CARRY) ((CARRY) ? 256 : 288)
 
 template <typename T> struct Dir2Args {
     const T* rows[2 * OPKB_MEM_MAX + 8];  // v0 | -, x, g, [lo], [hi], [ysrc], then (y_j, s_j) oldest..newest
@@ -39,17 +41,46 @@ template <typename T> struct Dir2Args {
     T* xout;
     T* gout;
     T* pout;                              // NULL for L-BFGS
+    // CARRY: the pair (s', y') = (x - x', g - g') that this trial point would
+    // form (src/quasinewton.jl:512-513) goes to two spare buffers, and every inner
+    // product the next two-loop recursion needs that involves it or the new v0
+    // is reduced in the same pass (see "incremental Gram" below)
+    T* sout;
+    T* yout;
 };
 
 // FUSE: 0 direction only; OPKB_OBJ_ROSENBROCK / OPKB_OBJ_QUADRATIC: + speculative trial.
 // MB >= m (unrolled pair loops, coefficients as constant-bank operands), TILE =
 // elements per staged row (compile time: every shared read is `LDS [base + imm]`).
-template <typename T, int FUSE, int MB, int TILE>
-__global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, ReduceScratch rs)
+//
+// CARRY (with FUSE): incremental Gram.  If the host accepts the speculative trial
+// point, the next iteration's Gram block (opkb_gram2.cuh) is known without another
+// sweep over the pairs: with F' = {p' != 0} the new free set (everything for L-BFGS)
+//   * s_j.v0', y_j.v0', s_j.y', y_j.y' on F' for every stored pair j, and the four
+//     products of the new pair, are "dense" sums accumulated here (4m+4 numbers)
+//     while the rows of S, Y sit in shared memory;
+//   * s_a.y_b, y_a.y_b (b >= a) between OLD pairs only change where the free set
+//     changes: the previous Gram block plus the signed products over the elements
+//     that enter or leave the free set ("corrections", m(m+1) numbers).  Each
+//     consumer warp walks its changed elements in a fixed order (ballot), lane r
+//     fetches row r of that element and lane l owns the entries l, l+32, ...
+// The host assembles the block in opkb_vmlmb_gram (no kernel launch at all).
+template <int MB> struct Dir2Carry {
+    static constexpr int ND = 4 * MB + 4;           // dense sums
+    static constexpr int NENT = MB * (MB + 1);      // corrections: SY(a<=b) then YY(a<=b)
+    static constexpr int CPL = (NENT + 31) / 32;    // correction entries per lane
+};
+
+template <typename T, int FUSE, int MB, int TILE, int CARRY>
+__global__ void __launch_bounds__(DIR2_NTHREADS(CARRY), 1) k_direction2(Dir2Args<T> A, ReduceScratch rs)
 {
+    constexpr int DIR2_THREADS = DIR2_NTHREADS(CARRY);
+    static_assert(!CARRY || (FUSE != 0 && 2 * MB <= 32), "CARRY needs the fused trial and 2*MB <= 32 rows");
     constexpr int VEC = VecOf<T>::N;
     constexpr int CWARPS = DIR2_THREADS / 32 - 1;
     constexpr int CTHREADS = CWARPS * 32;
+    static_assert(TILE <= CTHREADS * VEC && TILE % (32 * VEC) == 0,
+                  "one element pack per thread and tile, whole warps");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[DIR2_MAXSTAGE];
     __shared__ __align__(8) uint64_t empty_bar[DIR2_MAXSTAGE];
@@ -78,6 +109,41 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
     double acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+
+    // CARRY: cd[4j..4j+3] = s_j.v0', y_j.v0', s_j.y', y_j.y' (y' restricted to F');
+    // cd[4MB..] = s'.v0', y'.v0', s'.y', y'.y'; cq[t] = correction entry lane + 32 t
+    typedef Dir2Carry<MB> CY;
+    constexpr int ND = CARRY ? CY::ND : 1;
+    constexpr int CPL = CARRY ? CY::CPL : 1;
+    double cd[ND];
+    double cq[CPL];
+    int cl[CPL];   // source lanes (= pair rows) of the two factors of entry lane + 32 t: a | b << 8
+#pragma unroll
+    for (int i = 0; i < ND; ++i) cd[i] = 0.0;
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) {
+        cq[t] = 0.0;
+        cl[t] = 0;
+    }
+    if (CARRY) {
+        // entry idx: first the MB(MB+1)/2 products s_a.y_b (a <= b), then y_a.y_b (a <= b);
+        // stage rows of pair j: y_j at prow + 2j, s_j at prow + 2j + 1
+#pragma unroll
+        for (int t = 0; t < CPL; ++t) {
+            int idx = lane + 32 * t;
+            const int half = MB * (MB + 1) / 2;
+            const bool yy = idx >= half;
+            if (yy) idx -= half;
+            int a = 0;
+            while (a < MB && idx >= MB - a) {
+                idx -= MB - a;
+                ++a;
+            }
+            const int b = a + idx;
+            if (a < MB && b < MB) cl[t] = (yy ? 2 * a : 2 * a + 1) | ((2 * b) << 8);
+            else cl[t] = 31 | (31 << 8);   // no such entry (the host ignores the slot)
+        }
+    }
 
     if (warp == CWARPS) {
         int it = 0;
@@ -119,8 +185,15 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
                 }
                 named_bar_sync(1, CTHREADS);
             }
-            for (int e = tid * VEC; e < TILE; e += CTHREADS * VEC) {
-                if (partial && base + e >= A.n) break;
+            // One pack per thread and tile; the warps beyond the tile idle.  The zero
+            // padding of a partial tile runs through the arithmetic (it yields d = 0
+            // and contributes nothing) so that whole warps stay converged; every
+            // reduction of the trial point and every store is guarded per element.
+            const int e = tid * VEC;
+            if (e < TILE) {
+                bool ok[VEC];
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) ok[q] = !partial || (base + e + q < A.n);
                 Pack<T> px = ld_pack<T>(st + TILE, e / VEC);
                 Pack<T> pg = ld_pack<T>(st + 2 * TILE, e / VEC);
                 Pack<T> pl = (A.r_lo >= 0) ? ld_pack<T>(st + A.r_lo * TILE, e / VEC) : splat_pack<T>(A.lo_val);
@@ -140,12 +213,12 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
                 bool upd[VEC];
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) upd[q] = !A.masked || (pv.v[q] != T(0));
+                const T* pb = st + prow * TILE + e;
                 // apply_lbfgs! :716-745 / :747-779, rounding sequence of the reference
                 if (all_used) {
                     // every pair takes part (the usual case): unrolled and branch-free.  The
                     // chain also runs on the masked elements, whose result is then replaced
                     // by what the reference gives them, gamma*v0 (they are never updated).
-                    const T* pb = st + prow * TILE + e;
 #pragma unroll
                     for (int jj = 0; jj < MB; ++jj) {
                         const int j = MB - 1 - jj;
@@ -219,7 +292,7 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
 #pragma unroll
                         for (int q = 0; q < VEC; q += 2) {
                             gt.v[q] = gt.v[q + 1] = T(0);
-                            if (!partial || base + e + q < A.n)   // zero padding is not a variable
+                            if (ok[q])   // zero padding is not a variable
                                 rosenbrock_pair(xt.v[q], xt.v[q + 1], gt.v[q], gt.v[q + 1], acc[4], acc[5]);
                         }
                     } else {
@@ -229,17 +302,87 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
                     }
 #pragma unroll
                     for (int q = 0; q < VEC; ++q) {
-                        if (partial && base + e + q >= A.n) break;
                         const T xi = xt.v[q], gi = gt.v[q];
                         const T pi = A.bounded ? projdir(xi, pl.v[q], ph_.v[q], A.has_lo, A.has_hi, -1, gi) : gi;
                         pt.v[q] = pi;
-                        const T si = xi - px.v[q];              // s = x' - x0 (:427)
-                        acc[6] = dacc(pi, pi, acc[6]);          // |p'|^2 (:399)
-                        acc[7] = dacc(gi, si, acc[7]);          // g'.s (:432)
-                        acc[8] = dacc(gi, v.v[q], acc[8]);      // g'.d (:434)
-                        acc[9] = dacc(xi, xi, acc[9]);          // |x'|^2 (:446)
-                        acc[10] = dacc(si, si, acc[10]);        // |s|^2 (:448)
-                        acc[11] += (pi != T(0)) ? 1.0 : 0.0;
+                        if (ok[q]) {
+                            const T si = xi - px.v[q];              // s = x' - x0 (:427)
+                            acc[6] = dacc(pi, pi, acc[6]);          // |p'|^2 (:399)
+                            acc[7] = dacc(gi, si, acc[7]);          // g'.s (:432)
+                            acc[8] = dacc(gi, v.v[q], acc[8]);      // g'.d (:434)
+                            acc[9] = dacc(xi, xi, acc[9]);          // |x'|^2 (:446)
+                            acc[10] = dacc(si, si, acc[10]);        // |s|^2 (:448)
+                            acc[11] += (pi != T(0)) ? 1.0 : 0.0;
+                        }
+                    }
+                }
+                Pack<T> sn, yn;
+                if (CARRY) {
+                    // the pair this trial point would form: S[mark'] - x', Y[mark'] - g' (:512-513)
+                    T v0n[VEC], ynm[VEC];
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        sn.v[q] = px.v[q] - xt.v[q];
+                        yn.v[q] = pg.v[q] - gt.v[q];
+                        const bool frn = !A.masked || (pt.v[q] != T(0));
+                        v0n[q] = ok[q] ? pt.v[q] : T(0);                 // v0' = p' (g' for L-BFGS)
+                        ynm[q] = (ok[q] && frn) ? yn.v[q] : T(0);        // y' on the new free set
+                    }
+                    // exact products accumulated in Float64 whatever T (as every reduction
+                    // of the library; for Float32 each operand is widened once per element)
+                    double v0d[VEC], ynd[VEC];
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        v0d[q] = (double)v0n[q];
+                        ynd[q] = (double)ynm[q];
+                    }
+#pragma unroll
+                    for (int j = 0; j < MB; ++j) {
+                        if (j < m) {
+                            const Pack<T> y = ld_pack<T>(pb + 2 * j * TILE, 0);
+                            const Pack<T> sv = ld_pack<T>(pb + (2 * j + 1) * TILE, 0);
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) {
+                                const double sd = (double)sv.v[q], yd = (double)y.v[q];
+                                cd[4 * j + 0] = fma(sd, v0d[q], cd[4 * j + 0]);
+                                cd[4 * j + 1] = fma(yd, v0d[q], cd[4 * j + 1]);
+                                cd[4 * j + 2] = fma(sd, ynd[q], cd[4 * j + 2]);
+                                cd[4 * j + 3] = fma(yd, ynd[q], cd[4 * j + 3]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        const double sd = (double)sn.v[q], yd = (double)yn.v[q];
+                        cd[4 * MB + 0] = fma(sd, v0d[q], cd[4 * MB + 0]);
+                        cd[4 * MB + 1] = fma(yd, v0d[q], cd[4 * MB + 1]);
+                        cd[4 * MB + 2] = fma(sd, ynd[q], cd[4 * MB + 2]);
+                        cd[4 * MB + 3] = fma(yd, ynd[q], cd[4 * MB + 3]);
+                    }
+                    if (A.masked) {
+                        // elements that enter (+) or leave (-) the free set: signed products
+                        // between the stored pairs, one element at a time, whole warp
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) {
+                            const bool nf = (pt.v[q] != T(0));
+                            const bool chg = ok[q] && (nf != (pv.v[q] != T(0)));
+                            unsigned bal = __ballot_sync(0xffffffffu, chg);
+                            const unsigned nfb = __ballot_sync(0xffffffffu, nf);
+                            while (bal) {
+                                const int src = __ffs(bal) - 1;
+                                bal &= bal - 1;
+                                const int ec = (e - lane * VEC) + src * VEC + q;
+                                double val = 0.0;
+                                if (lane < 2 * m) val = (double)st[(prow + lane) * TILE + ec];
+                                const double sg = ((nfb >> src) & 1u) ? 1.0 : -1.0;
+#pragma unroll
+                                for (int t = 0; t < CPL; ++t) {
+                                    const double fa = __shfl_sync(0xffffffffu, val, cl[t] & 0xff);
+                                    const double fb = __shfl_sync(0xffffffffu, val, cl[t] >> 8);
+                                    cq[t] = fma(sg * fa, fb, cq[t]);
+                                }
+                            }
+                        }
                     }
                 }
                 if (!partial || base + e + VEC <= A.n) {
@@ -249,6 +392,10 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
                         st_pack<T>(A.xout, iv, xt);
                         st_pack<T>(A.gout, iv, gt);
                         if (A.pout) st_pack<T>(A.pout, iv, pt);
+                    }
+                    if (CARRY) {
+                        st_pack<T>(A.sout, iv, sn);
+                        st_pack<T>(A.yout, iv, yn);
                     }
                     if (A.Snext) {                      // (the workspace path aliases instead)
                         st_pack<T>(A.Snext, iv, px);    // vcopy!(S[mark], x) :562
@@ -261,6 +408,10 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
                             A.xout[base + e + q] = xt.v[q];
                             A.gout[base + e + q] = gt.v[q];
                             if (A.pout) A.pout[base + e + q] = pt.v[q];
+                        }
+                        if (CARRY) {
+                            A.sout[base + e + q] = sn.v[q];
+                            A.yout[base + e + q] = yn.v[q];
                         }
                         if (A.Snext) {
                             A.Snext[base + e + q] = px.v[q];
@@ -277,5 +428,81 @@ __global__ void __launch_bounds__(DIR2_THREADS, 1) k_direction2(Dir2Args<T> A, R
     acc[2] = (double)smin;
     acc[3] = (double)smax;
     __syncthreads();
-    block_reduce_publish<NACC, 8u, 4u>(acc, rs);  // slot 2: min, slot 3: max
+    if constexpr (!CARRY) {
+        block_reduce_publish<NACC, 8u, 4u>(acc, rs);  // slot 2: min, slot 3: max
+    } else {
+        // NACC + ND sums over all threads (slot 2: min, slot 3: max) and 32*CPL per-lane
+        // entries summed over the warps; the drained ring is the scratch.  Fixed order
+        // everywhere: butterfly, warps 0.., CTAs 0.. (last CTA by ticket).
+        constexpr int NT = NACC + ND;
+        constexpr int NTOT = NT + 32 * CPL;
+        constexpr int NWARPS = DIR2_THREADS / 32;
+        double* red = reinterpret_cast<double*>(smem_raw);   // [NWARPS][NTOT]
+        __shared__ unsigned int s_last2;
+#pragma unroll
+        for (int k = 0; k < NT; ++k) {
+            const int kind = (k == 2) ? OPKB_RMIN : ((k == 3) ? OPKB_RMAX : OPKB_RSUM);
+            double a = (k < NACC) ? acc[k < NACC ? k : 0] : cd[k >= NACC ? k - NACC : 0];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double b = __shfl_xor_sync(0xffffffffu, a, off);
+                a = rcombine_dyn(kind, a, b);
+            }
+            if (lane == 0) red[warp * NTOT + k] = a;
+        }
+#pragma unroll
+        for (int t = 0; t < CPL; ++t) red[warp * NTOT + NT + 32 * t + lane] = cq[t];
+        __syncthreads();
+        for (int k = tid; k < NTOT; k += DIR2_THREADS) {
+            const int kind = (k == 2) ? OPKB_RMIN : ((k == 3) ? OPKB_RMAX : OPKB_RSUM);
+            double a = red[k];
+            for (int w = 1; w < NWARPS; ++w) a = rcombine_dyn(kind, a, red[w * NTOT + k]);
+            rs.part[(size_t)blockIdx.x * NTOT + k] = a;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int t = atomicAdd(rs.ticket, 1u);
+            s_last2 = (t == gridDim.x - 1) ? 1u : 0u;
+        }
+        __syncthreads();
+        if (!s_last2) return;
+        __threadfence();
+        for (int k = tid; k < NTOT; k += DIR2_THREADS) {
+            const int kind = (k == 2) ? OPKB_RMIN : ((k == 3) ? OPKB_RMAX : OPKB_RSUM);
+            double a = __ldcg(&rs.part[k]);
+            for (unsigned b = 1; b < gridDim.x; ++b)
+                a = rcombine_dyn(kind, a, __ldcg(&rs.part[(size_t)b * NTOT + k]));
+            rs.res[k] = a;
+        }
+        if (tid == 0) *rs.ticket = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Launchers (instantiated in opkb_direction2_plain.cu / opkb_direction2_carry.cu so
+// that the translation units build in parallel).  `fuse`: 0 | OPKB_OBJ_ROSENBROCK |
+// OPKB_OBJ_QUADRATIC; (mb, tile) must be one of the instances listed there.
+#define DIR2_CARRY_ROWB 3584   // bytes per staged row of the CARRY instances (7 consumer warps x 512 B)
+template <typename T>
+int dir2_launch_plain(opkb_context* ctx, const Dir2Args<T>& B, int fuse, int mb, size_t smem, int grid);
+template <typename T>
+int dir2_launch_carry(opkb_context* ctx, const Dir2Args<T>& B, int fuse, int mb, size_t smem, int grid);
+
+template <typename T>
+static int dir2_do_launch(opkb_context* ctx, void (*kern)(Dir2Args<T>, ReduceScratch), const Dir2Args<T>& B,
+                          int threads, size_t smem, int grid)
+{
+    if (!kern) return opkb_set_error(OPKB_EINVAL, "no direction kernel instance for this shape");
+    OPKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ReduceScratch rs;
+    rs.part = ctx->d_part;
+    rs.ticket = ctx->d_ticket;
+    rs.res = ctx->d_res;
+    opkb_prof_begin(ctx, OPKB_K_DIRECTION);
+    kern<<<grid, threads, smem, ctx->stream>>>(B, rs);
+    opkb_prof_end(ctx);
+    ctx->launches += 1;
+    OPKB_CUDA(cudaGetLastError());
+    return 0;
 }

@@ -1,0 +1,26 @@
+// opkb_direction2_carry.cu -- instances of k_direction2 with the incremental Gram
+// (direction + speculative first trial + the next Gram block, see opkb_direction2.cuh).
+#include "opkb_internal.cuh"
+#include "opkb_direction2.cuh"
+
+template <typename T>
+int dir2_launch_carry(opkb_context* ctx, const Dir2Args<T>& B, int fuse, int mb, size_t smem, int grid)
+{
+    constexpr int TC = DIR2_CARRY_ROWB / (int)sizeof(T);
+    void (*kern)(Dir2Args<T>, ReduceScratch) = NULL;
+    if (B.tile != TC) return opkb_set_error(OPKB_EINVAL, "carry instances use %d-byte rows", DIR2_CARRY_ROWB);
+#define DIR2_PICK(F)                                                \
+    do {                                                            \
+        if (mb == 5) kern = k_direction2<T, F, 5, TC, 1>;           \
+        else if (mb == 8) kern = k_direction2<T, F, 8, TC, 1>;      \
+        else if (mb == 10) kern = k_direction2<T, F, 10, TC, 1>;    \
+        else if (mb == 12) kern = k_direction2<T, F, 12, TC, 1>;    \
+    } while (0)
+    if (fuse == OPKB_OBJ_ROSENBROCK) DIR2_PICK(OPKB_OBJ_ROSENBROCK);
+    else if (fuse == OPKB_OBJ_QUADRATIC) DIR2_PICK(OPKB_OBJ_QUADRATIC);
+#undef DIR2_PICK
+    return dir2_do_launch<T>(ctx, kern, B, DIR2_NTHREADS(1), smem, grid);
+}
+
+template int dir2_launch_carry<double>(opkb_context*, const Dir2Args<double>&, int, int, size_t, int);
+template int dir2_launch_carry<float>(opkb_context*, const Dir2Args<float>&, int, int, size_t, int);

@@ -35,6 +35,21 @@ struct opkb_vmlmb_ {
     void* spare_x;
     void* spare_y;
     int aliased_slot;      // -1: no aliasing active
+    // Incremental Gram (opkb_direction2.cuh, CARRY).  `Gc` is the Gram block the last
+    // opkb_vmlmb_gram call returned (for the pairs Gc_slots, oldest first).  After a
+    // fused direction + trial launch, `carry_*` hold what that launch reduced for the
+    // iteration the trial point would start; any other write to x, g, p or a pair
+    // invalidates them.  carry_s / carry_y: two spare n-vectors that receive the new pair.
+    double Gc[2 * OPKB_MEM_MAX * (OPKB_MEM_MAX + 1)];
+    int Gc_m, Gc_valid;
+    int Gc_slots[OPKB_MEM_MAX];
+    opkb_vector* carry_s;
+    opkb_vector* carry_y;
+    int carry_valid, carry_m, carry_mb, carry_mark, carry_off;   // carry_m: pairs of the launch
+    int carry_slots[OPKB_MEM_MAX];
+    double carry_dense[4 * OPKB_MEM_MAX + 4];
+    double carry_corr[OPKB_MEM_MAX * (OPKB_MEM_MAX + 1)];
+    int64_t carry_hits, carry_misses;
 };
 
 // x (and g|p) get their own buffers back before they are written again
@@ -139,6 +154,8 @@ extern "C" int opkb_vmlmb_destroy(opkb_vmlmb* ws)
     opkb_vector_destroy(ws->g);
     opkb_vector_destroy(ws->p);
     opkb_vector_destroy(ws->d);
+    opkb_vector_destroy(ws->carry_s);
+    opkb_vector_destroy(ws->carry_y);
     for (int k = 0; k < OPKB_MEM_MAX; ++k) {
         opkb_vector_destroy(ws->S[k]);
         opkb_vector_destroy(ws->Y[k]);
@@ -329,6 +346,7 @@ template <typename T>
 static int trial_launch(opkb_vmlmb* ws, int mark, double stp, int initial, int stage)
 {
     opkb_context* ctx = ws->ctx;
+    ws->carry_valid = 0;                 // another point than the speculated one
     if (stage != 2) vmlmb_unalias(ws);   // x, g|p are about to be overwritten
     TrialArgs<T> A;
     A.x0 = (const T*)ws->S[mark]->data;
@@ -419,6 +437,52 @@ extern "C" int opkb_vmlmb_trial_end(opkb_vmlmb* ws, int mark, double f, int init
 #include "opkb_direction2.cuh"
 #include <stdlib.h>
 
+// The Gram block of the pairs `slots` (the newest one still to be formed from the
+// accepted trial point) assembled from the previous block and what the fused
+// direction + trial launch reduced (Dir2Carry): no kernel, no HBM traffic.
+static int gram_from_carry(opkb_vmlmb* ws, int mark, int m, const int* slots, double* G)
+{
+    const int mo = ws->carry_m;                 // pairs the launch worked on
+    const int drop = (mo == ws->mem) ? 1 : 0;   // the oldest pair was recycled for the trial point
+    const int MB = ws->carry_mb;
+    const int W = m + 1, Wo = mo + 1;
+    const int half = MB * (MB + 1) / 2;
+    // index of entry (a <= b) inside one triangular half (Dir2Carry enumeration)
+    auto tri = [MB](int a, int b) { return a * MB - a * (a - 1) / 2 + (b - a); };
+    for (int i = 0; i < 2 * m * W; ++i) G[i] = 0.0;
+    const double* D = ws->carry_dense;
+    const double* Cq = ws->carry_corr;
+    const double* Go = ws->Gc;
+    const int nn = m - 1;
+    for (int a2 = 0; a2 < nn; ++a2) {
+        const int a = a2 + drop;
+        G[(2 * a2) * W] = D[4 * a + 0];             // s_a . v0'
+        G[(2 * a2 + 1) * W] = D[4 * a + 1];         // y_a . v0'
+        for (int b2 = a2; b2 < nn; ++b2) {
+            const int b = b2 + drop;
+            G[(2 * a2) * W + 1 + b2] = Go[(2 * a) * Wo + 1 + b] + Cq[tri(a, b)];
+            G[(2 * a2 + 1) * W + 1 + b2] = Go[(2 * a + 1) * Wo + 1 + b] + Cq[half + tri(a, b)];
+        }
+        G[(2 * a2) * W + 1 + nn] = D[4 * a + 2];    // s_a . y'
+        G[(2 * a2 + 1) * W + 1 + nn] = D[4 * a + 3];
+    }
+    G[(2 * nn) * W] = D[4 * MB + 0];
+    G[(2 * nn + 1) * W] = D[4 * MB + 1];
+    G[(2 * nn) * W + 1 + nn] = D[4 * MB + 2];
+    G[(2 * nn + 1) * W + 1 + nn] = D[4 * MB + 3];
+    // the pair itself was written to the spare buffers: swap them in (the buffers
+    // that held x0, g0 become the spares of the next launch)
+    void* t = ws->S[mark]->data;
+    ws->S[mark]->data = ws->carry_s->data;
+    ws->carry_s->data = t;
+    t = ws->Y[mark]->data;
+    ws->Y[mark]->data = ws->carry_y->data;
+    ws->carry_y->data = t;
+    ws->carry_valid = 0;
+    ws->carry_hits += 1;
+    return 0;
+}
+
 extern "C" int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots, double* G)
 {
     int rc = check_mark(ws, mark);
@@ -428,20 +492,98 @@ extern "C" int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots
         return opkb_set_error(OPKB_EINVAL, "the newest pair (slots[m-1]) must be `mark`");
     for (int j = 0; j < m; ++j)
         if (slots[j] < 0 || slots[j] >= ws->mem) return opkb_set_error(OPKB_EINVAL, "slot out of range");
-    const void* Sp[OPKB_MEM_MAX];
-    const void* Yp[OPKB_MEM_MAX];
-    for (int j = 0; j < m; ++j) {
-        Sp[j] = ws->S[slots[j]]->data;
-        Yp[j] = ws->Y[slots[j]]->data;
+    bool carried = false;
+    if (ws->carry_valid && ws->Gc_valid && mark == ws->carry_mark && m >= 2) {
+        // the caller took the speculated trial point (nothing else touched the
+        // workspace since) and asks for the pairs that launch foresaw
+        const int mo = ws->carry_m, drop = (mo == ws->mem) ? 1 : 0;
+        bool same = (m == mo + 1 - drop);
+        for (int j = 0; same && j < m - 1; ++j) same = (slots[j] == ws->carry_slots[j + drop]);
+        if (same) {
+            rc = gram_from_carry(ws, mark, m, slots, G);
+            if (rc) return rc;
+            carried = true;
+            if (getenv("OPKB_CARRY_CHECK")) {
+                // development aid: the same block by a sweep over the same state (the
+                // pair is already formed: x = g = 0 makes the in-place update the identity)
+                opkb_vector* z = NULL;
+                static thread_local double G2[2 * OPKB_MEM_MAX * (OPKB_MEM_MAX + 1)];
+                if (opkb_vector_create(ws->ctx, ws->eltype, ws->n, &z) == 0) {
+                    cudaMemsetAsync(z->data, 0, (size_t)ws->n * (ws->eltype == OPKB_DOUBLE ? 8 : 4), ws->ctx->stream);
+                    const void* Sp[OPKB_MEM_MAX];
+                    const void* Yp[OPKB_MEM_MAX];
+                    for (int j = 0; j < m; ++j) {
+                        Sp[j] = ws->S[slots[j]]->data;
+                        Yp[j] = ws->Y[slots[j]]->data;
+                    }
+                    const void* v0 = (ws->method == 2 ? ws->p->data : ws->g->data);
+                    if (ws->eltype == OPKB_DOUBLE)
+                        gram2_run<double>(ws->ctx, ws->n, m, Sp, Yp, v0, z->data, z->data, ws->method == 2, G2);
+                    else
+                        gram2_run<float>(ws->ctx, ws->n, m, Sp, Yp, v0, z->data, z->data, ws->method == 2, G2);
+                    opkb_vector_destroy(z);
+                    double worst = 0, scale = 0;
+                    int wr = -1, wc = -1;
+                    const int W = m + 1;
+                    for (int i = 0; i < 2 * m * W; ++i) scale = fmax(scale, fabs(G2[i]));
+                    for (int r = 0; r < 2 * m; ++r)
+                        for (int c = 0; c < W; ++c) {
+                            if (c > 0 && (c - 1) < r / 2) continue;
+                            const double dv = fabs(G[r * W + c] - G2[r * W + c]) / fmax(fabs(G2[r * W + c]), 1e-300);
+                            if (dv > worst) { worst = dv; wr = r; wc = c; }
+                        }
+                    fprintf(stderr, "[carry check] hit %lld m %d worst rel %.3e at (%d,%d): carried %.17g sweep %.17g (max |G| %.3e)\n",
+                            (long long)ws->carry_hits, m, worst, wr, wc, wr >= 0 ? G[wr * W + wc] : 0.0,
+                            wr >= 0 ? G2[wr * W + wc] : 0.0, scale);
+                }
+            }
+        }
     }
-    // v0 = p for VMLMB (mask p != 0), g otherwise; the gradient difference uses
-    // p for BLMVM (src/quasinewton.jl:513)
-    const void* v0 = (ws->method == 2 ? ws->p->data : ws->g->data);
-    const void* gcur = (ws->method == 1 ? ws->p->data : ws->g->data);
-    if (ws->eltype == OPKB_DOUBLE)
-        return gram2_run<double>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur,
-                                 ws->method == 2, G);
-    return gram2_run<float>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur, ws->method == 2, G);
+    if (!carried) {
+        if (ws->carry_valid) ws->carry_misses += 1;
+        ws->carry_valid = 0;
+        const void* Sp[OPKB_MEM_MAX];
+        const void* Yp[OPKB_MEM_MAX];
+        for (int j = 0; j < m; ++j) {
+            Sp[j] = ws->S[slots[j]]->data;
+            Yp[j] = ws->Y[slots[j]]->data;
+        }
+        // v0 = p for VMLMB (mask p != 0), g otherwise; the gradient difference uses
+        // p for BLMVM (src/quasinewton.jl:513)
+        const void* v0 = (ws->method == 2 ? ws->p->data : ws->g->data);
+        const void* gcur = (ws->method == 1 ? ws->p->data : ws->g->data);
+        if (ws->eltype == OPKB_DOUBLE)
+            rc = gram2_run<double>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur, ws->method == 2, G);
+        else
+            rc = gram2_run<float>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur, ws->method == 2, G);
+        if (rc) {
+            ws->Gc_valid = 0;
+            return rc;
+        }
+    }
+    memcpy(ws->Gc, G, sizeof(double) * 2 * m * (m + 1));
+    ws->Gc_m = m;
+    for (int j = 0; j < m; ++j) ws->Gc_slots[j] = slots[j];
+    ws->Gc_valid = 1;
+    return 0;
+}
+
+extern "C" int opkb_vmlmb_last_gram(const opkb_vmlmb* ws, int* m, int* slots, double* G)
+{
+    if (!ws || !m) return opkb_set_error(OPKB_EINVAL, "NULL argument");
+    *m = ws->Gc_valid ? ws->Gc_m : 0;
+    if (!ws->Gc_valid) return 0;
+    if (slots) for (int j = 0; j < ws->Gc_m; ++j) slots[j] = ws->Gc_slots[j];
+    if (G) memcpy(G, ws->Gc, sizeof(double) * 2 * ws->Gc_m * (ws->Gc_m + 1));
+    return 0;
+}
+
+extern "C" int opkb_vmlmb_carry_stats(const opkb_vmlmb* ws, int64_t* hits, int64_t* misses)
+{
+    if (!ws) return opkb_set_error(OPKB_EINVAL, "NULL workspace");
+    if (hits) *hits = ws->carry_hits;
+    if (misses) *misses = ws->carry_misses;
+    return 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -599,6 +741,7 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
                          const opkb_vector* pend_u = NULL, double pend_a = 0.0, double* out8 = NULL)
 {
     opkb_context* ctx = ws->ctx;
+    ws->carry_valid = 0;
     DirArgs<T> A;
     memset(&A, 0, sizeof(A));
     A.m = steepest ? 0 : m;
@@ -632,9 +775,15 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         A.pa = (T)pend_a;
         A.pw = (ws->method == 2) ? (const T*)ws->p->data : NULL;
     }
-    int kinds[12] = {OPKB_RSUM, OPKB_RSUM, OPKB_RMIN, OPKB_RMAX, OPKB_RSUM, OPKB_RSUM, OPKB_RSUM,
-                     OPKB_RSUM, OPKB_RSUM, OPKB_RSUM, OPKB_RSUM, OPKB_RSUM};
-    double part[2][12] = {{0, 0, INFINITY, 0}, {0, 0, INFINITY, 0}};
+    static thread_local int kinds[OPKB_NRED_MAX];
+    for (int k = 0; k < OPKB_NRED_MAX; ++k) kinds[k] = OPKB_RSUM;
+    kinds[2] = OPKB_RMIN;
+    kinds[3] = OPKB_RMAX;
+    static thread_local double part[2][OPKB_NRED_MAX];
+    for (int q = 0; q < 2; ++q) {
+        part[q][0] = part[q][1] = part[q][3] = 0.0;
+        part[q][2] = INFINITY;
+    }
     // speculative first trial of the next line search (stp = 1) in the same pass?
     const int fuse = (out8 && !steepest && A.m >= 1 && ws->method != 1 &&
                       (ws->obj == OPKB_OBJ_ROSENBROCK || ws->obj == OPKB_OBJ_QUADRATIC))
@@ -656,11 +805,33 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         if (A.bounded && A.lo.arr) { B.r_lo = nr; B.rows[nr++] = A.lo.arr; }
         if (A.bounded && A.hi.arr) { B.r_hi = nr; B.rows[nr++] = A.hi.arr; }
         if (A.ysrc != A.g) { B.r_ysrc = nr; B.rows[nr++] = A.ysrc; }
+        // incremental Gram (CARRY): only when the caller solves the two-loop recursion
+        // from the Gram block of exactly these pairs (opkb_vmlmb_gram just before)
+        int carry = 0;
         if (fuse) {
             // x', g' go to the buffers of the recycled slot, which become x and g
             B.xout = (T*)ws->S[mark_next]->data;
             B.gout = (T*)ws->Y[mark_next]->data;
             B.pout = ws->p ? (T*)ws->p->data : NULL;
+            carry = (A.m <= 12 && ws->Gc_valid && ws->Gc_m == A.m);
+            for (int j = 0; carry && j < A.m; ++j) carry = (ws->Gc_slots[j] == slots[j]);
+            // mark_next is the oldest pair when the memory is full, a free slot otherwise
+            if (carry && A.m == ws->mem && slots[0] != mark_next) carry = 0;
+            if (carry && A.m < ws->mem)
+                for (int j = 0; j < A.m; ++j) if (slots[j] == mark_next) carry = 0;
+            if (const char* e = getenv("OPKB_CARRY")) if (atoi(e) == 0) carry = 0;
+            if (carry && !ws->carry_s) {
+                if (opkb_vector_create(ctx, ws->eltype, ws->n, &ws->carry_s) != 0 ||
+                    opkb_vector_create(ctx, ws->eltype, ws->n, &ws->carry_y) != 0) {
+                    opkb_vector_destroy(ws->carry_s);   // not enough memory: plain fused launch
+                    ws->carry_s = ws->carry_y = NULL;
+                    carry = 0;
+                }
+            }
+            if (carry) {
+                B.sout = (T*)ws->carry_s->data;
+                B.yout = (T*)ws->carry_y->data;
+            }
         }
         for (int j = 0; j < A.m; ++j) {
             B.rows[nr++] = A.Y[j];
@@ -687,14 +858,17 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         B.d = A.d;
         B.Snext = A.Snext;
         B.Ynext = A.Ynext;
-        // ring geometry: 4 KB rows when two stages fit in ~220 KB, else 2 KB rows
+        // ring geometry: 4 KB rows when two stages fit in ~220 KB, else 2 KB rows; the
+        // CARRY instances use 3.5 KB rows (7 consumer warps) and need two stages of them
         const size_t budget = 220 * 1024;
+        if (carry && (size_t)nr * DIR2_CARRY_ROWB * 2 > budget) carry = 0;
         int tile = (int)(4096 / sizeof(T));
         if ((size_t)nr * tile * sizeof(T) * 2 > budget || A.m > 12) tile = (int)(2048 / sizeof(T));
         if (const char* e = getenv("OPKB_DIR_ROWB")) {   // tuning knob: 2048 | 4096 bytes per row
             const int rb = atoi(e);
             if (rb == 2048 || (rb == 4096 && A.m <= 12)) tile = rb / (int)sizeof(T);
         }
+        if (carry) tile = DIR2_CARRY_ROWB / (int)sizeof(T);
         size_t stage_bytes = (size_t)nr * tile * sizeof(T);
         int nstage = (int)(budget / stage_bytes);
         if (const char* e = getenv("OPKB_DIR_NSTAGE")) nstage = atoi(e);
@@ -705,29 +879,30 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
             B.nstage = nstage;
             B.n = ws->n;
             const size_t smem = stage_bytes * nstage;
-            // (MB, TILE) instances: 4 KB rows with up to 8 / 12 pairs, 2 KB rows with up to 12 / 20
-            constexpr int TB = 4096 / (int)sizeof(T), TS = 2048 / (int)sizeof(T);
-            void (*kern)(Dir2Args<T>, ReduceScratch) = NULL;
-#define DIR2_PICK(F)                                                                 \
-    do {                                                                             \
-        if (tile == TB) kern = (A.m <= 8) ? k_direction2<T, F, 8, TB> : k_direction2<T, F, 12, TB>;   \
-        else kern = (A.m <= 12) ? k_direction2<T, F, 12, TS> : k_direction2<T, F, 20, TS>;            \
-    } while (0)
-            if (fuse == OPKB_OBJ_ROSENBROCK) DIR2_PICK(OPKB_OBJ_ROSENBROCK);
-            else if (fuse == OPKB_OBJ_QUADRATIC) DIR2_PICK(OPKB_OBJ_QUADRATIC);
-            else DIR2_PICK(0);
-#undef DIR2_PICK
-            OPKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int mb;
+            if (carry) mb = (A.m <= 5) ? 5 : ((A.m <= 8) ? 8 : ((A.m <= 10) ? 10 : 12));
+            else if (tile * sizeof(T) == 4096) mb = (A.m <= 8) ? 8 : 12;
+            else mb = (A.m <= 12) ? 12 : 20;
+            const int nd = carry ? 4 * mb + 4 : 0;
+            const int ncorr = carry ? 32 * ((mb * (mb + 1) + 31) / 32) : 0;
             int64_t grid = ctx->sm_count;
             if (grid > ntiles) grid = ntiles;
-            opkb_prof_begin(ctx, OPKB_K_DIRECTION);
-            kern<<<(int)grid, DIR2_THREADS, smem, ctx->stream>>>(B, scratch(ctx));
-            opkb_prof_end(ctx);
-            ctx->launches += 1;
-            OPKB_CUDA(cudaGetLastError());
-            int rc = opkb_finish_reduction(ctx, fuse ? 12 : 4, kinds, part[nparts++]);
+            int rc = carry ? dir2_launch_carry<T>(ctx, B, fuse, mb, smem, (int)grid)
+                           : dir2_launch_plain<T>(ctx, B, fuse, mb, smem, (int)grid);
+            if (rc) return rc;
+            rc = opkb_finish_reduction(ctx, (fuse ? 12 : 4) + nd + ncorr, kinds, part[nparts++]);
             if (rc) return rc;
             done = B.n;
+            if (carry) {
+                const double* r = part[0] + 12;
+                memcpy(ws->carry_dense, r, sizeof(double) * nd);
+                memcpy(ws->carry_corr, r + nd, sizeof(double) * mb * (mb + 1));
+                ws->carry_m = A.m;
+                ws->carry_mb = mb;
+                ws->carry_mark = mark_next;
+                for (int j = 0; j < A.m; ++j) ws->carry_slots[j] = slots[j];
+                ws->carry_valid = 1;
+            }
             if (fuse) {
                 const double* r = part[0];
                 out8[0] = (fuse == OPKB_OBJ_ROSENBROCK) ? r[4] + r[5] : 0.5 * r[4];
@@ -844,6 +1019,7 @@ extern "C" int opkb_vmlmb_discard_trial(opkb_vmlmb* ws, int mark_next)
     // iterate again, S[mark'], Y[mark'] alias them, p is recomputed (:396)
     int rc = check_mark(ws, mark_next);
     if (rc) return rc;
+    ws->carry_valid = 0;
     void* t = ws->S[mark_next]->data;
     ws->S[mark_next]->data = ws->x->data;
     ws->x->data = t;
@@ -1049,6 +1225,8 @@ extern "C" int opkb_vmlmb_pair_update(opkb_vmlmb* ws, int mark, double out[2])
     if (rc) return rc;
     if (!out) return opkb_set_error(OPKB_EINVAL, "NULL result");
     opkb_context* ctx = ws->ctx;
+    ws->carry_valid = 0;
+    ws->Gc_valid = 0;    // the pairs change outside opkb_vmlmb_gram
     const opkb_vector* gs = (ws->method == 1 ? ws->p : ws->g);
     int grid = opkb_grid_for(ctx, ws->n / (ws->eltype == OPKB_DOUBLE ? 2 : 4), 4);
     if (ws->eltype == OPKB_DOUBLE)

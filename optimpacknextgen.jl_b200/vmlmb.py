@@ -808,6 +808,29 @@ class VMLMB:
             return x.reshape(self._shape)
         return self.x
 
+    def carry_stats(self):
+        """(hits, misses) of the incremental Gram of the fused path (opkb200.h,
+        opkb_vmlmb_carry_stats): Gram blocks assembled without a sweep / sweeps that
+        ran although a carry was armed."""
+        if not self._ws:
+            return (0, 0)
+        h, m = _lib.i64(), _lib.i64()
+        check(_lib.lib().opkb_vmlmb_carry_stats(self._ws, C.byref(h), C.byref(m)))
+        return (h.value, m.value)
+
+    def last_gram(self):
+        """(slots, G) of the last Gram block (2m x (m+1), row-major) or None."""
+        if not self._ws:
+            return None
+        m = C.c_int()
+        slots = (C.c_int * _lib.MEM_MAX)()
+        G = (f64 * (2 * _lib.MEM_MAX * (_lib.MEM_MAX + 1)))()
+        check(_lib.lib().opkb_vmlmb_last_gram(self._ws, C.byref(m), slots, G))
+        if m.value == 0:
+            return None
+        k = m.value
+        return list(slots[:k]), np.array(G[:2 * k * (k + 1)]).reshape(2 * k, k + 1)
+
     def free_mask(self) -> np.ndarray:
         """Free-variable mask {i : p[i] != 0} of this rank (all True for L-BFGS)."""
         if self.method == 0:
