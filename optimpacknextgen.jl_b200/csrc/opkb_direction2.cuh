@@ -71,7 +71,9 @@ template <int MB> struct Dir2Carry {
     static constexpr int CPL = (NENT + 31) / 32;    // correction entries per lane
 };
 
-template <typename T, int FUSE, int MB, int TILE, int CARRY>
+// EXACT: m == MB (and every pair takes part is still checked at run time): the
+// unrolled pair loops lose their guards.
+template <typename T, int FUSE, int MB, int TILE, int CARRY, int EXACT = 0>
 __global__ void __launch_bounds__(DIR2_NTHREADS(CARRY), 1) k_direction2(Dir2Args<T> A, ReduceScratch rs)
 {
     constexpr int DIR2_THREADS = DIR2_NTHREADS(CARRY);
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(DIR2_NTHREADS(CARRY), 1) k_direction2(Dir2Args
     __shared__ __align__(8) uint64_t full_bar[DIR2_MAXSTAGE];
     __shared__ __align__(8) uint64_t empty_bar[DIR2_MAXSTAGE];
 
-    const int NSTAGE = A.nstage, NR = A.nrows, m = A.m;
+    const int NSTAGE = A.nstage, NR = A.nrows, m = EXACT ? MB : A.m;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     T* const stage0 = reinterpret_cast<T*>(smem_raw);
     const int stage_elems = NR * TILE;
@@ -146,10 +148,9 @@ __global__ void __launch_bounds__(DIR2_NTHREADS(CARRY), 1) k_direction2(Dir2Args
     }
 
     if (warp == CWARPS) {
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const int s = it % NSTAGE;
-            const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= (uint32_t)(++s == NSTAGE), s = (s == NSTAGE) ? 0 : s) {
             const int64_t base = tile * TILE;
             uint32_t bytes = rowbytes;
             if (base + TILE > A.n) bytes = (uint32_t)(((A.n - base) * sizeof(T)) & ~(size_t)15);
@@ -166,10 +167,9 @@ __global__ void __launch_bounds__(DIR2_NTHREADS(CARRY), 1) k_direction2(Dir2Args
         }
     } else {
         const int prow = 3 + (A.r_lo >= 0) + (A.r_hi >= 0) + (A.r_ysrc >= 0);  // first pair row
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const int s = it % NSTAGE;
-            const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= (uint32_t)(++s == NSTAGE), s = (s == NSTAGE) ? 0 : s) {
             T* st = stage0 + s * stage_elems;
             const int64_t base = tile * TILE;
             mbar_wait(&full_bar[s], ph);
@@ -200,12 +200,17 @@ __global__ void __launch_bounds__(DIR2_NTHREADS(CARRY), 1) k_direction2(Dir2Args
                 Pack<T> ph_ = (A.r_hi >= 0) ? ld_pack<T>(st + A.r_hi * TILE, e / VEC) : splat_pack<T>(A.hi_val);
                 Pack<T> pys = (A.r_ysrc >= 0) ? ld_pack<T>(st + A.r_ysrc * TILE, e / VEC) : pg;
                 Pack<T> pv;
+                bool flo[VEC], fhi[VEC];   // x may decrease / increase (can_change, src/bounds.jl:638-648)
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    flo[q] = !A.has_lo | (px.v[q] > pl.v[q]);
+                    fhi[q] = !A.has_hi | (px.v[q] < ph_.v[q]);
+                }
                 if (A.v0_from_g) {
                     // p = project_direction!(p, x, lo, hi, -, g) (src/quasinewton.jl:396),
                     // bit-identical to the stored vector, without reading it
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q)
-                        pv.v[q] = projdir(px.v[q], pl.v[q], ph_.v[q], A.has_lo, A.has_hi, -1, pg.v[q]);
+                    for (int q = 0; q < VEC; ++q) pv.v[q] = projdir_m1(flo[q], fhi[q], pg.v[q]);
                 } else {
                     pv = ld_pack<T>(st, e / VEC);
                 }
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(DIR2_NTHREADS(CARRY), 1) k_direction2(Dir2Args
 #pragma unroll
                     for (int jj = 0; jj < MB; ++jj) {
                         const int j = MB - 1 - jj;
-                        if (j < m) {
+                        if (EXACT || j < m) {
                             const Pack<T> y = ld_pack<T>(pb + 2 * j * TILE, 0);
 #pragma unroll
                             for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + A.ma[j] * y.v[q];
@@ -232,7 +237,7 @@ __global__ void __launch_bounds__(DIR2_NTHREADS(CARRY), 1) k_direction2(Dir2Args
                     for (int q = 0; q < VEC; ++q) v.v[q] = A.gamma * v.v[q];
 #pragma unroll
                     for (int j = 0; j < MB; ++j) {
-                        if (j < m) {
+                        if (EXACT || j < m) {
                             const Pack<T> sv = ld_pack<T>(pb + (2 * j + 1) * TILE, 0);
 #pragma unroll
                             for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + A.cc[j] * sv.v[q];
@@ -267,12 +272,12 @@ __global__ void __launch_bounds__(DIR2_NTHREADS(CARRY), 1) k_direction2(Dir2Args
                 for (int q = 0; q < VEC; ++q) {
                     T di = v.v[q];
                     if (A.bounded)  // project_direction!(d, x, lo, hi, -, d) :535
-                        di = projdir(px.v[q], pl.v[q], ph_.v[q], A.has_lo, A.has_hi, -1, di);
+                        di = projdir_m1(flo[q], fhi[q], di);
                     v.v[q] = di;
                     acc[0] = dacc(pg.v[q], di, acc[0]);   // vdot(g, d) :537
                     acc[1] = dacc(di, di, acc[1]);        // vnorm2(d) :629
                     if (A.bounded)                        // step_limits(x, lo, hi, -1, d) :577
-                        step_limit_update(px.v[q], pl.v[q], ph_.v[q], A.has_lo, A.has_hi, -di, smin, smax);
+                        step_limit_update_fast(px.v[q], pl.v[q], ph_.v[q], A.has_lo, A.has_hi, -di, smin, smax);
                 }
                 Pack<T> xt, gt, pt;
                 if (FUSE) {
@@ -303,7 +308,8 @@ __global__ void __launch_bounds__(DIR2_NTHREADS(CARRY), 1) k_direction2(Dir2Args
 #pragma unroll
                     for (int q = 0; q < VEC; ++q) {
                         const T xi = xt.v[q], gi = gt.v[q];
-                        const T pi = A.bounded ? projdir(xi, pl.v[q], ph_.v[q], A.has_lo, A.has_hi, -1, gi) : gi;
+                        const T pi = A.bounded ? projdir_m1(!A.has_lo | (xi > pl.v[q]), !A.has_hi | (xi < ph_.v[q]), gi)
+                                               : gi;
                         pt.v[q] = pi;
                         if (ok[q]) {
                             const T si = xi - px.v[q];              // s = x' - x0 (:427)
@@ -338,7 +344,7 @@ __global__ void __launch_bounds__(DIR2_NTHREADS(CARRY), 1) k_direction2(Dir2Args
                     }
 #pragma unroll
                     for (int j = 0; j < MB; ++j) {
-                        if (j < m) {
+                        if (EXACT || j < m) {
                             const Pack<T> y = ld_pack<T>(pb + 2 * j * TILE, 0);
                             const Pack<T> sv = ld_pack<T>(pb + (2 * j + 1) * TILE, 0);
 #pragma unroll

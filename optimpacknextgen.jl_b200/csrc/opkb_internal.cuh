@@ -146,6 +146,43 @@ __device__ __forceinline__ T projdir(T x, T lo, T hi, int has_lo, int has_hi, in
     return ok ? d : T(0);
 }
 
+// projdir with orientation -1 (the one vmlmb uses) from the two "can move" flags of
+// x, flo = !has_lo || x > lo and fhi = !has_hi || x < hi: same result as projdir(),
+// branch-free, and the flags are shared by the calls that concern the same x.
+template <typename T>
+__device__ __forceinline__ T projdir_m1(bool flo, bool fhi, T d)
+{
+    const bool ok = ((d > T(0)) & flo) | ((d < T(0)) & fhi);
+    return ok ? d : T(0);
+}
+
+// step_limit_update() without the division when it cannot change smin or smax:
+// with an = |bound - x| signed like the step and sdn = |sd|, a = an / sdn, and
+// a > smax needs an > smax*sdn, a < smin needs an < smin*sdn; the filter leaves a
+// margin of 2^-40 for the roundings, then the exact quotient decides as in the
+// reference.  (Record-breaking quotients are rare: ~log(n) per thread.)
+template <typename T>
+__device__ __forceinline__ void step_limit_update_fast(T x, T lo, T hi, int has_lo, int has_hi, T sd,
+                                                       T& smin, T& smax)
+{
+    const T inf = T(INFINITY);
+    const bool up = sd > T(0), dn = sd < T(0);
+    if (!(up | dn)) return;
+    const bool has = up ? (has_hi != 0) : (has_lo != 0);
+    if (!has) {
+        smax = inf;
+        return;
+    }
+    const T num = (up ? hi : lo) - x;
+    const T an = up ? num : -num, sdn = up ? sd : -sd;
+    const T m = sizeof(T) == 8 ? T(9.094947017729282e-13) : T(1e-4);
+    if ((an > smax * sdn * (T(1) - m)) | ((an > T(0)) & (an < smin * sdn * (T(1) + m)))) {
+        const T a = num / sd;
+        if (T(0) < a && a < smin) smin = a;
+        if (a > smax) smax = a;
+    }
+}
+
 // one element of _step_limits: src/bounds.jl:456-506, :521-551, :566-596, :608-622.
 // `sd` = s*d[i] with s = +-1; smin/smax in the element type.
 template <typename T>

@@ -880,7 +880,7 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
             B.n = ws->n;
             const size_t smem = stage_bytes * nstage;
             int mb;
-            if (carry) mb = (A.m <= 5) ? 5 : ((A.m <= 8) ? 8 : ((A.m <= 10) ? 10 : 12));
+            if (carry) mb = (A.m <= 5) ? 5 : ((A.m <= 8) ? 8 : ((A.m == 10) ? 10 : 12));
             else if (tile * sizeof(T) == 4096) mb = (A.m <= 8) ? 8 : 12;
             else mb = (A.m <= 12) ? 12 : 20;
             const int nd = carry ? 4 * mb + 4 : 0;
