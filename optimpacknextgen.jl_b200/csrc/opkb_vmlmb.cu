@@ -819,7 +819,10 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
             if (carry && A.m == ws->mem && slots[0] != mark_next) carry = 0;
             if (carry && A.m < ws->mem)
                 for (int j = 0; j < A.m; ++j) if (slots[j] == mark_next) carry = 0;
-            if (const char* e = getenv("OPKB_CARRY")) if (atoi(e) == 0) carry = 0;
+            // Float32: the carry instances are issue-bound: opt-in
+            int carry_env = -1;
+            if (const char* e = getenv("OPKB_CARRY")) carry_env = atoi(e);
+            if (carry_env == 0 || (sizeof(T) == 4 && carry_env != 2)) carry = 0;
             if (carry && !ws->carry_s) {
                 if (opkb_vector_create(ctx, ws->eltype, ws->n, &ws->carry_s) != 0 ||
                     opkb_vector_create(ctx, ws->eltype, ws->n, &ws->carry_y) != 0) {

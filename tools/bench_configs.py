@@ -59,6 +59,7 @@ def run_vmlmb(ctx, name, obj, x0, lo, hi, mem, n, nglobal, K, es, walg, twoloop=
            "kernels_ms_per_iteration": {k: round(v[0] / max(it, 1), 4) for k, v in prof.items()},
            "kernel_launches_per_iteration": {k: round(v[1] / max(it, 1), 2) for k, v in prof.items()}}
     out["frac_of_measured_peak"] = out["alg_GBps_per_gpu"] / PEAK
+    out["incremental_gram_hits_misses"] = list(s.carry_stats())
     s.close()
     return out
 

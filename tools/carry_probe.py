@@ -23,7 +23,7 @@ def main():
     a = opk.VMLMB(pb["gpu_obj"], pb["x0"], **kw)
     b = opk.VMLMB(pb["gpu_obj"], pb["x0"], **kw)
     for it in range(40):
-        os.environ["OPKB_CARRY"] = "1"
+        os.environ["OPKB_CARRY"] = "2"
         a.iterate(1)
         os.environ["OPKB_CARRY"] = "0"
         b.iterate(1)
