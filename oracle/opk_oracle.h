@@ -12,7 +12,12 @@
  * this environment, so the oracle cannot be checked against outputs of the
  * reference itself.  It is pinned only against (i) the reference's own test
  * assertions (test/rosenbrock.jl:79,92,104: max|x-1| < 1e-3 for n=20) and
- * (ii) analytic known answers (tests/test_oracle.py).
+ * (ii) analytic known answers (tests/test_oracle.py), and two of its parts are
+ * pinned against independent published implementations shipped with SciPy
+ * (tests/test_pins_scipy.py): the More-Thuente search + cstep give bit-identical
+ * step sequences to SciPy's port of MINPACK-2 dcsrch/dcstep, and apply_lbfgs
+ * equals scipy.optimize.LbfgsInvHessProduct to rounding.  The driver
+ * trajectories themselves remain unpinned.
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference).  Two instances of the type-generic part exist: prefix
