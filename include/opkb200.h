@@ -165,6 +165,21 @@ int opkb_rosenbrock_fg(opkb_context* ctx, const opkb_vector* x, opkb_vector* g, 
 int opkb_quadratic_fg(opkb_context* ctx, const opkb_vector* a, const opkb_vector* c,
                       const opkb_vector* x, opkb_vector* g, double* f);
 
+/* A non-separable objective with a neighbour exchange (no reference
+ * code: north_star "bound-constrained convex quadratic", here the smoothness-
+ * regularised weighted least squares typical of the reference's users):
+ *   f(x) = 1/2 sum w_i (x_i - y_i)^2 + mu/2 sum over horizontal and vertical
+ *   neighbour pairs (x_i - x_j)^2 on a rows x cols grid (row-major, free boundary).
+ * A stand-alone `fg!(x, g) -> f` for the user-objective path of vmlmb / spg.  With
+ * several ranks the grid is sharded in blocks of whole rows (x, w, y, g hold this
+ * rank's rows); the last row of the previous rank and the first row of the next
+ * one are fetched into `up` / `dn` (vectors of `cols` elements, may be NULL on one
+ * rank) by ONE ncclSend/ncclRecv group over NVLink on a second stream while the
+ * rows that need no halo are processed; *f is the global value (every rank). */
+int opkb_smooth2d_fg(opkb_context* ctx, const opkb_vector* w, const opkb_vector* y, double mu,
+                     int64_t cols, const opkb_vector* x, opkb_vector* up, opkb_vector* dn,
+                     opkb_vector* g, double* f);
+
 /* ---- Tier 2: fused phases of `_vmlmb!` (src/quasinewton.jl:381-601) ------- */
 /* The workspace owns x, g, p, d and the mem pairs S[k], Y[k] (src/quasinewton.jl:358-369).
  * lo/hi handles must outlive the workspace. */

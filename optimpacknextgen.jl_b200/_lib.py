@@ -88,6 +88,7 @@ _SIGNATURES = {
     "opkb_free_variables": (C.c_int, [vp, vp, C.POINTER(i64), vp]),
     "opkb_rosenbrock_fg": (C.c_int, [vp, vp, vp, Pd]),
     "opkb_quadratic_fg": (C.c_int, [vp, vp, vp, vp, vp, Pd]),
+    "opkb_smooth2d_fg": (C.c_int, [vp, vp, vp, f64, i64, vp, vp, vp, vp, Pd]),
     "opkb_vmlmb_create": (C.c_int, [vp, C.c_int, i64, C.c_int, C.c_int, vp, f64, vp, f64,
                                     C.POINTER(vp)]),
     "opkb_vmlmb_destroy": (C.c_int, [vp]),

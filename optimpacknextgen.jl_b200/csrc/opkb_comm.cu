@@ -12,7 +12,7 @@
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat64 = 8 };
+enum { ncclFloat32 = 7, ncclFloat64 = 8 };
 
 static struct {
     void* handle;
@@ -21,6 +21,10 @@ static struct {
     ncclResult_t (*CommDestroy)(ncclComm_t);
     ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
     const char* (*GetErrorString)(ncclResult_t);
+    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)(void);
+    ncclResult_t (*GroupEnd)(void);
 } g_nccl;
 
 static int load_nccl(void)
@@ -36,6 +40,10 @@ static int load_nccl(void)
     g_nccl.AllGather = (ncclResult_t(*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))
         dlsym(h, "ncclAllGather");
     g_nccl.GetErrorString = (const char* (*)(ncclResult_t))dlsym(h, "ncclGetErrorString");
+    g_nccl.Send = (ncclResult_t(*)(const void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclSend");
+    g_nccl.Recv = (ncclResult_t(*)(void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclRecv");
+    g_nccl.GroupStart = (ncclResult_t(*)(void))dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (ncclResult_t(*)(void))dlsym(h, "ncclGroupEnd");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.GetErrorString)
         return opkb_set_error(OPKB_ENCCL, "libnccl lacks a required symbol");
     g_nccl.handle = h;
@@ -95,5 +103,32 @@ int opkb_nccl_allgather_f64(opkb_context* ctx, const double* send, double* recv,
     ncclResult_t r = g_nccl.AllGather(send, recv, (size_t)count, ncclFloat64,
                                       (ncclComm_t)ctx->nccl_comm, ctx->stream);
     if (r != 0) return nccl_fail(r, "ncclAllGather");
+    return 0;
+}
+
+// The one real data exchange of the library: the boundary rows of a
+// row-sharded grid go to the two neighbouring ranks, point to point over NVLink, as
+// ONE NCCL group (both directions at once) on the given stream.
+int opkb_nccl_halo(opkb_context* ctx, int eltype, size_t count, const void* send_prev, void* recv_prev,
+                   const void* send_next, void* recv_next, cudaStream_t stream)
+{
+    if (!ctx->nccl_comm) return opkb_set_error(OPKB_ENCCL, "communicator not initialised");
+    if (!g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart || !g_nccl.GroupEnd)
+        return opkb_set_error(OPKB_ENCCL, "libnccl lacks ncclSend/ncclRecv");
+    const int dt = (eltype == OPKB_DOUBLE) ? ncclFloat64 : ncclFloat32;
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    ncclResult_t r = g_nccl.GroupStart();
+    if (r != 0) return nccl_fail(r, "ncclGroupStart");
+    if (ctx->rank > 0) {
+        if (r == 0 && send_prev) r = g_nccl.Send(send_prev, count, dt, ctx->rank - 1, comm, stream);
+        if (r == 0 && recv_prev) r = g_nccl.Recv(recv_prev, count, dt, ctx->rank - 1, comm, stream);
+    }
+    if (ctx->rank < ctx->nranks - 1) {
+        if (r == 0 && send_next) r = g_nccl.Send(send_next, count, dt, ctx->rank + 1, comm, stream);
+        if (r == 0 && recv_next) r = g_nccl.Recv(recv_next, count, dt, ctx->rank + 1, comm, stream);
+    }
+    ncclResult_t r2 = g_nccl.GroupEnd();
+    if (r != 0) return nccl_fail(r, "ncclSend/ncclRecv");
+    if (r2 != 0) return nccl_fail(r2, "ncclGroupEnd");
     return 0;
 }

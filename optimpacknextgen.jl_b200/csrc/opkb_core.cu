@@ -81,6 +81,11 @@ extern "C" int opkb_context_destroy(opkb_context* ctx)
     cudaFree(ctx->d_res);
     if (ctx->d_all) cudaFree(ctx->d_all);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    if (ctx->halo_stream) {
+        cudaStreamDestroy(ctx->halo_stream);
+        cudaEventDestroy(ctx->ev_ready);
+        cudaEventDestroy(ctx->ev_halo);
+    }
     if (ctx->prof) {
         for (int i = 0; i < OPKB_PROF_RING; ++i) {
             cudaEventDestroy(ctx->prof[i].a);

@@ -47,6 +47,10 @@ struct opkb_context_ {
     opkb_prof_rec* prof;
     double prof_ms[OPKB_K_NCLASS];
     int64_t prof_cnt[OPKB_K_NCLASS];
+    // neighbour (halo) exchange of the stencil objective: its own stream and events,
+    // created on first use (opkb_stencil.cu)
+    cudaStream_t halo_stream;
+    cudaEvent_t ev_ready, ev_halo;
 };
 
 void opkb_prof_begin(opkb_context* ctx, int cls);
@@ -75,8 +79,11 @@ int opkb_check_cuda(cudaError_t err, const char* what);
 int opkb_finish_reduction(opkb_context* ctx, int nred, const int* kinds, double* out);
 int opkb_grid_for(const opkb_context* ctx, int64_t nwork_items, int ctas_per_sm);
 
-// NCCL (opkb_comm.cpp, loaded with dlopen)
+// NCCL (opkb_comm.cu, loaded with dlopen)
 int opkb_nccl_allgather_f64(opkb_context* ctx, const double* send, double* recv, int count);
+// rows to/from the previous and the next rank in one NCCL group on `stream` (NULL: nothing)
+int opkb_nccl_halo(opkb_context* ctx, int eltype, size_t count, const void* send_prev, void* recv_prev,
+                   const void* send_next, void* recv_next, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------
 // 16-byte packs: 2 doubles or 4 floats per thread and request.

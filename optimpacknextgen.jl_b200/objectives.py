@@ -4,6 +4,10 @@ synthetic inputs of the benchmarks.
 * `Rosenbrock`  -- test/rosenbrock.jl:16-29 (pairs (x[2i-1], x[2i])).
 * `Quadratic`   -- f = 1/2 sum a_i (x_i - c_i)^2 (BASELINE.json north_star).
 
+* `Smooth2D`    -- smoothness-regularised weighted least squares on a 2-D grid:
+                   non-separable, row-sharded, with a halo exchange over NVLink
+                   (SURVEY.md 8(f)-2); used through the user-objective path.
+
 A user objective is any callable `fg(x: Vector, g: Vector) -> float` working on
 device vectors (the reference's `fg!(x, g)`).
 """
@@ -89,6 +93,82 @@ class Quadratic:
         a = ctx.vector(n, dtype).fill_random(seed_a, first, 1.0, kappa, log_scale=True)
         c = ctx.vector(n, dtype).fill_random(seed_c, first, -1.0, 2.0)
         return cls(a, c)
+
+
+class Smooth2D:
+    """f(x) = 1/2 sum w (x - y)^2 + mu/2 sum_edges (x_i - x_j)^2 on a rows x cols grid
+    (row-major; horizontal and vertical neighbours; free boundary).  A callable
+    `fg(x, g) -> f` on device Vectors, i.e. a user objective for `vmlmb` / `spg`.
+
+    With several ranks (`ctx.nranks > 1`) every rank holds a block of whole rows of
+    x, w, y, g; the boundary rows are exchanged point to point (one ncclSend/ncclRecv
+    group) while the inner rows are processed (`opkb_smooth2d_fg`)."""
+
+    def __init__(self, w, y, mu: float, cols: int, ctx: Context = None):
+        from .vectors import default_context
+        self.ctx = ctx or (w.ctx if isinstance(w, Vector) else default_context())
+        self.w = w if isinstance(w, Vector) else self.ctx.from_numpy(np.ascontiguousarray(w).reshape(-1))
+        self.y = y if isinstance(y, Vector) else self.ctx.from_numpy(
+            np.ascontiguousarray(y, dtype=self.w.dtype).reshape(-1))
+        self.mu = float(mu)
+        self.cols = int(cols)
+        if self.w.n != self.y.n or self.w.n % self.cols:
+            raise ValueError("w, y must hold whole rows of `cols` elements")
+        self.up = self.dn = None
+        if self.ctx.nranks > 1:
+            self.up = self.ctx.vector(self.cols, self.w.dtype)
+            self.dn = self.ctx.vector(self.cols, self.w.dtype)
+        self._f = _lib.f64()
+
+    def __call__(self, x: Vector, g: Vector) -> float:
+        import ctypes as C
+        _lib.check(_lib.lib().opkb_smooth2d_fg(
+            self.ctx.handle, self.w.handle, self.y.handle, self.mu, self.cols, x.handle,
+            self.up.handle if self.up else None, self.dn.handle if self.dn else None, g.handle,
+            C.byref(self._f)))
+        return self._f.value
+
+    @staticmethod
+    def reference(w, y, mu, cols):
+        """The same objective as a numpy `fg(x, g) -> f` on the WHOLE grid (same
+        order of the elementwise operations: g is bit-identical); for parity
+        checks against the CPU oracle, which takes python callables."""
+        w = np.ascontiguousarray(w)
+        dt = w.dtype
+        w2 = w.reshape(-1, cols)
+        y2 = np.ascontiguousarray(y, dtype=dt).reshape(-1, cols)
+        mu_t = dt.type(mu)
+
+        def fg(x, g):
+            x2 = x.reshape(-1, cols)
+            r = x2 - y2
+            t = w2 * r
+            du = np.zeros_like(x2)
+            dd = np.zeros_like(x2)
+            dl = np.zeros_like(x2)
+            dr = np.zeros_like(x2)
+            du[1:, :] = x2[1:, :] - x2[:-1, :]
+            dd[:-1, :] = x2[:-1, :] - x2[1:, :]
+            dl[:, 1:] = x2[:, 1:] - x2[:, :-1]
+            dr[:, :-1] = x2[:, :-1] - x2[:, 1:]
+            s = ((du + dd) + dl) + dr
+            g.reshape(-1, cols)[...] = t + mu_t * s
+            fd = float(np.sum((t * r).astype(np.float64)))
+            fe = float(np.sum((du * du).astype(np.float64)) + np.sum((dl * dl).astype(np.float64)))
+            return 0.5 * fd + (0.5 * float(mu)) * fe
+        return fg
+
+    @staticmethod
+    def synthetic(rows: int, cols: int, dtype=np.float64, first_row: int = 0, seed: int = 11):
+        """Deterministic data for the benchmarks: y = a smooth image + noise in [0, 1.2],
+        w in [0.5, 1.5] (this rank's rows first_row .. first_row + rows - 1)."""
+        i = (np.arange(first_row, first_row + rows, dtype=np.float64))[:, None]
+        j = np.arange(cols, dtype=np.float64)[None, :]
+        u = uniform(seed, first_row * cols, rows * cols).reshape(rows, cols)
+        v = uniform(seed + 1, first_row * cols, rows * cols).reshape(rows, cols)
+        y = 0.6 + 0.4 * np.sin(i / 37.0) * np.cos(j / 53.0) + 0.4 * (u - 0.5)
+        w = 0.5 + v
+        return w.astype(dtype).reshape(-1), y.astype(dtype).reshape(-1)
 
 
 def is_builtin(fg) -> bool:

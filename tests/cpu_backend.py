@@ -29,6 +29,8 @@ class NumpyOps:
         self._mark = 0
 
     def _fg(self, x, g):
+        if callable(self.obj):                       # fg(x, g) -> this rank's part of f
+            return self.obj(x, g)
         if self.obj == "rosenbrock":
             return O.rosenbrock_fg(x, g)
         return O.quadratic_fg(self.obj[1], self.obj[2], x, g)
@@ -261,3 +263,45 @@ class ShardedNumpyOps(NumpyOps):
     def begin_search(self, mark):
         smin, smax = super().begin_search(mark)
         return tuple(self._allreduce([smin, smax], [2, 1]))
+
+
+class ShardedSmooth2D:
+    """CPU twin of `opkb_smooth2d_fg` on one rank of a row-sharded grid: the last
+    row of the previous rank and the first row of the next one are exchanged
+    (gloo isend / irecv), the vertical edge between two ranks is counted by the
+    lower one, and the call returns THIS rank's part of f (the caller sums the
+    parts in rank order).  Same element-wise arithmetic as Smooth2D.reference."""
+
+    def __init__(self, w, y, mu, cols):
+        self.w = np.ascontiguousarray(w).reshape(-1, cols)
+        self.y = np.ascontiguousarray(y).reshape(-1, cols)
+        self.mu, self.cols = mu, cols
+
+    def __call__(self, x, g):
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        x2 = x.reshape(-1, self.cols)
+        up = torch.zeros(self.cols, dtype=torch.float64)
+        dn = torch.zeros(self.cols, dtype=torch.float64)
+        reqs = []
+        if rank > 0:
+            reqs += [dist.isend(torch.from_numpy(x2[0].copy()), rank - 1), dist.irecv(up, rank - 1)]
+        if rank < world - 1:
+            reqs += [dist.isend(torch.from_numpy(x2[-1].copy()), rank + 1), dist.irecv(dn, rank + 1)]
+        for r in reqs:
+            r.wait()
+        xx = np.vstack(([up.numpy()] if rank > 0 else []) + [x2] + ([dn.numpy()] if rank < world - 1 else []))
+        o = 1 if rank > 0 else 0                      # offset of the first own row in xx
+        rows = x2.shape[0]
+        r = x2 - self.y
+        t = self.w * r
+        du, dd, dl, dr = (np.zeros_like(x2) for _ in range(4))
+        lo = 0 if rank > 0 else 1                     # own rows that have a row above
+        du[lo:, :] = xx[o + lo:o + rows, :] - xx[o + lo - 1:o + rows - 1, :]
+        hi = rows if rank < world - 1 else rows - 1   # own rows that have a row below
+        dd[:hi, :] = xx[o:o + hi, :] - xx[o + 1:o + hi + 1, :]
+        dl[:, 1:] = x2[:, 1:] - x2[:, :-1]
+        dr[:, :-1] = x2[:, :-1] - x2[:, 1:]
+        g.reshape(-1, self.cols)[...] = t + self.mu * (((du + dd) + dl) + dr)
+        return 0.5 * float(np.sum(t * r)) + 0.5 * self.mu * float(np.sum(du * du) + np.sum(dl * dl))

@@ -97,6 +97,65 @@ def test_two_ranks_match_single_rank_oracle(oracle, kind, n, kw):
     assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)
 
 
+def _smooth_worker(rank, world, port, rows, cols, q):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+
+    import opk_oracle as O
+    import opkb200 as opk
+    from cpu_backend import ShardedNumpyOps, ShardedSmooth2D
+    from opkb200.dist import shard_range
+
+    O.set_num_threads(1)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    n = rows * cols
+    w, y = opk.Smooth2D.synthetic(rows, cols)
+    r0, nr = shard_range(rows, rank, world, align=1)
+    sl = slice(r0 * cols, (r0 + nr) * cols)
+    obj = ShardedSmooth2D(w[sl], y[sl], 2.0, cols)
+    trace = []
+    s = opk.VMLMB(obj, np.full(nr * cols, 0.5), lower=0.0, upper=1.0, mem=5, maxiter=25, nglobal=n,
+                  observer=lambda s: trace.append((s.iter, s.eval, s.f, s.gnorm, s.stp)),
+                  mode=lambda solver, x0: ShardedNumpyOps(solver, x0, obj))
+    s.solve()
+    q.put((rank, np.array(s.x), trace))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_halo_exchange_smooth2d(oracle):
+    """The non-separable objective on two ranks: rows sharded, boundary
+    rows exchanged point to point, edge between the ranks counted once."""
+    import torch.multiprocessing as mp
+
+    import opkb200 as opk
+    world, rows, cols = 2, 31, 40
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_smooth_worker, args=(r, world, port, rows, cols, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][2] == res[1][2]                                   # identical decisions
+    w, y = opk.Smooth2D.synthetic(rows, cols)
+    xo, ro, tro = oracle.vmlmb(opk.Smooth2D.reference(w, y, 2.0, cols), np.full(rows * cols, 0.5), 0.0, 1.0,
+                               mem=5, maxiter=25, trace=True)
+    for g, wt in zip(res[0][2], tro):
+        if wt["iter"] > 20:
+            break
+        assert (g[0], g[1]) == (wt["iter"], wt["eval"])
+        assert abs(g[2] - wt["f"]) <= 1e-10 * abs(wt["f"])
+        assert abs(g[3] - wt["gnorm"]) <= 1e-10 * abs(wt["gnorm"])
+    x = np.concatenate([r[1] for r in res])
+    assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)
+
+
 def test_combine_partials_fixed_order():
     from opkb200.dist import combine_partials
     parts = [[1.0, 5.0, 3.0], [1e-17, 7.0, -2.0], [2.0, 6.0, 9.0]]

@@ -84,6 +84,49 @@ def main():
             ok = ok and good
             print(f"[{world} GPUs] {kind} n={n} {np.dtype(dtype).name} {kw}: same_decisions={same} "
                   f"worst_rel(f,|g|)={worst:.2e} rel(x)={ex:.2e} {'OK' if good else 'FAIL'}", flush=True)
+    # Smooth2D: the non-separable objective, rows sharded, boundary rows exchanged over NVLink
+    for dtype, (rows, cols), mem in ((np.float64, (301, 257), 7), (np.float64, (world, 1000), 3),
+                                     (np.float32, (128, 96), 5)):
+        n = rows * cols
+        w, y = opk.Smooth2D.synthetic(rows, cols, dtype)
+        r0, nr = shard_range(rows, rank, world, align=1)
+        sl = slice(r0 * cols, (r0 + nr) * cols)
+        x0 = np.full(n, 0.5, dtype=dtype)
+        trace = []
+        s = opk.VMLMB(opk.Smooth2D(w[sl].copy(), y[sl].copy(), 2.0, cols, ctx=ctx), x0[sl].copy(), lower=0.0,
+                      upper=1.0, mem=mem, maxiter=25, nglobal=n, ctx=ctx,
+                      observer=lambda s: trace.append((s.iter, s.eval, s.f, s.gnorm, s.stp)))
+        s.solve()
+        xloc = s.result()
+        s.close()
+        t = torch.tensor([v for row in trace for v in row], dtype=torch.float64, device="cuda")
+        tmax, tmin = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        same = bool(torch.equal(tmax, tmin))
+        per = shard_range(rows, 0, world, align=1)[1] * cols
+        buf = torch.zeros(per, dtype=torch.float64, device="cuda")
+        buf[:nr * cols] = torch.from_numpy(xloc.astype(np.float64)).cuda()
+        bufs = [torch.zeros_like(buf) for _ in range(world)]
+        dist.all_gather(bufs, buf)
+        if rank == 0:
+            x = np.concatenate([b.cpu().numpy()[:shard_range(rows, r, world, align=1)[1] * cols]
+                                for r, b in enumerate(bufs)])
+            xo, ro, tro = O.vmlmb(opk.Smooth2D.reference(w, y, 2.0, cols), x0, 0.0, 1.0, mem=mem, maxiter=25,
+                                  trace=True)
+            rtol = 1e-10 if dtype == np.float64 else 1e-4
+            worst = 0.0
+            for g, wt in zip(trace, tro):
+                if wt["iter"] > 12:      # (nearly solved afterwards: see tests/test_gpu_smooth2d.py)
+                    break
+                assert (g[0], g[1]) == (wt["iter"], wt["eval"]), (g, wt["iter"], wt["eval"])
+                worst = max(worst, abs(g[2] - wt["f"]) / abs(wt["f"]), abs(g[3] - wt["gnorm"]) / wt["gnorm"])
+            ex = np.linalg.norm(x - xo) / np.linalg.norm(xo)
+            good = same and worst <= rtol and ex <= 100 * rtol
+            ok = ok and good
+            print(f"[{world} GPUs] Smooth2D {rows}x{cols} {np.dtype(dtype).name} mem={mem} (halo exchange): "
+                  f"same_decisions={same} worst_rel(f,|g|)={worst:.2e} rel(x)={ex:.2e} "
+                  f"{'OK' if good else 'FAIL'}", flush=True)
     # SPG: the same sharding, one packed all-gather per function evaluation
     for kind, n, dtype, m in (("quad_box", 200001, np.float64, 10), ("rosen_box", 100000, np.float64, 10)):
         pb = problem(kind, n, dtype)
