@@ -22,7 +22,7 @@
 #
 module OptimPackB200
 
-export DeviceVector, BoundedSet, Rosenbrock, Quadratic, vmlmb, vmlmb!, vmlmb_native!, spg, spg!
+export DeviceVector, BoundedSet, Rosenbrock, Quadratic, Smooth2D, vmlmb, vmlmb!, vmlmb_native!, spg, spg!
 
 using Libdl
 import LazyAlgebra
@@ -269,6 +269,33 @@ end
 objective_code(::Rosenbrock) = (Cint(1), C_NULL, C_NULL)
 objective_code(q::Quadratic{<:DeviceVector}) = (Cint(2), q.a.ptr, q.c.ptr)
 objective_code(::Any) = (Cint(0), C_NULL, C_NULL)   # user fg!(x, g) on DeviceVectors
+
+"""
+    Smooth2D(w, y, mu, cols)
+
+a non-separable `fg!(x, g)`: `f = 1/2 sum(w.*(x-y).^2) + mu/2 * sum over neighbour pairs
+of (x_i - x_j)^2` on a rows x cols grid (`opkb_smooth2d_fg`).  With several ranks each
+one holds a block of whole rows; the boundary rows are exchanged between neighbouring
+ranks (ncclSend/ncclRecv) inside the call, overlapped with the inner rows.
+"""
+struct Smooth2D{T}
+    w::DeviceVector{T}
+    y::DeviceVector{T}
+    mu::Float
+    cols::Int
+    up::DeviceVector{T}     # halo rows (unused on one rank)
+    dn::DeviceVector{T}
+end
+Smooth2D(w::DeviceVector{T}, y::DeviceVector{T}, mu::Real, cols::Integer) where {T} =
+    Smooth2D{T}(w, y, Float(mu), Int(cols), DeviceVector{T}(w.ctx, cols), DeviceVector{T}(w.ctx, cols))
+function (obj::Smooth2D{T})(x::DeviceVector{T}, g::DeviceVector{T}) where {T}
+    f = Ref{Cdouble}(0)
+    check(ccall((:opkb_smooth2d_fg, libopkb200), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                 Ptr{Cvoid}, Ref{Cdouble}),
+                x.ctx.ptr, obj.w.ptr, obj.y.ptr, obj.mu, obj.cols, x.ptr, obj.up.ptr, obj.dn.ptr, g.ptr, f))
+    return f[]
+end
 
 to_device(ctx, b::Real, ::Type{T}) where {T} = Float(b)
 to_device(ctx, b::DeviceVector{T}, ::Type{T}) where {T} = b

@@ -39,6 +39,8 @@ def run_vmlmb(ctx, name, obj, x0, lo, hi, mem, n, nglobal, K, es, walg, twoloop=
     kw = dict(mem=mem, xtol=(0, 0), ftol=(0, 0), gtol=(0, 0), nglobal=nglobal, ctx=ctx, twoloop=twoloop)
     if lo is not None:
         kw.update(lower=lo, upper=hi)
+    if NATIVE and not isinstance(obj, (opk.Rosenbrock, opk.Quadratic)):
+        return {"config": name, "skipped": "native run loop needs a built-in objective"}
     s = (opk.NativeVMLMB if NATIVE else opk.VMLMB)(obj, x0, **kw)
     name += " [native driver]" if NATIVE else ""
     s.iterate((mem + 1 if prime is None else prime) + 3)
@@ -129,6 +131,18 @@ def main():
             tl = "gram" if c.endswith("gram") else None
             r = run_vmlmb(ctx, "%s VMLMB Rosenbrock box n=2^%d f32 m=7" % (c, int(math.log2(n))),
                           opk.Rosenbrock(), x0, lo, hi, 7, nl, n, 20, 4, 48, twoloop=tl)
+        elif c == "S2D":   # non-separable objective with a halo exchange (user-objective path)
+            rows = cols = 16384
+            n = rows * cols
+            r0, nr = shard_range(rows, rank, world, align=1)
+            nl = nr * cols
+            w = ctx.vector(nl, np.float64).fill_random(12, r0 * cols, 0.5, 1.0)
+            y = ctx.vector(nl, np.float64).fill_random(11, r0 * cols, 0.0, 1.2)
+            obj = opk.Smooth2D(w, y, 2.0, cols, ctx=ctx)
+            x0 = ctx.vector(nl, np.float64).fill(0.5)
+            # per iteration: trial_begin 5 + fg 4 + trial_end 7 + Gram sweep 2m+5 + direction 2m+6 passes
+            r = run_vmlmb(ctx, "S2D VMLMB Smooth2D 16384^2 f64 m=10, box [0,1], halo exchange", obj, x0,
+                          0.0, 1.0, 10, nl, n, 20, 8, 4 * 10 + 27)
         else:
             continue
         r["n_gpus"] = world
