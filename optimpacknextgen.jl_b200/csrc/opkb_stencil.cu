@@ -25,50 +25,67 @@ template <typename T> struct SmoothArgs {
     int64_t r0, r1;           // rows [r0, r1) are processed by this launch
 };
 
-// One CTA = 256 consecutive columns of one row; the neighbours in the row come from
-// the same cache lines, those of the rows above / below from L1 / L2 (each x element
-// is fetched from HBM once).  Arithmetic in T without contraction, in the fixed order
-// up, down, left, right, so that g is bit-identical to the obvious array expression.
-template <typename T>
+// One CTA = 256 x VEC consecutive columns of one row (VEC = the 16-byte pack when the
+// row length allows aligned packs, else 1); the neighbours in the row come from the
+// same pack or cache line, those of the rows above / below from L2 (each x element is
+// fetched from HBM once).  Arithmetic in T without contraction, in the fixed order up,
+// down, left, right, so that g is bit-identical to the obvious array expression.
+template <typename T> __device__ __forceinline__ void smooth_elem(
+    T xi, T wi, T yi, bool hu, T xu, bool hd, T xd, bool hl, T xl, bool hr, T xr, T mu, T& gi, double (&acc)[2])
+{
+    const T r = xi - yi;
+    const T t = wi * r;
+    acc[0] += (double)(T)(t * r);
+    T s = T(0);
+    if (hu) {
+        const T d = xi - xu;
+        s = s + d;
+        acc[1] += (double)(T)(d * d);      // vertical edge: owned by the lower row
+    }
+    if (hd) s = s + (xi - xd);
+    if (hl) {
+        const T d = xi - xl;
+        s = s + d;
+        acc[1] += (double)(T)(d * d);      // horizontal edge: owned by the right element
+    }
+    if (hr) s = s + (xi - xr);
+    gi = t + mu * s;
+}
+
+template <typename T, int VEC>
 __global__ void __launch_bounds__(OPKB_BLOCK) k_smooth2d(SmoothArgs<T> A, ReduceScratch rs)
 {
-    const int64_t ncb = (A.cols + OPKB_BLOCK - 1) / OPKB_BLOCK;
+    const int64_t ncb = (A.cols + OPKB_BLOCK * VEC - 1) / (OPKB_BLOCK * VEC);
     const int64_t nitems = (A.r1 - A.r0) * ncb;
     double acc[2] = {0.0, 0.0};   // 0: sum w r^2; 1: sum of squared differences over the owned edges
     for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int64_t row = A.r0 + item / ncb;
-        const int64_t col = (item % ncb) * OPKB_BLOCK + threadIdx.x;
+        const int64_t col = ((item % ncb) * OPKB_BLOCK + threadIdx.x) * VEC;
         if (col >= A.cols) continue;
         const int64_t i = row * A.cols + col;
-        const T xi = A.x[i];
-        const T r = xi - A.y[i];
-        const T t = A.w[i] * r;
-        acc[0] += (double)(T)(t * r);
-        T s = T(0);
-        bool has = false;
-        T xn = T(0);
-        // up
-        if (row > 0) { xn = A.x[i - A.cols]; has = true; }
-        else if (A.up) { xn = A.up[col]; has = true; }
-        if (has) {
-            const T d = xi - xn;
-            s = s + d;
-            acc[1] += (double)(T)(d * d);      // vertical edge owned by the lower row
+        const bool hu = (row > 0) || (A.up != NULL), hd = (row + 1 < A.rows) || (A.dn != NULL);
+        const T* xu = (row > 0) ? A.x + i - A.cols : A.up + col;
+        const T* xd = (row + 1 < A.rows) ? A.x + i + A.cols : A.dn + col;
+        if (VEC == 1) {
+            T gi;
+            smooth_elem<T>(A.x[i], A.w[i], A.y[i], hu, hu ? xu[0] : T(0), hd, hd ? xd[0] : T(0), col > 0,
+                           col > 0 ? A.x[i - 1] : T(0), col + 1 < A.cols, col + 1 < A.cols ? A.x[i + 1] : T(0),
+                           A.mu, gi, acc);
+            A.g[i] = gi;
+        } else {
+            constexpr int V = VecOf<T>::N;
+            const Pack<T> px = ld_pack<T>(A.x + i, 0), pw = ld_pack<T>(A.w + i, 0), py = ld_pack<T>(A.y + i, 0);
+            const Pack<T> pu = hu ? ld_pack<T>(xu, 0) : px, pd = hd ? ld_pack<T>(xd, 0) : px;
+            const T xl = (col > 0) ? A.x[i - 1] : T(0);
+            const T xr = (col + V < A.cols) ? A.x[i + V] : T(0);
+            Pack<T> pg;
+#pragma unroll
+            for (int q = 0; q < V; ++q)
+                smooth_elem<T>(px.v[q], pw.v[q], py.v[q], hu, pu.v[q], hd, pd.v[q], col + q > 0,
+                               q > 0 ? px.v[q > 0 ? q - 1 : 0] : xl, col + q + 1 < A.cols,
+                               q + 1 < V ? px.v[q + 1 < V ? q + 1 : 0] : xr, A.mu, pg.v[q], acc);
+            st_pack<T>(A.g + i, 0, pg);
         }
-        // down
-        has = false;
-        if (row + 1 < A.rows) { xn = A.x[i + A.cols]; has = true; }
-        else if (A.dn) { xn = A.dn[col]; has = true; }
-        if (has) s = s + (xi - xn);
-        // left
-        if (col > 0) {
-            const T d = xi - A.x[i - 1];
-            s = s + d;
-            acc[1] += (double)(T)(d * d);      // horizontal edge owned by the right element
-        }
-        // right
-        if (col + 1 < A.cols) s = s + (xi - A.x[i + 1]);
-        A.g[i] = t + A.mu * s;
     }
     block_reduce_publish<2, 0u, 0u>(acc, rs);
 }
@@ -77,7 +94,11 @@ template <typename T>
 static int smooth_launch(opkb_context* ctx, SmoothArgs<T> A, int slot)
 {
     if (A.r1 <= A.r0) return 0;
-    const int64_t ncb = (A.cols + OPKB_BLOCK - 1) / OPKB_BLOCK;
+    // 16-byte packs need rows that start on a 16-byte boundary
+    constexpr int V = VecOf<T>::N;
+    const bool vec = (A.cols % V == 0);
+    const int64_t per = (int64_t)OPKB_BLOCK * (vec ? V : 1);
+    const int64_t ncb = (A.cols + per - 1) / per;
     // (6 CTAs of 256 threads per SM: room is left for the NCCL send/recv kernel to run alongside)
     int grid = opkb_grid_for(ctx, (A.r1 - A.r0) * ncb * OPKB_BLOCK, 6);
     ReduceScratch rs;
@@ -85,7 +106,8 @@ static int smooth_launch(opkb_context* ctx, SmoothArgs<T> A, int slot)
     rs.ticket = ctx->d_ticket;
     rs.res = ctx->d_res + 2 * slot;
     opkb_prof_begin(ctx, OPKB_K_OBJECTIVE);
-    k_smooth2d<T><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
+    if (vec) k_smooth2d<T, V><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
+    else k_smooth2d<T, 1><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
     opkb_prof_end(ctx);
     ctx->launches += 1;
     OPKB_CUDA(cudaGetLastError());
