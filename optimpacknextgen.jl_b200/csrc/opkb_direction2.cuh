@@ -73,10 +73,14 @@ template <int MB> struct Dir2Carry {
 
 // EXACT: m == MB (and every pair takes part is still checked at run time): the
 // unrolled pair loops lose their guards.
-template <typename T, int FUSE, int MB, int TILE, int CARRY, int EXACT = 0>
-__global__ void __launch_bounds__(DIR2_NTHREADS(CARRY), 1) k_direction2(Dir2Args<T> A, ReduceScratch rs)
+// CW: consumer warps (+ 1 producer warp).  8 without CARRY; the CARRY instances run 7
+// (two warps per SM sub-partition: up to 255 registers for the 4 MB + 4 accumulators)
+// or, for few pairs (MB <= 5, where the fixed per-element work makes the kernel
+// issue-bound rather than memory-bound), 11 (three per sub-partition, <= 168 registers).
+template <typename T, int FUSE, int MB, int TILE, int CARRY, int EXACT = 0, int CW = (CARRY ? 7 : 8)>
+__global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, ReduceScratch rs)
 {
-    constexpr int DIR2_THREADS = DIR2_NTHREADS(CARRY);
+    constexpr int DIR2_THREADS = (CW + 1) * 32;
     static_assert(!CARRY || (FUSE != 0 && 2 * MB <= 32), "CARRY needs the fused trial and 2*MB <= 32 rows");
     constexpr int VEC = VecOf<T>::N;
     constexpr int CWARPS = DIR2_THREADS / 32 - 1;
@@ -475,11 +479,21 @@ __global__ void __launch_bounds__(DIR2_NTHREADS(CARRY), 1) k_direction2(Dir2Args
         if (!s_last2) return;
         __threadfence();
         for (int k = tid; k < NTOT; k += DIR2_THREADS) {
+            // four interleaved chains over the CTAs (independent loads in flight), fixed order
             const int kind = (k == 2) ? OPKB_RMIN : ((k == 3) ? OPKB_RMAX : OPKB_RSUM);
-            double a = __ldcg(&rs.part[k]);
-            for (unsigned b = 1; b < gridDim.x; ++b)
-                a = rcombine_dyn(kind, a, __ldcg(&rs.part[(size_t)b * NTOT + k]));
-            rs.res[k] = a;
+            double a[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[j] = rneutral_dyn(kind);
+            unsigned b = 0;
+#pragma unroll 4
+            for (; b + 4 <= gridDim.x; b += 4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    a[j] = rcombine_dyn(kind, a[j], __ldcg(&rs.part[(size_t)(b + j) * NTOT + k]));
+            }
+            for (int j = 0; b < gridDim.x; ++b, ++j)
+                a[j] = rcombine_dyn(kind, a[j], __ldcg(&rs.part[(size_t)b * NTOT + k]));
+            rs.res[k] = rcombine_dyn(kind, rcombine_dyn(kind, a[0], a[1]), rcombine_dyn(kind, a[2], a[3]));
         }
         if (tid == 0) *rs.ticket = 0u;
     }
@@ -489,7 +503,8 @@ __global__ void __launch_bounds__(DIR2_NTHREADS(CARRY), 1) k_direction2(Dir2Args
 // Launchers (instantiated in opkb_direction2_plain.cu / opkb_direction2_carry.cu so
 // that the translation units build in parallel).  `fuse`: 0 | OPKB_OBJ_ROSENBROCK |
 // OPKB_OBJ_QUADRATIC; (mb, tile) must be one of the instances listed there.
-#define DIR2_CARRY_ROWB 3584   // bytes per staged row of the CARRY instances (7 consumer warps x 512 B)
+#define DIR2_CARRY_ROWB 3584    // bytes per staged row of the CARRY instances (7 consumer warps x 512 B)
+#define DIR2_CARRY_ROWB5 5632   // same for the MB = 5 instances (11 consumer warps)
 template <typename T>
 int dir2_launch_plain(opkb_context* ctx, const Dir2Args<T>& B, int fuse, int mb, size_t smem, int grid);
 template <typename T>

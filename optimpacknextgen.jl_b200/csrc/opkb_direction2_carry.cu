@@ -6,14 +6,15 @@
 template <typename T>
 int dir2_launch_carry(opkb_context* ctx, const Dir2Args<T>& B, int fuse, int mb, size_t smem, int grid)
 {
-    constexpr int TC = DIR2_CARRY_ROWB / (int)sizeof(T);
+    constexpr int TC = DIR2_CARRY_ROWB / (int)sizeof(T), TC5 = DIR2_CARRY_ROWB5 / (int)sizeof(T);
     void (*kern)(Dir2Args<T>, ReduceScratch) = NULL;
-    if (B.tile != TC) return opkb_set_error(OPKB_EINVAL, "carry instances use %d-byte rows", DIR2_CARRY_ROWB);
+    if (B.tile != ((mb == 5) ? TC5 : TC))
+        return opkb_set_error(OPKB_EINVAL, "carry instances use %d / %d-byte rows", DIR2_CARRY_ROWB5, DIR2_CARRY_ROWB);
     // (MB, EXACT) instances: m < 5: (5, 0); m = 5: (5, 1); m <= 8: (8, 0); m = 10: (10, 1); else (12, 0)
 #define DIR2_PICK(F)                                                              \
     do {                                                                          \
-        if (mb == 5 && B.m == 5) kern = k_direction2<T, F, 5, TC, 1, 1>;          \
-        else if (mb == 5) kern = k_direction2<T, F, 5, TC, 1, 0>;                 \
+        if (mb == 5 && B.m == 5) kern = k_direction2<T, F, 5, TC5, 1, 1, 11>;     \
+        else if (mb == 5) kern = k_direction2<T, F, 5, TC5, 1, 0, 11>;            \
         else if (mb == 8) kern = k_direction2<T, F, 8, TC, 1, 0>;                 \
         else if (mb == 10 && B.m == 10) kern = k_direction2<T, F, 10, TC, 1, 1>;  \
         else if (mb == 12) kern = k_direction2<T, F, 12, TC, 1, 0>;               \
@@ -21,7 +22,7 @@ int dir2_launch_carry(opkb_context* ctx, const Dir2Args<T>& B, int fuse, int mb,
     if (fuse == OPKB_OBJ_ROSENBROCK) DIR2_PICK(OPKB_OBJ_ROSENBROCK);
     else if (fuse == OPKB_OBJ_QUADRATIC) DIR2_PICK(OPKB_OBJ_QUADRATIC);
 #undef DIR2_PICK
-    return dir2_do_launch<T>(ctx, kern, B, DIR2_NTHREADS(1), smem, grid);
+    return dir2_do_launch<T>(ctx, kern, B, (mb == 5) ? 384 : DIR2_NTHREADS(1), smem, grid);
 }
 
 template int dir2_launch_carry<double>(opkb_context*, const Dir2Args<double>&, int, int, size_t, int);

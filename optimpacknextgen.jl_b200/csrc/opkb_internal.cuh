@@ -313,25 +313,35 @@ __device__ void block_reduce_publish(double (&v)[NR], const ReduceScratch& rs)
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // last CTA: for each slot, strided partial over the CTAs then the same tree
+    // last CTA: for each slot, strided partial over the CTAs then the same tree.  All
+    // slots are fetched before the first barrier (independent loads in flight together).
+    double t[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) t[k] = rneutral_dyn(rkind(MAXM, MINM, k));
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < NR; ++k)
+            t[k] = rcombine_dyn(rkind(MAXM, MINM, k), t[k], __ldcg(&rs.part[(size_t)b * NR + k]));
+    }
+    __syncthreads();   // sm[][] of the first phase has been consumed by every thread
+#pragma unroll
     for (int k = 0; k < NR; ++k) {
         const int kind = rkind(MAXM, MINM, k);
-        double a = rneutral_dyn(kind);
-        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
-            a = rcombine_dyn(kind, a, __ldcg(&rs.part[(size_t)b * NR + k]));
+        double a = t[k];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             double c = __shfl_xor_sync(0xffffffffu, a, off);
             a = rcombine_dyn(kind, a, c);
         }
-        __syncthreads();
-        if (lane == 0) sm[0][warp] = a;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double r = sm[0][0];
-            for (int w = 1; w < nwarps; ++w) r = rcombine_dyn(kind, r, sm[0][w]);
-            rs.res[k] = r;
-        }
+        if (lane == 0) sm[k][warp] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < NR) {
+        const int k = threadIdx.x;
+        const int kind = rkind(MAXM, MINM, k);
+        double r = sm[k][0];
+        for (int w = 1; w < nwarps; ++w) r = rcombine_dyn(kind, r, sm[k][w]);
+        rs.res[k] = r;
     }
     if (threadIdx.x == 0) *rs.ticket = 0u;
 }

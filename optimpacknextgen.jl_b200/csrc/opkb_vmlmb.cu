@@ -864,14 +864,16 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         // ring geometry: 4 KB rows when two stages fit in ~220 KB, else 2 KB rows; the
         // CARRY instances use 3.5 KB rows (7 consumer warps) and need two stages of them
         const size_t budget = 220 * 1024;
-        if (carry && (size_t)nr * DIR2_CARRY_ROWB * 2 > budget) carry = 0;
+        const int carry_mb = (A.m <= 5) ? 5 : ((A.m <= 8) ? 8 : ((A.m == 10) ? 10 : 12));
+        const int carry_rowb = (carry_mb == 5) ? DIR2_CARRY_ROWB5 : DIR2_CARRY_ROWB;
+        if (carry && (size_t)nr * carry_rowb * 2 > budget) carry = 0;
         int tile = (int)(4096 / sizeof(T));
         if ((size_t)nr * tile * sizeof(T) * 2 > budget || A.m > 12) tile = (int)(2048 / sizeof(T));
         if (const char* e = getenv("OPKB_DIR_ROWB")) {   // tuning knob: 2048 | 4096 bytes per row
             const int rb = atoi(e);
             if (rb == 2048 || (rb == 4096 && A.m <= 12)) tile = rb / (int)sizeof(T);
         }
-        if (carry) tile = DIR2_CARRY_ROWB / (int)sizeof(T);
+        if (carry) tile = carry_rowb / (int)sizeof(T);
         size_t stage_bytes = (size_t)nr * tile * sizeof(T);
         int nstage = (int)(budget / stage_bytes);
         if (const char* e = getenv("OPKB_DIR_NSTAGE")) nstage = atoi(e);
@@ -883,7 +885,7 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
             B.n = ws->n;
             const size_t smem = stage_bytes * nstage;
             int mb;
-            if (carry) mb = (A.m <= 5) ? 5 : ((A.m <= 8) ? 8 : ((A.m == 10) ? 10 : 12));
+            if (carry) mb = carry_mb;
             else if (tile * sizeof(T) == 4096) mb = (A.m <= 8) ? 8 : 12;
             else mb = (A.m <= 12) ? 12 : 20;
             const int nd = carry ? 4 * mb + 4 : 0;
