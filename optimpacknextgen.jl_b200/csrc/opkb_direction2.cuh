@@ -478,23 +478,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
         __syncthreads();
         if (!s_last2) return;
         __threadfence();
-        for (int k = tid; k < NTOT; k += DIR2_THREADS) {
-            // four interleaved chains over the CTAs (independent loads in flight), fixed order
-            const int kind = (k == 2) ? OPKB_RMIN : ((k == 3) ? OPKB_RMAX : OPKB_RSUM);
-            double a[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) a[j] = rneutral_dyn(kind);
-            unsigned b = 0;
-#pragma unroll 4
-            for (; b + 4 <= gridDim.x; b += 4) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    a[j] = rcombine_dyn(kind, a[j], __ldcg(&rs.part[(size_t)(b + j) * NTOT + k]));
-            }
-            for (int j = 0; b < gridDim.x; ++b, ++j)
-                a[j] = rcombine_dyn(kind, a[j], __ldcg(&rs.part[(size_t)b * NTOT + k]));
-            rs.res[k] = rcombine_dyn(kind, rcombine_dyn(kind, a[0], a[1]), rcombine_dyn(kind, a[2], a[3]));
-        }
+        last_cta_combine(rs.part, rs.res, NTOT, gridDim.x,
+                         [](int k) { return (k == 2) ? OPKB_RMIN : ((k == 3) ? OPKB_RMAX : OPKB_RSUM); });
+        __syncthreads();
         if (tid == 0) *rs.ticket = 0u;
     }
 }

@@ -292,11 +292,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int s = tid; s < nslot; s += blockDim.x) {
-        double a = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) a += __ldcg(&rs.part[(size_t)b * nslot + s]);
-        rs.res[s] = a;
-    }
+    last_cta_combine(rs.part, rs.res, nslot, gridDim.x, [](int) { return (int)OPKB_RSUM; });
+    __syncthreads();
     if (tid == 0) *rs.ticket = 0u;
 }
 

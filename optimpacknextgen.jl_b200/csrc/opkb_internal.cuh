@@ -346,6 +346,40 @@ __device__ void block_reduce_publish(double (&v)[NR], const ReduceScratch& rs)
     if (threadIdx.x == 0) *rs.ticket = 0u;
 }
 
+// Last-CTA combination of per-CTA partials for kernels that reduce many slots
+// (Gram sweep, fused direction kernel): res[k] = combine_b part[b * N + k].  Warp w
+// takes the slots w, w + nwarps, ... two at a time; lane l combines the CTAs l, l + 32,
+// ... in that order, then the butterfly: every load of a warp is in flight at once
+// (one thread walking the CTAs serially costs ~500 cycles per CTA), fixed order.
+template <typename KindOf>
+__device__ __forceinline__ void last_cta_combine(const double* part, double* res, int N, unsigned nblk,
+                                                 KindOf kind_of)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int k0 = 2 * warp; k0 < N; k0 += 2 * nw) {
+        const int k1 = (k0 + 1 < N) ? k0 + 1 : k0;
+        const int kind0 = kind_of(k0), kind1 = kind_of(k1);
+        double a0 = rneutral_dyn(kind0), a1 = rneutral_dyn(kind1);
+        for (unsigned b = lane; b < nblk; b += 32) {
+            const double v0 = __ldcg(&part[(size_t)b * N + k0]);
+            const double v1 = __ldcg(&part[(size_t)b * N + k1]);
+            a0 = rcombine_dyn(kind0, a0, v0);
+            a1 = rcombine_dyn(kind1, a1, v1);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double c0 = __shfl_xor_sync(0xffffffffu, a0, off);
+            const double c1 = __shfl_xor_sync(0xffffffffu, a1, off);
+            a0 = rcombine_dyn(kind0, a0, c0);
+            a1 = rcombine_dyn(kind1, a1, c1);
+        }
+        if (lane == 0) {
+            res[k0] = a0;
+            if (k1 != k0) res[k1] = a1;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // mbarrier / bulk-async-copy (TMA, SASS UBLKCP) primitives of the shared-memory
 // rings of the Gram sweep (opkb_gram2.cuh) and of the direction kernel.
