@@ -320,6 +320,20 @@ function make_workspace(::Type{T}, ctx::Context, n::Int, mem::Int, method::Int, 
     finalizer(w -> ccall((:opkb_vmlmb_destroy, libopkb200), Cint, (Ptr{Cvoid},), w.ptr), ws)
     return ws
 end
+"""
+    carry_stats(ws) -> (hits, misses)
+
+how many Gram blocks of this workspace were assembled without a sweep over the pairs
+(the incremental Gram of the fused direction + trial kernel, DESIGN.md section 4) and how
+many sweeps ran although a carry was armed.  Diagnostics only: `vmlmb!` needs no change.
+"""
+function carry_stats(ws::Workspace)
+    h, m = Ref{Int64}(0), Ref{Int64}(0)
+    check(ccall((:opkb_vmlmb_carry_stats, libopkb200), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}),
+                ws.ptr, h, m))
+    return (h[], m[])
+end
+
 wsvector(ws::Workspace{T}, which::Char, slot::Integer = 0) where {T} =
     DeviceVector{T}(ws.ctx, ccall((:opkb_vmlmb_vector, libopkb200), Ptr{Cvoid},
                                   (Ptr{Cvoid}, Cint, Cint), ws.ptr, Cint(which), slot), ws.n)
