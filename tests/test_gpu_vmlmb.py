@@ -481,3 +481,29 @@ def test_full_size_spg(opk):
     assert runs["fused"] == runs["fused2"]
     for a, b in zip(runs["fused"], runs["primitive"]):
         assert a[:2] == b[:2] and abs(a[2] - b[2]) <= 1e-4 * abs(b[2])
+
+
+@pytest.mark.parametrize("mode,native", [("fused", False), ("primitive", False), ("fused", True)])
+def test_unconstrained_follows_scipy_lbfgsb(opk, mode, native):
+    """The CUDA path against an implementation that is NOT the oracle: without bounds
+    `vmlmb` is L-BFGS with `dcsrch`, and so is SciPy's L-BFGS-B (same line-search
+    constants, same first step, same H0 scaling; tests/test_pins_scipy.py).  The
+    iterates agree to the north_star tolerance over the first 20 iterations."""
+    from test_pins_scipy import NOSTOP, assert_follows_lbfgsb, lbfgsb_cases, lbfgsb_trajectory
+
+    for name, fg, oobj, gobj, x0, mem in lbfgsb_cases():
+        ref = lbfgsb_trajectory(fg, x0, mem, 25)
+        tr = []
+        cls = opk.NativeVMLMB if native else opk.VMLMB
+        kw = dict(mem=mem, maxiter=25, observer=lambda s: tr.append(dict(iter=s.iter, f=s.f, x=s.x.download())),
+                  **NOSTOP)
+        if not native:
+            kw["mode"] = mode
+        s = cls(gobj, x0, **kw)
+        if native:
+            while s.iterate(1):     # the native driver reports once per call
+                pass
+        else:
+            s.solve()
+        s.close()
+        assert_follows_lbfgsb(tr, ref)

@@ -120,3 +120,75 @@ def test_two_loop_equals_scipy_inverse_hessian_product(oracle):
             modif, _ = oracle.apply_lbfgs(S, Y, rho, 1.0, m, mark, got)
             assert modif
             assert np.linalg.norm(got - want) <= 1e-12 * np.linalg.norm(want)
+
+
+# ---------------------------------------------------------------------------
+# K11, method 0 (`_vmlmb!` without bounds = L-BFGS + More-Thuente,
+# src/quasinewton.jl:381-601 with :273 method 0 and the defaults of :276-278)
+# against SciPy's L-BFGS-B (the C translation of Zhu/Byrd/Lu/Nocedal's Fortran
+# code): without bounds L-BFGS-B reduces to L-BFGS with `dcsrch` (ftol = 1e-3,
+# gtol = 0.9, xtol = 0.1: the same three numbers as vmlmb's default line search), a
+# first step 1/|g| then 1, and H0 = (s.y / y.y) I -- the same algorithm, coded
+# independently (compact representation instead of the two-loop recursion).  The
+# iterate sequences must agree to rounding: 1e-10 over the first 20 iterations, the
+# north_star's own tolerance.
+def _rosen_np(x):
+    x1, x2 = x[0::2], x[1::2]
+    g2 = 200 * (x2 - x1 * x1)
+    g = np.empty_like(x)
+    g[1::2] = g2
+    g[0::2] = -2 * (x1 * g2 + (1 - x1))
+    return float(np.sum((1 - x1) ** 2) + np.sum((10 * (x2 - x1 * x1)) ** 2)), g
+
+
+def lbfgsb_trajectory(fg, x0, mem, niter):
+    """[(f_k, x_k)] for k = 1..niter from scipy.optimize's L-BFGS-B, no bounds."""
+    so = pytest.importorskip("scipy.optimize")
+    tr = []
+    so.minimize(fg, x0, jac=True, method="L-BFGS-B", callback=lambda xk: tr.append((fg(xk)[0], xk.copy())),
+                options=dict(maxcor=mem, ftol=0.0, gtol=0.0, maxiter=niter, maxls=20))
+    return tr
+
+
+def lbfgsb_cases():
+    import opkb200 as opk
+
+    for n, mem in ((20, 5), (20, 15), (1000, 5), (1000, 7), (100000, 5)):
+        x0 = opk.Rosenbrock.x0(n, np.float64, perturb_seed=7 if n > 20 else None)
+        yield "rosen%d-m%d" % (n, mem), _rosen_np, "rosenbrock", opk.Rosenbrock(), x0, mem
+    for n, mem in ((1003, 10), (5000, 3)):
+        a, c = opk.Quadratic.synthetic(n, np.float64, kappa=1e3)
+        yield ("quad%d-m%d" % (n, mem), lambda x, a=a, c=c: (float(0.5 * np.sum(a * (x - c) ** 2)), a * (x - c)),
+               ("quadratic", a, c), opk.Quadratic(a, c), np.full(n, 0.5), mem)
+
+
+def assert_follows_lbfgsb(trace, ref, niter=20, rtol=1e-10):
+    trace = [t for t in trace if t["iter"] > 0]
+    assert len(trace) >= niter and len(ref) >= niter
+    for k in range(niter):
+        f, x = ref[k]
+        assert trace[k]["iter"] == k + 1
+        assert abs(trace[k]["f"] - f) <= rtol * abs(f), (k, trace[k]["f"], f)
+        assert np.linalg.norm(trace[k]["x"] - x) <= rtol * np.linalg.norm(x), k
+
+
+NOSTOP = dict(xtol=(0.0, 0.0), ftol=(0.0, 0.0), gtol=(0.0, 0.0))
+
+
+def test_unconstrained_vmlmb_follows_scipy_lbfgsb(oracle):
+    from cpu_backend import NumpyOps
+
+    import opkb200 as opk
+
+    for name, fg, oobj, gobj, x0, mem in lbfgsb_cases():
+        ref = lbfgsb_trajectory(fg, x0, mem, 25)
+        _, ro, tro = oracle.vmlmb(oobj, x0, None, None, mem=mem, maxiter=25, trace=True, **NOSTOP)
+        assert_follows_lbfgsb(tro, ref)
+        if len(x0) > 5000:
+            continue
+        # the product's host stage machine (numpy vector ops: tests/cpu_backend.py)
+        tr = []
+        s = opk.VMLMB(gobj, x0, mem=mem, maxiter=25, mode=lambda solver, x, o=oobj: NumpyOps(solver, x, o),
+                      observer=lambda s: tr.append(dict(iter=s.iter, f=s.f, x=np.array(s.x))), **NOSTOP)
+        s.solve()
+        assert_follows_lbfgsb(tr, ref)
