@@ -180,6 +180,31 @@ int opkb_smooth2d_fg(opkb_context* ctx, const opkb_vector* w, const opkb_vector*
                      int64_t cols, const opkb_vector* x, opkb_vector* up, opkb_vector* dn,
                      opkb_vector* g, double* f);
 
+/* The same stencil as a linear operator: q = A.p, A = diag(w) + mu*L (the Hessian of
+ * the objective above; symmetric positive definite for w > 0), the `A` of `conjgrad`
+ * for this workload.  Same row sharding and halo exchange.  out[0] = p.q, out[1] = p.p
+ * (global values) are reduced in the same pass. */
+int opkb_smooth2d_apply(opkb_context* ctx, const opkb_vector* w, double mu, int64_t cols,
+                        const opkb_vector* p, opkb_vector* up, opkb_vector* dn, opkb_vector* q,
+                        double out[2]);
+
+/* ---- Tier 2: fused passes of `conjgrad!` ------------------------
+ * `conjgrad` / `conjgrad!` are re-exported by the reference from LazyAlgebra
+ * (src/OptimPackNextGen.jl:18-19, :36; call site test/conjgrad-tests.jl:30).  One
+ * iteration = direction (`vcombine!(p, beta, p, 1, r)`: opkb_vcombine), operator,
+ * curvature gamma = vdot(p, q), update.  All sums: exact products accumulated in double,
+ * fixed order, combined over the ranks. */
+/* x += alpha*p; r -= alpha*q (two `vupdate!`) and, from the same pass, out[0] = vdot(r, r),
+ * out[1] = vdot(x, x): 6 passes instead of 9 (11 with the x test). */
+int opkb_cg_update(opkb_context* ctx, opkb_vector* x, opkb_vector* r, const opkb_vector* p,
+                   const opkb_vector* q, double alpha, double out[2]);
+/* out[0] = vdot(p, q), out[1] = vdot(p, p) in one pass (user operators). */
+int opkb_cg_curvature(opkb_context* ctx, const opkb_vector* p, const opkb_vector* q, double out[2]);
+/* A = diag(a) (`vproduct!`): p = r (restart != 0) or beta*p + r; q = a.*p; out[0] = p.q,
+ * out[1] = p.p: direction + operator + curvature in 5 passes. */
+int opkb_cg_diag_step(opkb_context* ctx, const opkb_vector* a, opkb_vector* p, const opkb_vector* r,
+                      opkb_vector* q, double beta, int restart, double out[2]);
+
 /* ---- Tier 2: fused phases of `_vmlmb!` (src/quasinewton.jl:381-601) ------- */
 /* The workspace owns x, g, p, d and the mem pairs S[k], Y[k] (src/quasinewton.jl:358-369).
  * lo/hi handles must outlive the workspace. */

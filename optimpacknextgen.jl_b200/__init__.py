@@ -22,6 +22,9 @@ from .spg import SPG, spg, spg_, Info, BoxProjection, default_printer
 from .spg import getreason as _spg_getreason
 from .spg import (SEARCHING, INFNORM_CONVERGENCE, TWONORM_CONVERGENCE, FUNCTION_CONVERGENCE,
                   TOO_MANY_ITERATIONS, TOO_MANY_EVALUATIONS)
+from .conjgrad import (ConjGrad, conjgrad, conjgrad_, DiagonalOperator, Smooth2DOperator, CG_REASON,
+                       CG_SEARCHING, CG_GTEST, CG_FTEST, CG_XTEST, CG_TOO_MANY_ITERATIONS,
+                       CG_NOT_POSITIVE_DEFINITE)
 from . import dist
 
 

@@ -89,6 +89,10 @@ _SIGNATURES = {
     "opkb_rosenbrock_fg": (C.c_int, [vp, vp, vp, Pd]),
     "opkb_quadratic_fg": (C.c_int, [vp, vp, vp, vp, vp, Pd]),
     "opkb_smooth2d_fg": (C.c_int, [vp, vp, vp, f64, i64, vp, vp, vp, vp, Pd]),
+    "opkb_smooth2d_apply": (C.c_int, [vp, vp, f64, i64, vp, vp, vp, vp, Pd]),
+    "opkb_cg_update": (C.c_int, [vp, vp, vp, vp, vp, f64, Pd]),
+    "opkb_cg_curvature": (C.c_int, [vp, vp, vp, Pd]),
+    "opkb_cg_diag_step": (C.c_int, [vp, vp, vp, vp, vp, f64, C.c_int, Pd]),
     "opkb_vmlmb_create": (C.c_int, [vp, C.c_int, i64, C.c_int, C.c_int, vp, f64, vp, f64,
                                     C.POINTER(vp)]),
     "opkb_vmlmb_destroy": (C.c_int, [vp]),

@@ -30,29 +30,36 @@ template <typename T> struct SmoothArgs {
 // same pack or cache line, those of the rows above / below from L2 (each x element is
 // fetched from HBM once).  Arithmetic in T without contraction, in the fixed order up,
 // down, left, right, so that g is bit-identical to the obvious array expression.
-template <typename T> __device__ __forceinline__ void smooth_elem(
+// HESS: the same stencil as a linear operator, q = A.p with A = diag(w) + mu*L (the
+// Hessian of f, y plays no role), and the two sums a conjugate-gradient step needs from
+// that pass: acc[0] = p.q, acc[1] = p.p (exact products accumulated in double).
+template <typename T, bool HESS> __device__ __forceinline__ void smooth_elem(
     T xi, T wi, T yi, bool hu, T xu, bool hd, T xd, bool hl, T xl, bool hr, T xr, T mu, T& gi, double (&acc)[2])
 {
-    const T r = xi - yi;
+    const T r = HESS ? xi : xi - yi;
     const T t = wi * r;
-    acc[0] += (double)(T)(t * r);
+    if (!HESS) acc[0] += (double)(T)(t * r);
     T s = T(0);
     if (hu) {
         const T d = xi - xu;
         s = s + d;
-        acc[1] += (double)(T)(d * d);      // vertical edge: owned by the lower row
+        if (!HESS) acc[1] += (double)(T)(d * d);      // vertical edge: owned by the lower row
     }
     if (hd) s = s + (xi - xd);
     if (hl) {
         const T d = xi - xl;
         s = s + d;
-        acc[1] += (double)(T)(d * d);      // horizontal edge: owned by the right element
+        if (!HESS) acc[1] += (double)(T)(d * d);      // horizontal edge: owned by the right element
     }
     if (hr) s = s + (xi - xr);
     gi = t + mu * s;
+    if (HESS) {
+        acc[0] = dacc(xi, gi, acc[0]);
+        acc[1] = dacc(xi, xi, acc[1]);
+    }
 }
 
-template <typename T, int VEC>
+template <typename T, int VEC, bool HESS>
 __global__ void __launch_bounds__(OPKB_BLOCK) k_smooth2d(SmoothArgs<T> A, ReduceScratch rs)
 {
     const int64_t ncb = (A.cols + OPKB_BLOCK * VEC - 1) / (OPKB_BLOCK * VEC);
@@ -68,20 +75,21 @@ __global__ void __launch_bounds__(OPKB_BLOCK) k_smooth2d(SmoothArgs<T> A, Reduce
         const T* xd = (row + 1 < A.rows) ? A.x + i + A.cols : A.dn + col;
         if (VEC == 1) {
             T gi;
-            smooth_elem<T>(A.x[i], A.w[i], A.y[i], hu, hu ? xu[0] : T(0), hd, hd ? xd[0] : T(0), col > 0,
+            smooth_elem<T, HESS>(A.x[i], A.w[i], HESS ? T(0) : A.y[i], hu, hu ? xu[0] : T(0), hd, hd ? xd[0] : T(0), col > 0,
                            col > 0 ? A.x[i - 1] : T(0), col + 1 < A.cols, col + 1 < A.cols ? A.x[i + 1] : T(0),
                            A.mu, gi, acc);
             A.g[i] = gi;
         } else {
             constexpr int V = VecOf<T>::N;
-            const Pack<T> px = ld_pack<T>(A.x + i, 0), pw = ld_pack<T>(A.w + i, 0), py = ld_pack<T>(A.y + i, 0);
+            const Pack<T> px = ld_pack<T>(A.x + i, 0), pw = ld_pack<T>(A.w + i, 0);
+            const Pack<T> py = HESS ? px : ld_pack<T>(A.y + i, 0);
             const Pack<T> pu = hu ? ld_pack<T>(xu, 0) : px, pd = hd ? ld_pack<T>(xd, 0) : px;
             const T xl = (col > 0) ? A.x[i - 1] : T(0);
             const T xr = (col + V < A.cols) ? A.x[i + V] : T(0);
             Pack<T> pg;
 #pragma unroll
             for (int q = 0; q < V; ++q)
-                smooth_elem<T>(px.v[q], pw.v[q], py.v[q], hu, pu.v[q], hd, pd.v[q], col + q > 0,
+                smooth_elem<T, HESS>(px.v[q], pw.v[q], py.v[q], hu, pu.v[q], hd, pd.v[q], col + q > 0,
                                q > 0 ? px.v[q > 0 ? q - 1 : 0] : xl, col + q + 1 < A.cols,
                                q + 1 < V ? px.v[q + 1 < V ? q + 1 : 0] : xr, A.mu, pg.v[q], acc);
             st_pack<T>(A.g + i, 0, pg);
@@ -106,8 +114,11 @@ static int smooth_launch(opkb_context* ctx, SmoothArgs<T> A, int slot)
     rs.ticket = ctx->d_ticket;
     rs.res = ctx->d_res + 2 * slot;
     opkb_prof_begin(ctx, OPKB_K_OBJECTIVE);
-    if (vec) k_smooth2d<T, V><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
-    else k_smooth2d<T, 1><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
+    const bool hess = (A.y == NULL);
+    if (vec && hess) k_smooth2d<T, V, true><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
+    else if (vec) k_smooth2d<T, V, false><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
+    else if (hess) k_smooth2d<T, 1, true><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
+    else k_smooth2d<T, 1, false><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
     opkb_prof_end(ctx);
     ctx->launches += 1;
     OPKB_CUDA(cudaGetLastError());
@@ -118,6 +129,7 @@ template <typename T>
 static int smooth_run(opkb_context* ctx, const opkb_vector* w, const opkb_vector* y, double mu, int64_t cols,
                       const opkb_vector* x, opkb_vector* up, opkb_vector* dn, opkb_vector* g, double* f)
 {
+    // y == NULL: operator mode, f[0] = x.g, f[1] = x.x (opkb_smooth2d_apply)
     const int64_t rows = x->n / cols;
     const bool has_up = ctx->nranks > 1 && ctx->rank > 0;
     const bool has_dn = ctx->nranks > 1 && ctx->rank < ctx->nranks - 1;
@@ -142,7 +154,7 @@ static int smooth_run(opkb_context* ctx, const opkb_vector* w, const opkb_vector
     SmoothArgs<T> A;
     A.x = (const T*)x->data;
     A.w = (const T*)w->data;
-    A.y = (const T*)y->data;
+    A.y = y ? (const T*)y->data : NULL;
     A.up = has_up ? (const T*)up->data : NULL;
     A.dn = has_dn ? (const T*)dn->data : NULL;
     A.g = (T*)g->data;
@@ -175,7 +187,12 @@ static int smooth_run(opkb_context* ctx, const opkb_vector* w, const opkb_vector
     if (rc) return rc;
     // fixed order: interior, first row, last row
     const double fd = (r[0] + r[2]) + r[4], fe = (r[1] + r[3]) + r[5];
-    *f = 0.5 * fd + (0.5 * mu) * fe;
+    if (y) {
+        *f = 0.5 * fd + (0.5 * mu) * fe;
+    } else {
+        f[0] = fd;
+        f[1] = fe;
+    }
     return 0;
 }
 
@@ -193,4 +210,24 @@ extern "C" int opkb_smooth2d_fg(opkb_context* ctx, const opkb_vector* w, const o
     if (x == g) return opkb_set_error(OPKB_EINVAL, "g must not alias x");
     return (x->eltype == OPKB_DOUBLE) ? smooth_run<double>(ctx, w, y, mu, cols, x, up, dn, g, f)
                                       : smooth_run<float>(ctx, w, y, mu, cols, x, up, dn, g, f);
+}
+
+// q = A.p with A = diag(w) + mu*L, the Hessian of the objective above (symmetric positive
+// definite when w > 0): the linear operator of `conjgrad` for this workload, same row
+// sharding and halo exchange; out[0] = p.q and out[1] = p.p come out of the same pass
+// (the `vdot(p, q)` of a conjugate-gradient iteration costs no extra sweep).
+extern "C" int opkb_smooth2d_apply(opkb_context* ctx, const opkb_vector* w, double mu, int64_t cols,
+                                   const opkb_vector* p, opkb_vector* up, opkb_vector* dn, opkb_vector* q,
+                                   double out[2])
+{
+    if (!ctx || !w || !p || !q || !out) return opkb_set_error(OPKB_EINVAL, "NULL argument");
+    if (cols < 1 || p->n < cols || p->n % cols != 0)
+        return opkb_set_error(OPKB_EINVAL, "the local block must be a whole number of rows of %lld elements",
+                              (long long)cols);
+    if (w->n != p->n || q->n != p->n || w->eltype != p->eltype || q->eltype != p->eltype ||
+        (up && up->eltype != p->eltype) || (dn && dn->eltype != p->eltype))
+        return opkb_set_error(OPKB_EINVAL, "w, p, q must belong to the same space");
+    if (p == q || p->data == q->data) return opkb_set_error(OPKB_EINVAL, "q must not alias p");
+    return (p->eltype == OPKB_DOUBLE) ? smooth_run<double>(ctx, w, NULL, mu, cols, p, up, dn, q, out)
+                                      : smooth_run<float>(ctx, w, NULL, mu, cols, p, up, dn, q, out);
 }

@@ -125,6 +125,13 @@ typedef struct {
     int     status;
 } opko_spg_info;
 
+/* ---- conjgrad (LazyAlgebra, re-exported: src/OptimPackNextGen.jl:18-19) --- */
+typedef struct {
+    double  rho, phi, psi;
+    int64_t iter;
+    int     status;
+} opko_cg_info;
+
 /* ---- type-generic part: declared twice ---------------------------------- */
 #define OPKO_DECLARE(P, T)                                                     \
     typedef double (*P##fg_fn)(void* ctx, int64_t n, const T* x, T* g);        \
@@ -137,6 +144,10 @@ typedef struct {
                                 const T* p);                                   \
     typedef void (*P##spg_trace_fn)(void* ctx, const opko_spg_info* info,      \
                                     int64_t n, const T* x, const T* pg);       \
+    typedef void (*P##op_fn)(void* ctx, int64_t n, T* dst, const T* src);      \
+    typedef void (*P##cg_trace_fn)(void* ctx, int64_t iter, double phi,        \
+                                   double rho, int64_t n, const T* x,          \
+                                   const T* r);                                \
     /* LazyAlgebra vector ops (doc/algebra.md:84-116) */                       \
     double P##vdot(int64_t n, const T* x, const T* y);                         \
     double P##vdot_sel(int64_t nsel, const int64_t* sel, const T* x,           \
@@ -190,7 +201,13 @@ typedef struct {
     int    P##spg(P##fg_fn fg, void* fg_ctx, P##prj_fn prj, void* prj_ctx,     \
                   int64_t n, T* x, int64_t m, int64_t maxit, int64_t maxfc,    \
                   double eps1, double eps2, double eta, opko_spg_info* ws,     \
-                  P##spg_trace_fn trace, void* trace_ctx);
+                  P##spg_trace_fn trace, void* trace_ctx);                     \
+    int    P##conjgrad(P##op_fn apply, void* op_ctx, int64_t n, T* x,          \
+                       const T* b, double ftol, double gatol, double grtol,    \
+                       double xtol, int64_t maxiter, int64_t restart,          \
+                       opko_cg_info* info, P##cg_trace_fn trace,               \
+                       void* trace_ctx);                                       \
+    void   P##diag_apply(void* ctx, int64_t n, T* dst, const T* src);
 
 OPKO_DECLARE(opko_d_, double)
 OPKO_DECLARE(opko_f_, float)

@@ -57,6 +57,10 @@ class SpgInfo(C.Structure):
                 ("iter", i64), ("fcnt", i64), ("pcnt", i64), ("status", C.c_int)]
 
 
+class CgInfo(C.Structure):
+    _fields_ = [("rho", f64), ("phi", f64), ("psi", f64), ("iter", i64), ("status", C.c_int)]
+
+
 def build(force: bool = False) -> str:
     """Compile the oracle with its Makefile (gcc); returns the .so path."""
     so = os.path.join(_HERE, "libopkoracle.so")
@@ -127,6 +131,9 @@ def lib():
                 C.POINTER(VmlmbOptions), C.POINTER(VmlmbResult), C.c_void_p, C.c_void_p)
             sig("spg", C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, i64, P,
                 i64, i64, i64, f64, f64, f64, C.POINTER(SpgInfo), C.c_void_p, C.c_void_p)
+            sig("conjgrad", C.c_int, C.c_void_p, C.c_void_p, i64, P, P, f64, f64, f64, f64, i64, i64,
+                C.POINTER(CgInfo), C.c_void_p, C.c_void_p)
+            sig("diag_apply", None, C.c_void_p, i64, P, P)
         _LIB = L
     return _LIB
 
@@ -192,6 +199,12 @@ def vnorm2(x):
 def vnorminf(x):
     fn, ct = _fn(x, "vnorminf")
     return fn(x.size, _ptr(x, ct))
+
+
+def vcopy(dst, src):
+    fn, ct = _fn(dst, "vcopy")
+    fn(dst.size, _ptr(dst, ct), _ptr(src, ct))
+    return dst
 
 
 def vscale(x, alpha):
@@ -512,3 +525,47 @@ def spg(obj, x0, m, lower=None, upper=None, prj=None, *, maxit=None, maxfc=None,
                pgtwon=info.pgtwon, iter=info.iter, fcnt=info.fcnt,
                pcnt=info.pcnt, status=info.status)
     return x, out, records
+
+
+def conjgrad(A, b, x0=None, *, ftol=1e-8, gtol=(0.0, 0.0), xtol=0.0, maxiter=None, restart=None,
+             trace=False):
+    """Oracle `conjgrad` (LazyAlgebra, re-exported by src/OptimPackNextGen.jl:18-19, :36;
+    call site test/conjgrad-tests.jl:30).  A: ('diag', a) | python callable A(dst, src) on
+    numpy arrays.  Returns (x, info dict, trace list of dict(iter, phi, rho, x))."""
+    b = np.ascontiguousarray(b)
+    dtype = b.dtype
+    pre, ct = _ct(dtype)
+    L = lib()
+    P = C.POINTER(ct)
+    n = b.size
+    x = np.zeros(n, dtype=dtype) if x0 is None else np.array(x0, dtype=dtype, copy=True).reshape(-1)
+    keep = []
+    if isinstance(A, tuple) and A[0] == "diag":
+        a = np.ascontiguousarray(A[1], dtype=dtype)
+        keep.append(a)
+        app, actx = C.cast(getattr(L, pre + "diag_apply"), C.c_void_p), C.c_void_p(a.ctypes.data)
+    else:
+        OP = C.CFUNCTYPE(None, C.c_void_p, i64, P, P)
+
+        def _a(_ctx, nn, dp, sp):
+            A(np.ctypeslib.as_array(dp, shape=(nn,)), np.ctypeslib.as_array(sp, shape=(nn,)))
+
+        cb = OP(_a)
+        keep.append(cb)
+        app, actx = C.cast(cb, C.c_void_p), None
+    records = []
+    TR = C.CFUNCTYPE(None, C.c_void_p, i64, f64, f64, i64, P, P)
+
+    def _tr(_ctx, k, phi, rho, nn, xp, rp):
+        records.append(dict(iter=k, phi=phi, rho=rho, x=np.ctypeslib.as_array(xp, shape=(nn,)).copy()))
+
+    trcb = TR(_tr) if trace else None
+    info = CgInfo()
+    big = np.iinfo(np.int64).max
+    rc = getattr(L, pre + "conjgrad")(
+        app, actx, n, _ptr(x, ct), _ptr(b.reshape(-1), ct), ftol, gtol[0], gtol[1], xtol,
+        big if maxiter is None else maxiter, min(50, max(n, 1)) if restart is None else restart,
+        C.byref(info), C.cast(trcb, C.c_void_p) if trcb else None, None)
+    if rc != 0:
+        raise ValueError("invalid conjgrad option")
+    return x, dict(iter=info.iter, status=info.status, rho=info.rho, phi=info.phi, psi=info.psi), records

@@ -954,6 +954,99 @@ int FN(spg)(FN(fg_fn) fg, void* fg_ctx, FN(prj_fn) prj, void* prj_ctx,
     return 0;
 }
 
+/* ---- linear conjugate gradient (LazyAlgebra `conjgrad!`) ----------------- */
+/* `conjgrad` / `conjgrad!` are re-exported by the reference from LazyAlgebra.jl
+ * (src/OptimPackNextGen.jl:18-19, :36); LazyAlgebra is neither vendored nor version
+ * pinned (Project.toml:8, no [compat] entry), so this is a restatement of its
+ * PUBLISHED algorithm (LazyAlgebra src/conjgrad.jl, 0.2.x series: Hestenes-Stiefel
+ * recurrences with beta = rho/oldrho, keywords ftol, gtol = (gatol, grtol), xtol,
+ * maxiter, restart, strict), anchored on the reference's call site
+ * test/conjgrad-tests.jl:16-36 (`conjgrad(A!, b; verb, ftol=1e-16,
+ * maxiter=length(b))`, max|x - A\b| <= 1e-7 in Float64, 1e-5 in Float32).
+ * PARITY UNPINNED for the same reasons as the rest of this file.
+ *
+ * Minimises phi(x) = x'.A.x/2 - b'.x for a symmetric positive definite A given as
+ * `apply(ctx, n, dst, src)`; x holds the starting point on entry.  status:
+ * 1 = gtest, 2 = ftest, 3 = xtest, -1 = too many iterations, -2 = A is not
+ * positive definite. */
+int FN(conjgrad)(FN(op_fn) apply, void* op_ctx, int64_t n, REAL* x,
+                 const REAL* b, double ftol, double gatol, double grtol,
+                 double xtol, int64_t maxiter, int64_t restart,
+                 opko_cg_info* info, FN(cg_trace_fn) trace, void* trace_ctx)
+{
+    if (!(ftol >= 0 && gatol >= 0 && grtol >= 0 && xtol >= 0 && restart >= 1))
+        return -1;
+    size_t bytes = (size_t)(n > 0 ? n : 1) * sizeof(REAL);
+    REAL* p = (REAL*)malloc(bytes);
+    REAL* q = (REAL*)malloc(bytes);
+    REAL* r = (REAL*)malloc(bytes);
+    const int xtest = (xtol > 0);
+    int status = 0;
+    int64_t k = 0;
+    double rho, oldrho = 0, phi = 0, psi = 0, psimax = 0;
+
+    if (FN(vdot)(n, x, x) > 0) {       /* r = b - A.x (x0 may be non-zero) */
+        apply(op_ctx, n, r, x);
+        FN(vcombine)(n, r, 1, b, -1, r);
+    } else {                            /* spare one product when x0 = 0 */
+        FN(vcopy)(n, r, b);
+    }
+    rho = FN(vdot)(n, r, r);
+    const double gtest = jl_max(gatol, grtol * sqrt(rho));
+
+    for (;;) {
+        if (trace) trace(trace_ctx, k, phi, rho, n, x, r);
+        if (sqrt(rho) <= gtest) { status = 1; break; }
+        if (k >= maxiter) { status = -1; break; }
+
+        /* search direction */
+        if (k % restart == 0) {
+            if (k > 0) {                /* restart: true residuals */
+                apply(op_ctx, n, r, x);
+                FN(vcombine)(n, r, 1, b, -1, r);
+            }
+            FN(vcopy)(n, p, r);
+        } else {
+            double beta = rho / oldrho;
+            FN(vcombine)(n, p, beta, p, 1, r);
+        }
+
+        /* optimal step */
+        apply(op_ctx, n, q, p);
+        double gamma = FN(vdot)(n, p, q);
+        if (!(gamma > 0)) { status = -2; break; }
+        double alpha = rho / gamma;
+
+        /* variables, convergence in phi and in x */
+        FN(vupdate)(n, x, alpha, p);
+        psi = alpha * rho / 2;          /* phi(x_k) - phi(x_{k+1}) */
+        phi -= psi;
+        psimax = jl_max(psi, psimax);
+        if (psi <= ftol * psimax) { status = 2; k += 1; break; }
+        if (xtest && alpha * FN(vnorm2)(n, p) <= xtol * FN(vnorm2)(n, x)) {
+            status = 3; k += 1; break;
+        }
+
+        /* residuals */
+        FN(vupdate)(n, r, -alpha, q);
+        oldrho = rho;
+        rho = FN(vdot)(n, r, r);
+        k += 1;
+    }
+    if (info) {
+        info->iter = k; info->status = status; info->rho = rho;
+        info->phi = phi; info->psi = psi;
+    }
+    free(p); free(q); free(r);
+    return 0;
+}
+
+/* A = diag(a): `vproduct!` */
+void FN(diag_apply)(void* ctx, int64_t n, REAL* dst, const REAL* src)
+{
+    FN(vproduct)(n, dst, (const REAL*)ctx, src);
+}
+
 #undef REAL_INF
 #undef SUM_BLOCK
 #undef SUM_CHUNK

@@ -305,3 +305,49 @@ class ShardedSmooth2D:
         dr[:, :-1] = x2[:, :-1] - x2[:, 1:]
         g.reshape(-1, self.cols)[...] = t + self.mu * (((du + dd) + dl) + dr)
         return 0.5 * float(np.sum(t * r)) + 0.5 * self.mu * float(np.sum(du * du) + np.sum(dl * dl))
+
+
+class NumpyCgOps:
+    """Vector back end of `opkb200.ConjGrad` (same interface as conjgrad._DeviceOps) on
+    numpy arrays with the oracle's vector operations; `comm` (optional) sums the partial
+    dot products over the ranks in rank order, like the library's packed all-gather."""
+
+    def __init__(self, comm=None):
+        self.comm = comm
+
+    def _sum(self, *vals):
+        if self.comm is None:
+            return vals if len(vals) > 1 else vals[0]
+        out = self.comm(np.array(vals, dtype=np.float64))
+        return tuple(out) if len(vals) > 1 else float(out[0])
+
+    def workspace(self, b):
+        return np.empty_like(b), np.empty_like(b), np.empty_like(b)
+
+    def dot(self, x, y):
+        return self._sum(O.vdot(x, y))
+
+    def copy(self, dst, src):
+        O.vcopy(dst, src)
+
+    def combine(self, dst, a, x, b, y):
+        O.vcombine(dst, a, x, b, y)
+
+    def apply(self, A, dst, src):
+        A(dst, src)
+
+    def direction_apply(self, A, p, r, q, beta, first):
+        if first:
+            O.vcopy(p, r)
+        else:
+            O.vcombine(p, beta, p, 1.0, r)
+        A(q, p)
+        return self._sum(O.vdot(p, q), O.vdot(p, p))
+
+    def update_x(self, x, alpha, p):
+        O.vupdate(x, alpha, p)
+
+    def update(self, x, r, p, q, alpha):
+        O.vupdate(x, alpha, p)
+        O.vupdate(r, -alpha, q)
+        return self._sum(O.vdot(r, r), O.vdot(x, x))
