@@ -162,3 +162,70 @@ def test_combine_partials_fixed_order():
     out = combine_partials(parts, [0, 1, 2])
     assert out == [(1.0 + 1e-17) + 2.0, 7.0, -2.0]
     assert combine_partials([[1.0]], None) == [1.0]
+
+
+def _cg_worker(rank, world, port, rows, cols, q):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+
+    import opk_oracle as O
+    import opkb200 as opk
+    from cpu_backend import NumpyCgOps, ShardedSmooth2D
+    from opkb200.dist import combine_partials, shard_range
+
+    O.set_num_threads(1)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    w, y = opk.Smooth2D.synthetic(rows, cols)
+    r0, nr = shard_range(rows, rank, world, align=1)
+    sl = slice(r0 * cols, (r0 + nr) * cols)
+    stencil = ShardedSmooth2D(w[sl], np.zeros(nr * cols), 2.0, cols)     # y = 0: g = A.x
+
+    def A(dst, src):
+        stencil(src, dst)
+        return dst
+
+    def comm(vals):        # packed all-gather + fixed rank-order sum (opkb_finish_reduction)
+        t = torch.from_numpy(vals)
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return np.array(combine_partials([o.tolist() for o in out], None))
+
+    trace = []
+    s = opk.ConjGrad(A, (w * y)[sl].copy(), np.zeros(nr * cols), ops=NumpyCgOps(comm), ftol=0.0, maxiter=25,
+                     restart=10, quiet=True, nglobal=rows * cols,
+                     observer=lambda s: trace.append((s.iter, s.rho, s.phi)))
+    s.solve()
+    q.put((rank, np.array(s.x), trace, (s.iter, s.status)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_conjgrad_on_the_stencil_operator(oracle):
+    """`conjgrad` with the row-sharded stencil operator and its halo
+    exchange on two ranks: identical decisions, the single-rank oracle's iterates."""
+    import torch.multiprocessing as mp
+
+    import opkb200 as opk
+    world, rows, cols = 2, 31, 40
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cg_worker, args=(r, world, port, rows, cols, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][2] == res[1][2] and res[0][3] == res[1][3]          # identical decisions
+    w, y = opk.Smooth2D.synthetic(rows, cols)
+    xo, info, tro = oracle.conjgrad(opk.Smooth2DOperator.reference(w, 2.0, cols), w * y, ftol=0.0, maxiter=25,
+                                    restart=10, trace=True)
+    assert res[0][3] == (info["iter"], info["status"])
+    for g, wt in zip(res[0][2], tro):
+        assert g[0] == wt["iter"] and abs(g[1] - wt["rho"]) <= 1e-9 * wt["rho"]
+    x = np.concatenate([r[1] for r in res])
+    assert np.linalg.norm(x - xo) <= 1e-10 * np.linalg.norm(xo)

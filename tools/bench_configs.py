@@ -143,6 +143,37 @@ def main():
             # per iteration: trial_begin 5 + fg 4 + trial_end 7 + Gram sweep 2m+5 + direction 2m+6 passes
             r = run_vmlmb(ctx, "S2D VMLMB Smooth2D 16384^2 f64 m=10, box [0,1], halo exchange", obj, x0,
                           0.0, 1.0, 10, nl, n, 20, 8, 4 * 10 + 27)
+        elif c in ("CG", "CGD"):   # conjgrad, stencil (halo exchange) / diagonal operator
+            rows = cols = 16384
+            n = rows * cols
+            r0, nr = shard_range(rows, rank, world, align=1)
+            nl = nr * cols
+            w = ctx.vector(nl, np.float64).fill_random(12, r0 * cols, 0.5, 1.0)
+            b = ctx.vector(nl, np.float64).fill_random(11, r0 * cols, 0.0, 1.2)
+            if c == "CG":
+                A, passes, name = opk.Smooth2DOperator(w, 2.0, cols, ctx=ctx), 12, "stencil diag(w) + 2 L, halo exchange"
+            else:
+                A, passes, name = opk.DiagonalOperator(w, ctx=ctx), 11, "diag(w)"
+            s = opk.ConjGrad(A, b, ftol=0.0, restart=10 ** 9, nglobal=n, ctx=ctx, quiet=True)
+            for _ in range(5):
+                s.iterate()
+            ctx.synchronize()
+            ctx.profile(True)
+            i0, l0, K = s.iter, ctx.launch_count, 50
+            ctx.timer_start()
+            while s.iter < i0 + K and s.iterate():
+                pass
+            ms = ctx.timer_stop()
+            prof = ctx.profile_report()
+            ctx.profile(False)
+            it = max(s.iter - i0, 1)
+            r = {"config": "%s conjgrad 16384^2 f64, %s" % (c, name), "n": n, "iterations": it,
+                 "ms_per_iteration": ms / it, "iterations_per_s": it / (ms * 1e-3),
+                 "launches_per_iteration": (ctx.launch_count - l0) / it, "passes_per_iteration": passes,
+                 "alg_GBps_per_gpu": passes * 8 * nl / (ms * 1e-3 / it) / 1e9, "rho": s.rho,
+                 "kernels_ms_per_iteration": {k: round(v[0] / it, 4) for k, v in prof.items()},
+                 "kernel_launches_per_iteration": {k: round(v[1] / it, 2) for k, v in prof.items()}}
+            r["frac_of_measured_peak"] = r["alg_GBps_per_gpu"] / PEAK
         else:
             continue
         r["n_gpus"] = world
