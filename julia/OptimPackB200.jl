@@ -22,9 +22,11 @@
 #
 module OptimPackB200
 
-export DeviceVector, BoundedSet, Rosenbrock, Quadratic, Smooth2D, vmlmb, vmlmb!, vmlmb_native!, spg, spg!
+export DeviceVector, BoundedSet, Rosenbrock, Quadratic, Smooth2D, vmlmb, vmlmb!, vmlmb_native!, spg, spg!,
+    conjgrad, conjgrad!, DiagonalOperator, Smooth2DOperator
 
 using Libdl
+using Printf
 import LazyAlgebra
 import LazyAlgebra: vcreate, vcopy!, vcopy, vdot, vnorm2, vnorminf, vscale!, vupdate!,
     vcombine!, vproduct!, vfill!
@@ -736,5 +738,119 @@ function fused_spg!(fg!, box::BoundedSet, x::DeviceVector{T}, m::Int;
     end
     return x
 end
+
+# ---------------------------------------------------------------------------
+# conjgrad / conjgrad! (re-exported by the reference from LazyAlgebra:
+# src/OptimPackNextGen.jl:18-19, :36; call site test/conjgrad-tests.jl:30).  With plan (A)
+# LazyAlgebra's own `conjgrad!` already runs on `DeviceVector`s, one kernel per call.  This
+# is plan (B): the same loop with the update fused (`opkb_cg_update`: x += alpha p,
+# r -= alpha q, r.r and x.x in one pass) and the curvature p.q riding on the operator
+# when the operator is built in.
+
+"`A = diag(a)` (`vproduct!`): direction + product + curvature in one kernel."
+struct DiagonalOperator{T}
+    a::DeviceVector{T}
+end
+(A::DiagonalOperator{T})(dst::DeviceVector{T}, src::DeviceVector{T}) where {T} = vproduct!(dst, A.a, src)
+
+"`A = diag(w) + mu*L` on a rows x cols grid: the Hessian of `Smooth2D` (`opkb_smooth2d_apply`)."
+struct Smooth2DOperator{T}
+    w::DeviceVector{T}
+    mu::Float
+    cols::Int
+    up::DeviceVector{T}
+    dn::DeviceVector{T}
+end
+Smooth2DOperator(w::DeviceVector{T}, mu::Real, cols::Integer) where {T} =
+    Smooth2DOperator{T}(w, Float(mu), Int(cols), DeviceVector{T}(w.ctx, cols), DeviceVector{T}(w.ctx, cols))
+function apply_dot!(A::Smooth2DOperator{T}, q::DeviceVector{T}, p::DeviceVector{T}) where {T}
+    out = Vector{Cdouble}(undef, 2)
+    check(ccall((:opkb_smooth2d_apply, libopkb200), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                 Ptr{Cdouble}),
+                p.ctx.ptr, A.w.ptr, A.mu, A.cols, p.ptr, A.up.ptr, A.dn.ptr, q.ptr, out))
+    return out[1], out[2]
+end
+(A::Smooth2DOperator{T})(dst::DeviceVector{T}, src::DeviceVector{T}) where {T} = (apply_dot!(A, dst, src); dst)
+
+# direction (p = r | beta*p + r), q = A.p -> (p.q, p.p)
+function cg_direction!(A::DiagonalOperator{T}, p, r, q, beta::Float, first::Bool) where {T}
+    out = Vector{Cdouble}(undef, 2)
+    check(ccall((:opkb_cg_diag_step, libopkb200), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Cdouble}),
+                p.ctx.ptr, A.a.ptr, p.ptr, r.ptr, q.ptr, beta, first, out))
+    return out[1], out[2]
+end
+function cg_direction!(A::Smooth2DOperator, p, r, q, beta::Float, first::Bool)
+    first ? vcopy!(p, r) : vcombine!(p, beta, p, 1, r)
+    return apply_dot!(A, q, p)
+end
+function cg_direction!(A, p, r, q, beta::Float, first::Bool)      # any `A!(dst, src)`
+    first ? vcopy!(p, r) : vcombine!(p, beta, p, 1, r)
+    A(q, p)
+    out = Vector{Cdouble}(undef, 2)
+    check(ccall((:opkb_cg_curvature, libopkb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cdouble}),
+                p.ctx.ptr, p.ptr, q.ptr, out))
+    return out[1], out[2]
+end
+
+function conjgrad!(x::DeviceVector{T}, A, b::DeviceVector{T}, x0::DeviceVector{T} = vfill!(x, 0),
+                   p::DeviceVector{T} = vcreate(x), q::DeviceVector{T} = vcreate(x),
+                   r::DeviceVector{T} = vcreate(x);
+                   ftol::Real = 1e-8, gtol::NTuple{2,Real} = (0.0, 0.0), xtol::Real = 0.0,
+                   maxiter::Integer = typemax(Int), restart::Integer = min(50, length(b)),
+                   verb::Bool = false, io::IO = stdout, quiet::Bool = false,
+                   strict::Bool = true) where {T}
+    (ftol ≥ 0 && gtol[1] ≥ 0 && gtol[2] ≥ 0 && xtol ≥ 0) || throw(ArgumentError("bad tolerance"))
+    restart ≥ 1 || throw(ArgumentError("restart must be at least 1"))
+    x0 === x || vcopy!(x, x0)
+    if vdot(x, x) > 0
+        A(r, x); vcombine!(r, 1, b, -1, r)
+    else
+        vcopy!(r, b)
+    end
+    rho::Float = vdot(r, r)
+    oldrho::Float = 0; phi::Float = 0; psimax::Float = 0
+    gtest = max(Float(gtol[1]), Float(gtol[2])*sqrt(rho))
+    out = Vector{Cdouble}(undef, 2)
+    k = 0
+    while true
+        verb && @printf(io, " %6d %12.4e %12.4e\n", k, phi, sqrt(rho))
+        sqrt(rho) ≤ gtest && break
+        if k ≥ maxiter
+            quiet || @warn "Too many iteration(s)"
+            break
+        end
+        first = (rem(k, restart) == 0)
+        if first && k > 0
+            A(r, x); vcombine!(r, 1, b, -1, r)
+        end
+        gamma, pp = cg_direction!(A, p, r, q, first ? 0.0 : rho/oldrho, first)
+        if !(gamma > 0)
+            strict && error("Operator is not positive definite")
+            quiet || @warn "Operator is not positive definite"
+            break
+        end
+        alpha = rho/gamma
+        psi = alpha*rho/2
+        phi -= psi
+        psimax = max(psi, psimax)
+        if psi ≤ ftol*psimax
+            vupdate!(x, alpha, p)
+            break
+        end
+        check(ccall((:opkb_cg_update, libopkb200), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cdouble}),
+                    x.ctx.ptr, x.ptr, r.ptr, p.ptr, q.ptr, alpha, out))
+        k += 1
+        (xtol > 0 && alpha*sqrt(pp) ≤ xtol*sqrt(out[2])) && break
+        oldrho = rho
+        rho = out[1]
+    end
+    return x
+end
+
+conjgrad(A, b::DeviceVector{T}, x0::DeviceVector{T} = vfill!(vcreate(b), 0); kwds...) where {T} =
+    conjgrad!(vcreate(b), A, b, x0; kwds...)
 
 end # module
