@@ -495,8 +495,11 @@ def test_unconstrained_follows_scipy_lbfgsb(opk, mode, native):
         ref = lbfgsb_trajectory(fg, x0, mem, 25)
         tr = []
         cls = opk.NativeVMLMB if native else opk.VMLMB
-        kw = dict(mem=mem, maxiter=25, observer=lambda s: tr.append(dict(iter=s.iter, f=s.f, x=s.x.download())),
-                  **NOSTOP)
+        # (between calls of the native run loop `x` already holds the first trial point of
+        # the next line search: `current()` is the iterate)
+        kw = dict(mem=mem, maxiter=25, **NOSTOP,
+                  observer=lambda s: tr.append(dict(iter=s.iter, f=s.f,
+                                                    x=(s.current() if native else s.x).download())))
         if not native:
             kw["mode"] = mode
         s = cls(gobj, x0, **kw)
