@@ -154,6 +154,44 @@ def main():
             ok = ok and good
             print(f"[{world} GPUs] SPG {kind} n={n}: iter/fcnt={ws.iter}/{ws.fcnt} rel(x)={ex:.2e} "
                   f"{'OK' if good else 'FAIL'}", flush=True)
+    # conjgrad: the row-sharded stencil operator (halo exchange) and the
+    # diagonal one, sums combined by the packed all-gather
+    for dtype, (rows, cols), which in ((np.float64, (301, 257), "stencil"), (np.float64, (world, 1000), "stencil"),
+                                       (np.float32, (128, 96), "stencil"), (np.float64, (400, 500), "diag")):
+        n = rows * cols
+        w, y = opk.Smooth2D.synthetic(rows, cols, dtype)
+        r0, nr = shard_range(rows, rank, world, align=1)
+        sl = slice(r0 * cols, (r0 + nr) * cols)
+        b = (w * y).astype(dtype)
+        A = (opk.Smooth2DOperator(w[sl].copy(), 2.0, cols, ctx=ctx) if which == "stencil"
+             else opk.DiagonalOperator(w[sl].copy(), ctx=ctx))
+        trace = []
+        s = opk.ConjGrad(A, b[sl].copy(), ftol=0.0, maxiter=25, restart=10, nglobal=n, ctx=ctx, quiet=True,
+                         observer=lambda s: trace.append((s.iter, s.rho, s.phi)))
+        s.solve()
+        xloc = s.result()
+        t = torch.tensor([v for row in trace for v in row], dtype=torch.float64, device="cuda")
+        tmax, tmin = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        same = bool(torch.equal(tmax, tmin))
+        per = shard_range(rows, 0, world, align=1)[1] * cols
+        buf = torch.zeros(per, dtype=torch.float64, device="cuda")
+        buf[:nr * cols] = torch.from_numpy(xloc.astype(np.float64)).cuda()
+        bufs = [torch.zeros_like(buf) for _ in range(world)]
+        dist.all_gather(bufs, buf)
+        if rank == 0:
+            x = np.concatenate([bb.cpu().numpy()[:shard_range(rows, r, world, align=1)[1] * cols]
+                                for r, bb in enumerate(bufs)])
+            Ao = opk.Smooth2DOperator.reference(w, 2.0, cols) if which == "stencil" else ("diag", w)
+            xo, info, tro = O.conjgrad(Ao, b, ftol=0.0, maxiter=25, restart=10, trace=True)
+            rtol = 1e-10 if dtype == np.float64 else 1e-4
+            worst = max(abs(g[1] - wt["rho"]) / wt["rho"] for g, wt in list(zip(trace, tro))[:21])
+            ex = np.linalg.norm(x - xo) / np.linalg.norm(xo)
+            good = same and (s.iter, s.status) == (info["iter"], info["status"]) and worst <= 100 * rtol and ex <= rtol
+            ok = ok and good
+            print(f"[{world} GPUs] conjgrad {which} {rows}x{cols} {np.dtype(dtype).name}: same_decisions={same} "
+                  f"worst_rel(rho)={worst:.2e} rel(x)={ex:.2e} {'OK' if good else 'FAIL'}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:
