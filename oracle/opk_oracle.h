@@ -16,8 +16,12 @@
  * pinned against independent published implementations shipped with SciPy
  * (tests/test_pins_scipy.py): the More-Thuente search + cstep give bit-identical
  * step sequences to SciPy's port of MINPACK-2 dcsrch/dcstep, and apply_lbfgs
- * equals scipy.optimize.LbfgsInvHessProduct to rounding.  The driver
- * trajectories themselves remain unpinned.
+ * equals scipy.optimize.LbfgsInvHessProduct to rounding, and the unconstrained
+ * driver (method 0) follows SciPy's L-BFGS-B (Nocedal's code; same line-search
+ * constants, first step and H0 scaling) to 1e-10 over the first 20 iterations.
+ * The bound-constrained and SPG trajectories remain unpinned.  `conjgrad`
+ * (LazyAlgebra's, re-exported by the reference) is a restatement of the published
+ * algorithm anchored on test/conjgrad-tests.jl and scipy.sparse.linalg.cg.
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference).  Two instances of the type-generic part exist: prefix
