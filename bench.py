@@ -274,12 +274,14 @@ def ours(args):
     # survey's yardstick W_alg = 4m+20.
     # When the first trial of the next line search is fused into P4 (speculation, the
     # default with a built-in objective) that kernel also writes x, g, p: 2m+9; with the
-    # incremental Gram it reads S, Y, x, g, lo, hi and writes d, x', g', p', s', y': 2m+10
+    # incremental Gram it reads S, Y, x, g, lo, hi and writes d, x', g', s', y': 2m+9 (p' is
+    # not written any more: the next launch recomputes it, OPKB_LAZY_P; 2m+10 with the write)
     # (the objective's data a, c -- 2 more vectors -- are not counted as algorithmic).
+    lazy_p = 0 if os.environ.get("OPKB_LAZY_P", "1") == "0" else 1
     fused_trial = prof.get("trial", (0.0, 0))[1] < K / 2
     carried = hits >= K / 2
     passes = {"trial": 7, "gram": 2 * m + 5,
-              "direction": 2 * m + (10 if carried else (9 if fused_trial else 6))}
+              "direction": 2 * m + ((9 + (1 - lazy_p)) if carried else ((8 + (1 - lazy_p)) if fused_trial else 6))}
     kern = {}
     for name, npass in passes.items():
         if name in prof:

@@ -23,6 +23,13 @@ template <typename T> struct SmoothArgs {
     T mu;
     int64_t rows, cols;       // of this rank's block
     int64_t r0, r1;           // rows [r0, r1) are processed by this launch
+    // conjugate-gradient step (k_stencil_strip<.., PRE = 1>): the field the stencil is
+    // applied to is u = r (restart) or beta*x + r with x = the old direction; u is also
+    // stored (the new direction); up / dn then hold rows of u
+    const T* r;
+    T* uout;
+    T beta;
+    int restart;
 };
 
 // One CTA = 256 x VEC consecutive columns of one row (VEC = the 16-byte pack when the
@@ -98,6 +105,140 @@ __global__ void __launch_bounds__(OPKB_BLOCK) k_smooth2d(SmoothArgs<T> A, Reduce
     block_reduce_publish<2, 0u, 0u>(acc, rs);
 }
 
+
+// ---------------------------------------------------------------------------
+// Row-strip version.  One item = STRIP_ROWS consecutive rows x (256 x V) columns; a thread
+// owns one pack of columns and walks down the strip with a three-row window in registers
+// (above, centre, below), so every element of the field is fetched ONCE per strip instead
+// of three times (as centre, as "above", as "below": the L2 -> SM traffic of k_smooth2d), the
+// horizontal neighbours come from the adjacent lanes (shuffles; only the first and the last
+// lane of a warp fetch theirs).  Same arithmetic, same order: bit-identical results.
+// PRE = 1: the field is not stored but formed on the fly from two vectors, u = beta*x + r
+// (`vcombine!(p, beta, p, 1, r)` of conjgrad; u = r on a restart), written to `uout`: the
+// direction update, the operator and p.q, p.p of a CG iteration in ONE pass.
+#define STRIP_ROWS 8
+
+template <typename T, int V, int PRE>
+__device__ __forceinline__ void strip_field(const SmoothArgs<T>& A, int64_t row, int64_t col, bool active,
+                                            T (&u)[V])
+{
+#pragma unroll
+    for (int q = 0; q < V; ++q) u[q] = T(0);
+    if (!active) return;
+    if (row < 0 || row >= A.rows) {              // halo row: already the field itself
+        const T* h = (row < 0) ? A.up : A.dn;
+        if (V == VecOf<T>::N) {
+            const Pack<T> pk = ld_pack<T>(h + col, 0);
+#pragma unroll
+            for (int q = 0; q < V; ++q) u[q] = pk.v[q];
+        } else {
+            u[0] = h[col];
+        }
+        return;
+    }
+    const int64_t i = row * A.cols + col;
+    if (V == VecOf<T>::N) {
+        const Pack<T> px = (PRE == 1 && A.restart) ? ld_pack<T>(A.r + i, 0) : ld_pack<T>(A.x + i, 0);
+        if (PRE == 1 && !A.restart) {
+            const Pack<T> pr = ld_pack<T>(A.r + i, 0);
+#pragma unroll
+            for (int q = 0; q < V; ++q) u[q] = A.beta * px.v[q] + pr.v[q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < V; ++q) u[q] = px.v[q];
+        }
+    } else {
+        if (PRE == 1) u[0] = A.restart ? A.r[i] : A.beta * A.x[i] + A.r[i];
+        else u[0] = A.x[i];
+    }
+}
+
+template <typename T, int PRE>
+__device__ __forceinline__ T strip_field1(const SmoothArgs<T>& A, int64_t row, int64_t col)
+{
+    const int64_t i = row * A.cols + col;
+    if (PRE == 1) return A.restart ? A.r[i] : A.beta * A.x[i] + A.r[i];
+    return A.x[i];
+}
+
+template <typename T, int V, bool HESS, int PRE>
+__global__ void __launch_bounds__(OPKB_BLOCK) k_stencil_strip(SmoothArgs<T> A, ReduceScratch rs)
+{
+    const int64_t ncb = (A.cols + OPKB_BLOCK * V - 1) / (OPKB_BLOCK * V);
+    const int64_t nstrips = (A.r1 - A.r0 + STRIP_ROWS - 1) / STRIP_ROWS;
+    const int64_t nitems = nstrips * ncb;
+    const int lane = threadIdx.x & 31;
+    double acc[2] = {0.0, 0.0};
+    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int64_t strip = item / ncb;
+        const int64_t col = ((item - strip * ncb) * OPKB_BLOCK + threadIdx.x) * V;
+        const bool active = col < A.cols;           // (whole warps stay in the loop: shuffles)
+        const int64_t ra = A.r0 + strip * STRIP_ROWS;
+        const int64_t rb = (ra + STRIP_ROWS < A.r1) ? ra + STRIP_ROWS : A.r1;
+        T uu[V], uc[V], ud[V];
+        bool hu = (ra > 0) || (A.up != NULL);
+        if (hu) strip_field<T, V, PRE>(A, ra - 1, col, active, uu);
+        else strip_field<T, V, PRE>(A, ra, col, false, uu);
+        strip_field<T, V, PRE>(A, ra, col, active, uc);
+#pragma unroll
+        for (int k = 0; k < STRIP_ROWS; ++k) {
+            const int64_t row = ra + k;
+            if (row < rb) {
+                const bool hd = (row + 1 < A.rows) || (A.dn != NULL);
+                strip_field<T, V, PRE>(A, row + 1, col, active && hd, ud);
+                T left = __shfl_up_sync(0xffffffffu, uc[V - 1], 1);
+                T right = __shfl_down_sync(0xffffffffu, uc[0], 1);
+                if (active) {
+                    if (lane == 0 && col > 0) left = strip_field1<T, PRE>(A, row, col - 1);
+                    if (lane == 31 && col + V < A.cols) right = strip_field1<T, PRE>(A, row, col + V);
+                    const int64_t i = row * A.cols + col;
+                    T wv[V], yv[V], gv[V];
+                    if (V == VecOf<T>::N) {
+                        const Pack<T> pw = ld_pack<T>(A.w + i, 0);
+#pragma unroll
+                        for (int q = 0; q < V; ++q) wv[q] = pw.v[q];
+                        if (!HESS) {
+                            const Pack<T> py = ld_pack<T>(A.y + i, 0);
+#pragma unroll
+                            for (int q = 0; q < V; ++q) yv[q] = py.v[q];
+                        }
+                    } else {
+                        wv[0] = A.w[i];
+                        if (!HESS) yv[0] = A.y[i];
+                    }
+#pragma unroll
+                    for (int q = 0; q < V; ++q)
+                        smooth_elem<T, HESS>(uc[q], wv[q], HESS ? T(0) : yv[q], hu, uu[q], hd, ud[q], col + q > 0,
+                                             q > 0 ? uc[q > 0 ? q - 1 : 0] : left, col + q + 1 < A.cols,
+                                             q + 1 < V ? uc[q + 1 < V ? q + 1 : 0] : right, A.mu, gv[q], acc);
+                    if (V == VecOf<T>::N) {
+                        Pack<T> pg;
+#pragma unroll
+                        for (int q = 0; q < V; ++q) pg.v[q] = gv[q];
+                        st_pack<T>(A.g + i, 0, pg);
+                        if (PRE == 1) {
+                            Pack<T> pu;
+#pragma unroll
+                            for (int q = 0; q < V; ++q) pu.v[q] = uc[q];
+                            st_pack<T>(A.uout + i, 0, pu);
+                        }
+                    } else {
+                        A.g[i] = gv[0];
+                        if (PRE == 1) A.uout[i] = uc[0];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < V; ++q) {
+                    uu[q] = uc[q];
+                    uc[q] = ud[q];
+                }
+                hu = true;
+            }
+        }
+    }
+    block_reduce_publish<2, 0u, 0u>(acc, rs);
+}
+
 template <typename T>
 static int smooth_launch(opkb_context* ctx, SmoothArgs<T> A, int slot)
 {
@@ -107,18 +248,31 @@ static int smooth_launch(opkb_context* ctx, SmoothArgs<T> A, int slot)
     const bool vec = (A.cols % V == 0);
     const int64_t per = (int64_t)OPKB_BLOCK * (vec ? V : 1);
     const int64_t ncb = (A.cols + per - 1) / per;
+    const bool hess = (A.y == NULL), cgstep = (A.r != NULL);
+    static const int use_strip = getenv("OPKB_STENCIL_STRIP") ? atoi(getenv("OPKB_STENCIL_STRIP")) : 1;
+    const bool strip = cgstep || use_strip;
+    const int64_t nrow_items = strip ? (A.r1 - A.r0 + STRIP_ROWS - 1) / STRIP_ROWS : (A.r1 - A.r0);
     // (6 CTAs of 256 threads per SM: room is left for the NCCL send/recv kernel to run alongside)
-    int grid = opkb_grid_for(ctx, (A.r1 - A.r0) * ncb * OPKB_BLOCK, 6);
+    int grid = opkb_grid_for(ctx, nrow_items * ncb * OPKB_BLOCK, 6);
     ReduceScratch rs;
     rs.part = ctx->d_part;
     rs.ticket = ctx->d_ticket;
     rs.res = ctx->d_res + 2 * slot;
     opkb_prof_begin(ctx, OPKB_K_OBJECTIVE);
-    const bool hess = (A.y == NULL);
-    if (vec && hess) k_smooth2d<T, V, true><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
-    else if (vec) k_smooth2d<T, V, false><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
-    else if (hess) k_smooth2d<T, 1, true><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
-    else k_smooth2d<T, 1, false><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
+    if (cgstep) {
+        if (vec) k_stencil_strip<T, V, true, 1><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
+        else k_stencil_strip<T, 1, true, 1><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
+    } else if (strip) {
+        if (vec && hess) k_stencil_strip<T, V, true, 0><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
+        else if (vec) k_stencil_strip<T, V, false, 0><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
+        else if (hess) k_stencil_strip<T, 1, true, 0><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
+        else k_stencil_strip<T, 1, false, 0><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
+    } else {
+        if (vec && hess) k_smooth2d<T, V, true><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
+        else if (vec) k_smooth2d<T, V, false><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
+        else if (hess) k_smooth2d<T, 1, true><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
+        else k_smooth2d<T, 1, false><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
+    }
     opkb_prof_end(ctx);
     ctx->launches += 1;
     OPKB_CUDA(cudaGetLastError());
@@ -127,8 +281,14 @@ static int smooth_launch(opkb_context* ctx, SmoothArgs<T> A, int slot)
 
 template <typename T>
 static int smooth_run(opkb_context* ctx, const opkb_vector* w, const opkb_vector* y, double mu, int64_t cols,
-                      const opkb_vector* x, opkb_vector* up, opkb_vector* dn, opkb_vector* g, double* f)
+                      const opkb_vector* x, opkb_vector* up, opkb_vector* dn, opkb_vector* g, double* f,
+                      const opkb_vector* cg_r = NULL, opkb_vector* cg_out = NULL, double beta = 0.0,
+                      int restart = 0, opkb_vector* up_r = NULL, opkb_vector* dn_r = NULL)
 {
+    // cg_r != NULL: conjugate-gradient step (opkb_cg_smooth2d_step): x is the old direction,
+    // the field is u = cg_r | beta*x + cg_r, written to cg_out; what travels between the ranks
+    // are the boundary rows of cg_r (into up_r / dn_r) and up / dn, which hold the neighbours'
+    // rows of the direction, are advanced with the same formula
     // y == NULL: operator mode, f[0] = x.g, f[1] = x.x (opkb_smooth2d_apply)
     const int64_t rows = x->n / cols;
     const bool has_up = ctx->nranks > 1 && ctx->rank > 0;
@@ -145,9 +305,12 @@ static int smooth_run(opkb_context* ctx, const opkb_vector* w, const opkb_vector
         // x is ready on the main stream -> exchange the boundary rows on the halo stream
         OPKB_CUDA(cudaEventRecord(ctx->ev_ready, ctx->stream));
         OPKB_CUDA(cudaStreamWaitEvent(ctx->halo_stream, ctx->ev_ready, 0));
-        const T* xd = (const T*)x->data;
-        int rc = opkb_nccl_halo(ctx, x->eltype, (size_t)cols, xd, has_up ? up->data : NULL,
-                                xd + (rows - 1) * cols, has_dn ? dn->data : NULL, ctx->halo_stream);
+        const T* xd = (const T*)(cg_r ? cg_r->data : x->data);
+        if (cg_r && ((has_up && (!up_r || up_r->n != cols)) || (has_dn && (!dn_r || dn_r->n != cols))))
+            return opkb_set_error(OPKB_EINVAL, "halo rows of %lld elements are needed", (long long)cols);
+        int rc = opkb_nccl_halo(ctx, x->eltype, (size_t)cols, xd,
+                                has_up ? (cg_r ? up_r->data : up->data) : NULL, xd + (rows - 1) * cols,
+                                has_dn ? (cg_r ? dn_r->data : dn->data) : NULL, ctx->halo_stream);
         if (rc) return rc;
         OPKB_CUDA(cudaEventRecord(ctx->ev_halo, ctx->halo_stream));
     }
@@ -161,6 +324,10 @@ static int smooth_run(opkb_context* ctx, const opkb_vector* w, const opkb_vector
     A.mu = (T)mu;
     A.rows = rows;
     A.cols = cols;
+    A.r = cg_r ? (const T*)cg_r->data : NULL;
+    A.uout = cg_out ? (T*)cg_out->data : NULL;
+    A.beta = (T)beta;
+    A.restart = restart;
     // rows that need no halo: meanwhile the boundary rows are in flight
     A.r0 = has_up ? 1 : 0;
     A.r1 = has_dn ? rows - 1 : rows;
@@ -169,6 +336,13 @@ static int smooth_run(opkb_context* ctx, const opkb_vector* w, const opkb_vector
     if (rc) return rc;
     if (has_up || has_dn) {
         OPKB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+        if (cg_r) {
+            // the neighbours' rows of the new direction, by the formula they use themselves
+            if (has_up) rc = restart ? opkb_vcopy(ctx, up, up_r) : opkb_vcombine(ctx, up, beta, up, 1.0, up_r);
+            if (rc) return rc;
+            if (has_dn) rc = restart ? opkb_vcopy(ctx, dn, dn_r) : opkb_vcombine(ctx, dn, beta, dn, 1.0, dn_r);
+            if (rc) return rc;
+        }
         if (has_up) {
             A.r0 = 0;
             A.r1 = 1;
@@ -230,4 +404,40 @@ extern "C" int opkb_smooth2d_apply(opkb_context* ctx, const opkb_vector* w, doub
     if (p == q || p->data == q->data) return opkb_set_error(OPKB_EINVAL, "q must not alias p");
     return (p->eltype == OPKB_DOUBLE) ? smooth_run<double>(ctx, w, NULL, mu, cols, p, up, dn, q, out)
                                       : smooth_run<float>(ctx, w, NULL, mu, cols, p, up, dn, q, out);
+}
+
+// One pass of `conjgrad!` for the stencil operator: p <- r (restart) | beta*p + r
+// (`vcombine!(p, beta, p, 1, r)`), q = A.p, out[0] = p.q, out[1] = p.p: read p, r, w; write p, q
+// = 5 passes (k_stencil_strip<.., PRE = 1>).  The new direction is written to `pscratch` and
+// the two buffers are swapped, so that p is updated "in place" for the caller while the
+// neighbours of an element still see the old direction during the pass.  With several ranks
+// only the boundary rows of r travel (into up_r / dn_r); up / dn keep the neighbours'
+// boundary rows of the direction from one call to the next.
+extern "C" int opkb_cg_smooth2d_step(opkb_context* ctx, const opkb_vector* w, double mu, int64_t cols,
+                                     opkb_vector* p, opkb_vector* pscratch, const opkb_vector* r,
+                                     opkb_vector* q, opkb_vector* up, opkb_vector* dn, opkb_vector* up_r,
+                                     opkb_vector* dn_r, double beta, int restart, double out[2])
+{
+    if (!ctx || !w || !p || !pscratch || !r || !q || !out) return opkb_set_error(OPKB_EINVAL, "NULL argument");
+    if (cols < 1 || p->n < cols || p->n % cols != 0)
+        return opkb_set_error(OPKB_EINVAL, "the local block must be a whole number of rows of %lld elements",
+                              (long long)cols);
+    const opkb_vector* all[4] = {w, pscratch, r, q};
+    for (int k = 0; k < 4; ++k)
+        if (all[k]->n != p->n || all[k]->eltype != p->eltype)
+            return opkb_set_error(OPKB_EINVAL, "w, p, pscratch, r, q must belong to the same space");
+    if ((up && up->eltype != p->eltype) || (dn && dn->eltype != p->eltype) ||
+        (up_r && up_r->eltype != p->eltype) || (dn_r && dn_r->eltype != p->eltype))
+        return opkb_set_error(OPKB_EINVAL, "halo rows of another element type");
+    if (p->data == pscratch->data || p->data == q->data || pscratch->data == q->data || r->data == q->data ||
+        r->data == pscratch->data || r->data == p->data || !p->owned || !pscratch->owned)
+        return opkb_set_error(OPKB_EINVAL, "p, pscratch, r, q must be distinct vectors (p, pscratch owned)");
+    int rc = (p->eltype == OPKB_DOUBLE)
+                 ? smooth_run<double>(ctx, w, NULL, mu, cols, p, up, dn, q, out, r, pscratch, beta, restart, up_r, dn_r)
+                 : smooth_run<float>(ctx, w, NULL, mu, cols, p, up, dn, q, out, r, pscratch, beta, restart, up_r, dn_r);
+    if (rc) return rc;
+    void* t = p->data;
+    p->data = pscratch->data;
+    pscratch->data = t;
+    return 0;
 }

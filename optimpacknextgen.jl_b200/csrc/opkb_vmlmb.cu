@@ -50,7 +50,22 @@ struct opkb_vmlmb_ {
     double carry_dense[4 * OPKB_MEM_MAX + 4];
     double carry_corr[OPKB_MEM_MAX * (OPKB_MEM_MAX + 1)];
     int64_t carry_hits, carry_misses;
+    // VMLMB (method 2): the fused direction + trial launch does NOT write p' (the next
+    // launch recomputes it from x, g, lo, hi and nothing else reads it in steady state);
+    // p_stale != 0 means p does not belong to the current (x, g) and is recomputed on
+    // demand (vmlmb_ensure_p) by whoever reads it: one pass less per iteration.
+    int p_stale;
 };
+
+static int vmlmb_ensure_p(opkb_vmlmb* ws)
+{
+    if (!ws->p_stale || !ws->p) return 0;
+    ws->p_stale = 0;
+    // project_direction!(p, x, lo, hi, -, g) src/quasinewton.jl:396: the bits the kernel
+    // would have written
+    return opkb_project_direction(ws->ctx, ws->p, ws->x, ws->lo, ws->lo_val, ws->hi, ws->hi_val,
+                                  OPKB_BACKWARD, ws->g);
+}
 
 // x (and g|p) get their own buffers back before they are written again
 static void vmlmb_unalias(opkb_vmlmb* ws)
@@ -200,7 +215,7 @@ extern "C" opkb_vector* opkb_vmlmb_vector(opkb_vmlmb* ws, int which, int slot)
     switch (which) {
     case 'x': return ws->x;
     case 'g': return ws->g;
-    case 'p': return ws->p;
+    case 'p': return (vmlmb_ensure_p(ws) == 0) ? ws->p : NULL;
     case 'd': return ws->d;
     case 'S': return (slot >= 0 && slot < ws->mem) ? ws->S[slot] : NULL;
     case 'Y': return (slot >= 0 && slot < ws->mem) ? ws->Y[slot] : NULL;
@@ -348,6 +363,7 @@ static int trial_launch(opkb_vmlmb* ws, int mark, double stp, int initial, int s
     opkb_context* ctx = ws->ctx;
     ws->carry_valid = 0;                 // another point than the speculated one
     if (stage != 2) vmlmb_unalias(ws);   // x, g|p are about to be overwritten
+    if (stage != 1) ws->p_stale = 0;     // this launch writes p
     TrialArgs<T> A;
     A.x0 = (const T*)ws->S[mark]->data;
     A.d = (const T*)ws->d->data;
@@ -503,7 +519,7 @@ extern "C" int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots
             rc = gram_from_carry(ws, mark, m, slots, G);
             if (rc) return rc;
             carried = true;
-            if (getenv("OPKB_CARRY_CHECK")) {
+            if (getenv("OPKB_CARRY_CHECK") && vmlmb_ensure_p(ws) == 0) {
                 // development aid: the same block by a sweep over the same state (the
                 // pair is already formed: x = g = 0 makes the in-place update the identity)
                 opkb_vector* z = NULL;
@@ -542,6 +558,8 @@ extern "C" int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots
     if (!carried) {
         if (ws->carry_valid) ws->carry_misses += 1;
         ws->carry_valid = 0;
+        rc = vmlmb_ensure_p(ws);
+        if (rc) return rc;
         const void* Sp[OPKB_MEM_MAX];
         const void* Yp[OPKB_MEM_MAX];
         for (int j = 0; j < m; ++j) {
@@ -790,6 +808,7 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
                          ? ws->obj : 0;
     if (out8) out8[7] = 0.0;
     int nparts = 0;
+    int ran_lazy_p = 0;
     int64_t done = 0;
 
     // ---- whole tiles through the bulk-async ring (m >= 1 pairs) ---------------------
@@ -813,6 +832,12 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
             B.xout = (T*)ws->S[mark_next]->data;
             B.gout = (T*)ws->Y[mark_next]->data;
             B.pout = ws->p ? (T*)ws->p->data : NULL;
+            // VMLMB: p' is not written (see p_stale); OPKB_LAZY_P=0 restores the write
+            static const int lazy_p = getenv("OPKB_LAZY_P") ? atoi(getenv("OPKB_LAZY_P")) : 1;
+            if (lazy_p && ws->method == 2) {
+                B.pout = NULL;
+                ran_lazy_p = 1;
+            }
             carry = (A.m <= 12 && ws->Gc_valid && ws->Gc_m == A.m);
             for (int j = 0; carry && j < A.m; ++j) carry = (ws->Gc_slots[j] == slots[j]);
             // mark_next is the oldest pair when the memory is full, a free slot otherwise
@@ -924,6 +949,10 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
 
     // ---- the rest (tail of the ring path, or everything) with the register kernel -----
     if (done < ws->n) {
+        {
+            int rc = vmlmb_ensure_p(ws);   // v0 / the mask are read from p here
+            if (rc) return rc;
+        }
         const int64_t off = done;
         for (int j = 0; j < A.m; ++j) {
             A.S[j] += off;
@@ -974,6 +1003,7 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
     if (fuse) {
         // S[mark'] <- x, Y[mark'] <- g (:562-563) and x, g <- the trial point just
         // written into the recycled buffers: two pointer swaps
+        if (ws->method == 2) ws->p_stale = ran_lazy_p;
         vmlmb_unalias(ws);
         void* t = ws->S[mark_next]->data;
         ws->S[mark_next]->data = ws->x->data;
@@ -1035,6 +1065,7 @@ extern "C" int opkb_vmlmb_discard_trial(opkb_vmlmb* ws, int mark_next)
         rc = opkb_project_direction(ws->ctx, ws->p, ws->x, ws->lo, ws->lo_val, ws->hi, ws->hi_val,
                                     OPKB_BACKWARD, ws->g);
         if (rc) return rc;
+        ws->p_stale = 0;
     }
     ws->aliased_slot = -1;
     vmlmb_alias(ws, mark_next);
@@ -1152,6 +1183,10 @@ static int step_run(opkb_vmlmb* ws, int first, const opkb_vector* u, double a, i
                     double out[3])
 {
     opkb_context* ctx = ws->ctx;
+    {
+        int rc = vmlmb_ensure_p(ws);
+        if (rc) return rc;
+    }
     StepArgs<T> A;
     memset(&A, 0, sizeof(A));
     const opkb_vector* src = first ? (ws->method == 2 ? ws->p : ws->g) : ws->d;   // vcopy!(d, p|g) :525/:528
