@@ -188,6 +188,18 @@ int opkb_smooth2d_apply(opkb_context* ctx, const opkb_vector* w, double mu, int6
                         const opkb_vector* p, opkb_vector* up, opkb_vector* dn, opkb_vector* q,
                         double out[2]);
 
+/* One pass of `conjgrad!` with that operator: p <- r (restart != 0) | beta*p + r
+ * (`vcombine!(p, beta, p, 1, r)`), q = A.p, out[0] = p.q, out[1] = p.p -- read p, r, w; write
+ * p, q: 5 passes instead of 3 + 3 (+ 2).  `pscratch` receives the new direction and the two
+ * buffers are swapped before returning (p is updated in place for the caller; both must be
+ * vectors created by opkb_vector_create).  With several ranks only the boundary rows of r
+ * travel (received in up_r / dn_r); up / dn keep the neighbours' boundary rows of the
+ * direction between calls (all four: `cols` elements, may be NULL on one rank). */
+int opkb_cg_smooth2d_step(opkb_context* ctx, const opkb_vector* w, double mu, int64_t cols,
+                          opkb_vector* p, opkb_vector* pscratch, const opkb_vector* r, opkb_vector* q,
+                          opkb_vector* up, opkb_vector* dn, opkb_vector* up_r, opkb_vector* dn_r,
+                          double beta, int restart, double out[2]);
+
 /* ---- Tier 2: fused passes of `conjgrad!` ------------------------
  * `conjgrad` / `conjgrad!` are re-exported by the reference from LazyAlgebra
  * (src/OptimPackNextGen.jl:18-19, :36; call site test/conjgrad-tests.jl:30).  One

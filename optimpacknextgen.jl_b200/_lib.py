@@ -90,6 +90,7 @@ _SIGNATURES = {
     "opkb_quadratic_fg": (C.c_int, [vp, vp, vp, vp, vp, Pd]),
     "opkb_smooth2d_fg": (C.c_int, [vp, vp, vp, f64, i64, vp, vp, vp, vp, Pd]),
     "opkb_smooth2d_apply": (C.c_int, [vp, vp, f64, i64, vp, vp, vp, vp, Pd]),
+    "opkb_cg_smooth2d_step": (C.c_int, [vp, vp, f64, i64, vp, vp, vp, vp, vp, vp, vp, vp, f64, C.c_int, Pd]),
     "opkb_cg_update": (C.c_int, [vp, vp, vp, vp, vp, f64, Pd]),
     "opkb_cg_curvature": (C.c_int, [vp, vp, vp, Pd]),
     "opkb_cg_diag_step": (C.c_int, [vp, vp, vp, vp, vp, f64, C.c_int, Pd]),

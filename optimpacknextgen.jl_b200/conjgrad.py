@@ -21,8 +21,8 @@ as q = A.p:
 * `Smooth2DOperator(w, mu, cols)` -- diag(w) + mu * (5-point Laplacian, free boundary),
   the Hessian of `Smooth2D`; row-sharded over the ranks with the halo exchange.
 
-Per iteration the vectors cross HBM 11 (diagonal) / 12 (stencil) / 14 (user operator,
-plus the operator) times instead of the reference's 15-17.
+Per iteration the vectors cross HBM 11 (diagonal, stencil) / 14 (user operator, plus the
+operator) times instead of the reference's 15-17.
 """
 from __future__ import annotations
 
@@ -90,6 +90,26 @@ class Smooth2DOperator:
             self.up = self.ctx.vector(self.cols, self.w.dtype)
             self.dn = self.ctx.vector(self.cols, self.w.dtype)
         self._out = (f64 * 2)()
+        self._scratch = None
+        self.up_r = self.dn_r = self.up_p = self.dn_p = None
+
+    def direction_apply(self, p: Vector, r: Vector, q: Vector, beta: float, restart: bool):
+        """p = r | beta*p + r; q = A.p -> (p.q, p.p): one kernel, 5 passes
+        (`opkb_cg_smooth2d_step`; the neighbours of an element must see the OLD direction
+        during the pass, so the new one goes to a scratch vector and the buffers are swapped)."""
+        if self._scratch is None or self._scratch.n != p.n:
+            self._scratch = self.ctx.vector(p.n, p.dtype)
+            if self.ctx.nranks > 1:
+                # the neighbours' boundary rows of r (received at every call) and of the
+                # direction (kept from call to call: they follow the same recurrence)
+                self.up_r, self.dn_r, self.up_p, self.dn_p = (self.ctx.vector(self.cols, p.dtype)
+                                                              for _ in range(4))
+        h = lambda v: v.handle if v is not None else None
+        check(_lib.lib().opkb_cg_smooth2d_step(
+            self.ctx.handle, self.w.handle, self.mu, self.cols, p.handle, self._scratch.handle, r.handle,
+            q.handle, h(self.up_p), h(self.dn_p), h(self.up_r), h(self.dn_r), float(beta), int(restart),
+            self._out))
+        return self._out[0], self._out[1]
 
     def apply_dot(self, q: Vector, p: Vector):
         """q = A.p -> (p.q, p.p), reduced in the same pass."""

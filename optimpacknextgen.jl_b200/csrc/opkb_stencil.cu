@@ -108,109 +108,122 @@ __global__ void __launch_bounds__(OPKB_BLOCK) k_smooth2d(SmoothArgs<T> A, Reduce
 
 // ---------------------------------------------------------------------------
 // Row-strip version.  One item = STRIP_ROWS consecutive rows x (256 x V) columns; a thread
-// owns one pack of columns and walks down the strip with a three-row window in registers
-// (above, centre, below), so every element of the field is fetched ONCE per strip instead
-// of three times (as centre, as "above", as "below": the L2 -> SM traffic of k_smooth2d), the
+// owns one pack of columns and holds the STRIP_ROWS + 2 rows of the field it needs in
+// registers (every load of the strip is in flight before the first use), so every element
+// of the field is fetched ONCE per strip (+ the two rows around it) instead of three times (as centre, as "above", as "below": the L2 -> SM traffic of k_smooth2d), the
 // horizontal neighbours come from the adjacent lanes (shuffles; only the first and the last
 // lane of a warp fetch theirs).  Same arithmetic, same order: bit-identical results.
 // PRE = 1: the field is not stored but formed on the fly from two vectors, u = beta*x + r
 // (`vcombine!(p, beta, p, 1, r)` of conjgrad; u = r on a restart), written to `uout`: the
 // direction update, the operator and p.q, p.p of a CG iteration in ONE pass.
-#define STRIP_ROWS 8
+#define STRIP_ROWS 4
 
-template <typename T, int V, int PRE>
-__device__ __forceinline__ void strip_field(const SmoothArgs<T>& A, int64_t row, int64_t col, bool active,
-                                            T (&u)[V])
+template <typename T, int V> struct StripVec { T v[V]; };
+
+template <typename T, int V>
+__device__ __forceinline__ StripVec<T, V> strip_ld(const T* p)
 {
-#pragma unroll
-    for (int q = 0; q < V; ++q) u[q] = T(0);
-    if (!active) return;
-    if (row < 0 || row >= A.rows) {              // halo row: already the field itself
-        const T* h = (row < 0) ? A.up : A.dn;
-        if (V == VecOf<T>::N) {
-            const Pack<T> pk = ld_pack<T>(h + col, 0);
-#pragma unroll
-            for (int q = 0; q < V; ++q) u[q] = pk.v[q];
-        } else {
-            u[0] = h[col];
-        }
-        return;
-    }
-    const int64_t i = row * A.cols + col;
+    StripVec<T, V> o;
     if (V == VecOf<T>::N) {
-        const Pack<T> px = (PRE == 1 && A.restart) ? ld_pack<T>(A.r + i, 0) : ld_pack<T>(A.x + i, 0);
-        if (PRE == 1 && !A.restart) {
-            const Pack<T> pr = ld_pack<T>(A.r + i, 0);
+        const Pack<T> pk = ld_pack<T>(p, 0);
 #pragma unroll
-            for (int q = 0; q < V; ++q) u[q] = A.beta * px.v[q] + pr.v[q];
-        } else {
-#pragma unroll
-            for (int q = 0; q < V; ++q) u[q] = px.v[q];
-        }
+        for (int q = 0; q < V; ++q) o.v[q] = pk.v[q];
     } else {
-        if (PRE == 1) u[0] = A.restart ? A.r[i] : A.beta * A.x[i] + A.r[i];
-        else u[0] = A.x[i];
+        o.v[0] = p[0];
     }
+    return o;
 }
 
-template <typename T, int PRE>
-__device__ __forceinline__ T strip_field1(const SmoothArgs<T>& A, int64_t row, int64_t col)
-{
-    const int64_t i = row * A.cols + col;
-    if (PRE == 1) return A.restart ? A.r[i] : A.beta * A.x[i] + A.r[i];
-    return A.x[i];
-}
-
-template <typename T, int V, bool HESS, int PRE>
-__global__ void __launch_bounds__(OPKB_BLOCK) k_stencil_strip(SmoothArgs<T> A, ReduceScratch rs)
+// Phase 1 issues every load of the strip from clamped, always valid addresses with no
+// dependent instruction and no branch in between (rows that do not exist and threads
+// beyond the last column load something valid that is never used): ~4 RB + 8 independent
+// 16-byte requests per thread are in flight before phase 2 forms the field and applies the
+// stencil.  (With the field formed right after each load the warp waited for DRAM once per
+// row: 2.7 TB/s.)
+template <typename T, int V, bool HESS, int PRE, int RB>
+__global__ void __launch_bounds__(OPKB_BLOCK, 2) k_stencil_strip(SmoothArgs<T> A, ReduceScratch rs)
 {
     const int64_t ncb = (A.cols + OPKB_BLOCK * V - 1) / (OPKB_BLOCK * V);
-    const int64_t nstrips = (A.r1 - A.r0 + STRIP_ROWS - 1) / STRIP_ROWS;
+    const int64_t nstrips = (A.r1 - A.r0 + RB - 1) / RB;
     const int64_t nitems = nstrips * ncb;
     const int lane = threadIdx.x & 31;
+    const bool restart = (PRE == 1) && A.restart;
+    // PRE = 1: u = beta*a + b with (a, b) = (old direction, r); on a restart u = b
+    const T* const srcA = restart ? A.r : A.x;
+    const T* const srcB = (PRE == 1) ? A.r : A.x;
     double acc[2] = {0.0, 0.0};
     for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int64_t strip = item / ncb;
         const int64_t col = ((item - strip * ncb) * OPKB_BLOCK + threadIdx.x) * V;
         const bool active = col < A.cols;           // (whole warps stay in the loop: shuffles)
-        const int64_t ra = A.r0 + strip * STRIP_ROWS;
-        const int64_t rb = (ra + STRIP_ROWS < A.r1) ? ra + STRIP_ROWS : A.r1;
-        T uu[V], uc[V], ud[V];
-        bool hu = (ra > 0) || (A.up != NULL);
-        if (hu) strip_field<T, V, PRE>(A, ra - 1, col, active, uu);
-        else strip_field<T, V, PRE>(A, ra, col, false, uu);
-        strip_field<T, V, PRE>(A, ra, col, active, uc);
+        const int64_t colc = active ? col : 0;
+        const int64_t ra = A.r0 + strip * RB;
+        const int64_t rb = (ra + RB < A.r1) ? ra + RB : A.r1;
+        // ---- phase 1: raw loads ---------------------------------------------------------------
+        StripVec<T, V> fa[RB + 2], fb[RB + 2], wv[RB], yv[RB];
+        T la[RB], lb[RB], rta[RB], rtb[RB];
+        bool halo[RB + 2];
 #pragma unroll
-        for (int k = 0; k < STRIP_ROWS; ++k) {
+        for (int k = 0; k < RB + 2; ++k) {
+            const int64_t row = ra - 1 + k;
+            const bool above = (row < 0), below = (row >= A.rows);
+            halo[k] = (above && A.up != NULL) || (below && A.dn != NULL);
+            const int64_t rowc = above ? 0 : (below ? A.rows - 1 : row);
+            const T* pa = srcA + rowc * A.cols + colc;
+            const T* pb = srcB + rowc * A.cols + colc;
+            if (above && A.up != NULL) pa = pb = A.up + colc;      // (pointer selects, no branch)
+            if (below && A.dn != NULL) pa = pb = A.dn + colc;
+            fa[k] = strip_ld<T, V>(pa);
+            if (PRE == 1) fb[k] = strip_ld<T, V>(pb);
+        }
+#pragma unroll
+        for (int k = 0; k < RB; ++k) {
             const int64_t row = ra + k;
-            if (row < rb) {
-                const bool hd = (row + 1 < A.rows) || (A.dn != NULL);
-                strip_field<T, V, PRE>(A, row + 1, col, active && hd, ud);
-                T left = __shfl_up_sync(0xffffffffu, uc[V - 1], 1);
-                T right = __shfl_down_sync(0xffffffffu, uc[0], 1);
+            const int64_t rowc = (row < A.rows) ? row : A.rows - 1;
+            const int64_t i = rowc * A.cols + colc;
+            wv[k] = strip_ld<T, V>(A.w + i);
+            if (!HESS) yv[k] = strip_ld<T, V>(A.y + i);
+            // the neighbours beyond the warp: only its first and last lanes need them
+            const int64_t il = rowc * A.cols + (colc > 0 ? colc - 1 : 0);
+            const int64_t ir = rowc * A.cols + (colc + V < A.cols ? colc + V : colc);
+            la[k] = (lane == 0) ? srcA[il] : T(0);
+            rta[k] = (lane == 31) ? srcA[ir] : T(0);
+            if (PRE == 1) {
+                lb[k] = (lane == 0) ? srcB[il] : T(0);
+                rtb[k] = (lane == 31) ? srcB[ir] : T(0);
+            }
+        }
+        // (the compiler would otherwise sink each load next to its first use to save registers)
+        __syncwarp();
+        // ---- phase 2: the field, then the stencil row by row -------------------------------------
+        T f[RB + 2][V];
+#pragma unroll
+        for (int k = 0; k < RB + 2; ++k) {
+#pragma unroll
+            for (int q = 0; q < V; ++q) {
+                T u = fa[k].v[q];
+                if (PRE == 1 && !restart && !halo[k]) u = A.beta * fa[k].v[q] + fb[k].v[q];
+                f[k][q] = u;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RB; ++k) {
+            const int64_t row = ra + k;
+            if (row < rb) {                          // (uniform over the CTA)
+                const bool hu = (row > 0) || (A.up != NULL), hd = (row + 1 < A.rows) || (A.dn != NULL);
+                T lf = __shfl_up_sync(0xffffffffu, f[k + 1][V - 1], 1);
+                T rt = __shfl_down_sync(0xffffffffu, f[k + 1][0], 1);
+                if (lane == 0) lf = (PRE == 1 && !restart) ? A.beta * la[k] + lb[k] : la[k];
+                if (lane == 31) rt = (PRE == 1 && !restart) ? A.beta * rta[k] + rtb[k] : rta[k];
                 if (active) {
-                    if (lane == 0 && col > 0) left = strip_field1<T, PRE>(A, row, col - 1);
-                    if (lane == 31 && col + V < A.cols) right = strip_field1<T, PRE>(A, row, col + V);
                     const int64_t i = row * A.cols + col;
-                    T wv[V], yv[V], gv[V];
-                    if (V == VecOf<T>::N) {
-                        const Pack<T> pw = ld_pack<T>(A.w + i, 0);
-#pragma unroll
-                        for (int q = 0; q < V; ++q) wv[q] = pw.v[q];
-                        if (!HESS) {
-                            const Pack<T> py = ld_pack<T>(A.y + i, 0);
-#pragma unroll
-                            for (int q = 0; q < V; ++q) yv[q] = py.v[q];
-                        }
-                    } else {
-                        wv[0] = A.w[i];
-                        if (!HESS) yv[0] = A.y[i];
-                    }
+                    T gv[V];
 #pragma unroll
                     for (int q = 0; q < V; ++q)
-                        smooth_elem<T, HESS>(uc[q], wv[q], HESS ? T(0) : yv[q], hu, uu[q], hd, ud[q], col + q > 0,
-                                             q > 0 ? uc[q > 0 ? q - 1 : 0] : left, col + q + 1 < A.cols,
-                                             q + 1 < V ? uc[q + 1 < V ? q + 1 : 0] : right, A.mu, gv[q], acc);
+                        smooth_elem<T, HESS>(f[k + 1][q], wv[k].v[q], HESS ? T(0) : yv[k].v[q], hu, f[k][q], hd,
+                                             f[k + 2][q], col + q > 0, q > 0 ? f[k + 1][q > 0 ? q - 1 : 0] : lf,
+                                             col + q + 1 < A.cols, q + 1 < V ? f[k + 1][q + 1 < V ? q + 1 : 0] : rt,
+                                             A.mu, gv[q], acc);
                     if (V == VecOf<T>::N) {
                         Pack<T> pg;
 #pragma unroll
@@ -219,20 +232,14 @@ __global__ void __launch_bounds__(OPKB_BLOCK) k_stencil_strip(SmoothArgs<T> A, R
                         if (PRE == 1) {
                             Pack<T> pu;
 #pragma unroll
-                            for (int q = 0; q < V; ++q) pu.v[q] = uc[q];
+                            for (int q = 0; q < V; ++q) pu.v[q] = f[k + 1][q];
                             st_pack<T>(A.uout + i, 0, pu);
                         }
                     } else {
                         A.g[i] = gv[0];
-                        if (PRE == 1) A.uout[i] = uc[0];
+                        if (PRE == 1) A.uout[i] = f[k + 1][0];
                     }
                 }
-#pragma unroll
-                for (int q = 0; q < V; ++q) {
-                    uu[q] = uc[q];
-                    uc[q] = ud[q];
-                }
-                hu = true;
             }
         }
     }
@@ -251,7 +258,9 @@ static int smooth_launch(opkb_context* ctx, SmoothArgs<T> A, int slot)
     const bool hess = (A.y == NULL), cgstep = (A.r != NULL);
     static const int use_strip = getenv("OPKB_STENCIL_STRIP") ? atoi(getenv("OPKB_STENCIL_STRIP")) : 1;
     const bool strip = cgstep || use_strip;
-    const int64_t nrow_items = strip ? (A.r1 - A.r0 + STRIP_ROWS - 1) / STRIP_ROWS : (A.r1 - A.r0);
+    static const int srows_env = getenv("OPKB_STRIP_ROWS") ? atoi(getenv("OPKB_STRIP_ROWS")) : STRIP_ROWS;
+    const int srows = (srows_env == 2) ? 2 : 4;
+    const int64_t nrow_items = strip ? (A.r1 - A.r0 + srows - 1) / srows : (A.r1 - A.r0);
     // (6 CTAs of 256 threads per SM: room is left for the NCCL send/recv kernel to run alongside)
     int grid = opkb_grid_for(ctx, nrow_items * ncb * OPKB_BLOCK, 6);
     ReduceScratch rs;
@@ -259,14 +268,19 @@ static int smooth_launch(opkb_context* ctx, SmoothArgs<T> A, int slot)
     rs.ticket = ctx->d_ticket;
     rs.res = ctx->d_res + 2 * slot;
     opkb_prof_begin(ctx, OPKB_K_OBJECTIVE);
-    if (cgstep) {
-        if (vec) k_stencil_strip<T, V, true, 1><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
-        else k_stencil_strip<T, 1, true, 1><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
-    } else if (strip) {
-        if (vec && hess) k_stencil_strip<T, V, true, 0><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
-        else if (vec) k_stencil_strip<T, V, false, 0><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
-        else if (hess) k_stencil_strip<T, 1, true, 0><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
-        else k_stencil_strip<T, 1, false, 0><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
+    if (strip) {
+#define STRIP_GO(VV, HH, PP)                                                                      \
+    do {                                                                                          \
+        if (srows == 2) k_stencil_strip<T, VV, HH, PP, 2><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs); \
+        else k_stencil_strip<T, VV, HH, PP, 4><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);      \
+    } while (0)
+        if (cgstep && vec) STRIP_GO(V, true, 1);
+        else if (cgstep) STRIP_GO(1, true, 1);
+        else if (vec && hess) STRIP_GO(V, true, 0);
+        else if (vec) STRIP_GO(V, false, 0);
+        else if (hess) STRIP_GO(1, true, 0);
+        else STRIP_GO(1, false, 0);
+#undef STRIP_GO
     } else {
         if (vec && hess) k_smooth2d<T, V, true><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);
         else if (vec) k_smooth2d<T, V, false><<<grid, OPKB_BLOCK, 0, ctx->stream>>>(A, rs);

@@ -151,7 +151,7 @@ def main():
             w = ctx.vector(nl, np.float64).fill_random(12, r0 * cols, 0.5, 1.0)
             b = ctx.vector(nl, np.float64).fill_random(11, r0 * cols, 0.0, 1.2)
             if c == "CG":
-                A, passes, name = opk.Smooth2DOperator(w, 2.0, cols, ctx=ctx), 12, "stencil diag(w) + 2 L, halo exchange"
+                A, passes, name = opk.Smooth2DOperator(w, 2.0, cols, ctx=ctx), 11, "stencil diag(w) + 2 L, halo exchange"
             else:
                 A, passes, name = opk.DiagonalOperator(w, ctx=ctx), 11, "diag(w)"
             s = opk.ConjGrad(A, b, ftol=0.0, restart=10 ** 9, nglobal=n, ctx=ctx, quiet=True)
