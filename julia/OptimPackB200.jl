@@ -781,9 +781,22 @@ function cg_direction!(A::DiagonalOperator{T}, p, r, q, beta::Float, first::Bool
                 p.ctx.ptr, A.a.ptr, p.ptr, r.ptr, q.ptr, beta, first, out))
     return out[1], out[2]
 end
-function cg_direction!(A::Smooth2DOperator, p, r, q, beta::Float, first::Bool)
-    first ? vcopy!(p, r) : vcombine!(p, beta, p, 1, r)
-    return apply_dot!(A, q, p)
+# direction + operator + p.q + p.p in ONE pass (`opkb_cg_smooth2d_step`): the new direction is
+# written to a scratch vector and the library swaps the two buffers; with several ranks only
+# the boundary rows of r travel, `pup` / `pdn` keep the neighbours' rows of the direction
+const CG_SCRATCH = IdDict{Any,Any}()
+function cg_direction!(A::Smooth2DOperator{T}, p, r, q, beta::Float, first::Bool) where {T}
+    sc = get!(CG_SCRATCH, A) do
+        (vcreate(p), ntuple(_ -> DeviceVector{T}(p.ctx, A.cols), 4))
+    end
+    scratch, (pup, pdn, rup, rdn) = sc
+    out = Vector{Cdouble}(undef, 2)
+    check(ccall((:opkb_cg_smooth2d_step, libopkb200), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                 Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Cdouble}),
+                p.ctx.ptr, A.w.ptr, A.mu, A.cols, p.ptr, scratch.ptr, r.ptr, q.ptr, pup.ptr, pdn.ptr,
+                rup.ptr, rdn.ptr, beta, first, out))
+    return out[1], out[2]
 end
 function cg_direction!(A, p, r, q, beta::Float, first::Bool)      # any `A!(dst, src)`
     first ? vcopy!(p, r) : vcombine!(p, beta, p, 1, r)
