@@ -110,3 +110,47 @@ def test_spg_golden(opk):
                 assert (g["iter"], g["fcnt"]) == (w["iter"], w["fcnt"])
                 assert abs(g["f"] - w["f"]) <= rtol * abs(w["f"]) + 1e-300
                 assert abs(g["pgtwon"] - w["pgtwon"]) <= rtol * abs(w["pgtwon"]) + 1e-300
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_spg_generic_convex_set(opk, oracle, dtype):
+    """`prj!` is ANY projector (src/spg.jl:64-78), not only a box: the Euclidean ball
+    {|x| <= R}, written with the `v*` operations on device Vectors, against the oracle running
+    the same projector on numpy arrays.  Objective: the built-in quadratic."""
+    n, R, m = 4001, 40.0, 10
+    a, c = opk.Quadratic.synthetic(n, dtype, kappa=1e3)
+    x0 = np.full(n, 0.5, dtype=dtype)
+
+    def ball(dst, src):                               # device Vectors
+        nrm = opk.vnorm2(src)
+        opk.vcopy_(dst, src)
+        if nrm > R:
+            opk.vscale_(dst, R / nrm)
+        return dst
+
+    def ball_np(dst, src):                            # numpy arrays, the oracle's vector operations
+        nrm = oracle.vnorm2(src)
+        oracle.vcopy(dst, src)
+        if nrm > R:
+            oracle.vscale(dst, R / nrm)
+
+    xo, io, tro = oracle.spg(("quadratic", a, c), x0, m, prj=ball_np, maxit=30, trace=True)
+    trace = []
+    ws = opk.Info()
+    s = opk.SPG(opk.Quadratic(a, c), ball, x0, m, maxit=30, ws=ws,
+                observer=lambda s: trace.append((s.iter, s.fcnt, s.f, s.pgtwon)))
+    s.solve()
+    x = s.result()
+    s.close()
+    rtol = 1e-10 if dtype == np.float64 else 1e-4
+    assert (ws.iter, ws.fcnt, ws.pcnt) == (io["iter"], io["fcnt"], io["pcnt"])
+    for g, w in zip(trace, tro):
+        if w["iter"] > 20:
+            break
+        assert (g[0], g[1]) == (w["iter"], w["fcnt"])
+        assert abs(g[2] - w["f"]) <= rtol * abs(w["f"])
+        if w["iter"] <= 10:      # (|pg| is a difference of O(R) terms: its rounding noise grows as it shrinks)
+            assert abs(g[3] - w["pgtwon"]) <= 100 * rtol * w["pgtwon"]
+    assert relerr(x, xo) <= 10 * rtol
+    assert np.linalg.norm(x.astype(np.float64)) <= R * (1 + 1e-6)          # feasible
+    assert np.linalg.norm(c.astype(np.float64)) > R                        # and the constraint is active
