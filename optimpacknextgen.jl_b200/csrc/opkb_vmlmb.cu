@@ -55,6 +55,10 @@ struct opkb_vmlmb_ {
     // p_stale != 0 means p does not belong to the current (x, g) and is recomputed on
     // demand (vmlmb_ensure_p) by whoever reads it: one pass less per iteration.
     int p_stale;
+    // packed free-set mask of the sequential two-loop recursion (k_twoloop_step): valid from
+    // the first step of a recursion until anything may change p
+    void* maskb;
+    int maskb_valid, maskb_failed;
 };
 
 static int vmlmb_ensure_p(opkb_vmlmb* ws)
@@ -168,6 +172,7 @@ extern "C" int opkb_vmlmb_destroy(opkb_vmlmb* ws)
     opkb_vector_destroy(ws->x);
     opkb_vector_destroy(ws->g);
     opkb_vector_destroy(ws->p);
+    if (ws->maskb) cudaFree(ws->maskb);
     opkb_vector_destroy(ws->d);
     opkb_vector_destroy(ws->carry_s);
     opkb_vector_destroy(ws->carry_y);
@@ -215,7 +220,9 @@ extern "C" opkb_vector* opkb_vmlmb_vector(opkb_vmlmb* ws, int which, int slot)
     switch (which) {
     case 'x': return ws->x;
     case 'g': return ws->g;
-    case 'p': return (vmlmb_ensure_p(ws) == 0) ? ws->p : NULL;
+    case 'p':
+        ws->maskb_valid = 0;   // the caller may write to it
+        return (vmlmb_ensure_p(ws) == 0) ? ws->p : NULL;
     case 'd': return ws->d;
     case 'S': return (slot >= 0 && slot < ws->mem) ? ws->S[slot] : NULL;
     case 'Y': return (slot >= 0 && slot < ws->mem) ? ws->Y[slot] : NULL;
@@ -364,6 +371,7 @@ static int trial_launch(opkb_vmlmb* ws, int mark, double stp, int initial, int s
     ws->carry_valid = 0;                 // another point than the speculated one
     if (stage != 2) vmlmb_unalias(ws);   // x, g|p are about to be overwritten
     if (stage != 1) ws->p_stale = 0;     // this launch writes p
+    ws->maskb_valid = 0;
     TrialArgs<T> A;
     A.x0 = (const T*)ws->S[mark]->data;
     A.d = (const T*)ws->d->data;
@@ -760,6 +768,7 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
 {
     opkb_context* ctx = ws->ctx;
     ws->carry_valid = 0;
+    ws->maskb_valid = 0;
     DirArgs<T> A;
     memset(&A, 0, sizeof(A));
     A.m = steepest ? 0 : m;
@@ -1055,6 +1064,7 @@ extern "C" int opkb_vmlmb_discard_trial(opkb_vmlmb* ws, int mark_next)
     int rc = check_mark(ws, mark_next);
     if (rc) return rc;
     ws->carry_valid = 0;
+    ws->maskb_valid = 0;
     void* t = ws->S[mark_next]->data;
     ws->S[mark_next]->data = ws->x->data;
     ws->x->data = t;
@@ -1118,6 +1128,11 @@ template <typename T> struct StepArgs {
     const T* z2;      // out[1] = <z2, z3>, out[2] = <z2, z2>, or NULL
     const T* z3;
     const T* w;       // free set {w != 0} or NULL
+    // the same set, one byte per 16-byte pack (bit e = element e of the pack is free): the
+    // first step of a two-loop recursion writes it (wb_out) while it reads p, the 2m - 1
+    // following steps read n/VEC bytes instead of a whole vector
+    const unsigned char* wb;
+    unsigned char* wb_out;
     T a, gamma;
     int has_scale;
     int64_t n;
@@ -1139,16 +1154,25 @@ __global__ void __launch_bounds__(OPKB_BLOCK) k_twoloop_step(StepArgs<T> A, Redu
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     double acc[3] = {0, 0, 0};
     for (int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += stride) {
-        Pack<T> v = ld_pack<T>(A.vsrc, iv), z = ld_pack<T>(A.z, iv), u = v, w = v, z2 = v, z3 = v;
+        Pack<T> v = ld_pack<T>(A.vsrc, iv), z = ld_pack<T>(A.z, iv), u = v, z2 = v, z3 = v;
         if (A.u) u = ld_pack<T>(A.u, iv);
-        if (A.w) w = ld_pack<T>(A.w, iv);
+        unsigned mb = 0xffu;
+        if (A.wb) {
+            mb = A.wb[iv];
+        } else if (A.w) {
+            const Pack<T> w = ld_pack<T>(A.w, iv);
+            mb = 0u;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) mb |= (w.v[e] != T(0)) ? (1u << e) : 0u;
+            if (A.wb_out) A.wb_out[iv] = (unsigned char)mb;
+        }
         if (A.z2) {
             z2 = ld_pack<T>(A.z2, iv);
             z3 = ld_pack<T>(A.z3, iv);
         }
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-            const bool fr = !A.w || (w.v[e] != T(0));
+            const bool fr = (mb >> e) & 1u;
             v.v[e] = step_elem(A, v.v[e], u.v[e], fr);
             if (fr) {
                 acc[0] = dacc(z.v[e], v.v[e], acc[0]);
@@ -1198,6 +1222,23 @@ static int step_run(opkb_vmlmb* ws, int first, const opkb_vector* u, double a, i
     A.z2 = z2 ? (const T*)z2->data : NULL;
     A.z3 = z3 ? (const T*)z3->data : NULL;
     A.w = (ws->method == 2) ? (const T*)ws->p->data : NULL;
+    if (A.w) {
+        static const int use_maskb = getenv("OPKB_MASKB") ? atoi(getenv("OPKB_MASKB")) : 1;   // 0: A/B switch
+        if (!use_maskb) ws->maskb_failed = 1;
+        if (!ws->maskb && !ws->maskb_failed) {
+            if (cudaMalloc(&ws->maskb, (size_t)(ws->n / VecOf<T>::N) + 16) != cudaSuccess) {
+                cudaGetLastError();
+                ws->maskb = NULL;
+                ws->maskb_failed = 1;      // no memory for it: every step reads p
+            }
+        }
+        if (ws->maskb && first) {
+            A.wb_out = (unsigned char*)ws->maskb;
+            ws->maskb_valid = 1;
+        } else if (ws->maskb && ws->maskb_valid) {
+            A.wb = (const unsigned char*)ws->maskb;
+        }
+    }
     A.a = (T)a;
     A.gamma = (T)gamma;
     A.has_scale = has_scale;
