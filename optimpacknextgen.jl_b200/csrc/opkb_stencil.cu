@@ -30,6 +30,7 @@ template <typename T> struct SmoothArgs {
     T* uout;
     T beta;
     int restart;
+    int64_t seg_rows;         // k_stencil_strip: rows per segment (one CTA per segment and column block)
 };
 
 // One CTA = 256 x VEC consecutive columns of one row (VEC = the 16-byte pack when the
@@ -134,56 +135,80 @@ __device__ __forceinline__ StripVec<T, V> strip_ld(const T* p)
     return o;
 }
 
-// Phase 1 issues every load of the strip from clamped, always valid addresses with no
-// dependent instruction and no branch in between (rows that do not exist and threads
-// beyond the last column load something valid that is never used): ~4 RB + 8 independent
-// 16-byte requests per thread are in flight before phase 2 forms the field and applies the
-// stencil.  (With the field formed right after each load the warp waited for DRAM once per
-// row: 2.7 TB/s.)
+// A CTA owns one column block (256 x V columns) of one SEGMENT of rows and walks down it strip
+// by strip (RB rows at a time), carrying the last two rows of the field in registers from one
+// strip to the next: every element of the field is loaded ONCE (plus two rows per segment).
+// (With independent strips scheduled grid-stride, the rows shared by neighbouring strips had
+// left L2 -- ~20 us of streaming -- by the time the other strip asked for them: +27 % DRAM
+// reads, ncu.)  Per strip, phase 1 issues every load from clamped, always valid addresses with
+// no dependent instruction and no branch in between (rows that do not exist and threads beyond
+// the last column load something valid that is never used), a __syncwarp() keeps ptxas from
+// sinking each load next to its consumer (which had the warp wait for DRAM once per row),
+// then phase 2 forms the field and applies the stencil.
 template <typename T, int V, bool HESS, int PRE, int RB>
 __global__ void __launch_bounds__(OPKB_BLOCK, 2) k_stencil_strip(SmoothArgs<T> A, ReduceScratch rs)
 {
     const int64_t ncb = (A.cols + OPKB_BLOCK * V - 1) / (OPKB_BLOCK * V);
-    const int64_t nstrips = (A.r1 - A.r0 + RB - 1) / RB;
-    const int64_t nitems = nstrips * ncb;
     const int lane = threadIdx.x & 31;
     const bool restart = (PRE == 1) && A.restart;
     // PRE = 1: u = beta*a + b with (a, b) = (old direction, r); on a restart u = b
     const T* const srcA = restart ? A.r : A.x;
     const T* const srcB = (PRE == 1) ? A.r : A.x;
     double acc[2] = {0.0, 0.0};
-    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int64_t strip = item / ncb;
-        const int64_t col = ((item - strip * ncb) * OPKB_BLOCK + threadIdx.x) * V;
-        const bool active = col < A.cols;           // (whole warps stay in the loop: shuffles)
-        const int64_t colc = active ? col : 0;
-        const int64_t ra = A.r0 + strip * RB;
-        const int64_t rb = (ra + RB < A.r1) ? ra + RB : A.r1;
-        // ---- phase 1: raw loads ---------------------------------------------------------------
-        StripVec<T, V> fa[RB + 2], fb[RB + 2], wv[RB], yv[RB];
-        T la[RB], lb[RB], rta[RB], rtb[RB];
-        bool halo[RB + 2];
+    const int64_t seg = blockIdx.x / ncb;
+    const int64_t col = ((blockIdx.x - seg * ncb) * OPKB_BLOCK + threadIdx.x) * V;
+    const bool active = col < A.cols;               // (whole warps stay in the loop: shuffles)
+    const int64_t colc = active ? col : 0;
+    const int64_t rs0 = A.r0 + seg * A.seg_rows;
+    const int64_t rs1 = (rs0 + A.seg_rows < A.r1) ? rs0 + A.seg_rows : A.r1;
+
+    // the field on row `row` (own rows, or the halo rows -1 and A.rows), raw loads
+    auto row_ptrs = [&](int64_t row, const T*& pa, const T*& pb, bool& halo) {
+        const bool above = (row < 0), below = (row >= A.rows);
+        halo = (above && A.up != NULL) || (below && A.dn != NULL);
+        const int64_t rowc = above ? 0 : (below ? A.rows - 1 : row);
+        pa = srcA + rowc * A.cols + colc;
+        pb = srcB + rowc * A.cols + colc;
+        if (above && A.up != NULL) pa = pb = A.up + colc;          // (pointer selects, no branch)
+        if (below && A.dn != NULL) pa = pb = A.dn + colc;
+    };
+    auto field = [&](const StripVec<T, V>& a, const StripVec<T, V>& b, bool halo, T (&u)[V]) {
 #pragma unroll
-        for (int k = 0; k < RB + 2; ++k) {
-            const int64_t row = ra - 1 + k;
-            const bool above = (row < 0), below = (row >= A.rows);
-            halo[k] = (above && A.up != NULL) || (below && A.dn != NULL);
-            const int64_t rowc = above ? 0 : (below ? A.rows - 1 : row);
-            const T* pa = srcA + rowc * A.cols + colc;
-            const T* pb = srcB + rowc * A.cols + colc;
-            if (above && A.up != NULL) pa = pb = A.up + colc;      // (pointer selects, no branch)
-            if (below && A.dn != NULL) pa = pb = A.dn + colc;
-            fa[k] = strip_ld<T, V>(pa);
-            if (PRE == 1) fb[k] = strip_ld<T, V>(pb);
+        for (int q = 0; q < V; ++q) {
+            T t = a.v[q];
+            if (PRE == 1 && !restart && !halo) t = A.beta * a.v[q] + b.v[q];
+            u[q] = t;
         }
+    };
+
+    T f[RB + 2][V];                                  // rows ra-1 .. ra+RB of the field
+    {
+        const T *pa, *pb;
+        bool h0, h1;
+        row_ptrs(rs0 - 1, pa, pb, h0);
+        const StripVec<T, V> a0 = strip_ld<T, V>(pa), b0 = (PRE == 1) ? strip_ld<T, V>(pb) : a0;
+        row_ptrs(rs0, pa, pb, h1);
+        const StripVec<T, V> a1 = strip_ld<T, V>(pa), b1 = (PRE == 1) ? strip_ld<T, V>(pb) : a1;
+        field(a0, b0, h0, f[0]);
+        field(a1, b1, h1, f[1]);
+    }
+    for (int64_t ra = rs0; ra < rs1; ra += RB) {
+        const int64_t rb = (ra + RB < rs1) ? ra + RB : rs1;
+        // ---- phase 1: raw loads of rows ra+1 .. ra+RB, of w, y and of the warp's outer neighbours
+        StripVec<T, V> fa[RB], fb[RB], wv[RB], yv[RB];
+        T la[RB], lb[RB], rta[RB], rtb[RB];
+        bool halo[RB];
 #pragma unroll
         for (int k = 0; k < RB; ++k) {
+            const T *pa, *pb;
+            row_ptrs(ra + 1 + k, pa, pb, halo[k]);
+            fa[k] = strip_ld<T, V>(pa);
+            if (PRE == 1) fb[k] = strip_ld<T, V>(pb);
             const int64_t row = ra + k;
             const int64_t rowc = (row < A.rows) ? row : A.rows - 1;
             const int64_t i = rowc * A.cols + colc;
             wv[k] = strip_ld<T, V>(A.w + i);
             if (!HESS) yv[k] = strip_ld<T, V>(A.y + i);
-            // the neighbours beyond the warp: only its first and last lanes need them
             const int64_t il = rowc * A.cols + (colc > 0 ? colc - 1 : 0);
             const int64_t ir = rowc * A.cols + (colc + V < A.cols ? colc + V : colc);
             la[k] = (lane == 0) ? srcA[il] : T(0);
@@ -193,19 +218,10 @@ __global__ void __launch_bounds__(OPKB_BLOCK, 2) k_stencil_strip(SmoothArgs<T> A
                 rtb[k] = (lane == 31) ? srcB[ir] : T(0);
             }
         }
-        // (the compiler would otherwise sink each load next to its first use to save registers)
         __syncwarp();
         // ---- phase 2: the field, then the stencil row by row -------------------------------------
-        T f[RB + 2][V];
 #pragma unroll
-        for (int k = 0; k < RB + 2; ++k) {
-#pragma unroll
-            for (int q = 0; q < V; ++q) {
-                T u = fa[k].v[q];
-                if (PRE == 1 && !restart && !halo[k]) u = A.beta * fa[k].v[q] + fb[k].v[q];
-                f[k][q] = u;
-            }
-        }
+        for (int k = 0; k < RB; ++k) field(fa[k], (PRE == 1) ? fb[k] : fa[k], halo[k], f[k + 2]);
 #pragma unroll
         for (int k = 0; k < RB; ++k) {
             const int64_t row = ra + k;
@@ -242,6 +258,11 @@ __global__ void __launch_bounds__(OPKB_BLOCK, 2) k_stencil_strip(SmoothArgs<T> A
                 }
             }
         }
+#pragma unroll
+        for (int q = 0; q < V; ++q) {                // the window moves down by RB rows
+            f[0][q] = f[RB][q];
+            f[1][q] = f[RB + 1][q];
+        }
     }
     block_reduce_publish<2, 0u, 0u>(acc, rs);
 }
@@ -257,12 +278,29 @@ static int smooth_launch(opkb_context* ctx, SmoothArgs<T> A, int slot)
     const int64_t ncb = (A.cols + per - 1) / per;
     const bool hess = (A.y == NULL), cgstep = (A.r != NULL);
     static const int use_strip = getenv("OPKB_STENCIL_STRIP") ? atoi(getenv("OPKB_STENCIL_STRIP")) : 1;
-    const bool strip = cgstep || use_strip;
+    // (one CTA per column block: rows of more than ~5e8 elements keep the grid-stride kernel)
+    const bool fits = ncb * 2 <= (int64_t)OPKB_MAX_GRID * OPKB_NRED_MAX / 2;
+    if (cgstep && !fits) return opkb_set_error(OPKB_EINVAL, "too many columns for the stencil step kernel");
+    const bool strip = cgstep || (use_strip && fits);
     static const int srows_env = getenv("OPKB_STRIP_ROWS") ? atoi(getenv("OPKB_STRIP_ROWS")) : STRIP_ROWS;
     const int srows = (srows_env == 2) ? 2 : 4;
-    const int64_t nrow_items = strip ? (A.r1 - A.r0 + srows - 1) / srows : (A.r1 - A.r0);
-    // (6 CTAs of 256 threads per SM: room is left for the NCCL send/recv kernel to run alongside)
-    int grid = opkb_grid_for(ctx, nrow_items * ncb * OPKB_BLOCK, 6);
+    int grid;
+    if (strip) {
+        // one CTA per (segment of rows, column block); as many segments as keep every SM's
+        // resident CTAs (2 per SM: 128 registers) busy in ONE wave
+        const int64_t nrows = A.r1 - A.r0;
+        static const int per_sm = getenv("OPKB_STRIP_CTAS") ? atoi(getenv("OPKB_STRIP_CTAS")) : 2;
+        int64_t nseg = ((int64_t)ctx->sm_count * per_sm) / ncb;
+        if (nseg < 1) nseg = 1;
+        int64_t seg_rows = (nrows + nseg - 1) / nseg;
+        seg_rows = ((seg_rows + srows - 1) / srows) * srows;
+        nseg = (nrows + seg_rows - 1) / seg_rows;
+        A.seg_rows = seg_rows;
+        grid = (int)(nseg * ncb);
+    } else {
+        // (6 CTAs of 256 threads per SM: room is left for the NCCL send/recv kernel to run alongside)
+        grid = opkb_grid_for(ctx, (A.r1 - A.r0) * ncb * OPKB_BLOCK, 6);
+    }
     ReduceScratch rs;
     rs.part = ctx->d_part;
     rs.ticket = ctx->d_ticket;
