@@ -89,6 +89,8 @@ extern "C" int opkb_comm_init(opkb_context* ctx, const void* id128, int rank, in
     ctx->rank = rank;
     ctx->nranks = nranks;
     OPKB_CUDA(cudaMalloc(&ctx->d_all, sizeof(double) * OPKB_NRED_MAX * (size_t)nranks));
+    OPKB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->d_res = ctx->d_res_dev;   // NCCL sends from device memory
     cudaFreeHost(ctx->h_res);
     OPKB_CUDA(cudaMallocHost(&ctx->h_res, sizeof(double) * OPKB_NRED_MAX * (size_t)nranks));
     return 0;

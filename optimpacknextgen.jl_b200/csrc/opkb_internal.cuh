@@ -35,7 +35,10 @@ struct opkb_context_ {
     void* nccl_comm;
     double* d_part;          // [OPKB_MAX_GRID * OPKB_NRED_MAX] per-CTA partials
     unsigned int* d_ticket;  // last-CTA-done ticket
-    double* d_res;           // [OPKB_NRED_MAX] this rank's reduced scalars
+    double* d_res;           // [OPKB_NRED_MAX] this rank's reduced scalars; on one rank this IS h_res
+                             // (pinned host memory is device-accessible under UVA: the last CTA
+                             // writes the few hundred bytes straight to the host, no D2H copy)
+    double* d_res_dev;       // the device allocation (used with several ranks: NCCL send buffer)
     double* d_all;           // [nranks * OPKB_NRED_MAX] after the all-gather
     double* h_res;           // pinned mirror of d_res / d_all
     cudaEvent_t ev0, ev1;
