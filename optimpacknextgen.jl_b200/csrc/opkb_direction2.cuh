@@ -284,6 +284,17 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                         step_limit_update_fast(px.v[q], pl.v[q], ph_.v[q], A.has_lo, A.has_hi, -di, smin, smax);
                 }
                 Pack<T> xt, gt, pt;
+                if (!FUSE && A.xout) {
+                    // user objective: only the trial point x' = project(x - 1*d) (:599, :386) is
+                    // formed here; the caller evaluates f, g' there (opkb_vmlmb_trial_begin with
+                    // stp = 1 then has nothing left to do)
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        T xi = px.v[q] + T(-1) * v.v[q];
+                        if (A.bounded) xi = fastclamp(xi, pl.v[q], ph_.v[q]);
+                        xt.v[q] = xi;
+                    }
+                }
                 if (FUSE) {
                     // x' = project(x - 1*d) (:599, :386); f, g' = fg(x') (:391); p' (:396)
                     Pack<T> pa, pc;
@@ -402,6 +413,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                         st_pack<T>(A.xout, iv, xt);
                         st_pack<T>(A.gout, iv, gt);
                         if (A.pout) st_pack<T>(A.pout, iv, pt);
+                    } else if (A.xout) {
+                        st_pack<T>(A.xout, iv, xt);
                     }
                     if (CARRY) {
                         st_pack<T>(A.sout, iv, sn);
@@ -418,6 +431,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                             A.xout[base + e + q] = xt.v[q];
                             A.gout[base + e + q] = gt.v[q];
                             if (A.pout) A.pout[base + e + q] = pt.v[q];
+                        } else if (A.xout) {
+                            A.xout[base + e + q] = xt.v[q];
                         }
                         if (CARRY) {
                             A.sout[base + e + q] = sn.v[q];

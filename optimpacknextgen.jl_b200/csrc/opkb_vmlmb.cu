@@ -59,6 +59,10 @@ struct opkb_vmlmb_ {
     // the first step of a recursion until anything may change p
     void* maskb;
     int maskb_valid, maskb_failed;
+    // user objective: the direction kernel already wrote x' = project(x - d) into the buffer
+    // that becomes x when the next line search starts (slot xspec_mark); a trial_begin with
+    // stp = 1 for that slot is then a pointer swap.  -1: nothing speculated.
+    int xspec_mark;
 };
 
 static int vmlmb_ensure_p(opkb_vmlmb* ws)
@@ -138,6 +142,7 @@ extern "C" int opkb_vmlmb_create(opkb_context* ctx, int eltype, int64_t n, int m
     opkb_vmlmb* ws = (opkb_vmlmb*)calloc(1, sizeof(opkb_vmlmb));
     if (!ws) return opkb_set_error(OPKB_ENOMEM, "out of host memory");
     ws->ctx = ctx;
+    ws->xspec_mark = -1;
     ws->eltype = eltype;
     ws->n = n;
     ws->mem = mem;
@@ -370,6 +375,12 @@ static int trial_launch(opkb_vmlmb* ws, int mark, double stp, int initial, int s
     opkb_context* ctx = ws->ctx;
     ws->carry_valid = 0;                 // another point than the speculated one
     if (stage != 2) vmlmb_unalias(ws);   // x, g|p are about to be overwritten
+    if (stage == 1 && !initial && ws->xspec_mark == mark && stp == 1.0) {
+        ws->xspec_mark = -1;             // x' is already there (written by the direction kernel)
+        ws->maskb_valid = 0;
+        return 0;
+    }
+    if (stage != 2) ws->xspec_mark = -1;
     if (stage != 1) ws->p_stale = 0;     // this launch writes p
     ws->maskb_valid = 0;
     TrialArgs<T> A;
@@ -769,6 +780,8 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
     opkb_context* ctx = ws->ctx;
     ws->carry_valid = 0;
     ws->maskb_valid = 0;
+    ws->xspec_mark = -1;
+    int xspec = 0;
     DirArgs<T> A;
     memset(&A, 0, sizeof(A));
     A.m = steepest ? 0 : m;
@@ -836,6 +849,14 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         // incremental Gram (CARRY): only when the caller solves the two-loop recursion
         // from the Gram block of exactly these pairs (opkb_vmlmb_gram just before)
         int carry = 0;
+        // user objective (VMLMB / L-BFGS): the trial point of the step the driver takes after a
+        // successful update, stp = 1, is formed in the same pass (one more write, no more reads)
+        static const int xspec_on = getenv("OPKB_XSPEC") ? atoi(getenv("OPKB_XSPEC")) : 1;
+        if (!fuse && xspec_on && ws->obj == OPKB_OBJ_USER && ws->method != 1 &&
+            ws->aliased_slot != mark_next) {
+            B.xout = (T*)ws->S[mark_next]->data;
+            xspec = 1;
+        }
         if (fuse) {
             // x', g' go to the buffers of the recycled slot, which become x and g
             B.xout = (T*)ws->S[mark_next]->data;
@@ -1024,6 +1045,7 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
     }
     // vcopy!(S[mark], x); vcopy!(Y[mark], g|p) :562-563, without a copy
     vmlmb_alias(ws, mark_next);
+    if (xspec && done == ws->n) ws->xspec_mark = mark_next;
     return 0;
 }
 
@@ -1065,6 +1087,7 @@ extern "C" int opkb_vmlmb_discard_trial(opkb_vmlmb* ws, int mark_next)
     if (rc) return rc;
     ws->carry_valid = 0;
     ws->maskb_valid = 0;
+    ws->xspec_mark = -1;
     void* t = ws->S[mark_next]->data;
     ws->S[mark_next]->data = ws->x->data;
     ws->x->data = t;
