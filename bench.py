@@ -25,6 +25,10 @@ import sys
 import threading
 import time
 
+# stdout carries ONE JSON line: whatever NCCL prints (e.g. "NCCL version ..." when the launcher
+# exports NCCL_DEBUG=VERSION) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "oracle")):
     if p not in sys.path:
