@@ -5,7 +5,8 @@ The reference (Julia) cannot run here and holds no golden vectors of its own
 suite checks the oracle still reproduces them and the GPU suite checks the CUDA
 path against them without needing anything outside the repo.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            # vmlmb + spg
+    python tests/golden/make_golden.py conjgrad   # conjgrad only
 """
 import json
 import os
@@ -38,6 +39,41 @@ SPG_CASES = [
 ]
 
 
+CG_CASES = [
+    # (operator, shape, dtype, keywords)
+    ("stencil", (24, 40), "float64", {"ftol": 0.0, "maxiter": 25, "restart": 10}),
+    ("stencil", (24, 40), "float32", {"ftol": 0.0, "maxiter": 25, "restart": 10}),
+    ("diag", (1, 1003), "float64", {"ftol": 0.0, "maxiter": 25}),
+    ("stencil", (17, 33), "float64", {}),                       # defaults: stops on the f test
+]
+
+
+def cg_problem(op, shape, dt):
+    """-> (oracle operator, b): the data of tests (Smooth2D.synthetic: deterministic)."""
+    import opkb200 as opk
+    rows, cols = shape
+    w, y = opk.Smooth2D.synthetic(rows, cols, np.dtype(dt))
+    A = opk.Smooth2DOperator.reference(w, 2.0, cols) if op == "stencil" else ("diag", w)
+    return A, (w * y).astype(dt), w
+
+
+def make_conjgrad(rev):
+    out = {"oracle_git": rev, "sum_mode": "accurate", "cases": []}
+    for op, shape, dt, kw in CG_CASES:
+        A, b, _ = cg_problem(op, shape, dt)
+        x, info, tr = O.conjgrad(A, b, trace=True, **kw)
+        out["cases"].append({
+            "operator": op, "shape": list(shape), "dtype": dt, "kw": kw,
+            "final": {k: info[k] for k in ("iter", "status", "rho", "phi")},
+            "x_final_head": [float(v) for v in x[:8]],
+            "trace": [{"iter": t["iter"], "rho": t["rho"], "phi": t["phi"],
+                       "x_head": [float(v) for v in t["x"][:8]]} for t in tr],
+        })
+    with open(os.path.join(HERE, "conjgrad_traces.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+    print("wrote", os.path.join(HERE, "conjgrad_traces.json"))
+
+
 def main():
     O.build()
     O.set_sum_mode(O.SUM_ACCURATE)
@@ -46,6 +82,8 @@ def main():
                              text=True).stdout.strip()
     except Exception:
         rev = "unknown"
+    if sys.argv[1:] == ["conjgrad"]:      # only the conjgrad fixture (the others stay as committed)
+        return make_conjgrad(rev)
     out = {"oracle_git": rev, "sum_mode": "accurate", "cases": []}
     for kind, n, dt, kw in VMLMB_CASES:
         pb = problem(kind, n, np.dtype(dt))

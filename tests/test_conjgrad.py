@@ -133,3 +133,27 @@ def test_smooth2d_operator_is_the_hessian_of_smooth2d():
     A(Az, z)
     assert np.allclose(g, Ax - w * y, rtol=0, atol=1e-12)
     assert abs(np.dot(z, Ax) - np.dot(x, Az)) <= 1e-10 * abs(np.dot(z, Ax))
+
+
+def test_oracle_reproduces_conjgrad_golden(oracle):
+    """tests/golden/conjgrad_traces.json (make_golden.py conjgrad): the committed fixture
+    the GPU suite is checked against must still be what the oracle produces."""
+    import json
+    import os
+    import sys
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    sys.path.insert(0, gdir)
+    from make_golden import cg_problem
+    with open(os.path.join(gdir, "conjgrad_traces.json")) as fh:
+        gold = json.load(fh)
+    assert len(gold["cases"]) >= 4
+    for case in gold["cases"]:
+        A, b, _ = cg_problem(case["operator"], tuple(case["shape"]), case["dtype"])
+        kw = dict(case["kw"])
+        x, info, tr = oracle.conjgrad(A, b, trace=True, **kw)
+        assert {k: info[k] for k in ("iter", "status", "rho", "phi")} == case["final"]
+        assert [float(v) for v in x[:8]] == case["x_final_head"]
+        assert len(tr) == len(case["trace"])
+        for t, w in zip(tr, case["trace"]):
+            assert (t["iter"], t["rho"], t["phi"]) == (w["iter"], w["rho"], w["phi"])
+            assert [float(v) for v in t["x"][:8]] == w["x_head"]

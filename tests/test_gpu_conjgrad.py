@@ -258,3 +258,31 @@ def test_large_grid_properties(opk):
     op(q, s.x)
     true_r = bv.download() - q.download()
     assert abs(np.dot(true_r, true_r) - res[1][0]) <= 1e-6 * res[1][0]
+
+
+def test_conjgrad_golden(opk):
+    """The CUDA path against the committed fixture (tests/golden/conjgrad_traces.json,
+    traces of the oracle): nothing outside the repository is needed."""
+    import json
+    import os
+    import sys
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    sys.path.insert(0, gdir)
+    from make_golden import cg_problem
+    with open(os.path.join(gdir, "conjgrad_traces.json")) as fh:
+        gold = json.load(fh)
+    for case in gold["cases"]:
+        dtype = np.dtype(case["dtype"])
+        rows, cols = case["shape"]
+        _, b, w = cg_problem(case["operator"], (rows, cols), case["dtype"])
+        A = opk.Smooth2DOperator(w, 2.0, cols) if case["operator"] == "stencil" else opk.DiagonalOperator(w)
+        rtol = F64_RTOL if dtype == np.float64 else F32_RTOL
+        got = []
+        s = opk.ConjGrad(A, b, quiet=True, observer=lambda s: got.append((s.iter, s.rho, s.x.download()[:8])),
+                         **case["kw"])
+        s.solve()
+        assert s.status == case["final"]["status"] and abs(s.iter - case["final"]["iter"]) <= 1
+        for (k, rho, xh), wt in list(zip(got, case["trace"]))[:21]:
+            assert k == wt["iter"] and abs(rho - wt["rho"]) <= 100 * rtol * wt["rho"]
+            ref = np.array(wt["x_head"])
+            assert np.linalg.norm(xh - ref) <= rtol * max(np.linalg.norm(ref), 1e-300) + 1e-300
