@@ -19,11 +19,7 @@
 
 static ReduceScratch cg_scratch(opkb_context* ctx)
 {
-    ReduceScratch rs;
-    rs.part = ctx->d_part;
-    rs.ticket = ctx->d_ticket;
-    rs.res = ctx->d_res;
-    return rs;
+    return opkb_make_scratch(ctx);
 }
 
 #define CG_LAUNCH(ctx, cls, kernel, grid, ...)                               \

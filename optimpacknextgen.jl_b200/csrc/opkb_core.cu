@@ -69,6 +69,11 @@ extern "C" int opkb_context_create(opkb_context** out, int device)
         // one rank: the kernels write their results directly into the pinned host buffer
         const char* e = getenv("OPKB_MAPPED_RES");
         if (!e || atoi(e) != 0) ctx->d_res = ctx->h_res;
+        // ... and a completion flag next to them, polled by the host (OPKB_SPIN=0: stream sync)
+        OPKB_CUDA(cudaMallocHost(&ctx->h_flag, 64));
+        *ctx->h_flag = 0u;
+        e = getenv("OPKB_SPIN");
+        ctx->spin = (!e || atoi(e) != 0) ? 1 : 0;
     }
     OPKB_CUDA(cudaEventCreate(&ctx->ev0));
     OPKB_CUDA(cudaEventCreate(&ctx->ev1));
@@ -100,6 +105,7 @@ extern "C" int opkb_context_destroy(opkb_context* ctx)
         free(ctx->prof);
     }
     cudaFreeHost(ctx->h_res);
+    if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -237,7 +243,19 @@ int opkb_finish_reduction(opkb_context* ctx, int nred, const int* kinds, double*
         if (ctx->d_res != ctx->h_res)
             OPKB_CUDA(cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(double) * nred,
                                       cudaMemcpyDeviceToHost, ctx->stream));
-        OPKB_CUDA(cudaStreamSynchronize(ctx->stream));
+        bool seen = false;
+        if (ctx->spin && ctx->d_res == ctx->h_res) {
+            // the last CTA of the latest reducing launch stores its sequence number after its
+            // results: poll it (sub-microsecond) instead of waking up through the driver; a
+            // stream query every few microseconds catches launches that do not publish, and errors
+            volatile unsigned int* flag = ctx->h_flag;
+            const unsigned int want = ctx->seq;
+            for (unsigned int it = 1;; ++it) {
+                if (*flag == want) { seen = true; break; }
+                if ((it & 4095u) == 0u && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) break;
+            }
+        }
+        if (!seen) OPKB_CUDA(cudaStreamSynchronize(ctx->stream));
         for (int k = 0; k < nred; ++k) out[k] = ctx->h_res[k];
         return 0;
     }
@@ -350,11 +368,7 @@ static int same_space(const opkb_vector* a, const opkb_vector* b)
 
 static ReduceScratch scratch(opkb_context* ctx)
 {
-    ReduceScratch rs;
-    rs.part = ctx->d_part;
-    rs.ticket = ctx->d_ticket;
-    rs.res = ctx->d_res;
-    return rs;
+    return opkb_make_scratch(ctx);
 }
 
 template <typename T>

@@ -495,8 +495,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
         __threadfence();
         last_cta_combine(rs.part, rs.res, NTOT, gridDim.x,
                          [](int k) { return (k == 2) ? OPKB_RMIN : ((k == 3) ? OPKB_RMAX : OPKB_RSUM); });
-        __syncthreads();
-        if (tid == 0) *rs.ticket = 0u;
+        reduce_done(rs);
     }
 }
 
@@ -517,10 +516,7 @@ static int dir2_do_launch(opkb_context* ctx, void (*kern)(Dir2Args<T>, ReduceScr
 {
     if (!kern) return opkb_set_error(OPKB_EINVAL, "no direction kernel instance for this shape");
     OPKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ReduceScratch rs;
-    rs.part = ctx->d_part;
-    rs.ticket = ctx->d_ticket;
-    rs.res = ctx->d_res;
+    ReduceScratch rs = opkb_make_scratch(ctx);
     opkb_prof_begin(ctx, OPKB_K_DIRECTION);
     kern<<<grid, threads, smem, ctx->stream>>>(B, rs);
     opkb_prof_end(ctx);

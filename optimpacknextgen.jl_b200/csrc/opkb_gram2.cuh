@@ -293,8 +293,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
     if (!s_last) return;
     __threadfence();
     last_cta_combine(rs.part, rs.res, nslot, gridDim.x, [](int) { return (int)OPKB_RSUM; });
-    __syncthreads();
-    if (tid == 0) *rs.ticket = 0u;
+    reduce_done(rs);
 }
 
 template <typename T, int BS, int TILE, int MAXT>
@@ -321,10 +320,7 @@ static int gram2_launch(opkb_context* ctx, Gram2Args<T>& A, int nroles, int* nsl
     int64_t grid = ctx->sm_count;   // one persistent CTA per SM
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
-    ReduceScratch rs;
-    rs.part = ctx->d_part;
-    rs.ticket = ctx->d_ticket;
-    rs.res = ctx->d_res;
+    ReduceScratch rs = opkb_make_scratch(ctx);
     opkb_prof_begin(ctx, OPKB_K_GRAM);
     kern<<<(int)grid, block, smem, ctx->stream>>>(A, rs);
     opkb_prof_end(ctx);

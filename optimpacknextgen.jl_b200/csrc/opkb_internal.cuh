@@ -41,6 +41,9 @@ struct opkb_context_ {
     double* d_res_dev;       // the device allocation (used with several ranks: NCCL send buffer)
     double* d_all;           // [nranks * OPKB_NRED_MAX] after the all-gather
     double* h_res;           // pinned mirror of d_res / d_all
+    unsigned int* h_flag;    // completion flag of the reducing kernels (pinned, see ReduceScratch)
+    unsigned int seq;        // sequence number of the last reducing launch
+    int spin;                // poll h_flag instead of cudaStreamSynchronize (one rank)
     cudaEvent_t ev0, ev1;
     int64_t launches;
     void* flush_buf;
@@ -257,7 +260,35 @@ struct ReduceScratch {
     double* part;
     unsigned int* ticket;
     double* res;
+    // completion flag in pinned host memory (one rank): the last CTA stores `seq` there after
+    // its results (system-scope fence), and the host polls it instead of synchronising the stream
+    unsigned int* flag;
+    unsigned int seq;
 };
+
+// last thing the last CTA of a reducing kernel does (all its threads call it, after their
+// writes to rs.res)
+__device__ __forceinline__ void reduce_done(const ReduceScratch& rs)
+{
+    if (rs.flag) __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *rs.ticket = 0u;
+        if (rs.flag) *(volatile unsigned int*)rs.flag = rs.seq;
+    }
+}
+
+// the scratch of the next reducing launch (results at ctx->d_res + res_offset)
+static inline ReduceScratch opkb_make_scratch(opkb_context* ctx, int res_offset = 0)
+{
+    ReduceScratch rs;
+    rs.part = ctx->d_part;
+    rs.ticket = ctx->d_ticket;
+    rs.res = ctx->d_res + res_offset;
+    rs.flag = (ctx->spin && ctx->nranks <= 1 && ctx->d_res == ctx->h_res) ? ctx->h_flag : NULL;
+    rs.seq = ++ctx->seq;
+    return rs;
+}
 
 __device__ __forceinline__ double rcombine_dyn(int kind, double a, double b)
 {
@@ -346,7 +377,7 @@ __device__ void block_reduce_publish(double (&v)[NR], const ReduceScratch& rs)
         for (int w = 1; w < nwarps; ++w) r = rcombine_dyn(kind, r, sm[k][w]);
         rs.res[k] = r;
     }
-    if (threadIdx.x == 0) *rs.ticket = 0u;
+    reduce_done(rs);
 }
 
 // Last-CTA combination of per-CTA partials for kernels that reduce many slots

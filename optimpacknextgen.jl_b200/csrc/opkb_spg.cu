@@ -236,10 +236,7 @@ static int spg_run(opkb_spg* ws, int mode, double lambda, double stp, double eta
     A.eta_is_one = (eta == 1.0);
     A.n = ws->n;
     int grid = opkb_grid_for(ctx, ws->n / VecOf<T>::N, 4);
-    ReduceScratch rs;
-    rs.part = ctx->d_part;
-    rs.ticket = ctx->d_ticket;
-    rs.res = ctx->d_res;
+    ReduceScratch rs = opkb_make_scratch(ctx);
 #define SPG_LAUNCH(OBJ, MODE)                                                     \
     do {                                                                          \
         opkb_prof_begin(ctx, OPKB_K_SPG);                                         \

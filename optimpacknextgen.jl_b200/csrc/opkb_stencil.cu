@@ -301,10 +301,7 @@ static int smooth_launch(opkb_context* ctx, SmoothArgs<T> A, int slot)
         // (6 CTAs of 256 threads per SM: room is left for the NCCL send/recv kernel to run alongside)
         grid = opkb_grid_for(ctx, (A.r1 - A.r0) * ncb * OPKB_BLOCK, 6);
     }
-    ReduceScratch rs;
-    rs.part = ctx->d_part;
-    rs.ticket = ctx->d_ticket;
-    rs.res = ctx->d_res + 2 * slot;
+    ReduceScratch rs = opkb_make_scratch(ctx, 2 * slot);
     opkb_prof_begin(ctx, OPKB_K_OBJECTIVE);
     if (strip) {
 #define STRIP_GO(VV, HH, PP)                                                                      \

@@ -107,11 +107,7 @@ static void vmlmb_alias(opkb_vmlmb* ws, int slot)
 
 static ReduceScratch scratch(opkb_context* ctx)
 {
-    ReduceScratch rs;
-    rs.part = ctx->d_part;
-    rs.ticket = ctx->d_ticket;
-    rs.res = ctx->d_res;
-    return rs;
+    return opkb_make_scratch(ctx);
 }
 
 template <typename T>
