@@ -515,7 +515,7 @@ static int dir2_do_launch(opkb_context* ctx, void (*kern)(Dir2Args<T>, ReduceScr
                           int threads, size_t smem, int grid)
 {
     if (!kern) return opkb_set_error(OPKB_EINVAL, "no direction kernel instance for this shape");
-    OPKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OPKB_CUDA(opkb_ensure_smem((const void*)kern, smem));
     ReduceScratch rs = opkb_make_scratch(ctx);
     opkb_prof_begin(ctx, OPKB_K_DIRECTION);
     kern<<<grid, threads, smem, ctx->stream>>>(B, rs);

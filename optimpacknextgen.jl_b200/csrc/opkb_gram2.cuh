@@ -315,7 +315,7 @@ static int gram2_launch(opkb_context* ctx, Gram2Args<T>& A, int nroles, int* nsl
     A.nstage = nstage;
     auto kern = k_gram2<T, BS, TILE, MAXT>;
     if (block > MAXT) return opkb_set_error(OPKB_EINVAL, "Gram launch: %d threads > %d", block, MAXT);
-    OPKB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OPKB_CUDA(opkb_ensure_smem((const void*)kern, smem));
     int64_t ntiles = (A.n + TILE - 1) / TILE;
     int64_t grid = ctx->sm_count;   // one persistent CTA per SM
     if (grid > ntiles) grid = ntiles;

@@ -278,6 +278,25 @@ __device__ __forceinline__ void reduce_done(const ReduceScratch& rs)
     }
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, size) instead of once per
+// launch (a microsecond or two of driver time per iteration of the small problems)
+static inline cudaError_t opkb_ensure_smem(const void* kern, size_t smem)
+{
+    static const void* seen_k[64];
+    static size_t seen_s[64];
+    static int nseen = 0;
+    for (int i = 0; i < nseen; ++i)
+        if (seen_k[i] == kern && seen_s[i] >= smem) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        int slot = -1;
+        for (int i = 0; i < nseen; ++i) if (seen_k[i] == kern) slot = i;
+        if (slot < 0 && nseen < 64) slot = nseen++;
+        if (slot >= 0) { seen_k[slot] = kern; seen_s[slot] = smem; }
+    }
+    return e;
+}
+
 // the scratch of the next reducing launch (results at ctx->d_res + res_offset)
 static inline ReduceScratch opkb_make_scratch(opkb_context* ctx, int res_offset = 0)
 {
