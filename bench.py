@@ -70,13 +70,15 @@ def config(args, n):
 
 # ---------------------------------------------------------------------------
 # CPU arm: the oracle port ("reference-faithful unfused" C restatement, OpenMP)
-def cpu_run(args, steps, warmup, log2n):
+def cpu_run(args, steps, warmup, log2n, threads=None):
     """Times `steps` VMLMB iterations of the oracle on the host cores on a
     bounded sample (n_s = 2^log2n) of the same workload.  Returns it/s at n_s."""
     import opk_oracle as O
     O.build()
     O.set_sum_mode(O.SUM_ACCURATE)
-    O.set_num_threads(int(os.environ.get("OPKB_CPU_THREADS", "0")))   # 0 = all host cores
+    if threads is None:
+        threads = int(os.environ.get("OPKB_CPU_THREADS", "0"))         # 0 = all host cores
+    O.set_num_threads(threads)
     cores = O.max_threads()
     ns = 1 << log2n
     sys.path.insert(0, ROOT)
@@ -362,6 +364,12 @@ def ours(args):
             "sample": "oracle port (C restatement of the reference's unfused CPU path, OpenMP, %d threads): "
                       "%d iterations at n_s=2^%d timed (%.2f s), scaled by n_s/n to n=2^%d"
                       % (r["cores"], args.cpu_steps, args.cpu_log2n, r["seconds"], args.log2n)}
+        # also the scalar figure (one thread, a smaller sample)
+        r1 = cpu_run(args, 3, 1, min(args.cpu_log2n, 21), threads=1)
+        line["cpu_baseline"]["single_thread"] = {
+            "value": r1["its_at_ns"] * r1["ns"] / n, "unit": UNIT, "cores": 1,
+            "sample": "same port, 1 thread: 3 iterations at n_s=2^%d (%.2f s), scaled to n=2^%d"
+                      % (min(args.cpu_log2n, 21), r1["seconds"], args.log2n)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     # explicit teardown, in dependency order
