@@ -10,7 +10,7 @@ from ._lib import OpkbError, SO_PATH, EXPORTED_SYMBOLS
 from .vectors import (Context, Vector, default_context, comm_unique_id, vcreate, vcopy, vcopy_,
                       vfill_, vdot, vnorm2, vnorminf, vscale_, vupdate_, vcombine_, vproduct_,
                       project_variables_, project_direction_, project_gradient_, step_limits,
-                      get_free_variables)
+                      get_free_variables, fastmin, fastmax, fastclamp)
 from .linesearches import (LineSearch, ArmijoLineSearch, MoreToraldoLineSearch,
                            MoreThuenteLineSearch, cstep, start_, iterate_, getstep, gettask,
                            getstatus, usederivatives)

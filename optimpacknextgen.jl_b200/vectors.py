@@ -212,6 +212,25 @@ def _bound(b, x: Vector, default: float):
     return None, float(b)
 
 
+def fastmin(x, y):
+    """src/bounds.jl:41: the least of x and y, or x if one of them is a NaN."""
+    return y if x > y else x
+
+
+def fastmax(x, y):
+    """src/bounds.jl:53: the greatest of x and y, or x if one of them is a NaN."""
+    return y if x < y else x
+
+
+def fastclamp(x, lo, hi):
+    """src/bounds.jl:65-67: x subject to the bounds (None = no bound); NaNs are not special."""
+    if hi is not None:
+        x = fastmin(x, hi)
+    if lo is not None:
+        x = fastmax(x, lo)
+    return x
+
+
 def vcreate(x: Vector) -> Vector:
     return x.similar()
 

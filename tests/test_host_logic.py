@@ -235,3 +235,16 @@ def test_shard_ranges():
                 prev = first + cnt
                 tot += cnt
             assert tot == n
+
+
+def test_fastmin_fastmax_fastclamp():
+    """The scalar helpers SimpleBounds exports (src/bounds.jl:41, :53, :65-67), NaN rules included."""
+    nan = float("nan")
+    assert opk.fastmin(1.0, 2.0) == 1.0 and opk.fastmin(2.0, 1.0) == 1.0
+    assert opk.fastmax(1.0, 2.0) == 2.0 and opk.fastmax(2.0, 1.0) == 2.0
+    assert math.isnan(opk.fastmin(nan, 1.0)) and opk.fastmin(1.0, nan) == 1.0      # "or x otherwise"
+    assert math.isnan(opk.fastmax(nan, 1.0)) and opk.fastmax(1.0, nan) == 1.0
+    assert opk.fastclamp(0.5, 0.0, 1.0) == 0.5 and opk.fastclamp(-1.0, 0.0, 1.0) == 0.0
+    assert opk.fastclamp(2.0, 0.0, 1.0) == 1.0 and opk.fastclamp(2.0, None, 1.0) == 1.0
+    assert opk.fastclamp(-2.0, 0.0, None) == 0.0 and opk.fastclamp(7.0, None, None) == 7.0
+    assert math.isnan(opk.fastclamp(nan, 0.0, 1.0))
