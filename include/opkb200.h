@@ -141,6 +141,15 @@ int opkb_vupdate_masked(opkb_context* ctx, opkb_vector* y, const opkb_vector* w,
 int opkb_vcombine(opkb_context* ctx, opkb_vector* dst, double alpha, const opkb_vector* x,
                   double beta, const opkb_vector* y);
 int opkb_vproduct(opkb_context* ctx, opkb_vector* dst, const opkb_vector* x, const opkb_vector* y);
+/* The rest of the vector-space contract (doc/algebra.md:31 vswap!, :50 vnorm1, :60-67 vcombine!
+ * with three terms = vcombine! then update!, same roundings; :116 vproduct!(dst, sel, x, y) with
+ * sel = {w != 0}, the other elements of dst are left alone).  Not called by vmlmb / spg. */
+int opkb_vswap(opkb_context* ctx, opkb_vector* x, opkb_vector* y);
+int opkb_vnorm1(opkb_context* ctx, const opkb_vector* x, double* result);
+int opkb_vcombine3(opkb_context* ctx, opkb_vector* dst, double alpha, const opkb_vector* x,
+                   double beta, const opkb_vector* y, double gamma, const opkb_vector* z);
+int opkb_vproduct_masked(opkb_context* ctx, opkb_vector* dst, const opkb_vector* w,
+                         const opkb_vector* x, const opkb_vector* y);
 /* project_variables!(dst,src,lo,hi), src/bounds.jl:137-213 */
 int opkb_project_variables(opkb_context* ctx, opkb_vector* dst, const opkb_vector* src,
                            const opkb_vector* lo, double lo_val,

@@ -28,8 +28,8 @@ export DeviceVector, BoundedSet, Rosenbrock, Quadratic, Smooth2D, vmlmb, vmlmb!,
 using Libdl
 using Printf
 import LazyAlgebra
-import LazyAlgebra: vcreate, vcopy!, vcopy, vdot, vnorm2, vnorminf, vscale!, vupdate!,
-    vcombine!, vproduct!, vfill!
+import LazyAlgebra: vcreate, vcopy!, vcopy, vdot, vnorm1, vnorm2, vnorminf, vscale!, vupdate!,
+    vcombine!, vproduct!, vfill!, vswap!
 import OptimPackNextGen
 import OptimPackNextGen.SimpleBounds: project_variables!, project_direction!, step_limits,
     get_free_variables!
@@ -175,6 +175,24 @@ function vcombine!(dst::DeviceVector{T}, alpha::Real, x::DeviceVector{T},
                 dst.ctx.ptr, dst.ptr, alpha, x.ptr, beta, y.ptr))
     return dst
 end
+# the rest of the vector-space contract (doc/algebra.md:31, :50, :60-67, :116)
+function vswap!(x::DeviceVector{T}, y::DeviceVector{T}) where {T}
+    check(ccall((:opkb_vswap, libopkb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), x.ctx.ptr, x.ptr, y.ptr))
+    return nothing
+end
+function vnorm1(x::DeviceVector)
+    r = Ref{Cdouble}(0)
+    check(ccall((:opkb_vnorm1, libopkb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Cdouble}), x.ctx.ptr, x.ptr, r))
+    return r[]
+end
+function vcombine!(dst::DeviceVector{T}, alpha::Real, x::DeviceVector{T}, beta::Real, y::DeviceVector{T},
+                   gamma::Real, z::DeviceVector{T}) where {T}
+    check(ccall((:opkb_vcombine3, libopkb200), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}),
+                dst.ctx.ptr, dst.ptr, alpha, x.ptr, beta, y.ptr, gamma, z.ptr))
+    return dst
+end
+
 function vproduct!(dst::DeviceVector{T}, x::DeviceVector{T}, y::DeviceVector{T}) where {T}
     check(ccall((:opkb_vproduct, libopkb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
                 dst.ctx.ptr, dst.ptr, x.ptr, y.ptr))
@@ -205,6 +223,12 @@ function vupdate!(y::DeviceVector{T}, sel::FreeMask{T}, alpha::Real, x::DeviceVe
                 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}),
                 y.ctx.ptr, y.ptr, sel.w.ptr, alpha, x.ptr))
     return y
+end
+function vproduct!(dst::DeviceVector{T}, sel::FreeMask{T}, x::DeviceVector{T}, y::DeviceVector{T}) where {T}
+    check(ccall((:opkb_vproduct_masked, libopkb200), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                dst.ctx.ptr, dst.ptr, sel.w.ptr, x.ptr, y.ptr))
+    return dst
 end
 
 # SimpleBounds on device vectors (src/bounds.jl:137-213, :321-409, :431-624).

@@ -8,7 +8,7 @@ call loads `libopkb200.so` and fails loudly if it is missing.
 """
 from ._lib import OpkbError, SO_PATH, EXPORTED_SYMBOLS
 from .vectors import (Context, Vector, default_context, comm_unique_id, vcreate, vcopy, vcopy_,
-                      vfill_, vdot, vnorm2, vnorminf, vscale_, vupdate_, vcombine_, vproduct_,
+                      vfill_, vdot, vnorm1, vnorm2, vnorminf, vswap_, vscale_, vupdate_, vcombine_, vproduct_,
                       project_variables_, project_direction_, project_gradient_, step_limits,
                       get_free_variables, fastmin, fastmax, fastclamp)
 from .linesearches import (LineSearch, ArmijoLineSearch, MoreToraldoLineSearch,

@@ -82,6 +82,10 @@ _SIGNATURES = {
     "opkb_vupdate_masked": (C.c_int, [vp, vp, vp, f64, vp]),
     "opkb_vcombine": (C.c_int, [vp, vp, f64, vp, f64, vp]),
     "opkb_vproduct": (C.c_int, [vp, vp, vp, vp]),
+    "opkb_vswap": (C.c_int, [vp, vp, vp]),
+    "opkb_vnorm1": (C.c_int, [vp, vp, Pd]),
+    "opkb_vcombine3": (C.c_int, [vp, vp, f64, vp, f64, vp, f64, vp]),
+    "opkb_vproduct_masked": (C.c_int, [vp, vp, vp, vp, vp]),
     "opkb_project_variables": (C.c_int, [vp, vp, vp, vp, f64, vp, f64]),
     "opkb_project_direction": (C.c_int, [vp, vp, vp, vp, f64, vp, f64, C.c_int, vp]),
     "opkb_step_limits": (C.c_int, [vp, vp, vp, f64, vp, f64, C.c_int, vp, Pd, Pd]),

@@ -465,7 +465,7 @@ k_reduce(const T* x, const T* y, const T* w, int64_t n, ReduceScratch rs)
         const bool two = iv2 < nvec;
         Pack<T> a0 = ld_pack<T>(x, iv), a1, b0, b1, w0, w1;
         if (two) a1 = ld_pack<T>(x, iv2);
-        if (MODE != 2) {
+        if (MODE < 2) {
             b0 = ld_pack<T>(y, iv);
             if (two) b1 = ld_pack<T>(y, iv2);
         }
@@ -478,6 +478,7 @@ k_reduce(const T* x, const T* y, const T* w, int64_t n, ReduceScratch rs)
             if (MODE == 0) acc[0] = dacc(a0.v[e], b0.v[e], acc[0]);
             if (MODE == 1 && w0.v[e] != T(0)) acc[0] = dacc(a0.v[e], b0.v[e], acc[0]);
             if (MODE == 2) { double t = fabs((double)a0.v[e]); acc[0] = (t > acc[0] ? t : acc[0]); }
+            if (MODE == 3) acc[0] += fabs((double)a0.v[e]);
         }
         if (two) {
 #pragma unroll
@@ -485,6 +486,7 @@ k_reduce(const T* x, const T* y, const T* w, int64_t n, ReduceScratch rs)
                 if (MODE == 0) acc[0] = dacc(a1.v[e], b1.v[e], acc[0]);
                 if (MODE == 1 && w1.v[e] != T(0)) acc[0] = dacc(a1.v[e], b1.v[e], acc[0]);
                 if (MODE == 2) { double t = fabs((double)a1.v[e]); acc[0] = (t > acc[0] ? t : acc[0]); }
+                if (MODE == 3) acc[0] += fabs((double)a1.v[e]);
             }
         }
     }
@@ -493,6 +495,7 @@ k_reduce(const T* x, const T* y, const T* w, int64_t n, ReduceScratch rs)
             if (MODE == 0) acc[0] = dacc(x[i], y[i], acc[0]);
             if (MODE == 1 && w[i] != T(0)) acc[0] = dacc(x[i], y[i], acc[0]);
             if (MODE == 2) { double t = fabs((double)x[i]); acc[0] = (t > acc[0] ? t : acc[0]); }
+            if (MODE == 3) acc[0] += fabs((double)x[i]);
         }
     }
     if (MODE == 2)
@@ -701,6 +704,110 @@ extern "C" int opkb_vproduct(opkb_context* ctx, opkb_vector* dst, const opkb_vec
     CHECK_SAME(dst, x);
     CHECK_SAME(dst, y);
     return ew_dispatch<5>(ctx, dst, x, y, NULL, 1, 1);
+}
+
+// ---------------------------------------------------------------------------
+// the remaining operators of the vector-space contract (doc/algebra.md:31, :50, :60-67, :116):
+// vswap!, vnorm1, vcombine! with three terms, vproduct! restricted to a free set.  None is
+// called by the loops of vmlmb / spg; they complete the plug-in interface.
+template <typename T, int OP>
+__global__ void __launch_bounds__(OPKB_BLOCK)
+k_contract(T* a, T* b, const T* x, const T* y, const T* z, T ca, T cb, T cc, int64_t n)
+{
+    // OP 0: swap(a, b); 1: a = (ca*x + cb*y) + cc*z; 2: a = x.*y where z != 0
+    constexpr int VEC = VecOf<T>::N;
+    const int64_t nvec = n / VEC;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += stride) {
+        if (OP == 0) {
+            const Pack<T> pa = ld_pack<T>(a, iv), pb = ld_pack<T>(b, iv);
+            st_pack<T>(a, iv, pb);
+            st_pack<T>(b, iv, pa);
+        } else if (OP == 1) {
+            const Pack<T> px = ld_pack<T>(x, iv), py = ld_pack<T>(y, iv), pz = ld_pack<T>(z, iv);
+            Pack<T> o;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) o.v[e] = (ca * px.v[e] + cb * py.v[e]) + cc * pz.v[e];
+            st_pack<T>(a, iv, o);
+        } else {
+            const Pack<T> px = ld_pack<T>(x, iv), py = ld_pack<T>(y, iv), pz = ld_pack<T>(z, iv);
+            Pack<T> o = ld_pack<T>(a, iv);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+                if (pz.v[e] != T(0)) o.v[e] = px.v[e] * py.v[e];
+            st_pack<T>(a, iv, o);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int64_t i = nvec * VEC; i < n; ++i) {
+            if (OP == 0) {
+                const T t = a[i];
+                a[i] = b[i];
+                b[i] = t;
+            } else if (OP == 1) {
+                a[i] = (ca * x[i] + cb * y[i]) + cc * z[i];
+            } else if (z[i] != T(0)) {
+                a[i] = x[i] * y[i];
+            }
+        }
+    }
+}
+
+template <int OP>
+static int contract_dispatch(opkb_context* ctx, opkb_vector* a, opkb_vector* b, const opkb_vector* x,
+                             const opkb_vector* y, const opkb_vector* z, double ca, double cb, double cc)
+{
+    int grid = opkb_grid_for(ctx, a->n / (a->eltype == OPKB_DOUBLE ? 2 : 4), 8);
+    if (a->eltype == OPKB_DOUBLE)
+        LAUNCH(ctx, OPKB_K_ELEMENTWISE, (k_contract<double, OP>), grid, (double*)a->data,
+               b ? (double*)b->data : NULL, x ? (const double*)x->data : NULL,
+               y ? (const double*)y->data : NULL, z ? (const double*)z->data : NULL, ca, cb, cc, a->n);
+    else
+        LAUNCH(ctx, OPKB_K_ELEMENTWISE, (k_contract<float, OP>), grid, (float*)a->data,
+               b ? (float*)b->data : NULL, x ? (const float*)x->data : NULL, y ? (const float*)y->data : NULL,
+               z ? (const float*)z->data : NULL, (float)ca, (float)cb, (float)cc, a->n);
+    return 0;
+}
+
+extern "C" int opkb_vswap(opkb_context* ctx, opkb_vector* x, opkb_vector* y)
+{
+    CHECK_CTX(ctx);
+    CHECK_SAME(x, y);
+    if (x == y || x->data == y->data) return 0;
+    if (x->owned && y->owned) {          // both own their storage: exchanging the buffers is the swap
+        void* t = x->data;
+        x->data = y->data;
+        y->data = t;
+        return 0;
+    }
+    return contract_dispatch<0>(ctx, x, y, NULL, NULL, NULL, 0, 0, 0);
+}
+
+extern "C" int opkb_vcombine3(opkb_context* ctx, opkb_vector* dst, double alpha, const opkb_vector* x,
+                              double beta, const opkb_vector* y, double gamma, const opkb_vector* z)
+{
+    CHECK_CTX(ctx);
+    CHECK_SAME(dst, x);
+    CHECK_SAME(dst, y);
+    CHECK_SAME(dst, z);
+    return contract_dispatch<1>(ctx, dst, NULL, x, y, z, alpha, beta, gamma);
+}
+
+extern "C" int opkb_vproduct_masked(opkb_context* ctx, opkb_vector* dst, const opkb_vector* w,
+                                    const opkb_vector* x, const opkb_vector* y)
+{
+    CHECK_CTX(ctx);
+    CHECK_SAME(dst, x);
+    CHECK_SAME(dst, y);
+    CHECK_SAME(dst, w);
+    return contract_dispatch<2>(ctx, dst, NULL, x, y, w, 0, 0, 0);
+}
+
+extern "C" int opkb_vnorm1(opkb_context* ctx, const opkb_vector* x, double* result)
+{
+    CHECK_CTX(ctx);
+    if (!x || !result) return opkb_set_error(OPKB_EINVAL, "NULL argument");
+    return reduce_dispatch<3>(ctx, x, x, NULL, result);
 }
 
 // ---------------------------------------------------------------------------

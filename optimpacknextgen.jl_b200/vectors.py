@@ -272,7 +272,25 @@ def vnorminf(x: Vector) -> float:
     return r.value
 
 
-def vscale_(x: Vector, alpha: float) -> Vector:
+def vnorm1(x: Vector) -> float:
+    """doc/algebra.md:50"""
+    r = f64()
+    check(_lib.lib().opkb_vnorm1(x.ctx.handle, x.handle, C.byref(r)))
+    return r.value
+
+
+def vswap_(x: Vector, y: Vector) -> None:
+    """vswap!(x, y) (doc/algebra.md:31): exchange the contents (the buffers, when both
+    vectors own theirs)."""
+    check(_lib.lib().opkb_vswap(x.ctx.handle, x.handle, y.handle))
+
+
+def vscale_(x: Vector, alpha: float, src: Vector = None) -> Vector:
+    """vscale!(x, alpha) or vscale!(dst, alpha, src) (= vcombine!(dst, alpha, src, 0, src),
+    doc/algebra.md:99-101)."""
+    if src is not None and src is not x:
+        check(_lib.lib().opkb_vcombine(x.ctx.handle, x.handle, float(alpha), src.handle, 0.0, src.handle))
+        return x
     check(_lib.lib().opkb_vscale(x.ctx.handle, x.handle, float(alpha)))
     return x
 
@@ -288,14 +306,30 @@ def vupdate_(y: Vector, *args) -> Vector:
     return y
 
 
-def vcombine_(dst: Vector, alpha: float, x: Vector, beta: float, y: Vector) -> Vector:
+def vcombine_(dst: Vector, alpha: float, x: Vector, beta: float, y: Vector, gamma: float = None,
+              z: Vector = None) -> Vector:
+    """vcombine!(dst, alpha, x, beta, y) or the three-term form (doc/algebra.md:60-67: vcombine!
+    then update!, one kernel here with the same roundings)."""
+    if z is not None:
+        check(_lib.lib().opkb_vcombine3(dst.ctx.handle, dst.handle, float(alpha), x.handle, float(beta),
+                                        y.handle, float(gamma), z.handle))
+        return dst
     check(_lib.lib().opkb_vcombine(dst.ctx.handle, dst.handle, float(alpha), x.handle, float(beta),
                                    y.handle))
     return dst
 
 
-def vproduct_(dst: Vector, x: Vector, y: Vector) -> Vector:
-    check(_lib.lib().opkb_vproduct(dst.ctx.handle, dst.handle, x.handle, y.handle))
+def vproduct_(dst: Vector, *args) -> Vector:
+    """vproduct!(dst, x, y), vproduct!(dst, src) = vproduct!(dst, dst, src), or
+    vproduct!(dst, sel, x, y) with sel = {w != 0} (doc/algebra.md:103, :116)."""
+    L = _lib.lib()
+    if len(args) == 1:
+        check(L.opkb_vproduct(dst.ctx.handle, dst.handle, dst.handle, args[0].handle))
+    elif len(args) == 2:
+        check(L.opkb_vproduct(dst.ctx.handle, dst.handle, args[0].handle, args[1].handle))
+    else:
+        w, x, y = args
+        check(L.opkb_vproduct_masked(dst.ctx.handle, dst.handle, w.handle, x.handle, y.handle))
     return dst
 
 

@@ -198,3 +198,48 @@ def test_apply_lbfgs_variants(opk, ctx, oracle, dtype):
     assert opk.apply_lbfgs_masked_(dS, dY, rho3, m, mark, got, [0.0] * mem, ctx.from_numpy(w)) == modif
     assert np.linalg.norm(got.download() - want) <= tol * np.linalg.norm(want)
     assert np.allclose(rho3, rho2, rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", (0, 1, 5, 1000, 100003))
+def test_rest_of_the_vector_space_contract(opk, ctx, dtype, n):
+    """doc/algebra.md:31 vswap!, :50 vnorm1, :60-67 vcombine! with three terms (= vcombine! then
+    update!: same roundings), :99-103 vscale!(dst, alpha, src) / vproduct!(dst, src), :116
+    vproduct!(dst, sel, x, y): element-wise results bit-exact against the array expressions."""
+    rng = np.random.default_rng(n + 7)
+    x, y, z, w = (rng.standard_normal(n).astype(dtype) for _ in range(4))
+    w[rng.random(n) < 0.5] = 0
+    vx, vy, vz, vw = (ctx.from_numpy(v) for v in (x, y, z, w))
+    T = np.dtype(dtype).type
+    a, b, c = 0.37, -1.25, 2.5
+    # three-term vcombine!
+    dst = ctx.vector(n, dtype)
+    opk.vcombine_(dst, a, vx, b, vy, c, vz)
+    assert np.array_equal(dst.download(), (T(a) * x + T(b) * y) + T(c) * z)
+    # vnorm1
+    assert opk.vnorm1(vx) == pytest.approx(float(np.abs(x.astype(np.float64)).sum()), rel=1e-14, abs=0)
+    # vproduct! on a free set, the other elements are left alone
+    d0 = rng.standard_normal(n).astype(dtype)
+    dst.upload(d0)
+    opk.vproduct_(dst, vw, vx, vy)
+    assert np.array_equal(dst.download(), np.where(w != 0, x * y, d0))
+    # vproduct!(dst, src) and vscale!(dst, alpha, src)
+    dst.upload(d0)
+    opk.vproduct_(dst, vx)
+    assert np.array_equal(dst.download(), d0 * x)
+    opk.vscale_(dst, a, vx)
+    assert np.array_equal(dst.download(), T(a) * x)
+    # vswap!: two owned vectors (buffers exchanged) and a borrowed one (element-wise)
+    opk.vswap_(vx, vy)
+    assert np.array_equal(vx.download(), y) and np.array_equal(vy.download(), x)
+    if n > 0:
+        s = opk.VMLMB(opk.Rosenbrock(), np.zeros(2 * ((n + 1) // 2), dtype=dtype), lower=0.0, mem=2)
+        g = s.ops.vector("g")                       # belongs to the workspace
+        other = ctx.from_numpy(np.arange(g.n, dtype=dtype))
+        g.upload(np.full(g.n, 3, dtype=dtype))
+        opk.vswap_(g, other)
+        assert np.array_equal(g.download(), np.arange(g.n, dtype=dtype))
+        assert np.array_equal(other.download(), np.full(g.n, 3, dtype=dtype))
+        s.close()
+    with pytest.raises(opk.OpkbError):
+        opk.vswap_(vx, ctx.vector(n + 1, dtype))
