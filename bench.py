@@ -56,13 +56,14 @@ def parse():
     return ap.parse_args()
 
 
-def config(args, n):
+def config(args, n, exchange="shared-memory mailbox written by the kernels, or a packed ncclAllGather"):
     return {
         "workload": "C4: VMLMB bound-constrained quadratic n=2^%d Float64 m=%d, array bounds [0,1], "
                     "More-Toraldo line search, fused path (direction + speculative trial + incremental "
                     "Gram in one kernel per iteration; P1 / P3 sweep as fall-backs)" % (int(math.log2(n)), args.mem),
         "n": n, "mem": args.mem, "eltype": "Float64", "kappa": KAPPA,
-        "sharding": "contiguous 1-D blocks, %d rank(s), one packed all-gather of partials per phase" % args.gpus,
+        "sharding": "contiguous 1-D blocks, %d rank(s), one exchange of the packed reduction partials per "
+                    "phase (%s)" % (args.gpus, exchange),
         "l2": "no flush needed: every kernel streams >= 18 GiB per rank at N=1 (>> 126 MB L2)",
         "priming": "mem+1 untimed iterations before the warm-up so that all m (s,y) pairs exist",
     }
@@ -352,7 +353,11 @@ def ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": config(args, n), "roofline": roofline,
+        "dtype": "f64", "data": "synthetic",
+        "config": config(args, n, "none: one rank" if world == 1 else
+                         ("shared-memory mailbox written by the last CTA of every rank" if ctx.uses_mailbox
+                          else "packed ncclAllGather")),
+        "roofline": roofline,
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "evals_per_s": evals / (ms * 1e-3), "final": {"f": f_final, "gnorm": gnorm_final},
     }

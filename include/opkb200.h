@@ -102,6 +102,11 @@ int opkb_flush_l2(opkb_context* ctx);
  * torch.distributed / MPI.jl), every rank calls opkb_comm_init. */
 int opkb_comm_unique_id(void* id128);
 int opkb_comm_init(opkb_context* ctx, const void* id128, int rank, int nranks);
+/* 1 if the reduced scalars of a phase travel through the shared-memory mailbox of the node
+ * (the last CTA of every rank writes its partials into a segment all processes have mapped and
+ * registered with CUDA, every process combines them in rank order), 0 if through the packed
+ * ncclAllGather (OPKB_MAILBOX=0, or a rank that cannot map the segment). */
+int opkb_comm_uses_mailbox(const opkb_context* ctx);
 int opkb_comm_rank(const opkb_context* ctx);
 int opkb_comm_size(const opkb_context* ctx);
 

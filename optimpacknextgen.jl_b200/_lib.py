@@ -61,6 +61,7 @@ _SIGNATURES = {
     "opkb_flush_l2": (C.c_int, [vp]),
     "opkb_comm_unique_id": (C.c_int, [vp]),
     "opkb_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+    "opkb_comm_uses_mailbox": (C.c_int, [vp]),
     "opkb_comm_rank": (C.c_int, [vp]),
     "opkb_comm_size": (C.c_int, [vp]),
     "opkb_vector_create": (C.c_int, [vp, C.c_int, i64, C.POINTER(vp)]),

@@ -4,7 +4,13 @@
 // library has no link-time dependency; inside a torch process this resolves to
 // the libnccl.so.2 torch has already loaded.
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
 
 #include "opkb_internal.cuh"
 
@@ -68,6 +74,63 @@ extern "C" int opkb_comm_unique_id(void* id128)
     return 0;
 }
 
+// Shared-memory mailbox of the ranks of one node (see opkb_context_).  The segment is named
+// after the NCCL unique id (the one thing every rank already shares), created by rank 0, mapped
+// and registered with CUDA by every rank, and unlinked once all ranks hold it.  Returns 1 if
+// this rank holds a registered mapping, 0 otherwise (the caller makes the ranks agree).
+static int mailbox_open(opkb_context* ctx, const void* id128, int rank, int nranks, void** host, void** dev,
+                        size_t* bytes_out, char* name_out)
+{
+    const unsigned char* id = (const unsigned char*)id128;
+    unsigned long long h = 1469598103934665603ull;
+    for (int i = 0; i < 128; ++i) h = (h ^ id[i]) * 1099511628211ull;
+    snprintf(name_out, 64, "/opkb200_%016llx", h);
+    const size_t bytes = (size_t)nranks * OPKB_MBOX_SLOT;
+    int fd = -1;
+    if (rank == 0) {
+        shm_unlink(name_out);
+        fd = shm_open(name_out, O_CREAT | O_EXCL | O_RDWR, 0600);
+        if (fd >= 0 && ftruncate(fd, (off_t)bytes) != 0) {
+            close(fd);
+            fd = -1;
+        }
+    } else {
+        for (int tries = 0; tries < 30000 && fd < 0; ++tries) {        // up to ~30 s
+            fd = shm_open(name_out, O_RDWR, 0600);
+            struct stat st;
+            if (fd >= 0 && (fstat(fd, &st) != 0 || (size_t)st.st_size < bytes)) {
+                close(fd);
+                fd = -1;
+            }
+            if (fd < 0) {
+                struct timespec ts = {0, 1000000};
+                nanosleep(&ts, NULL);
+            }
+        }
+    }
+    if (fd < 0) return 0;
+    void* p = mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) return 0;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        munmap(p, bytes);
+        return 0;
+    }
+    void* d = NULL;
+    if (cudaHostGetDevicePointer(&d, p, 0) != cudaSuccess) {
+        cudaGetLastError();
+        cudaHostUnregister(p);
+        munmap(p, bytes);
+        return 0;
+    }
+    (void)ctx;
+    *host = p;
+    *dev = d;
+    *bytes_out = bytes;
+    return 1;
+}
+
 extern "C" int opkb_comm_init(opkb_context* ctx, const void* id128, int rank, int nranks)
 {
     if (!ctx || !id128) return opkb_set_error(OPKB_EINVAL, "NULL argument");
@@ -93,7 +156,44 @@ extern "C" int opkb_comm_init(opkb_context* ctx, const void* id128, int rank, in
     ctx->d_res = ctx->d_res_dev;   // NCCL sends from device memory
     cudaFreeHost(ctx->h_res);
     OPKB_CUDA(cudaMallocHost(&ctx->h_res, sizeof(double) * OPKB_NRED_MAX * (size_t)nranks));
+    // The per-phase exchange of the reduced scalars: a shared-memory mailbox when every rank of
+    // the communicator can map it (one node), the packed ncclAllGather otherwise / OPKB_MAILBOX=0.
+    const char* e = getenv("OPKB_MAILBOX");
+    void *host = NULL, *dev = NULL;
+    size_t bytes = 0;
+    char name[64] = "";
+    int mine = 0;
+    if (!e || atoi(e) != 0) mine = mailbox_open(ctx, id128, rank, nranks, &host, &dev, &bytes, name);
+    // agreement (and the barrier after which the name can go): all-gather of the flags
+    double flag = (double)mine;
+    OPKB_CUDA(cudaMemcpyAsync(ctx->d_res_dev, &flag, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    int rc2 = opkb_nccl_allgather_f64(ctx, ctx->d_res_dev, ctx->d_all, 1);
+    if (rc2) return rc2;
+    OPKB_CUDA(cudaMemcpyAsync(ctx->h_res, ctx->d_all, sizeof(double) * nranks, cudaMemcpyDeviceToHost, ctx->stream));
+    OPKB_CUDA(cudaStreamSynchronize(ctx->stream));
+    int all = 1;
+    for (int q = 0; q < nranks; ++q) all = all && (ctx->h_res[q] == 1.0);
+    if (rank == 0 && name[0]) shm_unlink(name);
+    if (all) {
+        ctx->mbox = (unsigned char*)host;
+        ctx->mbox_dev = (unsigned char*)dev;
+        ctx->mbox_bytes = bytes;
+        ctx->phase = 0;
+    } else if (mine) {
+        cudaHostUnregister(host);
+        munmap(host, bytes);
+    }
     return 0;
+}
+
+extern "C" int opkb_comm_uses_mailbox(const opkb_context* ctx) { return (ctx && ctx->mbox) ? 1 : 0; }
+
+void opkb_mailbox_close(opkb_context* ctx)
+{
+    if (!ctx || !ctx->mbox) return;
+    cudaHostUnregister(ctx->mbox);
+    munmap(ctx->mbox, ctx->mbox_bytes);
+    ctx->mbox = ctx->mbox_dev = NULL;
 }
 
 extern "C" int opkb_comm_rank(const opkb_context* ctx) { return ctx ? ctx->rank : -1; }

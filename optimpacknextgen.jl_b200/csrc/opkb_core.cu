@@ -87,6 +87,7 @@ extern "C" int opkb_context_destroy(opkb_context* ctx)
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    opkb_mailbox_close(ctx);
     cudaFree(ctx->d_part);
     cudaFree(ctx->d_ticket);
     cudaFree(ctx->d_res_dev);
@@ -236,6 +237,54 @@ int opkb_grid_for(const opkb_context* ctx, int64_t nitems, int ctas_per_sm)
     return (int)(want < full ? want : full);
 }
 
+// Wait until the last CTA of the latest reducing launch has stored its sequence number in
+// `flag` (after its results, system-scope fence); a stream query every few microseconds catches
+// launches that publish nothing, and errors.  Returns true if the flag was seen.
+static bool wait_flag(opkb_context* ctx, volatile unsigned int* flag)
+{
+    const unsigned int want = ctx->seq;
+    for (unsigned int it = 1;; ++it) {
+        if (*flag == want) return true;
+        if ((it & 4095u) == 0u && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) return false;
+    }
+}
+
+// Several ranks, shared-memory mailbox (see opkb_context_): publish this rank's phase, wait for
+// the others, combine in rank order.
+static int opkb_mailbox_reduce(opkb_context* ctx, int nred, const int* kinds, double* out)
+{
+    unsigned char* mine = ctx->mbox + (size_t)ctx->rank * OPKB_MBOX_SLOT;
+    if (!wait_flag(ctx, (volatile unsigned int*)mine)) OPKB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const unsigned long long phase = ++ctx->phase;
+    __atomic_store_n((unsigned long long*)(mine + 64), phase, __ATOMIC_RELEASE);
+    const size_t buf = (size_t)(phase & 1ull) * OPKB_NRED_MAX;
+    for (int r = 0; r < ctx->nranks; ++r) {
+        unsigned char* slot = ctx->mbox + (size_t)r * OPKB_MBOX_SLOT;
+        if (r != ctx->rank) {
+            unsigned long long* ready = (unsigned long long*)(slot + 64);
+            unsigned long long spins = 0;
+            while (__atomic_load_n(ready, __ATOMIC_ACQUIRE) < phase) {
+                if ((++spins & 0xffffffull) == 0ull) {
+                    // a peer that died would hang every other rank: give up after ~2 minutes of CPU
+                    if (spins > (1ull << 36))
+                        return opkb_set_error(OPKB_ENCCL, "rank %d did not publish phase %llu", r, phase);
+                }
+            }
+        }
+        const double* res = (const double*)(slot + OPKB_MBOX_HDR) + buf;
+        for (int k = 0; k < nred; ++k) {
+            const double b = res[k];
+            if (r == 0) { out[k] = b; continue; }
+            const int kind = kinds ? kinds[k] : OPKB_RSUM;
+            const double a = out[k];
+            if (kind == OPKB_RSUM) out[k] = a + b;
+            else if (kind == OPKB_RMAX) out[k] = (b > a ? b : a);
+            else out[k] = (b < a ? b : a);
+        }
+    }
+    return 0;
+}
+
 int opkb_finish_reduction(opkb_context* ctx, int nred, const int* kinds, double* out)
 {
     if (nred > OPKB_NRED_MAX) return opkb_set_error(OPKB_EINVAL, "too many reduced scalars");
@@ -243,22 +292,14 @@ int opkb_finish_reduction(opkb_context* ctx, int nred, const int* kinds, double*
         if (ctx->d_res != ctx->h_res)
             OPKB_CUDA(cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(double) * nred,
                                       cudaMemcpyDeviceToHost, ctx->stream));
+        // poll the completion flag (sub-microsecond) instead of waking up through the driver
         bool seen = false;
-        if (ctx->spin && ctx->d_res == ctx->h_res) {
-            // the last CTA of the latest reducing launch stores its sequence number after its
-            // results: poll it (sub-microsecond) instead of waking up through the driver; a
-            // stream query every few microseconds catches launches that do not publish, and errors
-            volatile unsigned int* flag = ctx->h_flag;
-            const unsigned int want = ctx->seq;
-            for (unsigned int it = 1;; ++it) {
-                if (*flag == want) { seen = true; break; }
-                if ((it & 4095u) == 0u && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) break;
-            }
-        }
+        if (ctx->spin && ctx->d_res == ctx->h_res) seen = wait_flag(ctx, ctx->h_flag);
         if (!seen) OPKB_CUDA(cudaStreamSynchronize(ctx->stream));
         for (int k = 0; k < nred; ++k) out[k] = ctx->h_res[k];
         return 0;
     }
+    if (ctx->mbox) return opkb_mailbox_reduce(ctx, nred, kinds, out);
     // one packed all-gather per phase, then a fixed rank-order combination
     int rc = opkb_nccl_allgather_f64(ctx, ctx->d_res, ctx->d_all, nred);
     if (rc != 0) return rc;

@@ -41,6 +41,16 @@ struct opkb_context_ {
     double* d_res_dev;       // the device allocation (used with several ranks: NCCL send buffer)
     double* d_all;           // [nranks * OPKB_NRED_MAX] after the all-gather
     double* h_res;           // pinned mirror of d_res / d_all
+    // Several ranks on one node: a POSIX shared-memory segment, registered with CUDA in every
+    // process (opkb_comm.cu).  Slot r = { completion flag of rank r's kernels (GPU-written) |
+    // `ready` = last phase rank r has published (host-written) | two result buffers, by phase
+    // parity }.  The last CTA of a reducing kernel writes its partials and the flag straight
+    // into its rank's slot, every process polls the slots of all ranks and combines them in
+    // rank order: no NCCL call, no D2H copy, no stream synchronisation per phase.
+    unsigned char* mbox;     // host address of the segment (NULL: packed ncclAllGather instead)
+    unsigned char* mbox_dev; // device address of the same memory
+    size_t mbox_bytes;
+    unsigned long long phase;  // phases (opkb_finish_reduction calls) completed so far
     unsigned int* h_flag;    // completion flag of the reducing kernels (pinned, see ReduceScratch)
     unsigned int seq;        // sequence number of the last reducing launch
     int spin;                // poll h_flag instead of cudaStreamSynchronize (one rank)
@@ -85,6 +95,7 @@ int opkb_check_cuda(cudaError_t err, const char* what);
 int opkb_finish_reduction(opkb_context* ctx, int nred, const int* kinds, double* out);
 int opkb_grid_for(const opkb_context* ctx, int64_t nwork_items, int ctas_per_sm);
 
+void opkb_mailbox_close(opkb_context* ctx);
 // NCCL (opkb_comm.cu, loaded with dlopen)
 int opkb_nccl_allgather_f64(opkb_context* ctx, const double* send, double* recv, int count);
 // rows to/from the previous and the next rank in one NCCL group on `stream` (NULL: nothing)
@@ -297,14 +308,25 @@ static inline cudaError_t opkb_ensure_smem(const void* kern, size_t smem)
     return e;
 }
 
-// the scratch of the next reducing launch (results at ctx->d_res + res_offset)
+#define OPKB_MBOX_HDR 128                                              // flag | ready
+#define OPKB_MBOX_SLOT (OPKB_MBOX_HDR + 2 * OPKB_NRED_MAX * sizeof(double))
+// where the reducing launches of the current phase write their results (device address)
+static inline double* opkb_res_ptr(opkb_context* ctx)
+{
+    if (ctx->mbox)
+        return (double*)(ctx->mbox_dev + (size_t)ctx->rank * OPKB_MBOX_SLOT + OPKB_MBOX_HDR) +
+               ((ctx->phase + 1) & 1ull) * OPKB_NRED_MAX;
+    return ctx->d_res;
+}
+// the scratch of the next reducing launch (results at opkb_res_ptr(ctx) + res_offset)
 static inline ReduceScratch opkb_make_scratch(opkb_context* ctx, int res_offset = 0)
 {
     ReduceScratch rs;
     rs.part = ctx->d_part;
     rs.ticket = ctx->d_ticket;
-    rs.res = ctx->d_res + res_offset;
-    rs.flag = (ctx->spin && ctx->nranks <= 1 && ctx->d_res == ctx->h_res) ? ctx->h_flag : NULL;
+    rs.res = opkb_res_ptr(ctx) + res_offset;
+    if (ctx->mbox) rs.flag = (unsigned int*)(ctx->mbox_dev + (size_t)ctx->rank * OPKB_MBOX_SLOT);
+    else rs.flag = (ctx->spin && ctx->nranks <= 1 && ctx->d_res == ctx->h_res) ? ctx->h_flag : NULL;
     rs.seq = ++ctx->seq;
     return rs;
 }

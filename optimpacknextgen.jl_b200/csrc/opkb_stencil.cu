@@ -344,7 +344,7 @@ static int smooth_run(opkb_context* ctx, const opkb_vector* w, const opkb_vector
     const bool has_dn = ctx->nranks > 1 && ctx->rank < ctx->nranks - 1;
     if ((has_up && (!up || up->n != cols)) || (has_dn && (!dn || dn->n != cols)))
         return opkb_set_error(OPKB_EINVAL, "halo rows of %lld elements are needed", (long long)cols);
-    OPKB_CUDA(cudaMemsetAsync(ctx->d_res, 0, 6 * sizeof(double), ctx->stream));
+    OPKB_CUDA(cudaMemsetAsync(opkb_res_ptr(ctx), 0, 6 * sizeof(double), ctx->stream));
     if (ctx->nranks > 1) {
         if (!ctx->halo_stream) {
             OPKB_CUDA(cudaStreamCreateWithFlags(&ctx->halo_stream, cudaStreamNonBlocking));

@@ -92,6 +92,12 @@ class Context:
     def flush_l2(self) -> None:
         check(_lib.lib().opkb_flush_l2(self._h))
 
+    @property
+    def uses_mailbox(self) -> bool:
+        """True when the reduced scalars of a phase travel through the node's shared-memory
+        mailbox (written by the last CTA of every rank) rather than a packed ncclAllGather."""
+        return bool(_lib.lib().opkb_comm_uses_mailbox(self._h))
+
     def comm_init(self, unique_id: bytes, rank: int, nranks: int) -> None:
         buf = C.create_string_buffer(bytes(unique_id), 128)
         check(_lib.lib().opkb_comm_init(self._h, buf, int(rank), int(nranks)))

@@ -34,6 +34,9 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = init_context(local)
     assert ctx.nranks == world and ctx.rank == rank
+    if rank == 0:
+        print(f"[{world} GPUs] reduced scalars travel through: "
+              f"{'shared-memory mailbox' if ctx.uses_mailbox else 'packed ncclAllGather'}", flush=True)
     ok = True
     for kind, n, dtype, kw in (("quad_box", 200001, np.float64, dict(mem=10)),
                                ("rosen_box", 100000, np.float64, dict(mem=7)),
