@@ -140,7 +140,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "50"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -151,7 +151,7 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
-    def summary(self, t0, t1):
+    def summary(self, t0, t1, t_load0=None):
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -159,8 +159,13 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
             self.t.join(timeout=3)   # no daemon thread may outlive the interpreter
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        window = "timed region"
+        if t_load0 is not None and not any(t0 - 0.05 <= t <= t1 + 0.1 for t, _ in self.rows):
+            # a timed region shorter than the sampling period (many GPUs): the samples taken
+            # under the same load just before it (priming and warm-up iterations)
+            t0, window = t_load0, "priming + warm-up + timed region (the timed region is shorter than the sampling period)"
+        sm, mx, reasons = [], [], set()
         for t, line in self.rows:
             if not (t0 - 0.05 <= t <= t1 + 0.1):
                 continue
@@ -176,7 +181,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def measured_peak():
@@ -245,10 +250,13 @@ def ours(args):
     kw = dict(lower=lo, upper=hi, mem=m, xtol=(0, 0), ftol=(0, 0), gtol=(0, 0), nglobal=n, ctx=ctx)
 
     solver = opk.VMLMB(obj, x0, **kw)
+    # (nvidia-smi needs a few hundred ms before its first line: it is started before the
+    # priming iterations so that it is streaming when the timed region begins)
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_load0 = time.perf_counter()
     solver.iterate(m + 1)                               # priming: all m pairs exist (steady state)
     solver.iterate(W)                                   # warm-up (untimed)
     ctx.profile(True)
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     l0, e0, i0 = ctx.launch_count, solver.eval, solver.iter
     h0 = solver.carry_stats()[0]
@@ -265,7 +273,7 @@ def ours(args):
     prof = ctx.profile_report()
     ctx.profile(False)
     hits = solver.carry_stats()[0] - h0
-    clocks = sampler.summary(t0, t1) if sampler else None
+    clocks = sampler.summary(t0, t1, t_load0) if sampler else None
     f_final, gnorm_final = solver.f, solver.gnorm
     solver.close()
     del solver
