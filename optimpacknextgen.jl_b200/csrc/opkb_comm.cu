@@ -1,6 +1,7 @@
-// opkb_comm.cu -- the only communication of the hot path: one small packed
-// all-gather of per-rank reduction partials per phase, over NCCL
-// (NVLink 5 / NVSwitch).  NCCL is loaded with dlopen so that the single-GPU
+// opkb_comm.cu -- the only communication of the hot path: one small exchange of the
+// per-rank reduction partials per phase: a shared-memory mailbox the last CTA
+// of every rank writes into (ranks of one node), or a packed all-gather over NCCL
+// (NVLink 5 / NVSwitch); plus the point-to-point halo rows of the stencil objective.  NCCL is loaded with dlopen so that the single-GPU
 // library has no link-time dependency; inside a torch process this resolves to
 // the libnccl.so.2 torch has already loaded.
 #include <dlfcn.h>

@@ -1,8 +1,9 @@
 """Multi-GPU plumbing: one process per GPU, every n-vector sharded in
-contiguous blocks, no data-path collective except one small packed all-gather
-of reduction partials per phase.  `torch.distributed` is used
-only to broadcast the NCCL unique id; the all-gathers themselves are issued by
-libopkb200 on its own stream."""
+contiguous blocks, no data-path communication except one small exchange of the
+packed reduction partials per phase: through a shared-memory
+mailbox the kernels write into when the ranks share a node, through a packed
+ncclAllGather otherwise (include/opkb200.h, opkb_comm_uses_mailbox).
+`torch.distributed` is used only to broadcast the NCCL unique id."""
 from __future__ import annotations
 
 from .vectors import Context, comm_unique_id
