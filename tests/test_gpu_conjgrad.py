@@ -286,3 +286,31 @@ def test_conjgrad_golden(opk):
             assert k == wt["iter"] and abs(rho - wt["rho"]) <= 100 * rtol * wt["rho"]
             ref = np.array(wt["x_head"])
             assert np.linalg.norm(xh - ref) <= rtol * max(np.linalg.norm(ref), 1e-300) + 1e-300
+
+
+def test_edge_cases(opk, oracle):
+    """Empty and one-element systems, b = 0, x0 already the solution, a 1 x 1 grid."""
+    ctx = opk.default_context()
+    assert not ctx.uses_mailbox                                        # one rank: no exchange at all
+    # n = 0: nothing to do, converged at once
+    x = opk.conjgrad(opk.DiagonalOperator(np.zeros(0)), np.zeros(0))
+    assert x.shape == (0,)
+    # n = 1: a scalar equation, solved in one iteration
+    s = opk.ConjGrad(opk.DiagonalOperator(np.array([4.0])), np.array([2.0]), ftol=0.0, maxiter=5)
+    s.solve()
+    assert s.result()[0] == 0.5 and s.iter == 1 and s.status == opk.CG_GTEST
+    # b = 0 and x0 = 0: |r| = 0 <= gtest = 0
+    s = opk.ConjGrad(opk.DiagonalOperator(np.ones(10)), np.zeros(10))
+    s.solve()
+    assert s.iter == 0 and s.status == opk.CG_GTEST and not s.result().any()
+    # x0 is the solution already: r = b - A.x0 = 0
+    a, c = opk.Quadratic.synthetic(1000, np.float64, kappa=10.0)
+    s = opk.ConjGrad(opk.DiagonalOperator(a), a * c, c.copy(), ftol=0.0, gtol=(1e-12, 0.0), maxiter=10)
+    s.solve()
+    assert s.iter <= 1 and np.abs(s.result() - c).max() <= 1e-12
+    # a 1 x 1 grid: the stencil operator is w itself
+    w = np.array([3.0])
+    x = opk.conjgrad(opk.Smooth2DOperator(w, 2.0, 1), np.array([6.0]), ftol=0.0, maxiter=3)
+    assert x[0] == 2.0
+    xo, info, _ = oracle.conjgrad(opk.Smooth2DOperator.reference(w, 2.0, 1), np.array([6.0]), ftol=0.0, maxiter=3)
+    assert xo[0] == 2.0
