@@ -72,6 +72,7 @@ typedef struct opkb_context_ opkb_context;
 typedef struct opkb_vector_  opkb_vector;
 typedef struct opkb_vmlmb_   opkb_vmlmb;
 typedef struct opkb_spg_     opkb_spg;
+typedef struct opkb_spg_solver_ opkb_spg_solver;
 
 const char* opkb_last_error(void);
 int         opkb_version(void);
@@ -395,6 +396,18 @@ int opkb_spg_step(opkb_spg* ws, double lambda, double eta, double out[8]);
 int opkb_spg_backtrack(opkb_spg* ws, double lambda, double stp, double eta, double out[8]);
 /* :342-345: xbest = x (no copy; the buffer is simply not reused) */
 int opkb_spg_mark_best(opkb_spg* ws);
+
+/* ---- Tier 3: the loop of `_spg!` (src/spg.jl:245-380) inside the library, for a workspace with a
+ * built-in objective and the box projection; keywords of `spg!` (src/spg.jl:168-178).  `run` performs
+ * `niter` iterations (or stops at termination): *searching = 1 while the status is SEARCHING.
+ * `info` = the fields of SPG.Info (:38-47) + whether the solution is 'x' or 'b' (xbest, :401). */
+int opkb_spg_solver_create(opkb_spg* ws, int m, int64_t maxit, int64_t maxfc, double eps1, double eps2,
+                           double eta, opkb_spg_solver** solver);
+int opkb_spg_solver_destroy(opkb_spg_solver* solver);
+int opkb_spg_solver_run(opkb_spg_solver* solver, int64_t niter, int* searching);
+int opkb_spg_solver_info(const opkb_spg_solver* solver, double* f, double* fbest, double* pginfn,
+                         double* pgtwon, int64_t* iter, int64_t* fcnt, int64_t* pcnt, int* status,
+                         int* best_is_x);
 
 #ifdef __cplusplus
 }

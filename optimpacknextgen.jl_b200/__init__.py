@@ -18,7 +18,7 @@ from .linesearches import getreason as _ls_getreason
 from .objectives import Rosenbrock, Quadratic, Smooth2D, splitmix64, uniform
 from .vmlmb import (VMLMB, NativeVMLMB, vmlmb, vmlmb_, BoundedSet, EMULATE_BLMVM, apply_lbfgs_,
                     apply_lbfgs_masked_, sufficient_descent, print_iteration, verbose)
-from .spg import SPG, spg, spg_, Info, BoxProjection, default_printer
+from .spg import SPG, NativeSPG, spg, spg_, Info, BoxProjection, default_printer
 from .spg import getreason as _spg_getreason
 from .spg import (SEARCHING, INFNORM_CONVERGENCE, TWONORM_CONVERGENCE, FUNCTION_CONVERGENCE,
                   TOO_MANY_ITERATIONS, TOO_MANY_EVALUATIONS)

@@ -137,6 +137,11 @@ _SIGNATURES = {
     "opkb_spg_step": (C.c_int, [vp, f64, f64, Pd]),
     "opkb_spg_backtrack": (C.c_int, [vp, f64, f64, f64, Pd]),
     "opkb_spg_mark_best": (C.c_int, [vp]),
+    "opkb_spg_solver_create": (C.c_int, [vp, C.c_int, i64, i64, f64, f64, f64, C.POINTER(vp)]),
+    "opkb_spg_solver_destroy": (C.c_int, [vp]),
+    "opkb_spg_solver_run": (C.c_int, [vp, i64, Pi]),
+    "opkb_spg_solver_info": (C.c_int, [vp, Pd, Pd, Pd, Pd, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64),
+                                      Pi, Pi]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -332,3 +332,175 @@ extern "C" int opkb_spg_mark_best(opkb_spg* ws)
     ws->ibest = ws->ix;  // vcopy!(xbest, x) :344 without a copy
     return 0;
 }
+
+// ---------------------------------------------------------------------------
+// Tier 3: the loop of `_spg!` (src/spg.jl:245-380) inside the library, for the built-in
+// objectives and the box projection: one call runs `niter` iterations (or to termination),
+// the host only reads the counters.  Same stage logic as the Python / Julia hosts, line by
+// line (spg.py: SPG.iterate); all scalars double.
+struct opkb_spg_solver_ {
+    opkb_spg* ws;
+    int m;
+    int64_t maxit, maxfc;
+    double eps1, eps2, eta;
+    double lmin, lmax, ftol, amin, amax;      // :201-205
+    int64_t iter, fcnt, pcnt;
+    int status, started, finished;
+    double f, f0, fbest, pgtwon, pginfn, lambda;
+    double* lastfv;
+    double out[8];
+};
+
+static double jl_clamp(double x, double lo, double hi) { return x > hi ? hi : (x < lo ? lo : x); }
+
+extern "C" int opkb_spg_solver_create(opkb_spg* ws, int m, int64_t maxit, int64_t maxfc, double eps1,
+                                      double eps2, double eta, opkb_spg_solver** out)
+{
+    if (!ws || !out) return opkb_set_error(OPKB_EINVAL, "NULL argument");
+    *out = NULL;
+    if (!(m >= 1 && eps1 >= 0 && eps2 >= 0 && eta > 0))                       // :197-200
+        return opkb_set_error(OPKB_EINVAL, "spg: m >= 1, eps1 >= 0, eps2 >= 0, eta > 0 are required");
+    if (ws->obj != OPKB_OBJ_ROSENBROCK && ws->obj != OPKB_OBJ_QUADRATIC)
+        return opkb_set_error(OPKB_EINVAL, "the native SPG loop needs a built-in objective");
+    opkb_spg_solver* s = (opkb_spg_solver*)calloc(1, sizeof(opkb_spg_solver));
+    if (!s) return opkb_set_error(OPKB_ENOMEM, "out of host memory");
+    s->lastfv = (double*)malloc(sizeof(double) * (size_t)m);
+    if (!s->lastfv) {
+        free(s);
+        return opkb_set_error(OPKB_ENOMEM, "out of host memory");
+    }
+    for (int i = 0; i < m; ++i) s->lastfv[i] = -INFINITY;                     // :222
+    s->ws = ws;
+    s->m = m;
+    s->maxit = maxit;
+    s->maxfc = maxfc;
+    s->eps1 = eps1;
+    s->eps2 = eps2;
+    s->eta = eta;
+    s->lmin = 1e-30;
+    s->lmax = 1e+30;
+    s->ftol = 1e-4;
+    s->amin = 0.1;
+    s->amax = 0.9;
+    s->pgtwon = s->pginfn = INFINITY;
+    *out = s;
+    return 0;
+}
+
+extern "C" int opkb_spg_solver_destroy(opkb_spg_solver* s)
+{
+    if (!s) return 0;
+    free(s->lastfv);
+    free(s);
+    return 0;
+}
+
+// one trip of the main loop; returns 1 while searching, 0 once finished, < 0 on error
+static int spg_solver_iterate(opkb_spg_solver* s)
+{
+    opkb_spg* ws = s->ws;
+    int rc;
+    if (s->finished) return 0;
+    if (!s->started) {                                                        // :230-241
+        rc = opkb_spg_start(ws, s->eta, s->out);
+        if (rc) return rc;
+        s->f = s->out[0];
+        s->pcnt += 1;
+        s->fcnt += 1;
+        s->fbest = s->f;
+        s->started = 1;
+    }
+    double fmin, fmax;
+    int fconst = 0;
+    if (s->m > 1) {                                                           // :249-255
+        s->lastfv[s->iter % s->m] = s->f;
+        fmin = fmax = s->lastfv[0];
+        for (int i = 1; i < s->m; ++i) {
+            const double v = s->lastfv[i];       // Julia's min / max propagate NaN
+            fmin = (fmin != fmin) ? fmin : ((v != v) ? v : (v < fmin ? v : fmin));
+            fmax = (fmax != fmax) ? fmax : ((v != v) ? v : (v > fmax ? v : fmax));
+        }
+        fconst = !(fmin < fmax);
+    } else {
+        fmin = fmax = s->f;
+    }
+    s->pgtwon = sqrt(s->out[2]);                                              // :259-262
+    s->pginfn = s->out[3];
+    s->pcnt += 1;
+    // :278-302
+    if (s->pginfn <= s->eps1) { s->status = 1; s->finished = 1; return 0; }
+    if (s->pgtwon <= s->eps2) { s->status = 2; s->finished = 1; return 0; }
+    if (fconst) { s->status = 3; s->finished = 1; return 0; }
+    if (s->iter >= s->maxit) { s->status = -1; s->finished = 1; return 0; }
+    if (s->fcnt >= s->maxfc) { s->status = -2; s->finished = 1; return 0; }
+    double lam;                                                               // :305-319
+    if (s->iter == 0) {
+        lam = jl_clamp(1 / s->pginfn, s->lmin, s->lmax);
+    } else {
+        const double sty = s->out[4], sts = s->out[5];
+        lam = (sty > 0) ? jl_clamp(sts / sty, s->lmin, s->lmax) : s->lmax;
+    }
+    s->f0 = s->f;                                                             // :324
+    s->lambda = lam;
+    rc = opkb_spg_step(ws, lam, s->eta, s->out);                              // :327-336
+    if (rc) return rc;
+    s->f = s->out[0];
+    const double delta = s->out[1];
+    s->pcnt += 1;
+    double stp = 1.0;                                                         // :333
+    for (;;) {
+        s->fcnt += 1;                                                         // :337
+        if (s->f < s->fbest) {                                                // :342-345
+            s->fbest = s->f;
+            opkb_spg_mark_best(ws);
+        }
+        if (s->f <= fmax + stp * s->ftol * delta) break;                      // :348
+        if (s->fcnt >= s->maxfc) {                                            // :352-356
+            s->status = -2;
+            break;
+        }
+        const double q = -delta * (stp * stp);                                // :359-365
+        const double r = (s->f - s->f0 - stp * delta) * 2;
+        if (r > 0 && s->amin * r <= q && q <= s->amax * stp * r) stp = q / r;
+        else stp /= 2;
+        rc = opkb_spg_backtrack(ws, lam, stp, s->eta, s->out);                // :368, :336
+        if (rc) return rc;
+        s->f = s->out[0];
+    }
+    if (s->status != 0) {                                                     // :371-375
+        s->finished = 1;
+        return 0;
+    }
+    s->iter += 1;                                                             // :378
+    return 1;
+}
+
+extern "C" int opkb_spg_solver_run(opkb_spg_solver* s, int64_t niter, int* searching)
+{
+    if (!s) return opkb_set_error(OPKB_EINVAL, "NULL solver");
+    int alive = s->finished ? 0 : 1;
+    const int64_t target = (niter > INT64_MAX - s->iter) ? INT64_MAX : s->iter + niter;
+    while (alive == 1 && s->iter < target) {
+        alive = spg_solver_iterate(s);
+        if (alive < 0) return alive;
+    }
+    if (searching) *searching = alive;
+    return 0;
+}
+
+extern "C" int opkb_spg_solver_info(const opkb_spg_solver* s, double* f, double* fbest, double* pginfn,
+                                    double* pgtwon, int64_t* iter, int64_t* fcnt, int64_t* pcnt, int* status,
+                                    int* best_is_x)
+{
+    if (!s) return opkb_set_error(OPKB_EINVAL, "NULL solver");
+    if (f) *f = s->f;
+    if (fbest) *fbest = s->fbest;
+    if (pginfn) *pginfn = s->pginfn;
+    if (pgtwon) *pgtwon = s->pgtwon;
+    if (iter) *iter = s->iter;
+    if (fcnt) *fcnt = s->fcnt;
+    if (pcnt) *pcnt = s->pcnt;
+    if (status) *status = s->status;
+    if (best_is_x) *best_is_x = !(s->fbest < s->f);       // :401: the solution is 'b' when fbest < f
+    return 0;
+}

@@ -347,9 +347,65 @@ class SPG:
         return v
 
 
-def spg_(fg, prj, x, m, **kwds):
-    """`spg!(fg!, prj!, x, m; kwds...) -> x` (src/spg.jl:168-191)."""
-    solver = SPG(fg, prj, x, m, **kwds)
+class NativeSPG(SPG):
+    """`spg!` with the loop inside libopkb200 (`opkb_spg_solver_*`): same keywords and results
+    as `SPG` for a built-in objective and a box (`BoundedSet`), one native call per `iterate(k)` /
+    `solve()`.  `printer` / `verb` are host-side hooks of the Python loop and are not called here
+    (use `observer`, invoked after every `iterate` call)."""
+
+    def __init__(self, fg, prj, x0, m, **kw):
+        kw.pop("mode", None)
+        super().__init__(fg, prj, x0, m, mode="fused", **kw)
+        if not self.fused:
+            raise TypeError("the native SPG loop needs a built-in objective and a BoundedSet")
+        self._solver = vp()
+        big = 2 ** 63 - 1
+        check(_lib.lib().opkb_spg_solver_create(self._h, self.m, min(self.maxit, big), min(self.maxfc, big),
+                                                self.eps1, self.eps2, self.eta, C.byref(self._solver)))
+        self._best_is_x = True
+
+    def close(self):
+        if getattr(self, "_solver", None):
+            _lib.lib().opkb_spg_solver_destroy(self._solver)
+            self._solver = None
+        super().close()
+
+    def _refresh(self):
+        f, fb, pi, p2 = f64(), f64(), f64(), f64()
+        it, fc, pc = _lib.i64(), _lib.i64(), _lib.i64()
+        st, bx = C.c_int(), C.c_int()
+        check(_lib.lib().opkb_spg_solver_info(self._solver, C.byref(f), C.byref(fb), C.byref(pi), C.byref(p2),
+                                              C.byref(it), C.byref(fc), C.byref(pc), C.byref(st), C.byref(bx)))
+        self.f, self.fbest, self.pginfn, self.pgtwon = f.value, fb.value, pi.value, p2.value
+        self.iter, self.fcnt, self.pcnt, self.status = it.value, fc.value, pc.value, st.value
+        self._best_is_x = bool(bx.value)
+
+    def iterate(self, niter: int = 1) -> bool:
+        if self.finished:
+            return False
+        alive = C.c_int()
+        check(_lib.lib().opkb_spg_solver_run(self._solver, int(min(niter, 2 ** 62)), C.byref(alive)))
+        self._refresh()
+        if self.observer is not None:
+            self.observer(self)
+        if not alive.value:
+            self.finished = True
+            self._fill(self.fbest)
+        return bool(alive.value)
+
+    def solve(self):
+        while self.iterate(2 ** 62):
+            pass
+        return self.solution()
+
+    def solution(self) -> Vector:
+        return self._vec("x") if self._best_is_x else self._vec("b")
+
+
+def spg_(fg, prj, x, m, driver="python", **kwds):
+    """`spg!(fg!, prj!, x, m; kwds...) -> x` (src/spg.jl:168-191).  `driver="native"` runs the
+    loop inside the library (built-in objective and box only)."""
+    solver = (NativeSPG if driver == "native" else SPG)(fg, prj, x, m, **kwds)
     solver.solve()
     if isinstance(x, Vector):
         sol = solver.solution()

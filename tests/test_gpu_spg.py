@@ -154,3 +154,61 @@ def test_spg_generic_convex_set(opk, oracle, dtype):
     assert relerr(x, xo) <= 10 * rtol
     assert np.linalg.norm(x.astype(np.float64)) <= R * (1 + 1e-6)          # feasible
     assert np.linalg.norm(c.astype(np.float64)) > R                        # and the constraint is active
+
+
+@pytest.mark.parametrize("kind,n,dtype,m", CASES)
+def test_native_spg_driver_equals_python_driver(opk, oracle, kind, n, dtype, m):
+    """`opkb_spg_solver_*` (the loop of `_spg!` in the library) takes the decisions of the Python
+    host bit for bit: same kernels, same double arithmetic on the same scalars."""
+    pb = problem(kind, n, dtype)
+    lo = -math.inf if pb["lower"] is None else pb["lower"]
+    hi = math.inf if pb["upper"] is None else pb["upper"]
+    res = []
+    for cls in (opk.SPG, opk.NativeSPG):
+        tr = []
+        ws = opk.Info()
+        s = cls(pb["gpu_obj"], opk.BoxProjection(lo, hi), pb["x0"], m, maxit=30, ws=ws,
+                observer=lambda s: tr.append((s.iter, s.fcnt, s.pcnt, s.f, s.fbest)))
+        if cls is opk.NativeSPG:
+            while s.iterate(1):
+                pass
+        else:
+            s.solve()
+        res.append((s.result().copy(), (ws.iter, ws.fcnt, ws.pcnt, ws.status, ws.f, ws.fbest, ws.pgtwon, ws.pginfn), tr))
+        s.close()
+    assert res[0][1] == res[1][1]
+    assert np.array_equal(res[0][0], res[1][0])
+    # the native observer runs after an iteration, the Python one at its printer site: the
+    # (iter, fcnt) sequences coincide from the second entry on
+    assert [t[:2] for t in res[1][2][:-1]] == [t[:2] for t in res[0][2][1:len(res[1][2])]]
+    xo, io, _ = oracle.spg(pb["oracle_obj"], pb["x0"], m, pb["lower"], pb["upper"], maxit=30)
+    assert (res[1][1][0], res[1][1][1], res[1][1][3]) == (io["iter"], io["fcnt"], io["status"])
+    assert relerr(res[1][0], xo) <= (1e-10 if dtype == np.float64 else 1e-4)
+
+
+def test_native_spg_driver_api(opk):
+    a, c = opk.Quadratic.synthetic(5000, np.float64, kappa=1e2)
+    box = opk.BoxProjection(0.0, 1.0)
+    x0 = np.full(5000, 0.5)
+    x1 = opk.spg(opk.Quadratic(a, c), box, x0, 10, maxit=40)
+    x2 = opk.spg(opk.Quadratic(a, c), box, x0, 10, maxit=40, driver="native")
+    assert np.array_equal(x1, x2)
+    ws = opk.Info()
+    s = opk.NativeSPG(opk.Quadratic(a, c), box, x0, 10, maxfc=3, eps1=0, eps2=0, ws=ws)
+    s.solve()
+    assert ws.status == opk.TOO_MANY_EVALUATIONS and ws.fcnt == 3
+    s.close()
+    s = opk.NativeSPG(opk.Quadratic(a, c), box, x0, 10, eps1=0, eps2=0)
+    assert s.iterate(7) and s.iter == 7 and s.iterate(5) and s.iter == 12    # resumable
+    s.close()
+    with pytest.raises(TypeError):
+        opk.NativeSPG(lambda x, g: 0.0, box, x0, 10)                          # user objective: Python loop
+    with pytest.raises(opk.OpkbError):
+        from opkb200 import _lib
+        import ctypes as C
+        sp = opk.SPG(opk.Quadratic(a, c), box, x0, 10)
+        h = _lib.vp()
+        try:
+            _lib.check(_lib.lib().opkb_spg_solver_create(sp._h, 0, 10, 10, 0.0, 0.0, 1.0, C.byref(h)))  # m = 0
+        finally:
+            sp.close()
