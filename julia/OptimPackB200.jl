@@ -23,6 +23,7 @@
 module OptimPackB200
 
 export DeviceVector, BoundedSet, Rosenbrock, Quadratic, Smooth2D, vmlmb, vmlmb!, vmlmb_native!, spg, spg!,
+    spg_native!,
     conjgrad, conjgrad!, DiagonalOperator, Smooth2DOperator
 
 using Libdl
@@ -758,6 +759,49 @@ function fused_spg!(fg!, box::BoundedSet, x::DeviceVector{T}, m::Int;
         ws.iter = iter; ws.fcnt = fcnt; ws.pcnt = pcnt; ws.status = status
         vcopy!(x, spgvec(fbest < f ? 'b' : 'x'))
     finally
+        ccall((:opkb_spg_destroy, libopkb200), Cint, (Ptr{Cvoid},), h)
+    end
+    return x
+end
+
+# ---------------------------------------------------------------------------
+# spg! with the loop inside the library (`opkb_spg_solver_*`, Tier 3): built-in objective + box.
+function spg_native!(fg!, box::BoundedSet, x::DeviceVector{T}, m::Integer;
+                     ws::OptimPackNextGen.SPG.Info = OptimPackNextGen.SPG.Info(),
+                     maxit::Integer = typemax(Int), maxfc::Integer = typemax(Int),
+                     eps1::Real = 1e-6, eps2::Real = 1e-6, eta::Real = 1.0) where {T}
+    ctx = x.ctx
+    lo = to_device(ctx, box.lower, T); hi = to_device(ctx, box.upper, T)
+    (lp, lv), (hp, hv) = bound_args(lo, -Inf), bound_args(hi, +Inf)
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:opkb_spg_create, libopkb200), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cdouble, Ref{Ptr{Cvoid}}),
+                ctx.ptr, eltype_code(T), length(x), lp, lv, hp, hv, ref))
+    h = ref[]
+    sref = Ref{Ptr{Cvoid}}(C_NULL)
+    spgvec(which::Char) = DeviceVector{T}(ctx, ccall((:opkb_spg_vector, libopkb200), Ptr{Cvoid},
+                                                     (Ptr{Cvoid}, Cint), h, Cint(which)), length(x))
+    try
+        kind, pa, pc = objective_code(fg!)
+        check(ccall((:opkb_spg_set_objective, libopkb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
+                    h, kind, pa, pc))
+        vcopy!(spgvec('x'), x)
+        check(ccall((:opkb_spg_solver_create, libopkb200), Cint,
+                    (Ptr{Cvoid}, Cint, Int64, Int64, Cdouble, Cdouble, Cdouble, Ref{Ptr{Cvoid}}),
+                    h, m, maxit, maxfc, eps1, eps2, eta, sref))
+        alive = Ref{Cint}(1)
+        check(ccall((:opkb_spg_solver_run, libopkb200), Cint, (Ptr{Cvoid}, Int64, Ref{Cint}),
+                    sref[], typemax(Int64), alive))
+        f = Ref{Cdouble}(0); fb = Ref{Cdouble}(0); pi = Ref{Cdouble}(0); p2 = Ref{Cdouble}(0)
+        it = Ref{Int64}(0); fc = Ref{Int64}(0); pc_ = Ref{Int64}(0); st = Ref{Cint}(0); bx = Ref{Cint}(1)
+        check(ccall((:opkb_spg_solver_info, libopkb200), Cint,
+                    (Ptr{Cvoid}, Ref{Cdouble}, Ref{Cdouble}, Ref{Cdouble}, Ref{Cdouble}, Ref{Int64}, Ref{Int64},
+                     Ref{Int64}, Ref{Cint}, Ref{Cint}), sref[], f, fb, pi, p2, it, fc, pc_, st, bx))
+        ws.f = fb[]; ws.fbest = fb[]; ws.pginfn = pi[]; ws.pgtwon = p2[]
+        ws.iter = it[]; ws.fcnt = fc[]; ws.pcnt = pc_[]; ws.status = st[]
+        vcopy!(x, spgvec(bx[] != 0 ? 'x' : 'b'))
+    finally
+        sref[] != C_NULL && ccall((:opkb_spg_solver_destroy, libopkb200), Cint, (Ptr{Cvoid},), sref[])
         ccall((:opkb_spg_destroy, libopkb200), Cint, (Ptr{Cvoid},), h)
     end
     return x
