@@ -98,18 +98,23 @@ def main():
             obj = opk.Quadratic.synthetic_device(ctx, nl, np.float32, kappa=1e3, first=first)
             lo, hi = ctx.vector(nl, np.float32).fill(0.0), ctx.vector(nl, np.float32).fill(1.0)
             x0 = ctx.vector(nl, np.float32).fill(0.5)
-            s = opk.SPG(obj, opk.BoxProjection(lo, hi), x0, 10, eps1=0, eps2=0, ctx=ctx)
+            s = (opk.NativeSPG if NATIVE else opk.SPG)(obj, opk.BoxProjection(lo, hi), x0, 10, eps1=0, eps2=0,
+                                                       ctx=ctx)
             for _ in range(5):
                 s.iterate()
             ctx.synchronize()
             i0, f0c = s.iter, s.fcnt
             ctx.timer_start()
             K = 200
-            while s.iter < i0 + K and s.iterate():
-                pass
+            if NATIVE:
+                s.iterate(K)                      # one native call for the K iterations
+            else:
+                while s.iter < i0 + K and s.iterate():
+                    pass
             ms = ctx.timer_stop()
             it = s.iter - i0
-            r = {"config": "C3 SPG quadratic box n=1e8 f32 (m=10)", "n": n, "iterations": it,
+            r = {"config": "C3 SPG quadratic box n=1e8 f32 (m=10)" + (" [native driver]" if NATIVE else ""),
+                 "n": n, "iterations": it,
                  "ms_per_iteration": ms / it, "iterations_per_s": it / (ms * 1e-3),
                  "evals_per_iteration": (s.fcnt - f0c) / it,
                  "alg_GBps_per_gpu": 8 * 4 * nl / (ms * 1e-3 / it) / 1e9, "f": s.f}
