@@ -240,12 +240,20 @@ int opkb_grid_for(const opkb_context* ctx, int64_t nitems, int ctas_per_sm)
 // Wait until the last CTA of the latest reducing launch has stored its sequence number in
 // `flag` (after its results, system-scope fence); a stream query every few microseconds catches
 // launches that publish nothing, and errors.  Returns true if the flag was seen.
+static inline void cpu_relax()
+{
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();      // spin-wait hint: leaves the core's resources to its sibling thread
+#endif
+}
+
 static bool wait_flag(opkb_context* ctx, volatile unsigned int* flag)
 {
     const unsigned int want = ctx->seq;
     for (unsigned int it = 1;; ++it) {
         if (*flag == want) return true;
         if ((it & 4095u) == 0u && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) return false;
+        cpu_relax();
     }
 }
 
@@ -264,9 +272,10 @@ static int opkb_mailbox_reduce(opkb_context* ctx, int nred, const int* kinds, do
             unsigned long long* ready = (unsigned long long*)(slot + 64);
             unsigned long long spins = 0;
             while (__atomic_load_n(ready, __ATOMIC_ACQUIRE) < phase) {
+                cpu_relax();
                 if ((++spins & 0xffffffull) == 0ull) {
                     // a peer that died would hang every other rank: give up after ~2 minutes of CPU
-                    if (spins > (1ull << 36))
+                    if (spins > (1ull << 34))
                         return opkb_set_error(OPKB_ENCCL, "rank %d did not publish phase %llu", r, phase);
                 }
             }
