@@ -7,6 +7,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <time.h>
+
 #include "opkb_internal.cuh"
 
 // ---------------------------------------------------------------------------
@@ -271,12 +273,15 @@ static int opkb_mailbox_reduce(opkb_context* ctx, int nred, const int* kinds, do
         if (r != ctx->rank) {
             unsigned long long* ready = (unsigned long long*)(slot + 64);
             unsigned long long spins = 0;
+            time_t t_start = 0;
             while (__atomic_load_n(ready, __ATOMIC_ACQUIRE) < phase) {
                 cpu_relax();
-                if ((++spins & 0xffffffull) == 0ull) {
-                    // a peer that died would hang every other rank: give up after ~2 minutes of CPU
-                    if (spins > (1ull << 34))
-                        return opkb_set_error(OPKB_ENCCL, "rank %d did not publish phase %llu", r, phase);
+                if ((++spins & 0xfffffull) == 0ull) {
+                    // a peer that died would hang every other rank: give up after two minutes
+                    const time_t now = time(NULL);
+                    if (t_start == 0) t_start = now;
+                    else if (now - t_start > 120)
+                        return opkb_set_error(OPKB_ENCCL, "rank %d did not publish phase %llu within 120 s", r, phase);
                 }
             }
         }
