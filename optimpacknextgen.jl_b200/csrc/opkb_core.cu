@@ -277,11 +277,15 @@ static int opkb_mailbox_reduce(opkb_context* ctx, int nred, const int* kinds, do
             while (__atomic_load_n(ready, __ATOMIC_ACQUIRE) < phase) {
                 cpu_relax();
                 if ((++spins & 0xfffffull) == 0ull) {
-                    // a peer that died would hang every other rank: give up after two minutes
+                    // a peer that died would hang every other rank for ever: give up after
+                    // OPKB_MAILBOX_TIMEOUT seconds (default: half an hour; ranks may legitimately
+                    // be far apart, e.g. a slow user objective on one shard)
+                    static const long limit = getenv("OPKB_MAILBOX_TIMEOUT") ? atol(getenv("OPKB_MAILBOX_TIMEOUT")) : 1800;
                     const time_t now = time(NULL);
                     if (t_start == 0) t_start = now;
-                    else if (now - t_start > 120)
-                        return opkb_set_error(OPKB_ENCCL, "rank %d did not publish phase %llu within 120 s", r, phase);
+                    else if (now - t_start > limit)
+                        return opkb_set_error(OPKB_ENCCL, "rank %d did not publish phase %llu within %ld s", r,
+                                              phase, limit);
                 }
             }
         }
