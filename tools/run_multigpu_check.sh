@@ -4,13 +4,15 @@
 N=${1:-2}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 mkdir -p gpurun_out
-# second argument "bench": skip the parity tool and the e2e leg (large N is charged N times)
+# second argument "bench": skip the parity tool and the e2e leg (large N is charged N times);
+# "parity": the parity tool only
 E2E=""
 if [ "$2" != "bench" ]; then
 $TR --master-port 29511 tools/multigpu_parity.py > gpurun_out/parity_n$N.log 2>&1; echo rc=$? >> gpurun_out/parity_n$N.log
 else
 E2E="--no-e2e"; : > gpurun_out/parity_n$N.log
 fi
+if [ "$2" = "parity" ]; then grep "GPUs\]\|rc=\|Error\|error" gpurun_out/parity_n$N.log | tail -20; exit 0; fi
 $TR --master-port 29513 bench.py --gpus $N $E2E > gpurun_out/bench_n${N}_mbox.json 2> gpurun_out/bench_n${N}_mbox.err
 OPKB_MAILBOX=0 $TR --master-port 29514 bench.py --gpus $N --no-e2e > gpurun_out/bench_n${N}_nccl.json 2> gpurun_out/bench_n${N}_nccl.err
 grep "GPUs\]\|rc=\|Error\|error" gpurun_out/parity_n$N.log | tail -20
