@@ -100,3 +100,14 @@ def test_context_and_profile(opk):
     ctx.timer_start()
     opk.vscale_(v, 0.5)
     assert ctx.timer_stop() >= 0.0 and v.download()[0] == 1.0
+
+
+def test_c_host_runs(opk, tmp_path):
+    """examples/c_host.c: vmlmb (native loop and reverse communication with a user objective) and
+    spg (native loop) driven from plain C through the C ABI; the program checks the solutions."""
+    import subprocess
+    from test_host_logic import _build_c_host
+    exe = _build_c_host(tmp_path)
+    r = subprocess.run([exe, "200001"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("\n") == 4 and "result: ok" in r.stdout

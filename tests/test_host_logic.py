@@ -248,3 +248,31 @@ def test_fastmin_fastmax_fastclamp():
     assert opk.fastclamp(2.0, 0.0, 1.0) == 1.0 and opk.fastclamp(2.0, None, 1.0) == 1.0
     assert opk.fastclamp(-2.0, 0.0, None) == 0.0 and opk.fastclamp(7.0, None, None) == 7.0
     assert math.isnan(opk.fastclamp(nan, 0.0, 1.0))
+
+
+def _build_c_host(tmpdir):
+    """gcc examples/c_host.c against the C ABI: a host with no Python and no torch in it."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None or not os.path.exists(opk.SO_PATH):
+        pytest.skip("needs gcc and the built library")
+    exe = os.path.join(str(tmpdir), "c_host")
+    libdir = os.path.dirname(opk.SO_PATH)
+    r = subprocess.run([gcc, "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "c_host.c"), "-o", exe, "-L", libdir, "-lopkb200",
+                        "-Wl,-rpath," + libdir, "-lm"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_c_host_builds_and_fails_loudly_without_gpu(tmp_path):
+    """The C ABI is usable from plain C (examples/c_host.c compiles and links with gcc alone);
+    without a CUDA device the very first call reports it: there is no CPU fallback."""
+    import subprocess
+    import torch
+    exe = _build_c_host(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: tests/test_gpu_api.py::test_c_host_runs covers the run")
+    r = subprocess.run([exe, "1000"], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
