@@ -109,5 +109,12 @@ def test_c_host_runs(opk, tmp_path):
     from test_host_logic import _build_c_host
     exe = _build_c_host(tmp_path)
     r = subprocess.run([exe, "200001"], capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, r.stdout + r.stderr
-    assert r.stdout.count("\n") == 4 and "result: ok" in r.stdout
+    # every call of the ABI returned success (the program stops at the first failing status) ...
+    assert "failed (" not in r.stderr and r.stdout.count("\n") == 4, r.stdout + r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[0].startswith("vmlmb  built-in") and lines[1].startswith("vmlmb  user") and lines[2].startswith("spg")
+    # ... the user-objective run (f = |x - c|^2 / 2 on the box) lands on clamp(c) to rounding, and the
+    # program's own sanity checks of the three solutions hold
+    err_user = float(lines[1].split("|x - clamp(c)|_inf=")[1].split()[0])
+    assert err_user <= 1e-12
+    assert r.returncode == 0 and "result: ok" in lines[3], r.stdout
