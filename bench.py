@@ -49,79 +49,137 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=28)
     ap.add_argument("--mem", type=int, default=10)
-    ap.add_argument("--cpu-log2n", type=int, default=23, help="size of the bounded CPU sample")
-    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--cpu-log2n", type=int, default=25,
+                    help="size of the bounded CPU sample of the cpu_baseline leg of the GPU arm")
+    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--ref-budget-s", type=float, default=float(os.environ.get("OPKB_REF_BUDGET_S", "270")),
+                    help="wall-time cap of the reference arm's solver run (priming + warm-up + timed)")
+    ap.add_argument("--driver", default="native", choices=["native", "python"],
+                    help="host of the stage machine: the C++ driver inside the library, or the Python twin")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
-def config(args, n, exchange="shared-memory mailbox written by the kernels, or a packed ncclAllGather"):
+def config(args, n):
+    """ONE description of the workload, identical for both arms (the driver compares them)."""
     return {
         "workload": "C4: VMLMB bound-constrained quadratic n=2^%d Float64 m=%d, array bounds [0,1], "
-                    "More-Toraldo line search, fused path (direction + speculative trial + incremental "
-                    "Gram in one kernel per iteration; P1 / P3 sweep as fall-backs)" % (int(math.log2(n)), args.mem),
+                    "More-Toraldo line search; a step = one VMLMB iteration (accepted line search) in steady "
+                    "state (all m pairs stored)" % (int(math.log2(n)), args.mem),
         "n": n, "mem": args.mem, "eltype": "Float64", "kappa": KAPPA,
-        "sharding": "contiguous 1-D blocks, %d rank(s), one exchange of the packed reduction partials per "
-                    "phase (%s)" % (args.gpus, exchange),
-        "l2": "no flush needed: every kernel streams >= 18 GiB per rank at N=1 (>> 126 MB L2)",
+        "sharding": "contiguous 1-D blocks over %d rank(s) (GPU arm); the CPU arm runs the whole n on the "
+                    "host cores of rank 0" % args.gpus,
+        "l2": "no flush needed: every pass streams %.3g GiB vectors (>> 126 MB L2, >> host caches)" % (n * 8 / 2 ** 30),
         "priming": "mem+1 untimed iterations before the warm-up so that all m (s,y) pairs exist",
     }
 
 
 # ---------------------------------------------------------------------------
 # CPU arm: the oracle port ("reference-faithful unfused" C restatement, OpenMP)
-def cpu_run(args, steps, warmup, log2n, threads=None):
-    """Times `steps` VMLMB iterations of the oracle on the host cores on a
-    bounded sample (n_s = 2^log2n) of the same workload.  Returns it/s at n_s."""
+def host_ram_bytes():
+    try:
+        return os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES")
+    except Exception:
+        return 0
+
+
+def cpu_vectors(mem):
+    """n-vectors alive during an oracle run: a, c, lo, hi, x0 (inputs) + x, g, p, d, 2m pairs."""
+    return 5 + 4 + 2 * mem
+
+
+def cpu_run(args, steps, warmup, log2n, threads=None, budget_s=None):
+    """Times VMLMB iterations of the oracle on the host cores at n_s = 2^log2n, in ONE solver run:
+    the oracle's `printer` hook (src/quasinewton.jl:501-503) timestamps every iteration; the first
+    mem+1 iterations (priming: the pairs fill up) and `warmup` more are not timed, the next `steps`
+    are.  With a wall-time budget the number of timed iterations is reduced (never below 3) from a
+    calibration run at a small size, and reported."""
     import opk_oracle as O
     O.build()
     O.set_sum_mode(O.SUM_ACCURATE)
     if threads is None:
         threads = int(os.environ.get("OPKB_CPU_THREADS", "0"))         # 0 = all host cores
     O.set_num_threads(threads)
-    cores = O.max_threads()
-    ns = 1 << log2n
+    cores = O.max_threads() if threads == 0 else threads
     sys.path.insert(0, ROOT)
     import opkb200 as opk
-    a, c = opk.Quadratic.synthetic(ns, np.float64, kappa=KAPPA)
-    lo, hi = np.zeros(ns), np.ones(ns)
-    x0 = np.full(ns, 0.5)
     kw = dict(mem=args.mem, xtol=(0, 0), ftol=(0, 0), gtol=(0, 0))
+    prime = args.mem + 1
 
-    def run(k):
-        t0 = time.perf_counter()
-        x, res, _ = O.vmlmb(("quadratic", a, c), x0, lo, hi, maxiter=k, **kw)
-        return time.perf_counter() - t0, res
+    def run(log2, nwarm, nsteps):
+        ns = 1 << log2
+        a, c = opk.Quadratic.synthetic(ns, np.float64, kappa=KAPPA)
+        lo, hi = np.zeros(ns), np.ones(ns)
+        x0 = np.full(ns, 0.5)
+        stamps = []
 
-    # warm-up iterations are part of a run (the solver cannot be resumed): time
-    # (warmup + steps) and (warmup) iterations and take the difference
-    tw, _ = run(max(warmup, 1))
-    tt, res = run(max(warmup, 1) + steps)
-    dt = max(tt - tw, 1e-9)
-    its = steps / dt
-    evals_per_iter = res["eval"] / max(res["iter"], 1)
-    return dict(its_at_ns=its, ns=ns, cores=cores, seconds=dt, evals_per_iter=evals_per_iter)
+        def tick(rec):
+            stamps.append((rec["iter"], rec["eval"], time.perf_counter()))
+
+        t_begin = time.perf_counter()
+        _, res, _ = O.vmlmb(("quadratic", a, c), x0, lo, hi, maxiter=prime + nwarm + nsteps, trace=tick, **kw)
+        by_iter = {it: (ev, t) for it, ev, t in stamps}
+        i0, i1 = prime + nwarm, prime + nwarm + nsteps
+        if i0 not in by_iter or i1 not in by_iter:
+            raise SystemExit("oracle stopped after %d iterations (%s)" % (res["iter"], res["reason"]))
+        dt = by_iter[i1][1] - by_iter[i0][1]
+        return dict(ns=ns, seconds=dt, steps=nsteps, warmup=nwarm, its=nsteps / max(dt, 1e-9),
+                    evals_per_iter=(by_iter[i1][0] - by_iter[i0][0]) / nsteps,
+                    total_seconds=time.perf_counter() - t_begin, f=res["f"])
+
+    note = ""
+    if budget_s is not None:
+        cal_log2 = min(log2n, 22)
+        cal = run(cal_log2, 1, 3)
+        t_iter = (1.0 / cal["its"]) * (1 << (log2n - cal_log2))   # predicted seconds per iteration at n_s
+        # priming iterations work on fewer pairs (about half the passes on average)
+        avail = budget_s - t_iter * (0.6 * prime)
+        k = int(avail / t_iter) - warmup
+        if k < steps:
+            if k < 3:
+                warmup = max(1, min(warmup, int(avail / t_iter) - 3))
+                k = 3
+            note = ("; %d of the %d requested iterations timed to stay within the %.0f s budget "
+                    "(predicted %.2f s per iteration)" % (k, steps, budget_s, t_iter))
+            steps = k
+    r = run(log2n, warmup, steps)
+    r.update(cores=cores, note=note)
+    return r
 
 
 def reference_line(args):
+    """`--impl reference`: the reference's CPU path for this workload (the oracle port: the reference is
+    Julia and cannot run here) at the REAL n when the host has the memory for it."""
     n = 1 << args.log2n
-    r = cpu_run(args, args.steps, args.warmup, args.cpu_log2n)
+    need = cpu_vectors(args.mem) * 8 * n * 1.08
+    ram = host_ram_bytes()
+    log2 = args.log2n
+    while log2 > 20 and ram and cpu_vectors(args.mem) * 8 * (1 << log2) * 1.08 > 0.9 * ram:
+        log2 -= 1
+    r = cpu_run(args, args.steps, args.warmup, log2, budget_s=args.ref_budget_s)
     scale = r["ns"] / n
-    value = r["its_at_ns"] * scale
-    sample = ("oracle port (C restatement of the reference's unfused CPU path, OpenMP, %d threads): "
-              "%d iterations at n_s=2^%d timed (%.2f s), iterations/s scaled by n_s/n to n=2^%d; "
-              "the Julia reference itself cannot run here (no Julia runtime)"
-              % (r["cores"], args.steps, args.cpu_log2n, r["seconds"], args.log2n))
+    value = r["its"] * scale
+    where = ("at the full n=2^%d" % args.log2n) if log2 == args.log2n else (
+        "at n_s=2^%d -- the host has %.0f GiB, the full size needs %.0f GiB -- and SCALED by n_s/n (an "
+        "extrapolation, flagged in `extrapolated`)" % (log2, ram / 2 ** 30, need / 2 ** 30))
+    sample = ("oracle port (C restatement of the reference's unfused CPU path, OpenMP, %d threads) %s: one "
+              "solver run, every iteration timestamped at the reference's printer site; %d priming + %d "
+              "warm-up iterations untimed, %d iterations timed in %.2f s (whole run %.1f s)%s; the Julia "
+              "reference itself cannot run here (no Julia runtime)"
+              % (r["cores"], where, args.mem + 1, r["warmup"], r["steps"], r["seconds"],
+                 r["total_seconds"], r["note"]))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
+        "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": 1e3 / value,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": config(args, n),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "extrapolated": log2 != args.log2n,
+        "requested": {"steps": args.steps, "warmup": args.warmup},
+        "evals_per_iter": r["evals_per_iter"], "final": {"f": r["f"]},
     }
     print(json.dumps(line), flush=True)
 
@@ -193,16 +251,22 @@ def measured_peak():
 
 
 def traffic_for(kernel, n_local):
-    """dram bytes per launch of `kernel` from the committed ncu capture, if any."""
+    """(dram bytes per launch of `kernel`, note) from the committed ncu capture, if any.  The capture
+    was taken at one size; for another shard length of the same streaming kernel the bytes are scaled
+    by n_local / n_captured (every byte of traffic is per element) and the note says so."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             t = json.load(fh)
         e = t.get(kernel)
-        if e and int(e["n"]) == int(n_local):
-            return float(e["dram_bytes_per_launch"])
+        if e:
+            b = float(e["dram_bytes_per_launch"])
+            if int(e["n"]) == int(n_local):
+                return b, "ncu capture at this size (%s)" % e.get("source", "profiles/")
+            return (b * n_local / float(e["n"]),
+                    "ncu capture at n=%d (%s) scaled by n_local/n to this shard" % (int(e["n"]), e.get("source", "profiles/")))
     except Exception:
         pass
-    return None
+    return None, None
 
 
 def ours(args):
@@ -249,7 +313,8 @@ def ours(args):
     x0 = ctx.vector(nloc, dt).fill(0.5)
     kw = dict(lower=lo, upper=hi, mem=m, xtol=(0, 0), ftol=(0, 0), gtol=(0, 0), nglobal=n, ctx=ctx)
 
-    solver = opk.VMLMB(obj, x0, **kw)
+    Solver = opk.NativeVMLMB if args.driver == "native" else opk.VMLMB
+    solver = Solver(obj, x0, **kw)
     # (nvidia-smi needs a few hundred ms before its first line: it is started before the
     # priming iterations so that it is streaming when the timed region begins)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -308,21 +373,33 @@ def ours(args):
                           "frac": ach / peak}
     dom = max(kern, key=lambda k: kern[k]["avg_ms"] * kern[k]["launches"])
     names = {"trial": "k_trial", "gram": "k_gram2", "direction": "k_direction2"}
+    traffic, traffic_note = traffic_for(dom, nloc)
+    # what ONE steady-state launch of the fused kernel has to move (compulsory): read S, Y (2m), x, g,
+    # lo, hi, a, c; write d, x', g', s', y' = 2m+11 passes (2m+9 "algorithmic" + the objective's a, c)
+    moved = sum(v["launches"] * (v["alg_bytes_per_launch"] + (2 * es * nloc if k != "gram" else 0))
+                for k, v in kern.items()) / K * world
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": kern[dom]["achieved_gbs"], "peak": peak,
-                "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": traffic_for(dom, nloc),
+                "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peak_src, "kernels": kern, "trial_fused_into_direction": fused_trial,
                 "incremental_gram_iterations": hits,
                 "note": "k_direction2 = direction + speculative trial" +
                         (" + incremental Gram (the Gram sweep ran %d times in %d iterations)"
                          % (prof.get("gram", (0.0, 0))[1], K) if carried else ""),
-                "iteration": {"alg_bytes": (4 * m + 20) * es * n, "evals_per_iter": evals / K,
-                              "yardstick": "SURVEY 8(d) W_alg = 4m+20 passes of a 3-phase iteration; the "
-                                           "path moves fewer bytes, so this fraction may exceed 1",
-                              "moved_bytes_per_iter": sum(v["launches"] * (v["alg_bytes_per_launch"] +
-                                                          (2 * es * nloc if k != "gram" else 0))
-                                                          for k, v in kern.items()) / K * world,
-                              "achieved_gbs": (4 * m + 20) * es * n / (ms * 1e-3 / K) / 1e9 / world,
-                              "frac_per_gpu": (4 * m + 20) * es * n / (ms * 1e-3 / K) / 1e9 / world / peak}}
+                "iteration": {
+                    "evals_per_iter": evals / K,
+                    "compulsory_model": {
+                        "passes": 2 * m + 11, "bytes": (2 * m + 11) * es * n,
+                        "what": "ONE kernel per iteration: read S, Y (2m), x, g, lo, hi, a, c; write d, x', g', "
+                                "s', y' (p recomputed, saves by aliasing, trial fused, S and Y cross HBM once)",
+                        "achieved_gbs_per_gpu": (2 * m + 11) * es * n / (ms * 1e-3 / K) / 1e9 / world,
+                        "frac_per_gpu": (2 * m + 11) * es * n / (ms * 1e-3 / K) / 1e9 / world / peak},
+                    "moved_bytes_per_iter": moved,
+                    "survey_yardstick": {
+                        "passes": 4 * m + 20, "bytes": (4 * m + 20) * es * n,
+                        "what": "SURVEY 8(d) W_alg of a 3-phase iteration (P1 + P3 + P4); obsolete for this "
+                                "design, which moves 2m+11 passes -- the fraction below exceeds 1 for that "
+                                "reason, not because the kernel beats the HBM peak",
+                        "frac_per_gpu": (4 * m + 20) * es * n / (ms * 1e-3 / K) / 1e9 / world / peak}}}
 
     # ---- e2e: the public call with HOST (pinned) buffers -------------------------------
     e2e = None
@@ -337,34 +414,44 @@ def ours(args):
         del obj, lo, hi, x0
         barrier()
         te0 = time.perf_counter()
-        s2 = opk.VMLMB(opk.Quadratic(host["a"][1], host["c"][1]), host["x0"][1], lower=host["lo"][1],
-                       upper=host["hi"][1], mem=m, maxiter=K, xtol=(0, 0), ftol=(0, 0), gtol=(0, 0),
-                       nglobal=n, ctx=ctx)
+        s2 = Solver(opk.Quadratic(host["a"][1], host["c"][1]), host["x0"][1], lower=host["lo"][1],
+                    upper=host["hi"][1], mem=m, maxiter=K, xtol=(0, 0), ftol=(0, 0), gtol=(0, 0),
+                    nglobal=n, ctx=ctx)
         ctx.synchronize()
         te1 = time.perf_counter()
         s2.solve()
         ctx.synchronize()
         te2 = time.perf_counter()
         s2.x.download(out_t.numpy())
+        te3 = time.perf_counter()
         barrier()
         te = max_over_ranks(time.perf_counter() - te0)
+        # PCIe floor of this call: the 5 input vectors and the result cross the link once each
+        h2d_gbs = 5 * nloc * es / max(te1 - te0, 1e-9) / 1e9
         e2e = {"value": s2.iter / te, "unit": UNIT, "h2d_bytes_per_step": 5 * nloc * es * world / K,
                "d2h_bytes_per_step": nloc * es * world / K,
-               "what": "opkb200.VMLMB(Quadratic(a, c), x0, lower, upper, mem=%d, maxiter=%d).solve() "
+               "what": "opkb200.%s(Quadratic(a, c), x0, lower, upper, mem=%d, maxiter=%d).solve() "
                        "with pinned host arrays in, host array out (setup, uploads, %d iterations, "
-                       "download inside the timed region)" % (m, K, s2.iter),
+                       "download inside the timed region)" % (Solver.__name__, m, K, s2.iter),
                "seconds": te,
-               "breakdown_s": {"create_and_upload": te1 - te0, "solve": te2 - te1,
-                               "download": time.perf_counter() - te2}}
+               "breakdown_s": {"create_and_upload": max_over_ranks(te1 - te0), "solve": max_over_ranks(te2 - te1),
+                               "download": max_over_ranks(te3 - te2),
+                               "note": "max over ranks of each part; create_and_upload moves 5 vectors over "
+                                       "PCIe (%.1f GB/s on rank 0): with K = %d iterations the transfers, not "
+                                       "the iterations, bound this figure" % (h2d_gbs, K)}}
         s2.close()
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": config(args, n, "none: one rank" if world == 1 else
-                         ("shared-memory mailbox written by the last CTA of every rank" if ctx.uses_mailbox
-                          else "packed ncclAllGather")),
+        "config": config(args, n),
+        "path": "fused: direction + speculative trial + incremental Gram in ONE kernel per iteration (P1 trial and "
+                "P3 Gram sweep only when the speculated step is not taken); stage machine, line search and m x m "
+                "two-loop solve on the host (%s driver)" % args.driver,
+        "exchange": ("none: one rank" if world == 1 else
+                     ("packed partials of each phase written by the last CTA of every rank into a shared-memory "
+                      "mailbox" if ctx.uses_mailbox else "packed ncclAllGather per phase")),
         "roofline": roofline,
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "evals_per_s": evals / (ms * 1e-3), "final": {"f": f_final, "gnorm": gnorm_final},
@@ -373,16 +460,20 @@ def ours(args):
         r = cpu_run(args, args.cpu_steps, 1, args.cpu_log2n)
         scale = r["ns"] / n
         line["cpu_baseline"] = {
-            "value": r["its_at_ns"] * scale, "unit": UNIT, "cores": r["cores"], "kind": "port",
-            "sample": "oracle port (C restatement of the reference's unfused CPU path, OpenMP, %d threads): "
-                      "%d iterations at n_s=2^%d timed (%.2f s), scaled by n_s/n to n=2^%d"
-                      % (r["cores"], args.cpu_steps, args.cpu_log2n, r["seconds"], args.log2n)}
-        # also the scalar figure (one thread, a smaller sample)
-        r1 = cpu_run(args, 3, 1, min(args.cpu_log2n, 21), threads=1)
+            "value": r["its"] * scale, "unit": UNIT, "cores": r["cores"], "kind": "port",
+            "sample": "oracle port (C restatement of the reference's unfused CPU path, OpenMP, %d threads) on a "
+                      "bounded sample: n_s=2^%d (256 MB per vector, far beyond the host caches), %d priming + 1 "
+                      "warm-up iterations untimed, %d iterations timed in %.2f s, iterations/s scaled by n_s/n to "
+                      "n=2^%d; `bench.py --impl reference` measures the same port at the full n"
+                      % (r["cores"], args.cpu_log2n, m + 1, r["steps"], r["seconds"], args.log2n)}
+        # also the scalar figure (one thread, a smaller sample) -- the Julia reference is
+        # single-threaded
+        l1 = min(args.cpu_log2n, 22)
+        r1 = cpu_run(args, 3, 1, l1, threads=1)
         line["cpu_baseline"]["single_thread"] = {
-            "value": r1["its_at_ns"] * r1["ns"] / n, "unit": UNIT, "cores": 1,
-            "sample": "same port, 1 thread: 3 iterations at n_s=2^%d (%.2f s), scaled to n=2^%d"
-                      % (min(args.cpu_log2n, 21), r1["seconds"], args.log2n)}
+            "value": r1["its"] * r1["ns"] / n, "unit": UNIT, "cores": 1,
+            "sample": "same port, 1 thread: 3 iterations at n_s=2^%d (%.2f s) after %d priming + 1 warm-up, "
+                      "scaled to n=2^%d" % (l1, r1["seconds"], m + 1, args.log2n)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     # explicit teardown, in dependency order

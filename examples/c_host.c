@@ -94,7 +94,7 @@ int main(int argc, char** argv)
         CHECK(opkb_solver_start(sv, &task));
         int64_t nfg = 0;
         while (task == OPKB_TASK_COMPUTE_FG) {
-            opkb_vector* x = opkb_vmlmb_vector(ws, 'x', 0);     /* (handles may change between calls) */
+            opkb_vector* x = opkb_vmlmb_vector(ws, 'x', 0);     /* the handles are stable; their DATA POINTERS move between calls */
             opkb_vector* g = opkb_vmlmb_vector(ws, 'g', 0);
             double gg;
             CHECK(opkb_vcombine(ctx, g, 1.0, x, -1.0, c));      /* g = x - c */

@@ -26,8 +26,26 @@
  *    holds a contiguous shard and one small packed all-gather per call
  *    combines the partials (no other data-path communication exists).
  *  - calls are synchronous w.r.t. returned scalars and asynchronous (stream
- *    ordered) otherwise; a context is not re-entrant.
+ *    ordered) otherwise; a context is not re-entrant.  All kernels of a context
+ *    run on ONE private non-blocking stream, opkb_context_stream().
  *  - there is no CPU fallback: every entry point needs a CUDA device.
+ *
+ * Raw device pointers (callers that run their own kernels on the vectors, e.g. a
+ * user objective written with CUDA.jl / CUDA C / torch):
+ *  - a HANDLE is stable for the life of its object, its DATA POINTER is not: the
+ *    vectors of a VMLMB or SPG workspace (`x`, `g`, `p`, `S`, `Y`, ...) trade
+ *    buffers instead of copying (the saves of src/quasinewton.jl:562-563, the
+ *    speculative trial point, the pair of the incremental Gram).  Call
+ *    opkb_vector_data() again after EVERY solver / workspace call; never cache it.
+ *  - ordering: either submit your kernels to opkb_context_stream(ctx), or
+ *      * read x only after opkb_vmlmb_trial_begin / opkb_solver_start /
+ *        opkb_solver_iterate have returned (with a user objective these calls
+ *        return once x is complete in device memory), and
+ *      * before opkb_vmlmb_trial_end / opkb_solver_iterate, make your writes to g
+ *        visible to the library: synchronise your stream, or call
+ *        opkb_context_wait_stream(ctx, your_stream).
+ *  - every entry point makes the device of its context current (cudaSetDevice) and
+ *    leaves it so.
  */
 #ifndef OPKB200_H
 #define OPKB200_H
@@ -84,6 +102,16 @@ int opkb_context_destroy(opkb_context* ctx);
 int opkb_context_synchronize(opkb_context* ctx);
 int opkb_context_device(const opkb_context* ctx);
 int opkb_context_sm_count(const opkb_context* ctx);
+/* the context's stream (a cudaStream_t) and a one-way dependency on another stream of the
+ * caller: everything submitted to `user_stream` so far completes before anything the library
+ * launches afterwards (event record + cudaStreamWaitEvent, no host synchronisation) */
+void* opkb_context_stream(const opkb_context* ctx);
+int   opkb_context_wait_stream(opkb_context* ctx, void* user_stream);
+/* Device memory of destroyed vectors is kept by the context and handed out again to vectors
+ * of the same size (a second solve in the same process pays no cudaMalloc); trim releases it
+ * to the driver (also done automatically when an allocation fails); OPKB_POOL=0 disables. */
+int     opkb_context_trim(opkb_context* ctx);
+int64_t opkb_context_cached_bytes(const opkb_context* ctx);
 /* number of kernels launched by this context so far (bench `gpu_launches`) */
 int64_t opkb_context_launch_count(const opkb_context* ctx);
 /* CUDA-event timer on the context's stream */
@@ -235,6 +263,9 @@ int opkb_cg_diag_step(opkb_context* ctx, const opkb_vector* a, opkb_vector* p, c
 /* ---- Tier 2: fused phases of `_vmlmb!` (src/quasinewton.jl:381-601) ------- */
 /* The workspace owns x, g, p, d and the mem pairs S[k], Y[k] (src/quasinewton.jl:358-369).
  * lo/hi handles must outlive the workspace. */
+/* mem: any value in 1..256 (the reference accepts any, src/quasinewton.jl:227, :328).  The
+ * Gram-form entry points (opkb_vmlmb_gram, _direction, _direction_trial) work on m <= 20 pairs;
+ * beyond that the hosts use the step-by-step form (opkb_vmlmb_twoloop_step), which has no limit. */
 int opkb_vmlmb_create(opkb_context* ctx, int eltype, int64_t n, int mem, int method,
                       const opkb_vector* lo, double lo_val,
                       const opkb_vector* hi, double hi_val, opkb_vmlmb** ws);
@@ -365,8 +396,21 @@ int  opkb_solver_destroy(opkb_solver* solver);
 /* reverse communication: start -> COMPUTE_FG; then iterate(f) after every evaluation */
 int  opkb_solver_start(opkb_solver* solver, int* task);
 int  opkb_solver_iterate(opkb_solver* solver, double f, int* task);
-/* built-in objective: run until `iter` has advanced by niter or termination */
+/* built-in objective, or a user objective with a device callback (below): run until `iter`
+ * has advanced by niter or termination */
 int  opkb_solver_run(opkb_solver* solver, int64_t niter, int* task);
+/* Device-callback objective (cf. the callback style of the reference's C
+ * solvers, src/cobyla.jl:184-193): `fn(user, n, x_dev, g_dev, stream, &f)` must compute
+ * f(x) and write the gradient to g_dev (n local elements of the workspace's element type),
+ * with kernels submitted to `stream` (the context's cudaStream_t: ordered with the library's
+ * own work) or otherwise completed before it returns; it returns 0, or non-zero to abort
+ * (opkb_solver_run then fails with OPKB_EINVAL).  With several ranks *f is this rank's value
+ * of a separable objective when `f_is_partial` != 0 (the library sums it over the ranks in rank
+ * order), the global value otherwise.  Then opkb_solver_run drives the whole reverse-
+ * communication loop inside the library: no host round trip between trial_begin and trial_end. */
+typedef int (*opkb_fg_callback)(void* user, int64_t n, const void* x_dev, void* g_dev, void* stream,
+                                double* f);
+int  opkb_solver_set_fg_callback(opkb_solver* solver, opkb_fg_callback fn, void* user, int f_is_partial);
 int  opkb_solver_status(const opkb_solver* solver, int64_t* iter, int64_t* eval, int64_t* rejects,
                         double* f, double* gnorm, double* stp, int* stage, int* new_x);
 const char* opkb_solver_reason(const opkb_solver* solver);

@@ -446,6 +446,16 @@ function vmlmb!(fg!, x::DeviceVector{T};
     if lower isa BoundedSet
         lower, upper = lower.lower, lower.upper
     end
+    if T === Float32 || min(mem, nglobal) > MEM_MAX_GRAM
+        # The host loop below solves the two-loop recursion in coefficient space from one Gram
+        # sweep: Float64 and at most 20 pairs.  Float32 data (whose parity-grade form keeps the
+        # roundings of the intermediate vector) and larger memories (the reference accepts any
+        # `mem`, src/quasinewton.jl:227, :328) run the step-by-step recursion of the native driver.
+        return vmlmb_native!(fg!, x; mem=mem, lower=lower, upper=upper, blmvm=blmvm, fmin=fmin,
+                             maxiter=maxiter, maxeval=maxeval, xtol=xtol, ftol=ftol, gtol=gtol,
+                             epsilon=epsilon, verb=verb, printer=printer, output=output, lnsrch=lnsrch,
+                             nglobal=nglobal)
+    end
     ctx = x.ctx
     lo = to_device(ctx, lower, T); hi = to_device(ctx, upper, T)
     bounds = 0
@@ -630,13 +640,83 @@ struct NativeOptions          # opkb_vmlmb_options of include/opkb200.h (same la
 end
 
 const TASK_COMPUTE_FG = Cint(1)
+const MEM_MAX_GRAM = 20       # pairs the Gram-form kernels hold (OPKB_MEM_MAX); beyond: sequential two-loop
 
+# options of the reference's line-search objects -> opkb_vmlmb_options (OPKB_LS_*)
+function native_linesearch(ls)
+    ls === nothing && return (Cint(0), 1e-3, 0.9, 0.1, 0.1, 0.5, Cint(0))
+    if ls isa MoreThuenteLineSearch
+        return (Cint(3), Float(ls.ftol), Float(ls.gtol), Float(ls.xtol), 0.1, 0.5, Cint(0))
+    elseif ls isa MoreToraldoLineSearch
+        return (Cint(2), Float(ls.ftol), 0.9, 0.1, Float(ls.gamma1), Float(ls.gamma2), Cint(ls.strict))
+    elseif ls isa ArmijoLineSearch
+        return (Cint(1), Float(ls.ftol), 0.9, 0.1, 0.1, 0.5, Cint(0))
+    end
+    throw(ArgumentError("the native driver knows the three line searches of the reference"))
+end
+
+# Device-callback objective (opkb_solver_set_fg_callback): the reverse-communication loop runs
+# inside the library and calls back into Julia; style of src/cobyla.jl:184-193 (`@cfunction` +
+# `unsafe_pointer_to_objref`).  The raw pointers are those of the workspace vectors `x`, `g`
+# (whose HANDLES are stable while their data pointers move): `fg!` is called on the handles.
+mutable struct CallbackState{F,V}
+    fg::F
+    x::V
+    g::V
+    err::Any
+end
+
+function fg_trampoline(user::Ptr{Cvoid}, n::Int64, xp::Ptr{Cvoid}, gp::Ptr{Cvoid}, stream::Ptr{Cvoid},
+                       fout::Ptr{Cdouble})::Cint
+    st = unsafe_pointer_to_objref(user)
+    try
+        unsafe_store!(fout, Float(st.fg(st.x, st.g)))
+        return Cint(0)
+    catch err
+        st.err = err
+        return Cint(1)
+    end
+end
+
+function solver_status(solver)
+    iter = Ref{Int64}(0); eval = Ref{Int64}(0); rej = Ref{Int64}(0)
+    f = Ref{Cdouble}(0); gnorm = Ref{Cdouble}(0); stp = Ref{Cdouble}(0)
+    stage = Ref{Cint}(0); newx = Ref{Cint}(0)
+    check(ccall((:opkb_solver_status, libopkb200), Cint,
+                (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Cdouble}, Ref{Cdouble}, Ref{Cdouble},
+                 Ref{Cint}, Ref{Cint}), solver, iter, eval, rej, f, gnorm, stp, stage, newx))
+    return (iter[], eval[], rej[], f[], gnorm[], stp[], stage[], newx[] != 0)
+end
+
+"""
+    vmlmb_native!(fg!, x; kwds...) -> x
+
+`vmlmb!` with the driver loop inside libopkb200 (`opkb_solver_*`): the keywords of
+`vmlmb!` (src/quasinewton.jl:227-242) plus
+
+* `twoloop = :default | :gram | :sequential` -- coefficient-space two-loop from one Gram
+  sweep (Float64 default, `mem ≤ 20`) or the reference's step-by-step recursion
+  (parity-grade; default for Float32 data and for `mem > 20`);
+* `callback = true` -- a user `fg!` is installed as a device callback
+  (`opkb_solver_set_fg_callback`): one `ccall` for the whole run.
+
+`printer` is called at every iteration boundary when `verb > 0` (the run then
+advances one iteration per `ccall`).
+"""
 function vmlmb_native!(fg!, x::DeviceVector{T}; mem::Integer = min(5, length(x)),
                        lower = -Inf, upper = +Inf, blmvm::Bool = false, fmin::Real = -Inf,
                        maxiter::Integer = typemax(Int), maxeval::Integer = typemax(Int),
                        xtol::NTuple{2,Real} = (0.0, 1e-7), ftol::NTuple{2,Real} = (0.0, 1e-8),
                        gtol::NTuple{2,Real} = (0.0, 1e-6), epsilon::Real = 0.0,
+                       verb::Integer = false,
+                       printer::Function = OptimPackNextGen.QuasiNewton.print_iteration,
+                       output::IO = stdout,
+                       lnsrch::Union{LineSearch{Float},Nothing} = nothing,
+                       twoloop::Symbol = :default, callback::Bool = false,
                        nglobal::Integer = length(x)) where {T}
+    if lower isa BoundedSet
+        lower, upper = lower.lower, lower.upper
+    end
     ctx = x.ctx
     lo = to_device(ctx, lower, T); hi = to_device(ctx, upper, T)
     bounded = (lo isa DeviceVector || lo > -Inf) || (hi isa DeviceVector || hi < +Inf)
@@ -648,24 +728,57 @@ function vmlmb_native!(fg!, x::DeviceVector{T}; mem::Integer = min(5, length(x))
                 ws.ptr, kind, pa, pc))
     xw = wsvector(ws, 'x'); gw = wsvector(ws, 'g')
     vcopy!(xw, x)
+    lscode, lsftol, lsgtol, lsxtol, lsg1, lsg2, lsstrict = native_linesearch(lnsrch)
+    tl = twoloop === :default ? Cint(-1) : twoloop === :gram ? Cint(0) : twoloop === :sequential ? Cint(1) :
+         throw(ArgumentError("twoloop must be :default, :gram or :sequential"))
     opt = Ref(NativeOptions(blmvm, fmin, maxiter, maxeval, xtol[1], xtol[2], ftol[1], ftol[2],
-                            gtol[1], gtol[2], epsilon, 0, 1e-3, 0.9, 0.1, 0.1, 0.5, 0, -1, 1))
+                            gtol[1], gtol[2], epsilon, lscode, lsftol, lsgtol, lsxtol, lsg1, lsg2, lsstrict,
+                            tl, 1))
     sref = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:opkb_solver_create, libopkb200), Cint, (Ptr{Cvoid}, Ref{NativeOptions}, Ref{Ptr{Cvoid}}),
                 ws.ptr, opt, sref))
     solver = sref[]
     task = Ref{Cint}(0)
+    report() = begin
+        iter, eval, rej, f, gnorm, stp, stage, newx = solver_status(solver)
+        (newx && verb > 0 && iter % verb == 0) && printer(output, iter, eval, rej, f, gnorm, stp)
+        stage
+    end
+    state = CallbackState(fg!, xw, gw, nothing)
     try
-        if kind != 0      # built-in objective: the whole run in one call
-            check(ccall((:opkb_solver_run, libopkb200), Cint, (Ptr{Cvoid}, Int64, Ref{Cint}),
-                        solver, typemax(Int64), task))
-        else              # reverse communication
+        if kind != 0 || callback
+            if kind == 0      # user objective as a device callback: the loop stays inside the library
+                cfg = @cfunction(fg_trampoline, Cint,
+                                 (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cdouble}))
+                check(ccall((:opkb_solver_set_fg_callback, libopkb200), Cint,
+                            (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint), solver, cfg,
+                            pointer_from_objref(state), Cint(0)))
+            end
+            GC.@preserve state begin
+                step = verb > 0 ? Int64(1) : typemax(Int64) ÷ 2
+                while true    # the whole run in one call, or one iteration per call when printing
+                    rc = ccall((:opkb_solver_run, libopkb200), Cint, (Ptr{Cvoid}, Int64, Ref{Cint}),
+                               solver, step, task)
+                    state.err === nothing || throw(state.err)
+                    check(rc)
+                    report()
+                    task[] == TASK_COMPUTE_FG || break
+                end
+            end
+        else                  # reverse communication, one ccall per evaluation
             check(ccall((:opkb_solver_start, libopkb200), Cint, (Ptr{Cvoid}, Ref{Cint}), solver, task))
             while task[] == TASK_COMPUTE_FG
                 fx = Float(fg!(xw, gw))
                 check(ccall((:opkb_solver_iterate, libopkb200), Cint, (Ptr{Cvoid}, Cdouble, Ref{Cint}),
                             solver, fx, task))
+                report()
             end
+        end
+        if verb > 0
+            stage = solver_status(solver)[7]
+            reason = unsafe_string(ccall((:opkb_solver_reason, libopkb200), Cstring, (Ptr{Cvoid},), solver))
+            printstyled(output, "# ", (stage > 3 ? "WARNING: " : "CONVERGENCE: "), reason, "\n";
+                        color = (stage > 3 ? :red : :green))
         end
         vcopy!(x, xw)
     finally

@@ -15,7 +15,7 @@ from .linesearches import (LineSearch, ArmijoLineSearch, MoreToraldoLineSearch,
                            MoreThuenteLineSearch, cstep, start_, iterate_, getstep, gettask,
                            getstatus, usederivatives)
 from .linesearches import getreason as _ls_getreason
-from .objectives import Rosenbrock, Quadratic, Smooth2D, splitmix64, uniform
+from .objectives import Rosenbrock, Quadratic, Smooth2D, DeviceObjective, splitmix64, uniform
 from .vmlmb import (VMLMB, NativeVMLMB, vmlmb, vmlmb_, BoundedSet, EMULATE_BLMVM, apply_lbfgs_,
                     apply_lbfgs_masked_, sufficient_descent, print_iteration, verbose)
 from .spg import SPG, NativeSPG, spg, spg_, Info, BoxProjection, default_printer

@@ -15,7 +15,9 @@ FLOAT, DOUBLE = 0, 1
 METHOD_LBFGS, METHOD_BLMVM, METHOD_VMLMB = 0, 1, 2
 OBJ_USER, OBJ_ROSENBROCK, OBJ_QUADRATIC = 0, 1, 2
 FORWARD, BACKWARD = 1, -1
-MEM_MAX = 20
+MEM_MAX = 20        # pairs of the Gram-form kernels
+SLOTS_MAX = 256     # pairs a workspace can store (sequential two-loop beyond MEM_MAX)
+FG_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double))
 
 i64 = C.c_int64
 f64 = C.c_double
@@ -52,6 +54,10 @@ _SIGNATURES = {
     "opkb_context_synchronize": (C.c_int, [vp]),
     "opkb_context_device": (C.c_int, [vp]),
     "opkb_context_sm_count": (C.c_int, [vp]),
+    "opkb_context_stream": (vp, [vp]),
+    "opkb_context_wait_stream": (C.c_int, [vp, vp]),
+    "opkb_context_trim": (C.c_int, [vp]),
+    "opkb_context_cached_bytes": (i64, [vp]),
     "opkb_context_launch_count": (i64, [vp]),
     "opkb_timer_start": (C.c_int, [vp]),
     "opkb_timer_stop": (C.c_int, [vp, Pd]),
@@ -125,6 +131,7 @@ _SIGNATURES = {
     "opkb_solver_start": (C.c_int, [vp, Pi]),
     "opkb_solver_iterate": (C.c_int, [vp, f64, Pi]),
     "opkb_solver_run": (C.c_int, [vp, i64, Pi]),
+    "opkb_solver_set_fg_callback": (C.c_int, [vp, vp, vp, C.c_int]),
     "opkb_solver_status": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), Pd, Pd, Pd,
                                      Pi, Pi]),
     "opkb_solver_reason": (C.c_char_p, [vp]),

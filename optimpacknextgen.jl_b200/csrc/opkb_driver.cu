@@ -228,7 +228,11 @@ struct opkb_solver_ {
     // fused-phase cache
     double r[8], limits[2], spec[8];
     int saved_for, need_steepest, spec_valid, spec_mark;
-    double rho[OPKB_MEM_MAX], alpha[OPKB_MEM_MAX];
+    double rho[OPKB_SLOTS_MAX], alpha[OPKB_SLOTS_MAX];
+    // device-callback objective (opkb_solver_set_fg_callback)
+    opkb_fg_callback fg;
+    void* fg_user;
+    int fg_partial;
 };
 
 extern "C" void opkb_vmlmb_default_options(opkb_vmlmb_options* o)
@@ -252,6 +256,7 @@ extern "C" void opkb_vmlmb_default_options(opkb_vmlmb_options* o)
 
 // accessors of the workspace needed here (opkb_vmlmb.cu)
 int opkb_vmlmb_info(const opkb_vmlmb* ws, int* mem, int* method, int* eltype, int* obj);
+int opkb_vmlmb_trial_end_mode(opkb_vmlmb* ws, int mark, double f, int initial, int f_mode, double out[8]);
 
 extern "C" int opkb_solver_create(opkb_vmlmb* ws, const opkb_vmlmb_options* opt, opkb_solver** out)
 {
@@ -272,6 +277,12 @@ extern "C" int opkb_solver_create(opkb_vmlmb* ws, const opkb_vmlmb_options* opt,
     opkb_vmlmb_info(ws, &s->mem, &s->method, &s->eltype, &obj);
     s->builtin = (obj != OPKB_OBJ_USER);
     s->twoloop = (o.twoloop < 0) ? (s->eltype == OPKB_DOUBLE ? 0 : 1) : (o.twoloop ? 1 : 0);
+    // the reference accepts any `mem` (src/quasinewton.jl:227, :328); the Gram-form kernels hold
+    // OPKB_MEM_MAX pairs, beyond that the step-by-step recursion (no such limit) runs
+    if (s->mem > OPKB_MEM_MAX) {
+        if (o.twoloop == 0) { free(s); return opkb_set_error(OPKB_EINVAL, "twoloop = Gram needs mem <= %d", OPKB_MEM_MAX); }
+        s->twoloop = 1;
+    }
     int kind = o.lnsrch;                                        // :276-284
     if (kind == 0) kind = (s->method == 0 ? LS_MORE_THUENTE : LS_MORE_TORALDO);
     if (kind < 1 || kind > 3) { free(s); return opkb_set_error(OPKB_EINVAL, "invalid line search"); }
@@ -602,12 +613,12 @@ extern "C" int opkb_solver_start(opkb_solver* s, int* task)
 }
 
 // The caller has written g (workspace vector 'g') and passes f = f(x).
-extern "C" int opkb_solver_iterate(opkb_solver* s, double f, int* task)
+static int solver_iterate(opkb_solver* s, double f, int f_mode, int* task)
 {
     if (!s || !task) return opkb_set_error(OPKB_EINVAL, "NULL argument");
     if (s->finished) { *task = task_of(s); return 0; }
     if (!s->awaiting_f) return opkb_set_error(OPKB_EINVAL, "call opkb_solver_start first");
-    int rc = opkb_vmlmb_trial_end(s->ws, s->mark, f, s->eval == 0, s->r);
+    int rc = opkb_vmlmb_trial_end_mode(s->ws, s->mark, f, s->eval == 0, f_mode, s->r);
     if (rc) return rc;
     s->awaiting_f = 0;
     rc = after_evaluation(s);
@@ -621,12 +632,57 @@ extern "C" int opkb_solver_iterate(opkb_solver* s, double f, int* task)
     return 0;
 }
 
-// Built-in objective: run until `iter` has advanced by niter (or termination).
+extern "C" int opkb_solver_iterate(opkb_solver* s, double f, int* task)
+{
+    return solver_iterate(s, f, 1, task);
+}
+
+extern "C" int opkb_solver_set_fg_callback(opkb_solver* s, opkb_fg_callback fn, void* user, int f_is_partial)
+{
+    if (!s) return opkb_set_error(OPKB_EINVAL, "NULL solver");
+    if (s->builtin) return opkb_set_error(OPKB_EINVAL, "the workspace has a built-in objective");
+    s->fg = fn;
+    s->fg_user = user;
+    s->fg_partial = f_is_partial ? 1 : 0;
+    return 0;
+}
+
+// user objective through the device callback: the whole reverse-communication loop in here
+static int solver_run_callback(opkb_solver* s, int64_t target, int* task)
+{
+    int rc = 0;
+    if (s->eval == 0 && !s->awaiting_f) {
+        rc = opkb_solver_start(s, task);
+        if (rc) return rc;
+    }
+    opkb_context* ctx = opkb_vmlmb_vector(s->ws, 'x', 0)->ctx;
+    while (!s->finished && s->iter < target) {
+        // the data pointers move between calls (buffers are traded, not copied): asked for every time
+        opkb_vector* x = opkb_vmlmb_vector(s->ws, 'x', 0);
+        opkb_vector* g = opkb_vmlmb_vector(s->ws, 'g', 0);
+        double f = 0.0;
+        if (s->fg(s->fg_user, x->n, x->data, g->data, (void*)ctx->stream, &f) != 0) {
+            *task = OPKB_TASK_ERROR;
+            return opkb_set_error(OPKB_EINVAL, "the objective callback failed");
+        }
+        rc = solver_iterate(s, f, s->fg_partial ? 2 : 1, task);
+        if (rc) return rc;
+    }
+    *task = task_of(s);
+    return 0;
+}
+
+// Built-in objective (or device callback): run until `iter` has advanced by niter (or termination).
 extern "C" int opkb_solver_run(opkb_solver* s, int64_t niter, int* task)
 {
     if (!s || !task) return opkb_set_error(OPKB_EINVAL, "NULL argument");
-    if (!s->builtin) return opkb_set_error(OPKB_EINVAL, "opkb_solver_run needs a built-in objective");
     const int64_t target = (niter > INT64_MAX - s->iter) ? INT64_MAX : s->iter + niter;
+    if (!s->builtin) {
+        if (!s->fg)
+            return opkb_set_error(OPKB_EINVAL, "opkb_solver_run needs a built-in objective or a device callback "
+                                  "(opkb_solver_set_fg_callback)");
+        return solver_run_callback(s, target, task);
+    }
     while (!s->finished && s->iter < target) {
         int rc = 0;
         if (s->spec_valid && s->eval > 0 && s->spec_mark == s->mark && s->stp == 1.0) {

@@ -14,7 +14,8 @@
 #define OPKB_BLOCK 256          // threads per CTA of the streaming kernels
 #define OPKB_MAX_GRID 2048      // upper bound of any grid (partials buffer)
 #define OPKB_NRED_MAX 1024      // scalars one launch may reduce
-#define OPKB_MEM_MAX 20         // pairs the fused Gram path supports
+#define OPKB_MEM_MAX 20         // pairs the Gram-form kernels (Gram sweep, fused direction) support
+#define OPKB_SLOTS_MAX 256      // pairs a workspace can store (beyond OPKB_MEM_MAX: sequential two-loop only)
 
 // kernel classes of the per-kernel profile (opkb_profile_*)
 enum { OPKB_K_OTHER = 0, OPKB_K_TRIAL = 1, OPKB_K_GRAM = 2, OPKB_K_DIRECTION = 3, OPKB_K_SPG = 4,
@@ -67,7 +68,15 @@ struct opkb_context_ {
     // created on first use (opkb_stencil.cu)
     cudaStream_t halo_stream;
     cudaEvent_t ev_ready, ev_halo;
+    cudaEvent_t ev_user;     // opkb_context_wait_stream
+    // freed vector blocks, handed out again to requests of the same size (opkb_core.cu)
+    struct opkb_pool_block* pool;
+    int pool_n, pool_cap;
+    size_t pool_bytes;
 };
+
+int opkb_dev_alloc(opkb_context* ctx, size_t bytes, void** out);
+void opkb_dev_free(opkb_context* ctx, void* ptr, size_t bytes);
 
 void opkb_prof_begin(opkb_context* ctx, int cls);
 void opkb_prof_end(opkb_context* ctx);
@@ -281,31 +290,57 @@ struct ReduceScratch {
 // writes to rs.res)
 __device__ __forceinline__ void reduce_done(const ReduceScratch& rs)
 {
-    if (rs.flag) __threadfence_system();
+    if (rs.flag) __threadfence_system();   // every writer's results are visible system-wide ...
     __syncthreads();
     if (threadIdx.x == 0) {
         *rs.ticket = 0u;
-        if (rs.flag) *(volatile unsigned int*)rs.flag = rs.seq;
+        if (rs.flag) {
+            // ... and the flag store is ordered after them by a fence of the storing thread itself
+            // (release pattern: the barrier alone does not order thread 0's store against the other
+            // threads' fenced writes at system scope)
+            __threadfence_system();
+            *(volatile unsigned int*)rs.flag = rs.seq;
+        }
     }
 }
 
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, size) instead of once per
-// launch (a microsecond or two of driver time per iteration of the small problems)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel, size) instead of once
+// per launch (a microsecond or two of driver time per iteration of the small problems).  The
+// attribute is per device; the table is shared by the host threads of the process (one context per
+// thread and GPU in the single-process multi-GPU mode): a tiny spin lock guards it.
 static inline cudaError_t opkb_ensure_smem(const void* kern, size_t smem)
 {
-    static const void* seen_k[64];
-    static size_t seen_s[64];
+    static const void* seen_k[256];
+    static size_t seen_s[256];
+    static int seen_d[256];
     static int nseen = 0;
+    static volatile int lock = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    while (__atomic_exchange_n(&lock, 1, __ATOMIC_ACQUIRE)) { }
     for (int i = 0; i < nseen; ++i)
-        if (seen_k[i] == kern && seen_s[i] >= smem) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (seen_k[i] == kern && seen_d[i] == dev && seen_s[i] >= smem) {
+            __atomic_store_n(&lock, 0, __ATOMIC_RELEASE);
+            return cudaSuccess;
+        }
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
         int slot = -1;
-        for (int i = 0; i < nseen; ++i) if (seen_k[i] == kern) slot = i;
-        if (slot < 0 && nseen < 64) slot = nseen++;
-        if (slot >= 0) { seen_k[slot] = kern; seen_s[slot] = smem; }
+        for (int i = 0; i < nseen; ++i) if (seen_k[i] == kern && seen_d[i] == dev) slot = i;
+        if (slot < 0 && nseen < 256) slot = nseen++;
+        if (slot >= 0) { seen_k[slot] = kern; seen_s[slot] = smem; seen_d[slot] = dev; }
     }
+    __atomic_store_n(&lock, 0, __ATOMIC_RELEASE);
     return e;
+}
+
+// Every public entry point works on the device of its context, whatever device the host has made
+// current in between (e.g. `torch.cuda.device(...)`): allocations and launches bind it first.
+static inline void opkb_bind_device(const opkb_context* ctx)
+{
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != ctx->device) cudaSetDevice(ctx->device);
 }
 
 #define OPKB_MBOX_HDR 128                                              // flag | ready
@@ -321,6 +356,7 @@ static inline double* opkb_res_ptr(opkb_context* ctx)
 // the scratch of the next reducing launch (results at opkb_res_ptr(ctx) + res_offset)
 static inline ReduceScratch opkb_make_scratch(opkb_context* ctx, int res_offset = 0)
 {
+    opkb_bind_device(ctx);
     ReduceScratch rs;
     rs.part = ctx->d_part;
     rs.ticket = ctx->d_ticket;

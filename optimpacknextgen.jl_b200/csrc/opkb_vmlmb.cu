@@ -26,8 +26,8 @@ struct opkb_vmlmb_ {
     const opkb_vector* qa;
     const opkb_vector* qc;
     opkb_vector *x, *g, *p, *d;
-    opkb_vector* S[OPKB_MEM_MAX];
-    opkb_vector* Y[OPKB_MEM_MAX];
+    opkb_vector* S[OPKB_SLOTS_MAX];
+    opkb_vector* Y[OPKB_SLOTS_MAX];
     // The saves vcopy!(S[mark], x); vcopy!(Y[mark], g|p) (src/quasinewton.jl:562-563)
     // are done by aliasing: after a direction phase S[mark'] / Y[mark'] share the
     // buffers of x / g|p, and the buffers of the recycled slot become the targets
@@ -63,7 +63,20 @@ struct opkb_vmlmb_ {
     // that becomes x when the next line search starts (slot xspec_mark); a trial_begin with
     // stp = 1 for that slot is then a pointer swap.  -1: nothing speculated.
     int xspec_mark;
+    // switches read ONCE, when the workspace is created (every rank of a job sees the same
+    // environment: the decisions they drive are then identical on all ranks)
+    int opt_carry;      // OPKB_CARRY: -1 default (Float64 only), 0 off, 2 also Float32
+    int opt_lazy_p;     // OPKB_LAZY_P (default 1)
+    int opt_xspec;      // OPKB_XSPEC (default 1)
+    int opt_maskb;      // OPKB_MASKB (default 1)
+    int opt_carry_check;
 };
+
+static int env_int(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 
 static int vmlmb_ensure_p(opkb_vmlmb* ws)
 {
@@ -130,8 +143,8 @@ extern "C" int opkb_vmlmb_create(opkb_context* ctx, int eltype, int64_t n, int m
     *out = NULL;
     if (eltype != OPKB_FLOAT && eltype != OPKB_DOUBLE)
         return opkb_set_error(OPKB_EINVAL, "invalid element type");
-    if (mem < 1 || mem > OPKB_MEM_MAX)
-        return opkb_set_error(OPKB_EINVAL, "mem must be in 1..%d for the fused path", OPKB_MEM_MAX);
+    if (mem < 1 || mem > OPKB_SLOTS_MAX)
+        return opkb_set_error(OPKB_EINVAL, "mem must be in 1..%d", OPKB_SLOTS_MAX);
     if (method < 0 || method > 2) return opkb_set_error(OPKB_EINVAL, "invalid method");
     if ((lo && (lo->n != n || lo->eltype != eltype)) || (hi && (hi->n != n || hi->eltype != eltype)))
         return opkb_set_error(OPKB_EINVAL, "bounds of a different space");
@@ -149,6 +162,11 @@ extern "C" int opkb_vmlmb_create(opkb_context* ctx, int eltype, int64_t n, int m
     ws->hi_val = hi_val;
     ws->obj = OPKB_OBJ_USER;
     ws->aliased_slot = -1;
+    ws->opt_carry = env_int("OPKB_CARRY", -1);
+    ws->opt_lazy_p = env_int("OPKB_LAZY_P", 1);
+    ws->opt_xspec = env_int("OPKB_XSPEC", 1);
+    ws->opt_maskb = env_int("OPKB_MASKB", 1);
+    ws->opt_carry_check = getenv("OPKB_CARRY_CHECK") ? 1 : 0;
     int rc = 0;
     rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->x);
     rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->g);
@@ -157,6 +175,14 @@ extern "C" int opkb_vmlmb_create(opkb_context* ctx, int eltype, int64_t n, int m
     for (int k = 0; k < mem && !rc; ++k) {
         rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->S[k]);
         rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->Y[k]);
+    }
+    // the two spare buffers of the incremental Gram (the fused direction kernel writes the pair
+    // the speculated trial point would form): allocated HERE, not lazily at the first launch that
+    // wants them, so that whether a rank carries never depends on a rank-local allocation
+    if (!rc && method != 1 && mem <= 12 && ws->opt_carry != 0 &&
+        (eltype == OPKB_DOUBLE || ws->opt_carry == 2)) {
+        rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->carry_s);
+        rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->carry_y);
     }
     if (rc) {
         opkb_vmlmb_destroy(ws);
@@ -177,7 +203,7 @@ extern "C" int opkb_vmlmb_destroy(opkb_vmlmb* ws)
     opkb_vector_destroy(ws->d);
     opkb_vector_destroy(ws->carry_s);
     opkb_vector_destroy(ws->carry_y);
-    for (int k = 0; k < OPKB_MEM_MAX; ++k) {
+    for (int k = 0; k < OPKB_SLOTS_MAX; ++k) {
         opkb_vector_destroy(ws->S[k]);
         opkb_vector_destroy(ws->Y[k]);
     }
@@ -248,6 +274,9 @@ template <typename T> struct TrialArgs {
     int64_t n;
     int initial;
     int bounded;
+    // STAGE 2 (user objective): this rank's share of a separable objective, published in slot 0
+    // so that the ranks' values are summed in rank order with the other partials
+    double f_partial;
 };
 
 template <typename T>
@@ -362,11 +391,12 @@ __global__ void __launch_bounds__(OPKB_BLOCK) k_trial(TrialArgs<T> A, ReduceScra
             }
         }
     }
+    if (STAGE == 2 && blockIdx.x == 0 && threadIdx.x == 0) acc[0] = A.f_partial;
     if (STAGE != 1) block_reduce_publish<8, 0u, 0u>(acc, rs);
 }
 
 template <typename T>
-static int trial_launch(opkb_vmlmb* ws, int mark, double stp, int initial, int stage)
+static int trial_launch(opkb_vmlmb* ws, int mark, double stp, int initial, int stage, double f_partial = 0.0)
 {
     opkb_context* ctx = ws->ctx;
     ws->carry_valid = 0;                 // another point than the speculated one
@@ -393,6 +423,7 @@ static int trial_launch(opkb_vmlmb* ws, int mark, double stp, int initial, int s
     A.n = ws->n;
     A.initial = initial;
     A.bounded = ws->method > 0;
+    A.f_partial = f_partial;
     int grid = opkb_grid_for(ctx, ws->n / VecOf<T>::N, 4);
     ReduceScratch rs = scratch(ctx);
     if (stage == 1)
@@ -411,7 +442,8 @@ static int trial_collect(opkb_vmlmb* ws, double f_user, int user, double out[8])
     double r[8];
     int rc = opkb_finish_reduction(ws->ctx, 8, NULL, r);
     if (rc) return rc;
-    double f = user ? f_user
+    // user: 1 = f_user is the global value; 2 = the ranks' shares were summed in slot 0
+    double f = user ? (user == 2 ? r[0] : f_user)
                     : (ws->obj == OPKB_OBJ_ROSENBROCK ? r[0] + r[1] : 0.5 * r[0]);
     out[0] = f;
     out[1] = r[2];
@@ -447,19 +479,31 @@ extern "C" int opkb_vmlmb_trial_begin(opkb_vmlmb* ws, int mark, double stp, int 
 {
     int rc = check_mark(ws, mark);
     if (rc) return rc;
-    if (initial && ws->method == 0) return 0;  // x unchanged
-    return (ws->eltype == OPKB_DOUBLE) ? trial_launch<double>(ws, mark, stp, initial, 1)
-                                       : trial_launch<float>(ws, mark, stp, initial, 1);
+    if (!(initial && ws->method == 0)) {   // (x unchanged otherwise)
+        rc = (ws->eltype == OPKB_DOUBLE) ? trial_launch<double>(ws, mark, stp, initial, 1)
+                                         : trial_launch<float>(ws, mark, stp, initial, 1);
+        if (rc) return rc;
+    }
+    // A user objective may run on a stream of its own (CUDA.jl, torch, ...): x is complete in
+    // device memory when this call returns (include/opkb200.h, "raw device pointers").
+    if (ws->obj == OPKB_OBJ_USER) OPKB_CUDA(cudaStreamSynchronize(ws->ctx->stream));
+    return 0;
+}
+
+// f_mode 1: `f` is the global value; 2: this rank's share of a separable objective
+int opkb_vmlmb_trial_end_mode(opkb_vmlmb* ws, int mark, double f, int initial, int f_mode, double out[8])
+{
+    int rc = check_mark(ws, mark);
+    if (rc) return rc;
+    rc = (ws->eltype == OPKB_DOUBLE) ? trial_launch<double>(ws, mark, 0.0, initial, 2, f)
+                                     : trial_launch<float>(ws, mark, 0.0, initial, 2, f);
+    if (rc) return rc;
+    return trial_collect(ws, f, f_mode, out);
 }
 
 extern "C" int opkb_vmlmb_trial_end(opkb_vmlmb* ws, int mark, double f, int initial, double out[8])
 {
-    int rc = check_mark(ws, mark);
-    if (rc) return rc;
-    rc = (ws->eltype == OPKB_DOUBLE) ? trial_launch<double>(ws, mark, 0.0, initial, 2)
-                                     : trial_launch<float>(ws, mark, 0.0, initial, 2);
-    if (rc) return rc;
-    return trial_collect(ws, f, 1, out);
+    return opkb_vmlmb_trial_end_mode(ws, mark, f, initial, 1, out);
 }
 
 // ---------------------------------------------------------------------------
@@ -519,6 +563,9 @@ extern "C" int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots
     int rc = check_mark(ws, mark);
     if (rc) return rc;
     if (m < 1 || m > ws->mem || !slots || !G) return opkb_set_error(OPKB_EINVAL, "invalid m/slots/G");
+    if (m > OPKB_MEM_MAX)
+        return opkb_set_error(OPKB_EINVAL, "the Gram-form two-loop supports m <= %d pairs: use the sequential "
+                              "form (opkb_vmlmb_twoloop_step) beyond", OPKB_MEM_MAX);
     if (slots[m - 1] != mark)
         return opkb_set_error(OPKB_EINVAL, "the newest pair (slots[m-1]) must be `mark`");
     for (int j = 0; j < m; ++j)
@@ -534,7 +581,7 @@ extern "C" int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots
             rc = gram_from_carry(ws, mark, m, slots, G);
             if (rc) return rc;
             carried = true;
-            if (getenv("OPKB_CARRY_CHECK") && vmlmb_ensure_p(ws) == 0) {
+            if (ws->opt_carry_check && vmlmb_ensure_p(ws) == 0) {
                 // development aid: the same block by a sweep over the same state (the
                 // pair is already formed: x = g = 0 makes the in-place update the identity)
                 opkb_vector* z = NULL;
@@ -847,8 +894,7 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         int carry = 0;
         // user objective (VMLMB / L-BFGS): the trial point of the step the driver takes after a
         // successful update, stp = 1, is formed in the same pass (one more write, no more reads)
-        static const int xspec_on = getenv("OPKB_XSPEC") ? atoi(getenv("OPKB_XSPEC")) : 1;
-        if (!fuse && xspec_on && ws->obj == OPKB_OBJ_USER && ws->method != 1 &&
+        if (!fuse && ws->opt_xspec && ws->obj == OPKB_OBJ_USER && ws->method != 1 &&
             ws->aliased_slot != mark_next) {
             B.xout = (T*)ws->S[mark_next]->data;
             xspec = 1;
@@ -859,8 +905,7 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
             B.gout = (T*)ws->Y[mark_next]->data;
             B.pout = ws->p ? (T*)ws->p->data : NULL;
             // VMLMB: p' is not written (see p_stale); OPKB_LAZY_P=0 restores the write
-            static const int lazy_p = getenv("OPKB_LAZY_P") ? atoi(getenv("OPKB_LAZY_P")) : 1;
-            if (lazy_p && ws->method == 2) {
+            if (ws->opt_lazy_p && ws->method == 2) {
                 B.pout = NULL;
                 ran_lazy_p = 1;
             }
@@ -870,18 +915,9 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
             if (carry && A.m == ws->mem && slots[0] != mark_next) carry = 0;
             if (carry && A.m < ws->mem)
                 for (int j = 0; j < A.m; ++j) if (slots[j] == mark_next) carry = 0;
-            // Float32: the carry instances are issue-bound: opt-in
-            int carry_env = -1;
-            if (const char* e = getenv("OPKB_CARRY")) carry_env = atoi(e);
-            if (carry_env == 0 || (sizeof(T) == 4 && carry_env != 2)) carry = 0;
-            if (carry && !ws->carry_s) {
-                if (opkb_vector_create(ctx, ws->eltype, ws->n, &ws->carry_s) != 0 ||
-                    opkb_vector_create(ctx, ws->eltype, ws->n, &ws->carry_y) != 0) {
-                    opkb_vector_destroy(ws->carry_s);   // not enough memory: plain fused launch
-                    ws->carry_s = ws->carry_y = NULL;
-                    carry = 0;
-                }
-            }
+            // the spare buffers exist iff the workspace was created for it (Float64, or Float32
+            // with OPKB_CARRY=2: those instances are issue-bound): same on every rank
+            if (!ws->carry_s || !ws->carry_y) carry = 0;
             if (carry) {
                 B.sout = (T*)ws->carry_s->data;
                 B.yout = (T*)ws->carry_y->data;
@@ -930,7 +966,9 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         if (const char* e = getenv("OPKB_DIR_NSTAGE")) nstage = atoi(e);
         if (nstage > DIR2_MAXSTAGE) nstage = DIR2_MAXSTAGE;
         const int64_t ntiles = (ws->n + tile - 1) / tile;
-        if (nstage >= 2 && ntiles >= 1) {
+        // (an EMPTY shard still runs the ring kernel -- one CTA, no tile: neutral partials -- so
+        // that every rank of a job reduces the same slots and takes the same carry decision)
+        if (nstage >= 2) {
             B.tile = tile;
             B.nstage = nstage;
             B.n = ws->n;
@@ -943,6 +981,7 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
             const int ncorr = carry ? 32 * ((mb * (mb + 1) + 31) / 32) : 0;
             int64_t grid = ctx->sm_count;
             if (grid > ntiles) grid = ntiles;
+            if (grid < 1) grid = 1;
             int rc = carry ? dir2_launch_carry<T>(ctx, B, fuse, mb, smem, (int)grid)
                            : dir2_launch_plain<T>(ctx, B, fuse, mb, smem, (int)grid);
             if (rc) return rc;
@@ -1050,8 +1089,8 @@ extern "C" int opkb_vmlmb_direction(opkb_vmlmb* ws, int m, const int* slots, con
 {
     int rc = check_mark(ws, mark_next);
     if (rc) return rc;
-    if (m < 1 || m > ws->mem || !slots || !alpha || !c || !out)
-        return opkb_set_error(OPKB_EINVAL, "invalid argument");
+    if (m < 1 || m > ws->mem || m > OPKB_MEM_MAX || !slots || !alpha || !c || !out)
+        return opkb_set_error(OPKB_EINVAL, "invalid argument (the Gram-form direction supports m <= 20)");
     for (int j = 0; j < m; ++j)
         if (slots[j] < 0 || slots[j] >= ws->mem) return opkb_set_error(OPKB_EINVAL, "slot out of range");
     return (ws->eltype == OPKB_DOUBLE)
@@ -1065,8 +1104,8 @@ extern "C" int opkb_vmlmb_direction_trial(opkb_vmlmb* ws, int m, const int* slot
 {
     int rc = check_mark(ws, mark_next);
     if (rc) return rc;
-    if (m < 1 || m > ws->mem || !slots || !alpha || !c || !out || !trial)
-        return opkb_set_error(OPKB_EINVAL, "invalid argument");
+    if (m < 1 || m > ws->mem || m > OPKB_MEM_MAX || !slots || !alpha || !c || !out || !trial)
+        return opkb_set_error(OPKB_EINVAL, "invalid argument (the Gram-form direction supports m <= 20)");
     for (int j = 0; j < m; ++j)
         if (slots[j] < 0 || slots[j] >= ws->mem) return opkb_set_error(OPKB_EINVAL, "slot out of range");
     return (ws->eltype == OPKB_DOUBLE)
@@ -1242,8 +1281,7 @@ static int step_run(opkb_vmlmb* ws, int first, const opkb_vector* u, double a, i
     A.z3 = z3 ? (const T*)z3->data : NULL;
     A.w = (ws->method == 2) ? (const T*)ws->p->data : NULL;
     if (A.w) {
-        static const int use_maskb = getenv("OPKB_MASKB") ? atoi(getenv("OPKB_MASKB")) : 1;   // 0: A/B switch
-        if (!use_maskb) ws->maskb_failed = 1;
+        if (!ws->opt_maskb) ws->maskb_failed = 1;   // OPKB_MASKB=0: A/B switch
         if (!ws->maskb && !ws->maskb_failed) {
             if (cudaMalloc(&ws->maskb, (size_t)(ws->n / VecOf<T>::N) + 16) != cudaSuccess) {
                 cudaGetLastError();

@@ -32,8 +32,13 @@ def splitmix64(seed: int, idx) -> np.ndarray:
 
 def uniform(seed: int, first: int, n: int) -> np.ndarray:
     """u(seed, i) in [0, 1) for i = first .. first+n-1 (53-bit, Float64)."""
-    z = splitmix64(seed, np.arange(first, first + n, dtype=np.uint64))
-    return (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    out = np.empty(n, dtype=np.float64)
+    step = 1 << 22      # in chunks: the temporaries of a 2^28 vector would be several times its size
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        z = splitmix64(seed, np.arange(first + lo, first + hi, dtype=np.uint64))
+        out[lo:hi] = (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return out
 
 
 class Rosenbrock:
@@ -81,9 +86,13 @@ class Quadratic:
     def synthetic(n: int, dtype=np.float64, kappa: float = 1e4, first: int = 0, seed_a: int = 3,
                   seed_c: int = 5):
         """a_i = kappa^u(3,i), c_i = -1 + 3 u(5,i) (host arrays)."""
-        a = kappa ** uniform(seed_a, first, n)
-        c = -1.0 + 3.0 * uniform(seed_c, first, n)
-        return a.astype(dtype), c.astype(dtype)
+        a = uniform(seed_a, first, n)
+        c = uniform(seed_c, first, n)
+        step = 1 << 22
+        for lo in range(0, n, step):   # in place, chunk by chunk (same values as the array expressions)
+            a[lo:lo + step] = kappa ** a[lo:lo + step]
+            c[lo:lo + step] = -1.0 + 3.0 * c[lo:lo + step]
+        return a.astype(dtype, copy=False), c.astype(dtype, copy=False)
 
     @classmethod
     def synthetic_device(cls, ctx: Context, n: int, dtype=np.float64, kappa: float = 1e4,
@@ -169,6 +178,42 @@ class Smooth2D:
         y = 0.6 + 0.4 * np.sin(i / 37.0) * np.cos(j / 53.0) + 0.4 * (u - 0.5)
         w = 0.5 + v
         return w.astype(dtype).reshape(-1), y.astype(dtype).reshape(-1)
+
+
+class DeviceObjective:
+    """A user objective as a DEVICE CALLBACK for the native driver (`NativeVMLMB`,
+    `opkb_solver_set_fg_callback`): `fn(n, x_ptr, g_ptr, stream) -> f` receives raw device
+    pointers (integers) to this rank's x and g and the context's cudaStream_t; it must write the
+    gradient with kernels submitted to that stream (or completed before it returns) and return
+    f(x).  The whole reverse-communication loop then runs inside the library.  `partial=True`:
+    the returned value is this rank's share of a separable objective (summed over the ranks by the
+    library).  `fn` may also be a C function pointer of type `_lib.FG_CALLBACK` (e.g. the address
+    of a compiled CUDA objective), with `user` passed through."""
+
+    def __init__(self, fn, partial: bool = False, user=None):
+        self.partial = bool(partial)
+        self.user = user
+        self.error = None
+        if isinstance(fn, _lib.FG_CALLBACK):
+            self._cb = fn
+        else:
+            def _trampoline(_user, n, xp, gp, stream, fout):
+                try:
+                    fout[0] = float(fn(int(n), int(xp or 0), int(gp or 0), int(stream or 0)))
+                    return 0
+                except BaseException as e:   # never unwind through the C frames
+                    self.error = e
+                    return 1
+            self._cb = _lib.FG_CALLBACK(_trampoline)
+
+    def __call__(self, x: Vector, g: Vector) -> float:
+        """Also usable as an ordinary `fg(x, g)` (Python-hosted drivers): same callback, pointers
+        asked for at every call -- they move between solver calls."""
+        import ctypes as C
+        f = C.c_double()
+        if self._cb(self.user, x.n, x.data_ptr(), g.data_ptr(), x.ctx.stream, C.byref(f)) != 0:
+            raise self.error or RuntimeError("the objective callback failed")
+        return f.value
 
 
 def is_builtin(fg) -> bool:

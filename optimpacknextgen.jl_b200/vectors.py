@@ -93,6 +93,25 @@ class Context:
         check(_lib.lib().opkb_flush_l2(self._h))
 
     @property
+    def stream(self) -> int:
+        """The cudaStream_t every kernel of this context runs on (as an integer), for callers that
+        run their own kernels on the vectors (e.g. `torch.cuda.ExternalStream(ctx.stream)`)."""
+        return _lib.lib().opkb_context_stream(self._h) or 0
+
+    def wait_stream(self, user_stream: int) -> None:
+        """Everything submitted so far to `user_stream` (a cudaStream_t as an integer) completes
+        before anything this context launches afterwards (no host synchronisation)."""
+        check(_lib.lib().opkb_context_wait_stream(self._h, vp(int(user_stream))))
+
+    def trim(self) -> None:
+        """Release the device memory of destroyed vectors that the context keeps for reuse."""
+        check(_lib.lib().opkb_context_trim(self._h))
+
+    @property
+    def cached_bytes(self) -> int:
+        return _lib.lib().opkb_context_cached_bytes(self._h)
+
+    @property
     def uses_mailbox(self) -> bool:
         """True when the reduced scalars of a phase travel through the node's shared-memory
         mailbox (written by the last CTA of every rank) rather than a packed ncclAllGather."""

@@ -570,10 +570,15 @@ class VMLMB:
         # the roundings of the intermediate vector are part of the result, and
         # the chaotic Rosenbrock trajectory amplifies a 1-ulp change beyond the
         # 1e-4 gate within 20 iterations, so "sequential" is the Float32 default.
+        # The reference accepts any `mem` (src/quasinewton.jl:227, :328): the Gram-form kernels
+        # hold MEM_MAX pairs, beyond that the step-by-step recursion (no such limit) runs.
         if twoloop is None:
-            twoloop = "gram" if self.dtype == np.float64 else "sequential"
+            twoloop = "gram" if (self.dtype == np.float64 and self.mem <= _lib.MEM_MAX) else "sequential"
         if twoloop not in ("gram", "sequential"):
             raise ValueError("twoloop must be 'gram' or 'sequential'")
+        if twoloop == "gram" and self.mem > _lib.MEM_MAX and mode == "fused":
+            raise ValueError(f"twoloop='gram' supports mem <= {_lib.MEM_MAX}; the default "
+                             "(twoloop='sequential' beyond) has no limit")
         self.twoloop = twoloop
         # With a built-in objective the fused path evaluates the first trial point
         # of the next line search (stp = 1) inside the direction kernel; the result
@@ -589,8 +594,8 @@ class VMLMB:
             return
         L = _lib.lib()
         if mode == "fused":
-            if self.mem > _lib.MEM_MAX:
-                raise ValueError(f"mode='fused' supports mem <= {_lib.MEM_MAX}; use mode='primitive'")
+            if self.mem > _lib.SLOTS_MAX:
+                raise ValueError(f"mode='fused' stores at most {_lib.SLOTS_MAX} pairs; use mode='primitive'")
             ws = vp()
             lo_h = lo.handle if isinstance(lo, Vector) else None
             hi_h = hi.handle if isinstance(hi, Vector) else None
@@ -876,6 +881,10 @@ class NativeVMLMB(VMLMB):
         self._task = C.c_int(_lib.TASK_START)
         self._g = self.ops.vector("g")
         self._builtin = is_builtin(fg)
+        from .objectives import DeviceObjective
+        self._callback = isinstance(fg, DeviceObjective)
+        if self._callback:   # the reverse-communication loop runs inside the library
+            check(L.opkb_solver_set_fg_callback(self._solver, C.cast(fg._cb, vp), fg.user, int(fg.partial)))
 
     def close(self):
         if getattr(self, "_solver", None):
@@ -904,8 +913,15 @@ class NativeVMLMB(VMLMB):
         L = _lib.lib()
         if self.finished:
             return False
-        if self._builtin:
-            check(L.opkb_solver_run(self._solver, int(min(niter, 2 ** 62)), C.byref(self._task)))
+        if self._builtin or self._callback:
+            try:
+                check(L.opkb_solver_run(self._solver, int(min(niter, 2 ** 62)), C.byref(self._task)))
+            except _lib.OpkbError as e:
+                if self._callback and self.fg.error is not None:
+                    raise self.fg.error from e
+                if "line search" in str(e):
+                    raise ValueError(str(e)) from e
+                raise
             if self._refresh() and self.observer is not None:
                 self.observer(self)
             return not self.finished

@@ -422,7 +422,9 @@ def vmlmb(obj, x0, lower=None, upper=None, *, mem=5, blmvm=False, fmin=-math.inf
           ls_xtol=0.1, ls_gamma=(0.1, 0.5), ls_strict=False, trace=False):
     """Oracle `vmlmb` (src/quasinewton.jl:215).  Returns (x, result dict,
     trace list).  Each trace entry = dict(iter, eval, rejects, f, gnorm, stp,
-    x, mask) recorded at the reference's `printer` call site (:501-503)."""
+    x, mask) recorded at the reference's `printer` call site (:501-503).
+    `trace` may also be a callable: it is then called at that site with a dict of
+    the scalars and VIEWS of x and p (no copies; valid during the call only)."""
     x = np.array(x0, copy=True)
     dtype = x.dtype
     pre, ct = _ct(dtype)
@@ -454,6 +456,12 @@ def vmlmb(obj, x0, lower=None, upper=None, *, mem=5, blmvm=False, fmin=-math.inf
     TR = C.CFUNCTYPE(None, C.c_void_p, i64, i64, i64, f64, f64, f64, i64, P, P, P)
 
     def _tr(_ctx, it, ev, rej, f, gnorm, stp, nn, xp, gp, pp):
+        if callable(trace):
+            # light trace (large problems, timing): scalars + VIEWS valid during the call only
+            trace(dict(iter=it, eval=ev, rejects=rej, f=f, gnorm=gnorm, stp=stp,
+                       x=np.ctypeslib.as_array(xp, shape=(nn,)),
+                       p=np.ctypeslib.as_array(pp, shape=(nn,)) if pp else None))
+            return
         xx = np.ctypeslib.as_array(xp, shape=(nn,)).copy()
         if pp:
             mask = np.ctypeslib.as_array(pp, shape=(nn,)) != 0
@@ -510,6 +518,11 @@ def spg(obj, x0, m, lower=None, upper=None, prj=None, *, maxit=None, maxfc=None,
 
     def _tr(_ctx, nfo, nn, xp, pgp):
         nf = nfo.contents
+        if callable(trace):   # light trace: scalars + a VIEW of x (valid during the call only)
+            trace(dict(iter=nf.iter, fcnt=nf.fcnt, pcnt=nf.pcnt, f=nf.f, fbest=nf.fbest,
+                       pgtwon=nf.pgtwon, pginfn=nf.pginfn,
+                       x=np.ctypeslib.as_array(xp, shape=(nn,))))
+            return
         records.append(dict(iter=nf.iter, fcnt=nf.fcnt, pcnt=nf.pcnt, f=nf.f,
                             fbest=nf.fbest, pgtwon=nf.pgtwon, pginfn=nf.pginfn,
                             x=np.ctypeslib.as_array(xp, shape=(nn,)).copy()))

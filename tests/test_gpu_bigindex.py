@@ -12,6 +12,8 @@ N = (1 << 31) + 7 * 448 * 5 + 6      # > 2^31, whole ring tiles + a partial tile
 
 def _free_gib():
     import torch
+    import opkb200
+    opkb200.default_context().trim()   # blocks the context keeps for reuse count as free
     free, total = torch.cuda.mem_get_info()
     return free / 2 ** 30
 

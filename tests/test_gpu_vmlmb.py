@@ -410,6 +410,8 @@ def test_large_memory_and_tiny_problems(opk, oracle, dtype, driver):
 
 def _free_gib():
     import torch
+    import opkb200
+    opkb200.default_context().trim()   # blocks the context keeps for reuse count as free
     free, total = torch.cuda.mem_get_info()
     return free / 2 ** 30
 
