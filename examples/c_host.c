@@ -12,7 +12,10 @@
  *    scheme of the reference's own C API, src/wrappers.jl:1831-1859): f = 1/2 |x - c|^2, g = x - c,
  *    evaluated by the caller with the Tier 1 operators (`vcombine!`, `vdot`) on device vectors.
  * 3. spg with the native loop (`opkb_spg_solver_*`).
- * Prints one line per solver and returns 0 when the three agree with the known solutions.
+ * 4. run 1 again from this ONE process on a GROUP of ranks (`opkb_group_*`): one context per GPU
+ *    (both ranks on device 0 when the box has a single GPU -- the code path is the same), the
+ *    vectors sharded in contiguous blocks, the native drivers of all ranks on the library's threads.
+ * Prints one line per solver and returns 0 when they agree with the known solutions.
  */
 #include <math.h>
 #include <stdio.h>
@@ -141,6 +144,69 @@ int main(int argc, char** argv)
         bad |= !(err < 1e-4) || status < 1 || !(fabs(fbest - f_vmlmb) <= 1e-5 * fabs(fbest));
         CHECK(opkb_spg_solver_destroy(sv));
         CHECK(opkb_spg_destroy(ws));
+    }
+
+    /* ---- 4. one process, a group of ranks ------------------------------------------------- */
+    {
+        enum { G = 2 };
+        int have = 0, devices[G] = {0, 0};
+        opkb_group* grp = NULL;
+        {   /* (a second GPU if there is one) */
+            opkb_group* probe = NULL;
+            if (opkb_group_create(&probe, 0, NULL) == 0) {
+                have = opkb_group_size(probe);
+                opkb_group_destroy(probe);
+            }
+            if (have >= 2) devices[1] = 1;
+        }
+        CHECK(opkb_group_create(&grp, G, devices));
+        opkb_vector *ga[G], *gc[G], *glo[G], *ghi[G];
+        opkb_vmlmb* gws[G];
+        opkb_solver* gsv[G];
+        int tasks[G];
+        const int64_t per = ((n + G - 1) / G + 3) / 4 * 4;       /* blocks of a multiple of 4 elements */
+        for (int r = 0; r < G; ++r) {
+            opkb_context* cr = opkb_group_context(grp, r);
+            const int64_t first = (r * per < n) ? r * per : n;
+            const int64_t cnt = (first + per <= n) ? per : n - first;
+            CHECK(opkb_vector_create(cr, OPKB_DOUBLE, cnt, &ga[r]));
+            CHECK(opkb_vector_create(cr, OPKB_DOUBLE, cnt, &gc[r]));
+            CHECK(opkb_vector_create(cr, OPKB_DOUBLE, cnt, &glo[r]));
+            CHECK(opkb_vector_create(cr, OPKB_DOUBLE, cnt, &ghi[r]));
+            CHECK(opkb_vector_fill_random(ga[r], 3, first, 1.0, 1e3, 1));     /* the same a, c: `first` */
+            CHECK(opkb_vector_fill_random(gc[r], 5, first, -1.0, 2.0, 0));
+            CHECK(opkb_vector_fill(glo[r], 0.0));
+            CHECK(opkb_vector_fill(ghi[r], 1.0));
+            CHECK(opkb_vmlmb_create(cr, OPKB_DOUBLE, cnt, 10, OPKB_METHOD_VMLMB, glo[r], -INFINITY, ghi[r], INFINITY,
+                                    &gws[r]));
+            CHECK(opkb_vmlmb_set_objective(gws[r], OPKB_OBJ_QUADRATIC, ga[r], gc[r]));
+            CHECK(opkb_vector_fill(opkb_vmlmb_vector(gws[r], 'x', 0), 0.5));
+            opkb_vmlmb_options opt;
+            opkb_vmlmb_default_options(&opt);
+            opt.maxiter = 500;
+            opt.frtol = 0.0;
+            opt.xrtol = 0.0;
+            CHECK(opkb_solver_create(gws[r], &opt, &gsv[r]));
+            tasks[r] = OPKB_TASK_START;
+        }
+        CHECK(opkb_group_solver_run(grp, gsv, INT64_MAX / 2, tasks));
+        int64_t iter, eval, rej;
+        double f, gnorm, stp;
+        int stage, newx;
+        CHECK(opkb_solver_status(gsv[0], &iter, &eval, &rej, &f, &gnorm, &stp, &stage, &newx));
+        printf("vmlmb  group of %d ranks    n=%lld: %lld iterations, %lld evaluations, f=%.6e (%s)\n", G,
+               (long long)n, (long long)iter, (long long)eval, f, opkb_solver_reason(gsv[0]));
+        /* same problem, same algorithm: the minimum of run 1 (the sums are combined in another order) */
+        bad |= !(fabs(f - f_vmlmb) <= 1e-9 * fabs(f_vmlmb));
+        for (int r = 0; r < G; ++r) {
+            CHECK(opkb_solver_destroy(gsv[r]));
+            CHECK(opkb_vmlmb_destroy(gws[r]));
+            opkb_vector_destroy(ga[r]);
+            opkb_vector_destroy(gc[r]);
+            opkb_vector_destroy(glo[r]);
+            opkb_vector_destroy(ghi[r]);
+        }
+        CHECK(opkb_group_destroy(grp));
     }
 
     opkb_vector_destroy(a);

@@ -91,6 +91,8 @@ typedef struct opkb_vector_  opkb_vector;
 typedef struct opkb_vmlmb_   opkb_vmlmb;
 typedef struct opkb_spg_     opkb_spg;
 typedef struct opkb_spg_solver_ opkb_spg_solver;
+typedef struct opkb_solver_  opkb_solver;
+typedef struct opkb_group_   opkb_group;
 
 const char* opkb_last_error(void);
 int         opkb_version(void);
@@ -138,6 +140,25 @@ int opkb_comm_init(opkb_context* ctx, const void* id128, int rank, int nranks);
 int opkb_comm_uses_mailbox(const opkb_context* ctx);
 int opkb_comm_rank(const opkb_context* ctx);
 int opkb_comm_size(const opkb_context* ctx);
+
+/* ONE process, several GPUs.  A group owns one context per device; they are the
+ * ranks 0..G-1 of an in-process communicator (same mailbox layout and rank-order combination as
+ * the multi-process job: bit-identical results).  The host creates this rank's shard of every
+ * vector / workspace / solver on opkb_group_context(g, r) -- none of those calls blocks -- and
+ * then runs the native solvers of all ranks concurrently, one host thread per GPU inside the
+ * library: a single-process `vmlmb(fg!, x0; lower, upper)` (src/quasinewton.jl:215, :226-242)
+ * uses the whole box.  devices == NULL: devices 0..ndev-1 (ndev <= 0: all).  opkb_group_run is
+ * the generic form: fn(rank, user) on the group's threads, for hosts that drive the ranks with
+ * Tier 1 / Tier 2 calls themselves (any call that returns reduced scalars blocks until every rank
+ * has made it).  The halo exchange of opkb_smooth2d_* needs the multi-process mode (NCCL). */
+int           opkb_group_create(opkb_group** group, int ndev, const int* devices);
+int           opkb_group_destroy(opkb_group* group);
+int           opkb_group_size(const opkb_group* group);
+opkb_context* opkb_group_context(opkb_group* group, int rank);
+int           opkb_group_solver_run(opkb_group* group, opkb_solver* const* solvers, int64_t niter, int* tasks);
+int           opkb_group_spg_solver_run(opkb_group* group, opkb_spg_solver* const* solvers, int64_t niter,
+                                        int* searching);
+int           opkb_group_run(opkb_group* group, int (*fn)(int rank, void* user), void* user);
 
 /* vcreate (doc/algebra.md:27): a vector of `n` local elements (this rank's
  * shard).  The library owns the memory; host arrays are only borrowed during
@@ -387,7 +408,6 @@ typedef struct opkb_vmlmb_options {   /* keywords of vmlmb!, src/quasinewton.jl:
     int     twoloop;                  /* -1 default (Gram for Float64, sequential for Float32), 0 Gram, 1 sequential */
     int     speculate;                /* fuse the first trial of a line search into P4 (default 1) */
 } opkb_vmlmb_options;
-typedef struct opkb_solver_ opkb_solver;
 
 void opkb_vmlmb_default_options(opkb_vmlmb_options* opt);
 /* The workspace must hold the starting point in 'x' and have its objective set. */

@@ -26,6 +26,7 @@ from .conjgrad import (ConjGrad, conjgrad, conjgrad_, DiagonalOperator, Smooth2D
                        CG_SEARCHING, CG_GTEST, CG_FTEST, CG_XTEST, CG_TOO_MANY_ITERATIONS,
                        CG_NOT_POSITIVE_DEFINITE)
 from . import dist
+from .multi import Group, MultiVMLMB
 
 
 def getreason(obj):

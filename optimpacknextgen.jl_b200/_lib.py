@@ -70,6 +70,13 @@ _SIGNATURES = {
     "opkb_comm_uses_mailbox": (C.c_int, [vp]),
     "opkb_comm_rank": (C.c_int, [vp]),
     "opkb_comm_size": (C.c_int, [vp]),
+    "opkb_group_create": (C.c_int, [C.POINTER(vp), C.c_int, Pi]),
+    "opkb_group_destroy": (C.c_int, [vp]),
+    "opkb_group_size": (C.c_int, [vp]),
+    "opkb_group_context": (vp, [vp, C.c_int]),
+    "opkb_group_solver_run": (C.c_int, [vp, C.POINTER(vp), i64, Pi]),
+    "opkb_group_spg_solver_run": (C.c_int, [vp, C.POINTER(vp), i64, Pi]),
+    "opkb_group_run": (C.c_int, [vp, vp, vp]),
     "opkb_vector_create": (C.c_int, [vp, C.c_int, i64, C.POINTER(vp)]),
     "opkb_vector_destroy": (C.c_int, [vp]),
     "opkb_vector_length": (i64, [vp]),

@@ -34,7 +34,16 @@ class Context:
 
     def __init__(self, device: int = -1):
         self._h = vp()
+        self._owner = None
         check(_lib.lib().opkb_context_create(C.byref(self._h), int(device)))
+
+    @classmethod
+    def borrowed(cls, handle, owner) -> "Context":
+        """A context that belongs to `owner` (a `Group`): never destroyed from here."""
+        self = cls.__new__(cls)
+        self._h = vp(handle)
+        self._owner = owner
+        return self
 
     @property
     def handle(self):
@@ -122,9 +131,9 @@ class Context:
         check(_lib.lib().opkb_comm_init(self._h, buf, int(rank), int(nranks)))
 
     def close(self) -> None:
-        if self._h:
+        if self._h and getattr(self, "_owner", None) is None:
             _lib.lib().opkb_context_destroy(self._h)
-            self._h = vp()
+        self._h = vp()
 
     def __del__(self):
         try:

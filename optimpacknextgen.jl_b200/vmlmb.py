@@ -972,6 +972,16 @@ def vmlmb_(fg, x, **kwds):
     driver = kwds.pop("driver", "python")
     if driver not in ("python", "native"):
         raise ValueError("driver must be 'python' or 'native'")
+    ngpus, group = kwds.pop("ngpus", None), kwds.pop("group", None)
+    if ngpus is not None or group is not None:
+        # ONE process, several GPUs: the native driver of every rank on its own host thread
+        from .multi import MultiVMLMB
+        if isinstance(x, Vector):
+            raise TypeError("ngpus= shards a HOST array over the GPUs")
+        ms = MultiVMLMB(fg, x, group=group, ngpus=ngpus or 0, **kwds)
+        x[...] = ms.solve().astype(x.dtype, copy=False)
+        ms.close()
+        return x
     solver = (NativeVMLMB if driver == "native" else VMLMB)(fg, x, **kwds)
     solver.solve()
     if isinstance(x, Vector):

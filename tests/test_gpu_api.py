@@ -110,9 +110,12 @@ def test_c_host_runs(opk, tmp_path):
     exe = _build_c_host(tmp_path)
     r = subprocess.run([exe, "200001"], capture_output=True, text=True, timeout=300)
     # every call of the ABI returned success (the program stops at the first failing status) ...
-    assert "failed (" not in r.stderr and r.stdout.count("\n") == 4, r.stdout + r.stderr
+    assert "failed (" not in r.stderr and r.stdout.count("\n") == 5, r.stdout + r.stderr
     lines = r.stdout.splitlines()
     assert lines[0].startswith("vmlmb  built-in") and lines[1].startswith("vmlmb  user") and lines[2].startswith("spg")
+    assert lines[3].startswith("vmlmb  group of 2 ranks")
+    # the group run (one process, two ranks) takes the decisions of the one-rank run
+    assert lines[3].split(":")[1].split(", f=")[0] == lines[0].split(":")[1].split(", f=")[0]
     # ... the user-objective run (f = |x - c|^2 / 2 on the box) lands on clamp(c) to rounding, and the
     # program's own sanity checks of the three solutions hold
     err_user = float(lines[1].split("|x - clamp(c)|_inf=")[1].split()[0])
@@ -120,7 +123,7 @@ def test_c_host_runs(opk, tmp_path):
     # ... and so do the example's own checks of the three solutions (exit status 0, "result: ok"):
     # the one end-to-end gate of the native C driver (opkb_solver_run, opkb_solver_iterate,
     # opkb_spg_solver_run) from a plain C host
-    assert r.returncode == 0 and "result: ok" in lines[3], r.stdout + r.stderr
+    assert r.returncode == 0 and "result: ok" in lines[4], r.stdout + r.stderr
 
 
 # ---------------------------------------------------------------------------
