@@ -211,7 +211,7 @@ class DeviceObjective:
         asked for at every call -- they move between solver calls."""
         import ctypes as C
         f = C.c_double()
-        if self._cb(self.user, x.n, x.data_ptr(), g.data_ptr(), x.ctx.stream, C.byref(f)) != 0:
+        if self._cb(self.user, x.n, x.data_ptr, g.data_ptr, x.ctx.stream, C.byref(f)) != 0:
             raise self.error or RuntimeError("the objective callback failed")
         return f.value
 

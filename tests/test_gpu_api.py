@@ -156,9 +156,9 @@ def test_user_objective_on_a_foreign_stream_with_raw_pointers(opk):
     seen_x, seen_g = set(), set()
 
     def fg_raw(x, g):
-        seen_x.add(x.data_ptr())
-        seen_g.add(g.data_ptr())
-        xt, gt = _wrap(x.data_ptr(), n), _wrap(g.data_ptr(), n)
+        seen_x.add(x.data_ptr)
+        seen_g.add(g.data_ptr)
+        xt, gt = _wrap(x.data_ptr, n), _wrap(g.data_ptr, n)
         with torch.cuda.stream(side):
             f = float(((xt - t_torch) ** 2).sum().item())        # (.item() waits for `side`)
             gt.copy_(2 * xt - 2 * t_torch)                       # ... this kernel is still in flight
@@ -248,11 +248,11 @@ def test_device_memory_is_recycled(opk):
     ctx = opk.default_context()
     ctx.trim()
     v = ctx.vector(123457)
-    p = v.data_ptr()
+    p = v.data_ptr
     v.free()
     assert ctx.cached_bytes >= 123457 * 8
     w = ctx.vector(123457)
-    assert w.data_ptr() == p and ctx.cached_bytes == 0
+    assert w.data_ptr == p and ctx.cached_bytes == 0
     w.free()
     ctx.trim()
     assert ctx.cached_bytes == 0
