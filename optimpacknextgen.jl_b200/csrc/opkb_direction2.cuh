@@ -77,11 +77,27 @@ template <int MB> struct Dir2Carry {
 // (two warps per SM sub-partition: up to 255 registers for the 4 MB + 4 accumulators)
 // or, for few pairs (MB <= 5, where the fixed per-element work makes the kernel
 // issue-bound rather than memory-bound), 11 (three per sub-partition, <= 168 registers).
-template <typename T, int FUSE, int MB, int TILE, int CARRY, int EXACT = 0, int CW = (CARRY ? 7 : 8)>
+//
+// SPLIT (with CARRY; the Float32 instances): the 4 MB dense sums that involve the STORED pairs are
+// not accumulated by the thread that owns the elements (4 MB + 4 Float64 accumulators per thread:
+// 245 registers, 8 warps per SM, issue-latency bound at half the bytes per element) but in a
+// second phase of the same tile by a warp that owns the PAIR: every thread leaves v0' and the
+// masked y' of its pack in two rows of the stage that are free by then (row 0: v0 / unused, row 2:
+// g, already in registers), the consumer warps meet at a named barrier, and warp w then sweeps
+// the items w, w + CW, ... -- item = (pair, one fifth of the tile) -- with FFMA into 4 Float32
+// partial sums (8 products each) that are added to its 4 Float64 accumulators of that item, the
+// accumulation scheme of the Float32 Gram sweep (opkb_gram2.cuh).  4 ceil(5 MB / CW) + 4
+// accumulators per thread instead of 4 MB + 4: 10 consumer warps instead of 7, no Float32 ->
+// Float64 conversion of the pair rows.  Fixed item -> warp map and fixed part order: deterministic.
+template <typename T, int FUSE, int MB, int TILE, int CARRY, int EXACT = 0, int CW = (CARRY ? 7 : 8), int SPLIT = 0>
 __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, ReduceScratch rs)
 {
     constexpr int DIR2_THREADS = (CW + 1) * 32;
     static_assert(!CARRY || (FUSE != 0 && 2 * MB <= 32), "CARRY needs the fused trial and 2*MB <= 32 rows");
+    static_assert(!SPLIT || (CARRY && TILE == CW * 32 * VecOf<T>::N && (TILE / VecOf<T>::N) % (5 * 32) == 0),
+                  "SPLIT: one pack per thread and tile, five parts of whole warps of packs");
+    constexpr int NSPLIT = 5;                                         // parts of a tile
+    constexpr int IPW = SPLIT ? (MB * NSPLIT + CW - 1) / CW : 1;      // items per consumer warp
     constexpr int VEC = VecOf<T>::N;
     constexpr int CWARPS = DIR2_THREADS / 32 - 1;
     constexpr int CTHREADS = CWARPS * 32;
@@ -122,6 +138,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
     constexpr int ND = CARRY ? CY::ND : 1;
     constexpr int CPL = CARRY ? CY::CPL : 1;
     double cd[ND];
+    double ci[4 * IPW];   // SPLIT: the 4 sums of each item of this warp
+#pragma unroll
+    for (int i = 0; i < 4 * IPW; ++i) ci[i] = 0.0;
     double cq[CPL];
     int cl[CPL];   // source lanes (= pair rows) of the two factors of entry lane + 32 t: a | b << 8
 #pragma unroll
@@ -357,20 +376,33 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                         v0d[q] = (double)v0n[q];
                         ynd[q] = (double)ynm[q];
                     }
+                    if constexpr (!SPLIT) {
 #pragma unroll
-                    for (int j = 0; j < MB; ++j) {
-                        if (EXACT || j < m) {
-                            const Pack<T> y = ld_pack<T>(pb + 2 * j * TILE, 0);
-                            const Pack<T> sv = ld_pack<T>(pb + (2 * j + 1) * TILE, 0);
+                        for (int j = 0; j < MB; ++j) {
+                            if (EXACT || j < m) {
+                                const Pack<T> y = ld_pack<T>(pb + 2 * j * TILE, 0);
+                                const Pack<T> sv = ld_pack<T>(pb + (2 * j + 1) * TILE, 0);
 #pragma unroll
-                            for (int q = 0; q < VEC; ++q) {
-                                const double sd = (double)sv.v[q], yd = (double)y.v[q];
-                                cd[4 * j + 0] = fma(sd, v0d[q], cd[4 * j + 0]);
-                                cd[4 * j + 1] = fma(yd, v0d[q], cd[4 * j + 1]);
-                                cd[4 * j + 2] = fma(sd, ynd[q], cd[4 * j + 2]);
-                                cd[4 * j + 3] = fma(yd, ynd[q], cd[4 * j + 3]);
+                                for (int q = 0; q < VEC; ++q) {
+                                    const double sd = (double)sv.v[q], yd = (double)y.v[q];
+                                    cd[4 * j + 0] = fma(sd, v0d[q], cd[4 * j + 0]);
+                                    cd[4 * j + 1] = fma(yd, v0d[q], cd[4 * j + 1]);
+                                    cd[4 * j + 2] = fma(sd, ynd[q], cd[4 * j + 2]);
+                                    cd[4 * j + 3] = fma(yd, ynd[q], cd[4 * j + 3]);
+                                }
                             }
                         }
+                    } else {
+                        // v0' and the masked y' of this pack for the second phase: rows 0 and 2 of
+                        // the stage (this thread has read its packs of them; nobody else reads them)
+                        Pack<T> pv0, pym;
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) {
+                            pv0.v[q] = v0n[q];
+                            pym.v[q] = ynm[q];
+                        }
+                        st_pack<T>(st, e / VEC, pv0);
+                        st_pack<T>(st + 2 * TILE, e / VEC, pym);
                     }
 #pragma unroll
                     for (int q = 0; q < VEC; ++q) {
@@ -445,7 +477,38 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                     }
                 }
             }
-            if (partial) fence_proxy_async();
+            if constexpr (SPLIT) {
+                named_bar_sync(2, CTHREADS);      // every pack's v0', y' are in the stage
+                constexpr int PP = TILE / VEC / NSPLIT;   // packs per part
+#pragma unroll
+                for (int t = 0; t < IPW; ++t) {
+                    const int item = warp + CWARPS * t;
+                    const int pj = item / NSPLIT, part = item - pj * NSPLIT;
+                    if (item < MB * NSPLIT && pj < m) {
+                        const T* ys = st + (prow + 2 * pj) * TILE;    // y_j, then s_j
+                        float af0 = 0.0f, af1 = 0.0f, af2 = 0.0f, af3 = 0.0f;
+#pragma unroll
+                        for (int u = 0; u < PP / 32; ++u) {
+                            const int pk = part * PP + u * 32 + lane;
+                            const Pack<T> y = ld_pack<T>(ys, pk), sv = ld_pack<T>(ys + TILE, pk);
+                            const Pack<T> w0 = ld_pack<T>(st, pk), wy = ld_pack<T>(st + 2 * TILE, pk);
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) {
+                                af0 = fmaf((float)sv.v[q], (float)w0.v[q], af0);   // s_j . v0'
+                                af1 = fmaf((float)y.v[q], (float)w0.v[q], af1);    // y_j . v0'
+                                af2 = fmaf((float)sv.v[q], (float)wy.v[q], af2);   // s_j . y'
+                                af3 = fmaf((float)y.v[q], (float)wy.v[q], af3);    // y_j . y'
+                            }
+                        }
+                        ci[4 * t + 0] += (double)af0;
+                        ci[4 * t + 1] += (double)af1;
+                        ci[4 * t + 2] += (double)af2;
+                        ci[4 * t + 3] += (double)af3;
+                    }
+                }
+            }
+            // (SPLIT: rows 0 and 2 were written through the generic proxy)
+            if (partial || SPLIT) fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
         }
@@ -462,10 +525,12 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
         constexpr int NT = NACC + ND;
         constexpr int NTOT = NT + 32 * CPL;
         constexpr int NWARPS = DIR2_THREADS / 32;
-        double* red = reinterpret_cast<double*>(smem_raw);   // [NWARPS][NTOT]
+        double* red = reinterpret_cast<double*>(smem_raw);   // [NWARPS][NTOT] (+ SPLIT: [MB * NSPLIT][4])
+        double* itm = red + NWARPS * NTOT;
         __shared__ unsigned int s_last2;
 #pragma unroll
         for (int k = 0; k < NT; ++k) {
+            if (SPLIT && k >= NACC && k < NACC + 4 * MB) continue;   // reduced per item below
             const int kind = (k == 2) ? OPKB_RMIN : ((k == 3) ? OPKB_RMAX : OPKB_RSUM);
             double a = (k < NACC) ? acc[k < NACC ? k : 0] : cd[k >= NACC ? k - NACC : 0];
 #pragma unroll
@@ -475,13 +540,35 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
             }
             if (lane == 0) red[warp * NTOT + k] = a;
         }
+        if constexpr (SPLIT) {
+#pragma unroll
+            for (int t = 0; t < IPW; ++t) {
+                const int item = warp + CWARPS * t;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    double a = ci[4 * t + kk];
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+                    if (lane == 0 && warp < CWARPS && item < MB * NSPLIT) itm[item * 4 + kk] = a;
+                }
+            }
+        }
 #pragma unroll
         for (int t = 0; t < CPL; ++t) red[warp * NTOT + NT + 32 * t + lane] = cq[t];
         __syncthreads();
         for (int k = tid; k < NTOT; k += DIR2_THREADS) {
             const int kind = (k == 2) ? OPKB_RMIN : ((k == 3) ? OPKB_RMAX : OPKB_RSUM);
-            double a = red[k];
-            for (int w = 1; w < NWARPS; ++w) a = rcombine_dyn(kind, a, red[w * NTOT + k]);
+            double a;
+            if (SPLIT && k >= NACC && k < NACC + 4 * MB) {
+                // stored pair j: its NSPLIT parts in part order (pairs the launch does not hold: 0)
+                const int j = (k - NACC) >> 2, kk = (k - NACC) & 3;
+                a = 0.0;
+                if (j < m)
+                    for (int part = 0; part < NSPLIT; ++part) a += itm[(j * NSPLIT + part) * 4 + kk];
+            } else {
+                a = red[k];
+                for (int w = 1; w < NWARPS; ++w) a = rcombine_dyn(kind, a, red[w * NTOT + k]);
+            }
             rs.part[(size_t)blockIdx.x * NTOT + k] = a;
         }
         __threadfence();
@@ -505,6 +592,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
 // OPKB_OBJ_QUADRATIC; (mb, tile) must be one of the instances listed there.
 #define DIR2_CARRY_ROWB 3584    // bytes per staged row of the CARRY instances (7 consumer warps x 512 B)
 #define DIR2_CARRY_ROWB5 5632   // same for the MB = 5 instances (11 consumer warps)
+#define DIR2_SPLIT_ROWB 5120    // the SPLIT instances (Float32, MB = 8: 10 consumer warps x 512 B)
+#define DIR2_SPLIT_CW 10
 template <typename T>
 int dir2_launch_plain(opkb_context* ctx, const Dir2Args<T>& B, int fuse, int mb, size_t smem, int grid);
 template <typename T>

@@ -7,7 +7,19 @@ template <typename T>
 int dir2_launch_carry(opkb_context* ctx, const Dir2Args<T>& B, int fuse, int mb, size_t smem, int grid)
 {
     constexpr int TC = DIR2_CARRY_ROWB / (int)sizeof(T), TC5 = DIR2_CARRY_ROWB5 / (int)sizeof(T);
+    constexpr int TS = DIR2_SPLIT_ROWB / (int)sizeof(T);
     void (*kern)(Dir2Args<T>, ReduceScratch) = NULL;
+    if constexpr (sizeof(T) == 4) {
+        // Float32, up to 8 pairs: the dense sums of the stored pairs in a second phase by the warp
+        // that owns the pair (SPLIT, opkb_direction2.cuh): 10 consumer warps on 5 KB rows
+        if (mb == 8 && B.tile == TS) {
+            if (fuse == OPKB_OBJ_ROSENBROCK)
+                kern = k_direction2<T, OPKB_OBJ_ROSENBROCK, 8, TS, 1, 0, DIR2_SPLIT_CW, 1>;
+            else if (fuse == OPKB_OBJ_QUADRATIC)
+                kern = k_direction2<T, OPKB_OBJ_QUADRATIC, 8, TS, 1, 0, DIR2_SPLIT_CW, 1>;
+            return dir2_do_launch<T>(ctx, kern, B, (DIR2_SPLIT_CW + 1) * 32, smem, grid);
+        }
+    }
     if (B.tile != ((mb == 5) ? TC5 : TC))
         return opkb_set_error(OPKB_EINVAL, "carry instances use %d / %d-byte rows", DIR2_CARRY_ROWB5, DIR2_CARRY_ROWB);
     // (MB, EXACT) instances: m < 5: (5, 0); m = 5: (5, 1); m <= 8: (8, 0); m = 10: (10, 1); else (12, 0)

@@ -345,6 +345,7 @@ struct opkb_spg_solver_ {
     double eps1, eps2, eta;
     double lmin, lmax, ftol, amin, amax;      // :201-205
     int64_t iter, fcnt, pcnt;
+    int pg_valid;          // pgtwon / pginfn / pcnt already belong to the current iterate
     int status, started, finished;
     double f, f0, fbest, pgtwon, pginfn, lambda;
     double* lastfv;
@@ -424,9 +425,12 @@ static int spg_solver_iterate(opkb_spg_solver* s)
     } else {
         fmin = fmax = s->f;
     }
-    s->pgtwon = sqrt(s->out[2]);                                              // :259-262
-    s->pginfn = s->out[3];
-    s->pcnt += 1;
+    if (!s->pg_valid) {
+        s->pgtwon = sqrt(s->out[2]);                                          // :259-262
+        s->pginfn = s->out[3];
+        s->pcnt += 1;
+    }
+    s->pg_valid = 0;
     // :278-302
     if (s->pginfn <= s->eps1) { s->status = 1; s->finished = 1; return 0; }
     if (s->pgtwon <= s->eps2) { s->status = 2; s->finished = 1; return 0; }
@@ -472,6 +476,13 @@ static int spg_solver_iterate(opkb_spg_solver* s)
         return 0;
     }
     s->iter += 1;                                                             // :378
+    // the projected gradient of the new iterate (:259-262 of the next trip) came out of the same
+    // pass: what `opkb_spg_solver_info` reports at an iteration boundary is then the state the
+    // reference's `printer` sees (:265-275) -- f, both norms and `pcnt` of the SAME point
+    s->pgtwon = sqrt(s->out[2]);
+    s->pginfn = s->out[3];
+    s->pcnt += 1;
+    s->pg_valid = 1;
     return 1;
 }
 

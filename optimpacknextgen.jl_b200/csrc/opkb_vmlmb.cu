@@ -952,7 +952,11 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         // CARRY instances use 3.5 KB rows (7 consumer warps) and need two stages of them
         const size_t budget = 220 * 1024;
         const int carry_mb = (A.m <= 5) ? 5 : ((A.m <= 8) ? 8 : ((A.m == 10) ? 10 : 12));
-        const int carry_rowb = (carry_mb == 5) ? DIR2_CARRY_ROWB5 : DIR2_CARRY_ROWB;
+        int carry_rowb = (carry_mb == 5) ? DIR2_CARRY_ROWB5 : DIR2_CARRY_ROWB;
+        // Float32, 6..8 pairs: the SPLIT instances (10 consumer warps on 5 KB rows, two stages)
+        static const int split_on = env_int("OPKB_DIR_SPLIT", 1);
+        if (sizeof(T) == 4 && carry_mb == 8 && split_on && (size_t)nr * DIR2_SPLIT_ROWB * 2 <= budget)
+            carry_rowb = DIR2_SPLIT_ROWB;
         if (carry && (size_t)nr * carry_rowb * 2 > budget) carry = 0;
         int tile = (int)(4096 / sizeof(T));
         if ((size_t)nr * tile * sizeof(T) * 2 > budget || A.m > 12) tile = (int)(2048 / sizeof(T));

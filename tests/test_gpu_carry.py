@@ -34,8 +34,18 @@ def test_carried_gram_equals_sweep(kind, n, dtype, kw):
     import opkb200 as opk
     pb = problem(kind, n, dtype)
     kw = dict(kw, xtol=(0, 0), ftol=(0, 0), gtol=(0, 0))
-    a = _solver(opk, pb, **kw)     # incremental Gram
-    b = _solver(opk, pb, **kw)     # a sweep every iteration
+    # (the switch is read when a workspace is created: identical on every rank of a job)
+    old = os.environ.get("OPKB_CARRY")
+    try:
+        os.environ["OPKB_CARRY"] = "2"    # incremental Gram (2: also for Float32 workspaces, where it is opt-in)
+        a = _solver(opk, pb, **kw)
+        os.environ["OPKB_CARRY"] = "0"    # a sweep every iteration
+        b = _solver(opk, pb, **kw)
+    finally:
+        if old is None:
+            os.environ.pop("OPKB_CARRY", None)
+        else:
+            os.environ["OPKB_CARRY"] = old
     f64 = dtype == np.float64
     # The two runs differ by the summation order of the Gram entries only; the
     # (chaotic, for Rosenbrock) trajectory then amplifies that: rounding level
@@ -44,13 +54,10 @@ def test_carried_gram_equals_sweep(kind, n, dtype, kw):
     gtol_early, gtol_late = (1e-11, 1e-4) if f64 else (2e-4, 5e-2)
     ftol = 1e-8 if f64 else 1e-2
     niter = 30 if f64 else 12   # (Float32 Gram on Rosenbrock: 2e-3 after 14 iterations)
-    old = os.environ.get("OPKB_CARRY")
     try:
         checked = 0
         for it in range(niter):
-            os.environ["OPKB_CARRY"] = "2"    # (2: also for Float32 workspaces, where it is opt-in)
             alive_a = a.iterate(1)
-            os.environ["OPKB_CARRY"] = "0"
             alive_b = b.iterate(1)
             assert alive_a == alive_b
             if not alive_a:
@@ -78,10 +85,6 @@ def test_carried_gram_equals_sweep(kind, n, dtype, kw):
         assert checked >= 5
         assert hits >= 3, (hits, misses)
     finally:
-        if old is None:
-            os.environ.pop("OPKB_CARRY", None)
-        else:
-            os.environ["OPKB_CARRY"] = old
         a.close()
         b.close()
 

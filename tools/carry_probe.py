@@ -20,12 +20,12 @@ def main():
     lo, hi = gpu_bounds(pb)
     kw = dict(lower=lo, upper=hi, mode="fused", mem=mem, xtol=(0, 0), ftol=(0, 0), gtol=(0, 0),
               twoloop="gram")
+    os.environ["OPKB_CARRY"] = "2"          # (read when the workspace is created)
     a = opk.VMLMB(pb["gpu_obj"], pb["x0"], **kw)
+    os.environ["OPKB_CARRY"] = "0"
     b = opk.VMLMB(pb["gpu_obj"], pb["x0"], **kw)
     for it in range(40):
-        os.environ["OPKB_CARRY"] = "2"
         a.iterate(1)
-        os.environ["OPKB_CARRY"] = "0"
         b.iterate(1)
         ga, gb = a.last_gram(), b.last_gram()
         dev = -1.0
