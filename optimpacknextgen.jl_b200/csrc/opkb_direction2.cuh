@@ -242,55 +242,33 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) upd[q] = !A.masked || (pv.v[q] != T(0));
                 const T* pb = st + prow * TILE + e;
-                // apply_lbfgs! :716-745 / :747-779, rounding sequence of the reference
-                if (all_used) {
-                    // every pair takes part (the usual case): unrolled and branch-free.  The
-                    // chain also runs on the masked elements, whose result is then replaced
-                    // by what the reference gives them, gamma*v0 (they are never updated).
+                // apply_lbfgs! :716-745 / :747-779, rounding sequence of the reference: unrolled and
+                // branch-free per element.  A pair that does not take part (rho <= 0, :727 / :759 -- it
+                // stays in the memory for `mem` iterations) is skipped by a test that is uniform over
+                // the grid.  The chain also runs on the masked elements, whose result is then replaced
+                // by what the reference gives them, gamma*v0 (they are never updated).
 #pragma unroll
-                    for (int jj = 0; jj < MB; ++jj) {
-                        const int j = MB - 1 - jj;
-                        if (EXACT || j < m) {
-                            const Pack<T> y = ld_pack<T>(pb + 2 * j * TILE, 0);
+                for (int jj = 0; jj < MB; ++jj) {
+                    const int j = MB - 1 - jj;
+                    if ((EXACT || j < m) && (all_used || ((A.use >> j) & 1u))) {
+                        const Pack<T> y = ld_pack<T>(pb + 2 * j * TILE, 0);
 #pragma unroll
-                            for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + A.ma[j] * y.v[q];
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < VEC; ++q) v.v[q] = A.gamma * v.v[q];
-#pragma unroll
-                    for (int j = 0; j < MB; ++j) {
-                        if (EXACT || j < m) {
-                            const Pack<T> sv = ld_pack<T>(pb + (2 * j + 1) * TILE, 0);
-#pragma unroll
-                            for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + A.cc[j] * sv.v[q];
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < VEC; ++q)
-                        if (!upd[q]) v.v[q] = A.gamma * pv.v[q];
-                } else {
-                    for (int j = m - 1; j >= 0; --j) {
-                        if ((A.use >> j) & 1u) {
-                            const Pack<T> y = ld_pack<T>(st + (prow + 2 * j) * TILE, e / VEC);
-                            const T a = A.ma[j];
-#pragma unroll
-                            for (int q = 0; q < VEC; ++q)
-                                if (upd[q]) v.v[q] = v.v[q] + a * y.v[q];
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < VEC; ++q) v.v[q] = A.gamma * v.v[q];
-                    for (int j = 0; j < m; ++j) {
-                        if ((A.use >> j) & 1u) {
-                            const Pack<T> sv = ld_pack<T>(st + (prow + 2 * j + 1) * TILE, e / VEC);
-                            const T c = A.cc[j];
-#pragma unroll
-                            for (int q = 0; q < VEC; ++q)
-                                if (upd[q]) v.v[q] = v.v[q] + c * sv.v[q];
-                        }
+                        for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + A.ma[j] * y.v[q];
                     }
                 }
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) v.v[q] = A.gamma * v.v[q];
+#pragma unroll
+                for (int j = 0; j < MB; ++j) {
+                    if ((EXACT || j < m) && (all_used || ((A.use >> j) & 1u))) {
+                        const Pack<T> sv = ld_pack<T>(pb + (2 * j + 1) * TILE, 0);
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + A.cc[j] * sv.v[q];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < VEC; ++q)
+                    if (!upd[q]) v.v[q] = A.gamma * pv.v[q];
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {
                     T di = v.v[q];

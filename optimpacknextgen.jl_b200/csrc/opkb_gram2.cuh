@@ -183,7 +183,34 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
                 }
                 named_bar_sync(1, cthreads);
             }
-            if (writer) {
+            if (writer && sizeof(T) == 4) {
+                // Float32: the same work on 16-byte packs (lane l owns the packs l, l + 32 k, ... of
+                // its warp's share: the partition of the accumulation loop below)
+                constexpr int VEC = VecOf<T>::N;
+                for (int pk = sub * 32 + lane; pk < TILE / VEC; pk += 32 * k) {
+                    Pack<T> ps = ld_pack<T>(st + snew, pk), py = ld_pack<T>(st + ynew, pk);
+                    const Pack<T> px = ld_pack<T>(st + TILE, pk), pg = ld_pack<T>(st + 2 * TILE, pk);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        ps.v[q] = ps.v[q] - px.v[q];       // s_new = x0 - x (element type)
+                        py.v[q] = py.v[q] - pg.v[q];       // y_new = g0 - g
+                    }
+                    st_pack<T>(st + snew, pk, ps);
+                    st_pack<T>(st + ynew, pk, py);
+                    const int64_t e0 = base + (int64_t)pk * VEC;
+                    if (e0 + VEC <= A.n) {
+                        st_pack<T>(A.Snew, e0 / VEC, ps);
+                        st_pack<T>(A.Ynew, e0 / VEC, py);
+                    } else {
+                        for (int q = 0; q < VEC && e0 + q < A.n; ++q) {
+                            A.Snew[e0 + q] = ps.v[q];
+                            A.Ynew[e0 + q] = py.v[q];
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&pair_bar[s]);
+            } else if (writer) {
                 for (int e = sub * 32 + lane; e < TILE; e += 32 * k) {
                     const T sn = st[snew + e] - st[TILE + e];       // s_new = x0 - x (element type)
                     const T yn = st[ynew + e] - st[2 * TILE + e];   // y_new = g0 - g
@@ -220,33 +247,43 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
                         for (int c = 0; c < CT; ++c) acc[r][c] = fma(rv[r], cv[c], acc[r][c]);
                 }
             } else {
-                // Float32: widening every operand to Float64 is conversion-bound (the
-                // F2F pipe is 1/4 of the FP64 rate), so the products of ONE stage
-                // (<= 32 per lane) are accumulated with FFMA and each stage sum is
-                // then added to the Float64 accumulators.
+                // Float32: widening every operand to Float64 is conversion-bound (the F2F pipe is
+                // 1/4 of the FP64 rate), so the products of ONE stage (<= 32 per lane and entry) are
+                // accumulated with FFMA and each stage sum is then added to the Float64 accumulators.
+                // Every lane works on 16-byte packs (4 elements per LDS.128: a quarter of the
+                // shared-memory instructions of an element-per-lane loop).
+                constexpr int VEC = VecOf<T>::N;
                 float af[RT][CT];
 #pragma unroll
                 for (int r = 0; r < RT; ++r)
 #pragma unroll
                     for (int c = 0; c < CT; ++c) af[r][c] = 0.0f;
-#pragma unroll 2
-                for (int e = sub * 32 + lane; e < TILE; e += 32 * k) {
-                    const T* rp = st + rowbase + e;
-                    const T* c0 = st + col0 + e;
-                    const T* c1 = st + col1 + e;
-                    float rv[RT], cv[CT];
+                for (int pk = sub * 32 + lane; pk < TILE / VEC; pk += 32 * k) {
+                    const T* rp = st + rowbase;
+                    Pack<T> cv[CT];
+                    cv[0] = ld_pack<T>(st + col0, pk);
 #pragma unroll
-                    for (int r = 0; r < RT; ++r) rv[r] = rp[r * TILE];
-                    // branch-free mask: all-ones / all-zeros bit pattern ANDed with the column
-                    const int fm = (!masked || (st[e] != T(0))) ? -1 : 0;
-                    cv[0] = __int_as_float(__float_as_int((float)c0[0]) & fm);
+                    for (int c = 1; c < CT; ++c) cv[c] = ld_pack<T>(st + col1 + (c - 1) * 2 * TILE, pk);
+                    if (masked) {
+                        // branch-free mask: all-ones / all-zeros bit pattern ANDed with the columns
+                        const Pack<T> p0 = ld_pack<T>(st, pk);       // row 0 = p: free <=> p != 0
 #pragma unroll
-                    for (int c = 1; c < CT; ++c)
-                        cv[c] = __int_as_float(__float_as_int((float)c1[(c - 1) * 2 * TILE]) & fm);
+                        for (int q = 0; q < VEC; ++q) {
+                            const int fm = (p0.v[q] != T(0)) ? -1 : 0;
 #pragma unroll
-                    for (int r = 0; r < RT; ++r)
+                            for (int c = 0; c < CT; ++c)
+                                cv[c].v[q] = (T)__int_as_float(__float_as_int((float)cv[c].v[q]) & fm);
+                        }
+                    }
 #pragma unroll
-                        for (int c = 0; c < CT; ++c) af[r][c] = fmaf(rv[r], cv[c], af[r][c]);
+                    for (int r = 0; r < RT; ++r) {
+                        const Pack<T> rv = ld_pack<T>(rp + r * TILE, pk);
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q)
+#pragma unroll
+                            for (int c = 0; c < CT; ++c)
+                                af[r][c] = fmaf((float)rv.v[q], (float)cv[c].v[q], af[r][c]);
+                    }
                 }
 #pragma unroll
                 for (int r = 0; r < RT; ++r)

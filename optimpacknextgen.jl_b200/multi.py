@@ -99,6 +99,29 @@ class MultiVMLMB:
                 raise TypeError("fg must be a built-in objective or a per-rank factory of DeviceObjective")
             self.solvers.append(NativeVMLMB(obj, x0[first:first + cnt].copy(), lower=_shard(lower, first, cnt, self.dtype),
                                             upper=_shard(upper, first, cnt, self.dtype), nglobal=n, ctx=ctx, **kw))
+        self._bind()
+
+    @classmethod
+    def from_shards(cls, group: Group, solvers, n: int = None):
+        """The same driver over per-rank `NativeVMLMB` solvers the caller has built on
+        `group.contexts[r]` (e.g. with inputs generated on the devices)."""
+        self = cls.__new__(cls)
+        self._own_group = False
+        self.group = group
+        self.solvers = list(solvers)
+        assert len(self.solvers) == group.size
+        self.dtype = self.solvers[0].dtype
+        self.ranges, first = [], 0
+        for s in self.solvers:
+            self.ranges.append((first, s.n))
+            first += s.n
+        self.n = first if n is None else n
+        self._shape = (self.n,)
+        self._bind()
+        return self
+
+    def _bind(self):
+        G = self.group.size
         self._handles = (vp * G)(*[s._solver for s in self.solvers])
         self._tasks = (C.c_int * G)()
         self.finished = False
