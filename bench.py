@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--driver", default="native", choices=["native", "python"],
                     help="host of the stage machine: the C++ driver inside the library, or the Python twin")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short lines of the other BASELINE.json configurations (N = 1 only)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -456,6 +458,29 @@ def ours(args):
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "evals_per_s": evals / (ms * 1e-3), "final": {"f": f_final, "gnorm": gnorm_final},
     }
+    if world == 1 and not args.no_other_configs:
+        # The other configurations of BASELINE.json (parity-test cases, not bench lines): one short
+        # steady-state measurement each, same method (CUDA events around K iterations after the pairs
+        # have filled up), so that their rates are in the driver's record too.  C5s = the per-GPU shard
+        # of C5 (n = 2^28 Float32 of the 2^31) -- sequential two-loop (parity-grade Float32 default) and
+        # the Gram form; fractions are of the measured HBM peak by SURVEY 8(d)'s W_alg yardstick.
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        others = {}
+        try:
+            import bench_configs as BC
+            ctx.trim()
+            for name in ("C1", "C2", "C3", "C5s", "C5s-gram"):
+                try:
+                    r = BC.run_one(ctx, name, 0, 1, native=(args.driver == "native"))
+                    others[name] = {k: r[k] for k in ("config", "n", "iterations", "iterations_per_s", "ms_per_iteration",
+                                                      "evals_per_iteration", "frac_of_measured_peak", "twoloop",
+                                                      "incremental_gram_hits_misses") if k in r}
+                except Exception as e:      # never lose the headline line to a side measurement
+                    others[name] = {"error": repr(e)[:200]}
+                ctx.trim()
+        except Exception as e:
+            others = {"error": repr(e)[:200]}
+        line["other_configs"] = others
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_run(args, args.cpu_steps, 1, args.cpu_log2n)
         scale = r["ns"] / n

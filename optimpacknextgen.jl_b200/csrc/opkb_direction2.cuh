@@ -14,6 +14,7 @@
 #pragma once
 
 #define DIR2_MAXSTAGE 8
+#define DIR2_CORR_MAX 12    // changed elements per warp and step beyond which the incremental Gram gives up
 // 8 consumer warps + 1 producer warp; the CARRY instances run 7 + 1 (two warps per
 // SM sub-partition: up to 255 registers per thread for the extra accumulators)
 #define DIR2_NTHREADS(CARRY) ((CARRY) ? 256 : 288)
@@ -142,6 +143,15 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
 #pragma unroll
     for (int i = 0; i < 4 * IPW; ++i) ci[i] = 0.0;
     double cq[CPL];
+    // Corrections are serial work per changed element (~15 warp instructions each).  A trial point
+    // that throws a large part of the variables onto / off their bounds -- typically a step that
+    // the line search is going to reject anyway -- would make the launch several times longer
+    // (measured: 12.4 instead of 4.6 ms at C5), so a warp that finds more than DIR2_CORR_MAX
+    // changed elements among its 32 lanes gives up: it counts the event in the LAST correction slot
+    // (never a real entry: MB (MB + 1) < 32 CPL), and the host drops the carry of a launch whose
+    // count is not zero (the Gram sweep runs if that point is accepted after all).
+    static_assert(!CARRY || CY::NENT < 32 * CY::CPL, "the last correction slot must be free");
+    double cskip = 0.0;
     int cl[CPL];   // source lanes (= pair rows) of the two factors of entry lane + 32 t: a | b << 8
 #pragma unroll
     for (int i = 0; i < ND; ++i) cd[i] = 0.0;
@@ -399,6 +409,10 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                             const bool chg = ok[q] && (nf != (pv.v[q] != T(0)));
                             unsigned bal = __ballot_sync(0xffffffffu, chg);
                             const unsigned nfb = __ballot_sync(0xffffffffu, nf);
+                            if (__popc(bal) > DIR2_CORR_MAX) {
+                                cskip += 1.0;
+                                bal = 0u;
+                            }
                             while (bal) {
                                 const int src = __ffs(bal) - 1;
                                 bal &= bal - 1;
@@ -533,6 +547,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
         }
 #pragma unroll
         for (int t = 0; t < CPL; ++t) red[warp * NTOT + NT + 32 * t + lane] = cq[t];
+        if (lane == 31) red[warp * NTOT + NT + 32 * (CPL - 1) + 31] = cskip;   // (warp-uniform count)
         __syncthreads();
         for (int k = tid; k < NTOT; k += DIR2_THREADS) {
             const int kind = (k == 2) ? OPKB_RMIN : ((k == 3) ? OPKB_RMAX : OPKB_RSUM);

@@ -49,7 +49,7 @@ struct opkb_vmlmb_ {
     int carry_slots[OPKB_MEM_MAX];
     double carry_dense[4 * OPKB_MEM_MAX + 4];
     double carry_corr[OPKB_MEM_MAX * (OPKB_MEM_MAX + 1)];
-    int64_t carry_hits, carry_misses;
+    int64_t carry_hits, carry_misses, carry_skips;
     // VMLMB (method 2): the fused direction + trial launch does NOT write p' (the next
     // launch recomputes it from x, g, lo, hi and nothing else reads it in steady state);
     // p_stale != 0 means p does not belong to the current (x, g) and is recomputed on
@@ -1000,7 +1000,12 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
                 ws->carry_mb = mb;
                 ws->carry_mark = mark_next;
                 for (int j = 0; j < A.m; ++j) ws->carry_slots[j] = slots[j];
-                ws->carry_valid = 1;
+                // the last correction slot counts the warps that gave up on their corrections (too
+                // many variables change their status at this trial point, DIR2_CORR_MAX): the block
+                // cannot be assembled then.  The count is combined over the ranks like every other
+                // slot: the same decision everywhere.
+                ws->carry_valid = (r[nd + ncorr - 1] == 0.0) ? 1 : 0;
+                if (!ws->carry_valid) ws->carry_skips += 1;
             }
             if (fuse) {
                 const double* r = part[0];

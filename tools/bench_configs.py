@@ -66,19 +66,13 @@ def run_vmlmb(ctx, name, obj, x0, lo, hi, mem, n, nglobal, K, es, walg, twoloop=
     return out
 
 
-def main():
-    which = sys.argv[1:] or ["C1", "C2", "C3", "C4", "C5s"]
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ctx = init_context(local)
-    res = []
-    for c in which:
+def run_one(ctx, c, rank=0, world=1, native=None):
+    """One configuration line (a dict) on `ctx`; None for an unknown name."""
+    global NATIVE
+    if native is not None:
+        NATIVE = bool(native)
+    r = None
+    if True:
         if c == "C1":     # VMLMB unconstrained Rosenbrock n=1e6 f64 m=5, More-Thuente
             n = 10 ** 6
             first, nl = shard_range(n, rank, world)
@@ -180,10 +174,25 @@ def main():
                  "kernel_launches_per_iteration": {k: round(v[1] / it, 2) for k, v in prof.items()}}
             r["frac_of_measured_peak"] = r["alg_GBps_per_gpu"] / PEAK
         else:
-            continue
-        r["n_gpus"] = world
-        res.append(r)
-        if rank == 0:
+            return None
+    r["n_gpus"] = world
+    return r
+
+
+def main():
+    which = sys.argv[1:] or ["C1", "C2", "C3", "C4", "C5s"]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = init_context(local)
+    for c in which:
+        r = run_one(ctx, c, rank, world)
+        if r is not None and rank == 0:
             print(json.dumps(r), flush=True)
     if world > 1:
         import torch.distributed as dist
