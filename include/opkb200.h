@@ -346,9 +346,12 @@ int opkb_vmlmb_discard_trial(opkb_vmlmb* ws, int mark_next);
  * block is assembled on the host and the spare buffers are swapped in: no kernel
  * launch, S and Y cross HBM once per iteration instead of twice.  Any other use
  * of the workspace falls back to the sweep.  Same values up to the summation
- * order.  OPKB_CARRY=0 in the environment disables it; Float32 workspaces use it
- * only with OPKB_CARRY=2 (those instances are issue-bound).  carry_stats: how many
- * opkb_vmlmb_gram calls were served that way / fell back although armed. */
+ * order.  OPKB_CARRY=0 in the environment (read when the workspace is created) disables
+ * it; Float32 workspaces use it for mem <= 8 (beyond: only with OPKB_CARRY=2, those
+ * instances are issue-bound).  A launch whose trial point changes the status of more than
+ * a quarter of the variables gives the incremental block up (the sweep runs if that point
+ * is accepted).  carry_stats: how many opkb_vmlmb_gram calls were served that way / fell
+ * back although armed. */
 int opkb_vmlmb_carry_stats(const opkb_vmlmb* ws, int64_t* hits, int64_t* misses);
 /* the Gram block the last opkb_vmlmb_gram call returned (*m = 0: none), for checks */
 int opkb_vmlmb_last_gram(const opkb_vmlmb* ws, int* m, int* slots, double* G);

@@ -14,7 +14,8 @@
 #pragma once
 
 #define DIR2_MAXSTAGE 8
-#define DIR2_CORR_MAX 12    // changed elements per warp and step beyond which the incremental Gram gives up
+#define DIR2_CORR_SHARE 8    // a warp gives up its corrections beyond 8 / 32 changed elements on average ...
+#define DIR2_CORR_WARMUP 64  // ... over at least 64 steps (2048 elements) of its stream
 // 8 consumer warps + 1 producer warp; the CARRY instances run 7 + 1 (two warps per
 // SM sub-partition: up to 255 registers per thread for the extra accumulators)
 #define DIR2_NTHREADS(CARRY) ((CARRY) ? 256 : 288)
@@ -146,12 +147,15 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
     // Corrections are serial work per changed element (~15 warp instructions each).  A trial point
     // that throws a large part of the variables onto / off their bounds -- typically a step that
     // the line search is going to reject anyway -- would make the launch several times longer
-    // (measured: 12.4 instead of 4.6 ms at C5), so a warp that finds more than DIR2_CORR_MAX
-    // changed elements among its 32 lanes gives up: it counts the event in the LAST correction slot
-    // (never a real entry: MB (MB + 1) < 32 CPL), and the host drops the carry of a launch whose
-    // count is not zero (the Gram sweep runs if that point is accepted after all).
+    // (measured: 12.4 instead of 4.6 ms at C5).  Every warp therefore keeps the running share of
+    // changed elements in its own stream of tiles; once that share exceeds DIR2_CORR_SHARE / 32
+    // (after DIR2_CORR_WARMUP steps of 32 elements) it gives up for the rest of the launch and says
+    // so in the LAST correction slot (never a real entry: MB (MB + 1) < 32 CPL); the host drops the
+    // carry of a launch whose count is not zero (the Gram sweep runs if that point is accepted after
+    // all).  Below the threshold the extra work is bounded by ~45 % of the kernel.
     static_assert(!CARRY || CY::NENT < 32 * CY::CPL, "the last correction slot must be free");
     double cskip = 0.0;
+    int csteps = 0, cchanged = 0;
     int cl[CPL];   // source lanes (= pair rows) of the two factors of entry lane + 32 t: a | b << 8
 #pragma unroll
     for (int i = 0; i < ND; ++i) cd[i] = 0.0;
@@ -409,10 +413,11 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                             const bool chg = ok[q] && (nf != (pv.v[q] != T(0)));
                             unsigned bal = __ballot_sync(0xffffffffu, chg);
                             const unsigned nfb = __ballot_sync(0xffffffffu, nf);
-                            if (__popc(bal) > DIR2_CORR_MAX) {
-                                cskip += 1.0;
-                                bal = 0u;
-                            }
+                            csteps += 1;
+                            cchanged += __popc(bal);
+                            if (cskip == 0.0 && csteps >= DIR2_CORR_WARMUP && cchanged > DIR2_CORR_SHARE * csteps)
+                                cskip = 1.0;
+                            if (cskip != 0.0) bal = 0u;
                             while (bal) {
                                 const int src = __ffs(bal) - 1;
                                 bal &= bal - 1;

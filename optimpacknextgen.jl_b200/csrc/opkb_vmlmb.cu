@@ -65,7 +65,7 @@ struct opkb_vmlmb_ {
     int xspec_mark;
     // switches read ONCE, when the workspace is created (every rank of a job sees the same
     // environment: the decisions they drive are then identical on all ranks)
-    int opt_carry;      // OPKB_CARRY: -1 default (Float64 only), 0 off, 2 also Float32
+    int opt_carry;      // OPKB_CARRY: -1 default (Float64; Float32 up to 8 pairs), 0 off, 2 always
     int opt_lazy_p;     // OPKB_LAZY_P (default 1)
     int opt_xspec;      // OPKB_XSPEC (default 1)
     int opt_maskb;      // OPKB_MASKB (default 1)
@@ -179,8 +179,10 @@ extern "C" int opkb_vmlmb_create(opkb_context* ctx, int eltype, int64_t n, int m
     // the two spare buffers of the incremental Gram (the fused direction kernel writes the pair
     // the speculated trial point would form): allocated HERE, not lazily at the first launch that
     // wants them, so that whether a rank carries never depends on a rank-local allocation
+    // Float64: always (up to 12 pairs); Float32: up to 8 pairs, where the SPLIT / 11-warp instances
+    // run (the 7-warp Float32 instances of 9..12 pairs are issue-bound: only with OPKB_CARRY=2)
     if (!rc && method != 1 && mem <= 12 && ws->opt_carry != 0 &&
-        (eltype == OPKB_DOUBLE || ws->opt_carry == 2)) {
+        (eltype == OPKB_DOUBLE || ws->opt_carry == 2 || mem <= 8)) {
         rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->carry_s);
         rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->carry_y);
     }
