@@ -360,11 +360,53 @@ static inline void cpu_relax()
 #endif
 }
 
+// Polling with a budget.  Waits up to OPKB_SPIN_US microseconds (default 20000: every kernel of the
+// BASELINE configurations finishes well within it) are pure spinning -- that is what the flag is
+// for, and a nap costs at least the ~50 us timer slack of the kernel.  A longer wait (a slow user
+// objective, a peer that lags or died, a far larger problem) goes on with naps of elapsed/64
+// (2 us .. 200 us): the host core is then not pinned at 100 % while the wake-up delay stays below
+// ~1.5 % of the wait.  OPKB_SPIN_US=200 trades that 1.5 % for an idle core on large problems too.
+struct opkb_backoff {
+    struct timespec t0;
+    unsigned int it;
+    long spin_ns;
+};
+
+static inline void backoff_begin(opkb_backoff* b)
+{
+    static const long spin_us = getenv("OPKB_SPIN_US") ? atol(getenv("OPKB_SPIN_US")) : 20000;
+    b->it = 0;
+    b->spin_ns = spin_us * 1000L;
+    b->t0.tv_sec = 0;
+    b->t0.tv_nsec = 0;
+}
+
+static inline void backoff_pause(opkb_backoff* b)
+{
+    cpu_relax();
+    if ((++b->it & 255u) != 0u) return;
+    struct timespec now;
+    clock_gettime(CLOCK_MONOTONIC, &now);
+    if (b->t0.tv_sec == 0 && b->t0.tv_nsec == 0) {
+        b->t0 = now;
+        return;
+    }
+    const long long el = (long long)(now.tv_sec - b->t0.tv_sec) * 1000000000LL + (now.tv_nsec - b->t0.tv_nsec);
+    if (el < b->spin_ns) return;
+    long long nap = el / 64;
+    if (nap < 2000) nap = 2000;
+    if (nap > 200000) nap = 200000;
+    struct timespec ts = {0, (long)nap};
+    nanosleep(&ts, NULL);
+}
+
 // The flag is read with ACQUIRE semantics: the loads of the results that follow (h_res, the mailbox
 // buffers) cannot be reordered before it by a weakly ordered host CPU (aarch64: Grace).
 static bool wait_flag(opkb_context* ctx, volatile unsigned int* flag)
 {
     const unsigned int want = ctx->seq;
+    opkb_backoff bo;
+    backoff_begin(&bo);
     for (unsigned int it = 1;; ++it) {
         if (__atomic_load_n((const unsigned int*)flag, __ATOMIC_ACQUIRE) == want) return true;
         if ((it & 4095u) == 0u && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) {
@@ -372,7 +414,7 @@ static bool wait_flag(opkb_context* ctx, volatile unsigned int* flag)
             // landed by now (one last look, still with acquire semantics)
             return __atomic_load_n((const unsigned int*)flag, __ATOMIC_ACQUIRE) == want;
         }
-        cpu_relax();
+        backoff_pause(&bo);
     }
 }
 
@@ -391,9 +433,11 @@ static int opkb_mailbox_reduce(opkb_context* ctx, int nred, const int* kinds, do
             unsigned long long* ready = (unsigned long long*)(slot + 64);
             unsigned long long spins = 0;
             time_t t_start = 0;
+            opkb_backoff bo;
+            backoff_begin(&bo);
             while (__atomic_load_n(ready, __ATOMIC_ACQUIRE) < phase) {
-                cpu_relax();
-                if ((++spins & 0xfffffull) == 0ull) {
+                backoff_pause(&bo);
+                if ((++spins & 0xfffffull) == 0ull) {   // (a nap every 256 spins: about once per second)
                     // a peer that died would hang every other rank for ever: give up after
                     // OPKB_MAILBOX_TIMEOUT seconds (default: half an hour; ranks may legitimately
                     // be far apart, e.g. a slow user objective on one shard)
