@@ -13,7 +13,6 @@ $TR --nproc-per-node 8 --master-port 29531 bench.py --gpus 8 --steps 20 --warmup
 $TR --nproc-per-node 2 --master-port 29532 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r02d_bench_n2.json 2> gpurun_out/r02d_bench_n2.err; echo "bench2 rc=$?"
 python tools/bench_group.py 8 20 > gpurun_out/r02d_group_n8.jsonl 2> gpurun_out/r02d_group_n8.err; echo "group8 rc=$?"; cat gpurun_out/r02d_group_n8.jsonl
 OPKB_BENCH_NATIVE=1 $TR --nproc-per-node 8 --master-port 29533 tools/bench_configs.py C5 C5-gram > gpurun_out/r02d_c5_n8.jsonl 2> gpurun_out/r02d_c5_n8.err; echo "c5 rc=$?"
-OPKB_CARRY=2 OPKB_BENCH_NATIVE=1 $TR --nproc-per-node 8 --master-port 29534 tools/bench_configs.py C5-gram > gpurun_out/r02d_c5_n8_carry.jsonl 2>> gpurun_out/r02d_c5_n8.err; echo "c5 carry rc=$?"
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob('gpurun_out/r02d_*.json*')):
