@@ -211,6 +211,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
+    def ready(self, nrows=2):
+        """nvidia-smi needs a few hundred ms before its first line: True once it is streaming."""
+        return self.proc is None or len(self.rows) >= nrows
+
     def summary(self, t0, t1, t_load0=None):
         if self.proc is not None:
             self.proc.terminate()
@@ -242,6 +246,25 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
                 "samples": len(sm), "window": window}
+
+
+def bind_to_gpu_numa_node(device):
+    """Run this rank on the host cores next to its GPU (NVML's CPU affinity of the device): the pinned
+    buffers of the e2e leg are then first-touched on that NUMA node and cross PCIe without a hop over
+    the socket interconnect -- with 8 ranks the host side, not the links, bounds the uploads."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
 
 
 def measured_peak():
@@ -284,6 +307,8 @@ def ours(args):
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     torch.cuda.set_device(local)
+    if world > 1:       # (one rank: all host cores stay available to the CPU-baseline leg)
+        bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = init_context(local)
@@ -323,6 +348,20 @@ def ours(args):
     t_load0 = time.perf_counter()
     solver.iterate(m + 1)                               # priming: all m pairs exist (steady state)
     solver.iterate(W)                                   # warm-up (untimed)
+    # With many GPUs the timed region lasts a few tens of ms, less than nvidia-smi takes to start:
+    # more untimed iterations of the same load (the same number on every rank) until rank 0's
+    # sampler is streaming, so that the clocks line covers the timed region or the load just before it.
+    extra = 0
+    while world > 1 or (sampler is not None and not sampler.ready()):
+        go = 1.0 if (sampler is not None and not sampler.ready() and time.perf_counter() - t_load0 < 3.0) else 0.0
+        if world > 1:
+            t = torch.tensor([go], dtype=torch.float64, device="cuda")
+            dist.broadcast(t, src=0)
+            go = float(t.item())
+        if go == 0.0:
+            break
+        solver.iterate(10)
+        extra += 10
     ctx.profile(True)
     barrier()
     l0, e0, i0 = ctx.launch_count, solver.eval, solver.iter
