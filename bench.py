@@ -381,6 +381,7 @@ def ours(args):
     hits = solver.carry_stats()[0] - h0
     clocks = sampler.summary(t0, t1, t_load0) if sampler else None
     f_final, gnorm_final = solver.f, solver.gnorm
+    history = solver.history
     solver.close()
     del solver
     if not alive or iters != K:
@@ -401,8 +402,11 @@ def ours(args):
     lazy_p = 0 if os.environ.get("OPKB_LAZY_P", "1") == "0" else 1
     fused_trial = prof.get("trial", (0.0, 0))[1] < K / 2
     carried = hits >= K / 2
-    passes = {"trial": 7, "gram": 2 * m + 5,
-              "direction": 2 * m + ((9 + (1 - lazy_p)) if carried else ((8 + (1 - lazy_p)) if fused_trial else 6))}
+    # iterate history (default on the Gram path): the pairs are formed on the fly, s', y' are never
+    # written (fused kernel 2m + 7 algorithmic passes) and the sweep writes nothing (2m + 3)
+    hist = 1 if history == 1 else 0
+    passes = {"trial": 7, "gram": 2 * m + 5 - 2 * hist,
+              "direction": 2 * m + ((9 - 2 * hist + (1 - lazy_p)) if carried else ((8 + (1 - lazy_p)) if fused_trial else 6))}
     kern = {}
     for name, npass in passes.items():
         if name in prof:
@@ -422,18 +426,20 @@ def ours(args):
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": kern[dom]["achieved_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": kern[dom]["frac"], "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peak_src, "kernels": kern, "trial_fused_into_direction": fused_trial,
-                "incremental_gram_iterations": hits,
+                "incremental_gram_iterations": hits, "iterate_history": bool(hist),
                 "note": "k_direction2 = direction + speculative trial" +
                         (" + incremental Gram (the Gram sweep ran %d times in %d iterations)"
                          % (prof.get("gram", (0.0, 0))[1], K) if carried else ""),
                 "iteration": {
                     "evals_per_iter": evals / K,
                     "compulsory_model": {
-                        "passes": 2 * m + 11, "bytes": (2 * m + 11) * es * n,
-                        "what": "ONE kernel per iteration: read S, Y (2m), x, g, lo, hi, a, c; write d, x', g', "
-                                "s', y' (p recomputed, saves by aliasing, trial fused, S and Y cross HBM once)",
-                        "achieved_gbs_per_gpu": (2 * m + 11) * es * n / (ms * 1e-3 / K) / 1e9 / world,
-                        "frac_per_gpu": (2 * m + 11) * es * n / (ms * 1e-3 / K) / 1e9 / world / peak},
+                        "passes": 2 * m + 11 - 2 * hist, "bytes": (2 * m + 11 - 2 * hist) * es * n,
+                        "what": "ONE kernel per iteration: read the m pairs (2m rows), x, g, lo, hi, a, c; write d, x', g'" +
+                                ("" if hist else ", s', y'") + " (p recomputed, saves by aliasing, trial fused, the pairs "
+                                "cross HBM once" + ("; iterate history: the pairs are differences of stored iterates formed "
+                                                    "on the fly, nothing is written back)" if hist else ")"),
+                        "achieved_gbs_per_gpu": (2 * m + 11 - 2 * hist) * es * n / (ms * 1e-3 / K) / 1e9 / world,
+                        "frac_per_gpu": (2 * m + 11 - 2 * hist) * es * n / (ms * 1e-3 / K) / 1e9 / world / peak},
                     "moved_bytes_per_iter": moved,
                     "survey_yardstick": {
                         "passes": 4 * m + 20, "bytes": (4 * m + 20) * es * n,

@@ -307,13 +307,27 @@ int opkb_vmlmb_trial_end(opkb_vmlmb* ws, int mark, double f, int initial, double
 
 /* P3 "pair update + sweep" = :512-513 then every inner product apply_lbfgs!
  * needs (:728, :737, :758-764, :771) in ONE pass: slot `mark` is turned in
- * place into (S[mark]-x, Y[mark]-g) [Y[mark]-p for BLMVM], then with the m
+ * place into (S[mark]-x, Y[mark]-g) [Y[mark]-p for BLMVM] (not with the iterate history, see
+ * opkb_vmlmb_history below: the pair is then formed on the fly), then with the m
  * pairs ordered oldest..newest, slots[j] (j = 0 oldest), the Gram block
  *   G[r][c], r in {s_0,y_0,s_1,y_1,...} (2m rows), c in {v0,y_0,...,y_{m-1}} (m+1 cols)
  * restricted to the free set {i : p[i] != 0} for VMLMB (unrestricted otherwise,
  * v0 = p for VMLMB, g otherwise) is returned row-major in G[2m*(m+1)].  Only
  * the entries with age(col) >= age(row) and the v0 column are defined. */
 int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots, double* G);
+/* Representation of the pairs.  A workspace whose pairs are formed by opkb_vmlmb_gram keeps the
+ * ITERATE HISTORY instead of the differences: slot k holds (x_k, g_k) as saved when line search k
+ * started (:562-563), it is NOT turned in place into the difference of :512-513, and pair k is
+ * S[k] - S[k'] , Y[k] - Y[k'] with k' the slot saved next (the current x, g for the newest pair),
+ * formed on the fly by the kernels (the same bits: one rounding of the same operands).  Nothing is
+ * written back, the fused direction kernel moves 2m + 9 passes instead of 2m + 11, the sweep 2m + 3
+ * instead of 2m + 5.  `slots` must then list consecutive line searches (as `_vmlmb!` produces them).
+ * opkb_vmlmb_vector(ws, 'S' | 'Y', k) of such a workspace is the iterate, not the pair.  A workspace
+ * whose pairs are formed by opkb_vmlmb_pair_update (the step-by-step recursion), a BLMVM workspace,
+ * or any workspace created with OPKB_HISTORY=0 in the environment keeps the reference's stored
+ * differences (and opkb_vmlmb_gram then works on those).  1: history, 0: differences, -1: not yet
+ * decided (no pair formed). */
+int opkb_vmlmb_history(const opkb_vmlmb* ws);
 
 /* P4 "direction" = :525/:528 + the axpys of :729/:738/:761/:768/:772, :535,
  * :537, :629, :562-563, :577.  d = v0; for j newest..oldest d -= alpha[j]*y_j;

@@ -49,6 +49,12 @@ template <typename T> struct Dir2Args {
     // is reduced in the same pass (see "incremental Gram" below)
     T* sout;
     T* yout;
+    // HISTORY: the pair rows hold the ITERATES (g_j, x_j) at the start of the line search that
+    // formed pair j, not the differences: s_j = x_j - x_{j+1}, y_j = g_j - g_{j+1}, where the
+    // successor of the newest pair is the current (x, g).  The differences are formed in the
+    // stage (each thread for its own pack, while it walks the chain) and nothing is ever written
+    // back: with the incremental Gram the iteration moves 2m + 9 passes instead of 2m + 11.
+    int hist;
 };
 
 // FUSE: 0 direction only; OPKB_OBJ_ROSENBROCK / OPKB_OBJ_QUADRATIC: + speculative trial.
@@ -261,24 +267,70 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                 // stays in the memory for `mem` iterations) is skipped by a test that is uniform over
                 // the grid.  The chain also runs on the masked elements, whose result is then replaced
                 // by what the reference gives them, gamma*v0 (they are never updated).
+                if (!A.hist) {
 #pragma unroll
-                for (int jj = 0; jj < MB; ++jj) {
-                    const int j = MB - 1 - jj;
-                    if ((EXACT || j < m) && (all_used || ((A.use >> j) & 1u))) {
-                        const Pack<T> y = ld_pack<T>(pb + 2 * j * TILE, 0);
+                    for (int jj = 0; jj < MB; ++jj) {
+                        const int j = MB - 1 - jj;
+                        if ((EXACT || j < m) && (all_used || ((A.use >> j) & 1u))) {
+                            const Pack<T> y = ld_pack<T>(pb + 2 * j * TILE, 0);
 #pragma unroll
-                        for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + A.ma[j] * y.v[q];
+                            for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + A.ma[j] * y.v[q];
+                        }
                     }
-                }
 #pragma unroll
-                for (int q = 0; q < VEC; ++q) v.v[q] = A.gamma * v.v[q];
+                    for (int q = 0; q < VEC; ++q) v.v[q] = A.gamma * v.v[q];
 #pragma unroll
-                for (int j = 0; j < MB; ++j) {
-                    if ((EXACT || j < m) && (all_used || ((A.use >> j) & 1u))) {
-                        const Pack<T> sv = ld_pack<T>(pb + (2 * j + 1) * TILE, 0);
+                    for (int j = 0; j < MB; ++j) {
+                        if ((EXACT || j < m) && (all_used || ((A.use >> j) & 1u))) {
+                            const Pack<T> sv = ld_pack<T>(pb + (2 * j + 1) * TILE, 0);
 #pragma unroll
-                        for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + A.cc[j] * sv.v[q];
+                            for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + A.cc[j] * sv.v[q];
+                        }
                     }
+                } else {
+                    // HISTORY: y_j = g_j - g_{j+1} (the same bits as the stored difference of
+                    // src/quasinewton.jl:513), formed while the chain walks newest -> oldest, and left
+                    // in the stage in place of g_j for everything that follows (dense sums,
+                    // corrections, the second phase of SPLIT); likewise s_j = x_j - x_{j+1} oldest ->
+                    // newest.  One subtraction and one shared-memory store per row and pack.
+                    T* wb = const_cast<T*>(pb);
+                    Pack<T> gnext = pg;
+#pragma unroll
+                    for (int jj = 0; jj < MB; ++jj) {
+                        const int j = MB - 1 - jj;
+                        if (EXACT || j < m) {
+                            const Pack<T> gj = ld_pack<T>(pb + 2 * j * TILE, 0);
+                            Pack<T> y;
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) y.v[q] = gj.v[q] - gnext.v[q];
+                            st_pack<T>(wb + 2 * j * TILE, 0, y);
+                            gnext = gj;
+                            if (all_used || ((A.use >> j) & 1u)) {
+#pragma unroll
+                                for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + A.ma[j] * y.v[q];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) v.v[q] = A.gamma * v.v[q];
+                    Pack<T> xj = ld_pack<T>(pb + TILE, 0);          // x_0 (m >= 1)
+#pragma unroll
+                    for (int j = 0; j < MB; ++j) {
+                        if (EXACT || j < m) {
+                            Pack<T> xn = px;                            // successor of the newest pair
+                            if (j + 1 < MB && (EXACT || j + 1 < m)) xn = ld_pack<T>(pb + (2 * j + 3) * TILE, 0);
+                            Pack<T> sv;
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) sv.v[q] = xj.v[q] - xn.v[q];
+                            st_pack<T>(wb + (2 * j + 1) * TILE, 0, sv);
+                            xj = xn;
+                            if (all_used || ((A.use >> j) & 1u)) {
+#pragma unroll
+                                for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + A.cc[j] * sv.v[q];
+                            }
+                        }
+                    }
+                    __syncwarp();   // the corrections below read the packs of the other lanes of this warp
                 }
 #pragma unroll
                 for (int q = 0; q < VEC; ++q)
@@ -445,7 +497,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                     } else if (A.xout) {
                         st_pack<T>(A.xout, iv, xt);
                     }
-                    if (CARRY) {
+                    if (CARRY && A.sout) {              // (HISTORY: the pair is never materialised)
                         st_pack<T>(A.sout, iv, sn);
                         st_pack<T>(A.yout, iv, yn);
                     }
@@ -463,7 +515,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                         } else if (A.xout) {
                             A.xout[base + e + q] = xt.v[q];
                         }
-                        if (CARRY) {
+                        if (CARRY && A.sout) {
                             A.sout[base + e + q] = sn.v[q];
                             A.yout[base + e + q] = yn.v[q];
                         }
@@ -504,8 +556,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                     }
                 }
             }
-            // (SPLIT: rows 0 and 2 were written through the generic proxy)
-            if (partial || SPLIT) fence_proxy_async();
+            // (SPLIT: rows 0 and 2, HISTORY: the pair rows were written through the generic proxy)
+            if (partial || SPLIT || A.hist) fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
         }

@@ -61,6 +61,10 @@ template <typename T> struct Gram2Args {
     T* Ynew;
     int64_t n;
     int m, nb, kshare, masked, tile, nstage;
+    // HISTORY: the pair rows hold the iterates (x_q, g_q), pair q = (x_q - x_{q+1}, g_q - g_{q+1}) with
+    // (x, g) as the successor of the newest one; the consumers turn a stage into differences before
+    // they accumulate, nothing is written back (2m + 3 passes, all reads)
+    int hist;
 };
 
 // Stage layout (rows of TILE elements of T): 0: v0, 1: x, 2: g|p, then the pairs
@@ -183,7 +187,30 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
                 }
                 named_bar_sync(1, cthreads);
             }
-            if (writer && sizeof(T) == 4) {
+            if (A.hist) {
+                // every consumer thread converts its packs of all 2m pair rows, newest -> oldest
+                // (the original row is kept in registers as the successor of the next older pair)
+                constexpr int VEC = VecOf<T>::N;
+                for (int pk = tid; pk < TILE / VEC; pk += cthreads) {
+                    Pack<T> xn = ld_pack<T>(st + TILE, pk), gn = ld_pack<T>(st + 2 * TILE, pk);
+                    for (int q = m - 1; q >= 0; --q) {
+                        T* sx = st + (3 + 2 * q) * TILE;
+                        T* sg = st + (4 + 2 * q) * TILE;
+                        const Pack<T> xq = ld_pack<T>(sx, pk), gq = ld_pack<T>(sg, pk);
+                        Pack<T> ds, dy;
+#pragma unroll
+                        for (int u = 0; u < VEC; ++u) {
+                            ds.v[u] = xq.v[u] - xn.v[u];
+                            dy.v[u] = gq.v[u] - gn.v[u];
+                        }
+                        st_pack<T>(sx, pk, ds);
+                        st_pack<T>(sg, pk, dy);
+                        xn = xq;
+                        gn = gq;
+                    }
+                }
+                named_bar_sync(2, cthreads);
+            } else if (writer && sizeof(T) == 4) {
                 // Float32: the same work on 16-byte packs (lane l owns the packs l, l + 32 k, ... of
                 // its warp's share: the partition of the accumulation loop below)
                 constexpr int VEC = VecOf<T>::N;
@@ -228,6 +255,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
             } else if (needs_pair) {
                 mbar_wait(&pair_bar[s], ph);
             }
+            // (the chain of else-ifs: with HISTORY there is no writer role and nobody waits for it)
             if constexpr (sizeof(T) == 8) {
 #pragma unroll 2
                 for (int e = sub * 32 + lane; e < TILE; e += 32 * k) {
@@ -292,7 +320,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
             }
             // release the stage (the writer's generic-proxy stores into it must be
             // ordered before the next bulk copy)
-            if (partial || writer) fence_proxy_async();
+            if (partial || writer || A.hist) fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
         }
@@ -397,10 +425,11 @@ static int gram2_dispatch(opkb_context* ctx, Gram2Args<T>& A, int nroles, int* n
 
 template <typename T>
 static int gram2_run(opkb_context* ctx, int64_t n, int m, const void* const* Sp, const void* const* Yp,
-                     const void* v0, const void* x, const void* gcur, int masked, double* G)
+                     const void* v0, const void* x, const void* gcur, int masked, double* G, int hist = 0)
 {
     Gram2Args<T> A;
     memset(&A, 0, sizeof(A));
+    A.hist = hist;
     A.rows[0] = (const T*)v0;
     A.rows[1] = (const T*)x;
     A.rows[2] = (const T*)gcur;

@@ -70,6 +70,14 @@ struct opkb_vmlmb_ {
     int opt_xspec;      // OPKB_XSPEC (default 1)
     int opt_maskb;      // OPKB_MASKB (default 1)
     int opt_carry_check;
+    int opt_history;    // OPKB_HISTORY (default 1)
+    // Representation of the pairs on the Gram path.  hist = 1: slot k keeps the ITERATE (x_k, g_k)
+    // saved when line search k started (src/quasinewton.jl:562-563) and is never turned into the
+    // difference of :512-513: pair k is S[k] - S[succ(k)] (succ: the slot saved next, (x, g) for
+    // the newest pair), formed on the fly by the ring kernels -- the fused kernel then writes no
+    // s', y' (2m + 9 passes instead of 2m + 11).  hist = 0: the reference's stored differences
+    // (sequential two-loop, BLMVM, OPKB_HISTORY=0).  -1: not decided yet (no pair formed).
+    int hist;
 };
 
 static int env_int(const char* name, int dflt)
@@ -167,6 +175,8 @@ extern "C" int opkb_vmlmb_create(opkb_context* ctx, int eltype, int64_t n, int m
     ws->opt_xspec = env_int("OPKB_XSPEC", 1);
     ws->opt_maskb = env_int("OPKB_MASKB", 1);
     ws->opt_carry_check = getenv("OPKB_CARRY_CHECK") ? 1 : 0;
+    ws->opt_history = env_int("OPKB_HISTORY", 1);
+    ws->hist = (method == 1 || !ws->opt_history) ? 0 : -1;
     int rc = 0;
     rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->x);
     rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->g);
@@ -181,7 +191,8 @@ extern "C" int opkb_vmlmb_create(opkb_context* ctx, int eltype, int64_t n, int m
     // wants them, so that whether a rank carries never depends on a rank-local allocation
     // Float64: always (up to 12 pairs); Float32: up to 8 pairs, where the SPLIT / 11-warp instances
     // run (the 7-warp Float32 instances of 9..12 pairs are issue-bound: only with OPKB_CARRY=2)
-    if (!rc && method != 1 && mem <= 12 && ws->opt_carry != 0 &&
+    // (with the iterate history the new pair is never materialised: no spare buffers)
+    if (!rc && ws->hist == 0 && method != 1 && mem <= 12 && ws->opt_carry != 0 &&
         (eltype == OPKB_DOUBLE || ws->opt_carry == 2 || mem <= 8)) {
         rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->carry_s);
         rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->carry_y);
@@ -547,14 +558,16 @@ static int gram_from_carry(opkb_vmlmb* ws, int mark, int m, const int* slots, do
     G[(2 * nn + 1) * W] = D[4 * MB + 1];
     G[(2 * nn) * W + 1 + nn] = D[4 * MB + 2];
     G[(2 * nn + 1) * W + 1 + nn] = D[4 * MB + 3];
-    // the pair itself was written to the spare buffers: swap them in (the buffers
-    // that held x0, g0 become the spares of the next launch)
-    void* t = ws->S[mark]->data;
-    ws->S[mark]->data = ws->carry_s->data;
-    ws->carry_s->data = t;
-    t = ws->Y[mark]->data;
-    ws->Y[mark]->data = ws->carry_y->data;
-    ws->carry_y->data = t;
+    if (ws->hist != 1) {
+        // the pair itself was written to the spare buffers: swap them in (the buffers
+        // that held x0, g0 become the spares of the next launch)
+        void* t = ws->S[mark]->data;
+        ws->S[mark]->data = ws->carry_s->data;
+        ws->carry_s->data = t;
+        t = ws->Y[mark]->data;
+        ws->Y[mark]->data = ws->carry_y->data;
+        ws->carry_y->data = t;
+    }   // (iterate history: slot `mark` keeps (x0, g0); the pair is x0 - x, g0 - g on the fly)
     ws->carry_valid = 0;
     ws->carry_hits += 1;
     return 0;
@@ -572,6 +585,7 @@ extern "C" int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots
         return opkb_set_error(OPKB_EINVAL, "the newest pair (slots[m-1]) must be `mark`");
     for (int j = 0; j < m; ++j)
         if (slots[j] < 0 || slots[j] >= ws->mem) return opkb_set_error(OPKB_EINVAL, "slot out of range");
+    if (ws->hist < 0) ws->hist = 1;     // the Gram path keeps the iterate history (see opkb_vmlmb_)
     bool carried = false;
     if (ws->carry_valid && ws->Gc_valid && mark == ws->carry_mark && m >= 2) {
         // the caller took the speculated trial point (nothing else touched the
@@ -583,7 +597,7 @@ extern "C" int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots
             rc = gram_from_carry(ws, mark, m, slots, G);
             if (rc) return rc;
             carried = true;
-            if (ws->opt_carry_check && vmlmb_ensure_p(ws) == 0) {
+            if (ws->opt_carry_check && ws->hist != 1 && vmlmb_ensure_p(ws) == 0) {
                 // development aid: the same block by a sweep over the same state (the
                 // pair is already formed: x = g = 0 makes the in-place update the identity)
                 opkb_vector* z = NULL;
@@ -635,9 +649,9 @@ extern "C" int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots
         const void* v0 = (ws->method == 2 ? ws->p->data : ws->g->data);
         const void* gcur = (ws->method == 1 ? ws->p->data : ws->g->data);
         if (ws->eltype == OPKB_DOUBLE)
-            rc = gram2_run<double>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur, ws->method == 2, G);
+            rc = gram2_run<double>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur, ws->method == 2, G, ws->hist == 1);
         else
-            rc = gram2_run<float>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur, ws->method == 2, G);
+            rc = gram2_run<float>(ws->ctx, ws->n, m, Sp, Yp, v0, ws->x->data, gcur, ws->method == 2, G, ws->hist == 1);
         if (rc) {
             ws->Gc_valid = 0;
             return rc;
@@ -659,6 +673,8 @@ extern "C" int opkb_vmlmb_last_gram(const opkb_vmlmb* ws, int* m, int* slots, do
     if (G) memcpy(G, ws->Gc, sizeof(double) * 2 * ws->Gc_m * (ws->Gc_m + 1));
     return 0;
 }
+
+extern "C" int opkb_vmlmb_history(const opkb_vmlmb* ws) { return ws ? ws->hist : -1; }
 
 extern "C" int opkb_vmlmb_carry_stats(const opkb_vmlmb* ws, int64_t* hits, int64_t* misses)
 {
@@ -917,10 +933,14 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
             if (carry && A.m == ws->mem && slots[0] != mark_next) carry = 0;
             if (carry && A.m < ws->mem)
                 for (int j = 0; j < A.m; ++j) if (slots[j] == mark_next) carry = 0;
-            // the spare buffers exist iff the workspace was created for it (Float64, or Float32
-            // with OPKB_CARRY=2: those instances are issue-bound): same on every rank
-            if (!ws->carry_s || !ws->carry_y) carry = 0;
-            if (carry) {
+            if (ws->hist == 1) {
+                // iterate history: nothing to write, no spare buffers; same rule for the element types
+                if (ws->opt_carry == 0 || (sizeof(T) == 4 && ws->opt_carry != 2 && ws->mem > 8)) carry = 0;
+            } else if (!ws->carry_s || !ws->carry_y) {
+                // the spare buffers exist iff the workspace was created for it: same on every rank
+                carry = 0;
+            }
+            if (carry && ws->hist != 1) {
                 B.sout = (T*)ws->carry_s->data;
                 B.yout = (T*)ws->carry_y->data;
             }
@@ -939,6 +959,7 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         }
         B.use = A.use;
         B.m = A.m;
+        B.hist = (ws->hist == 1);
         B.nrows = nr;
         B.gamma = A.gamma;
         B.lo_val = A.lo.val;
@@ -1024,6 +1045,8 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
     }
 
     // ---- the rest (tail of the ring path, or everything) with the register kernel -----
+    if (done < ws->n && ws->hist == 1 && !steepest && A.m >= 1)
+        return opkb_set_error(OPKB_EINVAL, "the direction ring does not fit (m = %d): set OPKB_HISTORY=0", A.m);
     if (done < ws->n) {
         {
             int rc = vmlmb_ensure_p(ws);   // v0 / the mask are read from p here
@@ -1276,6 +1299,9 @@ static int step_run(opkb_vmlmb* ws, int first, const opkb_vector* u, double a, i
                     double out[3])
 {
     opkb_context* ctx = ws->ctx;
+    if (ws->hist == 1)
+        return opkb_set_error(OPKB_EINVAL, "this workspace keeps the iterate history of the Gram path: the "
+                              "step-by-step recursion needs its own workspace");
     {
         int rc = vmlmb_ensure_p(ws);
         if (rc) return rc;
@@ -1374,6 +1400,10 @@ extern "C" int opkb_vmlmb_pair_update(opkb_vmlmb* ws, int mark, double out[2])
     if (rc) return rc;
     if (!out) return opkb_set_error(OPKB_EINVAL, "NULL result");
     opkb_context* ctx = ws->ctx;
+    if (ws->hist == 1)
+        return opkb_set_error(OPKB_EINVAL, "this workspace keeps the iterate history of the Gram path "
+                              "(opkb_vmlmb_gram was used): the step-by-step recursion needs its own workspace");
+    ws->hist = 0;
     ws->carry_valid = 0;
     ws->Gc_valid = 0;    // the pairs change outside opkb_vmlmb_gram
     const opkb_vector* gs = (ws->method == 1 ? ws->p : ws->g);

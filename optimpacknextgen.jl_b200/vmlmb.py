@@ -823,6 +823,12 @@ class VMLMB:
         check(_lib.lib().opkb_vmlmb_carry_stats(self._ws, C.byref(h), C.byref(m)))
         return (h.value, m.value)
 
+    @property
+    def history(self) -> int:
+        """1: the workspace keeps the iterate history (pairs formed on the fly, nothing written
+        back); 0: the reference's stored differences; -1: not decided yet (opkb_vmlmb_history)."""
+        return _lib.lib().opkb_vmlmb_history(self._ws) if self._ws else 0
+
     def last_gram(self):
         """(slots, G) of the last Gram block (2m x (m+1), row-major) or None."""
         if not self._ws:

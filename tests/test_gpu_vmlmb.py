@@ -203,11 +203,16 @@ def test_linesearch_options_and_limits(opk, oracle):
         assert np.abs(x - 1).max() < 1e-3
 
 
-def test_phase_kernels_single_step(opk, oracle):
+@pytest.mark.parametrize("history", [0, 1], ids=["stored-differences", "iterate-history"])
+def test_phase_kernels_single_step(opk, oracle, history, monkeypatch):
     """P3/P4 from an identical state: Gram block vs numpy, direction vs the
-    oracle's apply_lbfgs! on the free set (tight tolerance, no chaos)."""
+    oracle's apply_lbfgs! on the free set (tight tolerance, no chaos) -- for both
+    representations of the pairs (include/opkb200.h, opkb_vmlmb_history): the stored
+    differences of the reference, and the iterate history whose differences the ring
+    kernels form on the fly."""
     import ctypes as C
     from opkb200 import _lib
+    monkeypatch.setenv("OPKB_HISTORY", str(history))     # (read when a workspace is created)
     rng = np.random.default_rng(3)
     ctx = opk.default_context()
     L = _lib.lib()
@@ -231,17 +236,37 @@ def test_phase_kernels_single_step(opk, oracle):
         mark = m - 1
         x0 = (x + S[mark]).astype(dtype)
         g0 = (g + Y[mark]).astype(dtype)
-        for k in range(mem):
-            ops.vector("S", k).upload(x0 if k == mark else S[k])
-            ops.vector("Y", k).upload(g0 if k == mark else Y[k])
-        S[mark] = x0 - x
-        Y[mark] = g0 - g
+        if history:
+            # slots 0 .. m-1 hold the ITERATES of m consecutive line searches, the current (x, g)
+            # ends the newest pair: the pairs are the rounded differences of neighbours
+            X = [None] * m + [x]
+            Gr = [None] * m + [g]
+            for k in range(m - 1, -1, -1):
+                X[k] = (X[k + 1] + S[k]).astype(dtype)
+                Gr[k] = (Gr[k + 1] + Y[k]).astype(dtype)
+            for k in range(m):
+                ops.vector("S", k).upload(X[k])
+                ops.vector("Y", k).upload(Gr[k])
+                S[k] = X[k] - X[k + 1]
+                Y[k] = Gr[k] - Gr[k + 1]
+            x0, g0 = X[mark], Gr[mark]
+        else:
+            for k in range(mem):
+                ops.vector("S", k).upload(x0 if k == mark else S[k])
+                ops.vector("Y", k).upload(g0 if k == mark else Y[k])
+            S[mark] = x0 - x
+            Y[mark] = g0 - g
         slots = list(range(m))
         G = (C.c_double * (2 * m * (m + 1)))()
         _lib.check(L.opkb_vmlmb_gram(s._ws, mark, m, (C.c_int * m)(*slots), G))
         G = np.array(G).reshape(2 * m, m + 1)
-        assert np.array_equal(ops.vector("S", mark).download(), S[mark])
-        assert np.array_equal(ops.vector("Y", mark).download(), Y[mark])
+        assert s.history == history
+        if history:      # nothing is written back: the slot still holds (x0, g0)
+            assert np.array_equal(ops.vector("S", mark).download(), x0)
+            assert np.array_equal(ops.vector("Y", mark).download(), g0)
+        else:
+            assert np.array_equal(ops.vector("S", mark).download(), S[mark])
+            assert np.array_equal(ops.vector("Y", mark).download(), Y[mark])
         free = p != 0
         # Float64: exact products, double accumulation.  Float32: the products of one
         # stage (<= 32 per lane) are summed with FFMA before the double accumulation
