@@ -190,7 +190,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
         }
     }
 
+    const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
     if (warp == CWARPS) {
+        const uint32_t stage_a = smem_u32(stage0);
         int s = 0;
         uint32_t ph = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= (uint32_t)(++s == NSTAGE), s = (s == NSTAGE) ? 0 : s) {
@@ -198,14 +200,14 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
             uint32_t bytes = rowbytes;
             if (base + TILE > A.n) bytes = (uint32_t)(((A.n - base) * sizeof(T)) & ~(size_t)15);
             if (lane == 0) {
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                mbar_expect_tx(&full_bar[s], bytes * (uint32_t)(NR - A.v0_from_g));
+                mbar_wait_a(empty_a + 8u * s, ph ^ 1u);
+                mbar_expect_tx_a(full_a + 8u * s, bytes * (uint32_t)(NR - A.v0_from_g));
             }
             __syncwarp();
-            T* dst = stage0 + s * stage_elems;
+            const uint32_t dst = stage_a + (uint32_t)(s * stage_elems) * (uint32_t)sizeof(T);
             if (bytes > 0) {
                 for (int r = lane + A.v0_from_g; r < NR; r += 32)
-                    bulk_g2s(dst + r * TILE, A.rows[r] + base, bytes, &full_bar[s]);
+                    bulk_g2s_a(dst + (uint32_t)r * rowbytes, A.rows[r] + base, bytes, full_a + 8u * s);
             }
         }
     } else {
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= (uint32_t)(++s == NSTAGE), s = (s == NSTAGE) ? 0 : s) {
             T* st = stage0 + s * stage_elems;
             const int64_t base = tile * TILE;
-            mbar_wait(&full_bar[s], ph);
+            mbar_wait_a(full_a + 8u * s, ph);
             const bool partial = (base + TILE > A.n);
             if (partial) {
                 // elements the 16-byte granular bulk copy left out, zero padding
@@ -559,7 +561,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
             // (SPLIT: rows 0 and 2, HISTORY: the pair rows were written through the generic proxy)
             if (partial || SPLIT || A.hist) fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (lane == 0) mbar_arrive_a(empty_a + 8u * s);
         }
     }
     acc[2] = (double)smin;

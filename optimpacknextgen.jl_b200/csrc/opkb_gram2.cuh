@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
 #pragma unroll
         for (int c = 0; c < CT; ++c) acc[r][c] = 0.0;
 
+    const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar), pair_a = smem_u32(pair_bar);
     if (warp == cwarps) {
         // ------------------------------ producer ---------------------------------
         // lane 0 waits for the stage and arms its barrier, then every lane issues
@@ -130,8 +131,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
             uint32_t bytes = rowbytes;
             if (base + TILE > A.n) bytes = (uint32_t)(((A.n - base) * sizeof(T)) & ~(size_t)15);
             if (lane == 0) {
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                mbar_expect_tx(&full_bar[s], bytes * (uint32_t)NRL);
+                mbar_wait_a(empty_a + 8u * s, ph ^ 1u);
+                mbar_expect_tx_a(full_a + 8u * s, bytes * (uint32_t)NRL);
             }
             __syncwarp();
             if (bytes > 0) {
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
             const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
             T* st = stage0 + s * stage_elems;
             const int64_t base = tile * TILE;
-            mbar_wait(&full_bar[s], ph);
+            mbar_wait_a(full_a + 8u * s, ph);
             const bool partial = (base + TILE > A.n);
             if (partial) {
                 // last tile: elements the 16-byte granular bulk copy left out, zero padding
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&pair_bar[s]);
+                if (lane == 0) mbar_arrive_a(pair_a + 8u * s);
             } else if (writer) {
                 for (int e = sub * 32 + lane; e < TILE; e += 32 * k) {
                     const T sn = st[snew + e] - st[TILE + e];       // s_new = x0 - x (element type)
@@ -251,9 +252,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
                 // a writer warp only reads back the elements it has just updated (same
                 // element partition in the loop below): no wait on the other writers
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&pair_bar[s]);
+                if (lane == 0) mbar_arrive_a(pair_a + 8u * s);
             } else if (needs_pair) {
-                mbar_wait(&pair_bar[s], ph);
+                mbar_wait_a(pair_a + 8u * s, ph);
             }
             // (the chain of else-ifs: with HISTORY there is no writer role and nobody waits for it)
             if constexpr (sizeof(T) == 8) {
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
             // ordered before the next bulk copy)
             if (partial || writer || A.hist) fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (lane == 0) mbar_arrive_a(empty_a + 8u * s);
         }
     }
     __syncthreads();

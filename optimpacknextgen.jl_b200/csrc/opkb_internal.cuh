@@ -530,6 +530,43 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         : "memory");
 }
 
+// The same on the 32-bit shared-memory address of the barrier (taken once, outside the tile loop:
+// the generic -> shared conversion and the polling loop were 14 % of the instructions of the fused
+// direction kernel), with a suspend-time hint: the warp sleeps in hardware until the phase completes
+// or the hint expires instead of spinning through the issue slots.
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP_A:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra WAIT_DONE_A;\n"
+        "bra WAIT_LOOP_A;\n"
+        "WAIT_DONE_A:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity), "r"(0x989680u)
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
 {
     asm volatile(
