@@ -212,7 +212,7 @@ def test_phase_kernels_single_step(opk, oracle, history, monkeypatch):
     kernels form on the fly."""
     import ctypes as C
     from opkb200 import _lib
-    monkeypatch.setenv("OPKB_HISTORY", str(history))     # (read when a workspace is created)
+    monkeypatch.setenv("OPKB_HISTORY", str(2 * history))  # (read at workspace creation; 2: also for Float32)
     rng = np.random.default_rng(3)
     ctx = opk.default_context()
     L = _lib.lib()
