@@ -12,6 +12,7 @@
 // 16-byte granularity, completed and zero-padded by the consumers, and its
 // results are stored element by element.
 #pragma once
+#include <type_traits>
 
 #define DIR2_MAXSTAGE 8
 #define DIR2_CORR_SHARE 8    // a warp gives up its corrections beyond 8 / 32 changed elements on average ...
@@ -97,7 +98,16 @@ template <int MB> struct Dir2Carry {
 // accumulation scheme of the Float32 Gram sweep (opkb_gram2.cuh).  4 ceil(5 MB / CW) + 4
 // accumulators per thread instead of 4 MB + 4: 10 consumer warps instead of 7, no Float32 ->
 // Float64 conversion of the pair rows.  Fixed item -> warp map and fixed part order: deterministic.
-template <typename T, int FUSE, int MB, int TILE, int CARRY, int EXACT = 0, int CW = (CARRY ? 7 : 8), int SPLIT = 0>
+//
+// SPEC = 1 (the headline instances): the grid-uniform flags of the common case -- VMLMB on a box
+// given by two arrays (bounded, masked, both bounds present as rows 3 and 4, v0 recomputed from g,
+// y = g differences), pairs kept as the iterate history -- are compile-time constants, and the tile
+// body is instantiated twice: without the per-element "is this a real element" predicates for the
+// whole tiles, with them for the last, partial one.  The generic instances (SPEC = 0) read the
+// flags from the arguments.
+struct Dir2RtBool { bool value; };
+template <typename T, int FUSE, int MB, int TILE, int CARRY, int EXACT = 0, int CW = (CARRY ? 7 : 8), int SPLIT = 0,
+          int SPEC = 0>
 __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, ReduceScratch rs)
 {
     constexpr int DIR2_THREADS = (CW + 1) * 32;
@@ -211,21 +221,27 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
             }
         }
     } else {
-        const int prow = 3 + (A.r_lo >= 0) + (A.r_hi >= 0) + (A.r_ysrc >= 0);  // first pair row
+        // grid-uniform flags: constants in the SPEC instances, arguments otherwise
+        const bool f_bounded = SPEC ? true : (A.bounded != 0);
+        const bool f_masked = SPEC ? true : (A.masked != 0);
+        const int f_has_lo = SPEC ? 1 : A.has_lo, f_has_hi = SPEC ? 1 : A.has_hi;
+        const int r_lo = SPEC ? 3 : A.r_lo, r_hi = SPEC ? 4 : A.r_hi, r_ysrc = SPEC ? -1 : A.r_ysrc;
+        const int f_v0g = SPEC ? 1 : A.v0_from_g;
+        const bool f_hist = SPEC ? true : (A.hist != 0);
+        const int prow = 3 + (r_lo >= 0) + (r_hi >= 0) + (r_ysrc >= 0);  // first pair row
         int s = 0;
         uint32_t ph = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= (uint32_t)(++s == NSTAGE), s = (s == NSTAGE) ? 0 : s) {
-            T* st = stage0 + s * stage_elems;
-            const int64_t base = tile * TILE;
-            mbar_wait_a(full_a + 8u * s, ph);
-            const bool partial = (base + TILE > A.n);
+        T* st = stage0;
+        int64_t base = 0;
+        auto tile_body = [&](auto partial_c) {
+            const bool partial = partial_c.value;
             if (partial) {
                 // elements the 16-byte granular bulk copy left out, zero padding
                 const int valid = (int)(A.n - base);
                 const int copied = (int)((((size_t)valid * sizeof(T)) & ~(size_t)15) / sizeof(T));
                 for (int idx = tid; idx < NR * TILE; idx += CTHREADS) {
                     const int r = idx / TILE, e = idx - r * TILE;
-                    if (e >= copied && r >= A.v0_from_g)
+                    if (e >= copied && r >= f_v0g)
                         st[r * TILE + e] = (e < valid) ? A.rows[r][base + e] : T(0);
                 }
                 named_bar_sync(1, CTHREADS);
@@ -241,17 +257,17 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                 for (int q = 0; q < VEC; ++q) ok[q] = !partial || (base + e + q < A.n);
                 Pack<T> px = ld_pack<T>(st + TILE, e / VEC);
                 Pack<T> pg = ld_pack<T>(st + 2 * TILE, e / VEC);
-                Pack<T> pl = (A.r_lo >= 0) ? ld_pack<T>(st + A.r_lo * TILE, e / VEC) : splat_pack<T>(A.lo_val);
-                Pack<T> ph_ = (A.r_hi >= 0) ? ld_pack<T>(st + A.r_hi * TILE, e / VEC) : splat_pack<T>(A.hi_val);
-                Pack<T> pys = (A.r_ysrc >= 0) ? ld_pack<T>(st + A.r_ysrc * TILE, e / VEC) : pg;
+                Pack<T> pl = (r_lo >= 0) ? ld_pack<T>(st + r_lo * TILE, e / VEC) : splat_pack<T>(A.lo_val);
+                Pack<T> ph_ = (r_hi >= 0) ? ld_pack<T>(st + r_hi * TILE, e / VEC) : splat_pack<T>(A.hi_val);
+                Pack<T> pys = (r_ysrc >= 0) ? ld_pack<T>(st + r_ysrc * TILE, e / VEC) : pg;
                 Pack<T> pv;
                 bool flo[VEC], fhi[VEC];   // x may decrease / increase (can_change, src/bounds.jl:638-648)
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {
-                    flo[q] = !A.has_lo | (px.v[q] > pl.v[q]);
-                    fhi[q] = !A.has_hi | (px.v[q] < ph_.v[q]);
+                    flo[q] = !f_has_lo | (px.v[q] > pl.v[q]);
+                    fhi[q] = !f_has_hi | (px.v[q] < ph_.v[q]);
                 }
-                if (A.v0_from_g) {
+                if (f_v0g) {
                     // p = project_direction!(p, x, lo, hi, -, g) (src/quasinewton.jl:396),
                     // bit-identical to the stored vector, without reading it
 #pragma unroll
@@ -262,14 +278,14 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                 Pack<T> v = pv;
                 bool upd[VEC];
 #pragma unroll
-                for (int q = 0; q < VEC; ++q) upd[q] = !A.masked || (pv.v[q] != T(0));
+                for (int q = 0; q < VEC; ++q) upd[q] = !f_masked || (pv.v[q] != T(0));
                 const T* pb = st + prow * TILE + e;
                 // apply_lbfgs! :716-745 / :747-779, rounding sequence of the reference: unrolled and
                 // branch-free per element.  A pair that does not take part (rho <= 0, :727 / :759 -- it
                 // stays in the memory for `mem` iterations) is skipped by a test that is uniform over
                 // the grid.  The chain also runs on the masked elements, whose result is then replaced
                 // by what the reference gives them, gamma*v0 (they are never updated).
-                if (!A.hist) {
+                if (!f_hist) {
 #pragma unroll
                     for (int jj = 0; jj < MB; ++jj) {
                         const int j = MB - 1 - jj;
@@ -340,13 +356,13 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {
                     T di = v.v[q];
-                    if (A.bounded)  // project_direction!(d, x, lo, hi, -, d) :535
+                    if (f_bounded)  // project_direction!(d, x, lo, hi, -, d) :535
                         di = projdir_m1(flo[q], fhi[q], di);
                     v.v[q] = di;
                     acc[0] = dacc(pg.v[q], di, acc[0]);   // vdot(g, d) :537
                     acc[1] = dacc(di, di, acc[1]);        // vnorm2(d) :629
-                    if (A.bounded)                        // step_limits(x, lo, hi, -1, d) :577
-                        step_limit_update_fast(px.v[q], pl.v[q], ph_.v[q], A.has_lo, A.has_hi, -di, smin, smax);
+                    if (f_bounded)                        // step_limits(x, lo, hi, -1, d) :577
+                        step_limit_update_fast(px.v[q], pl.v[q], ph_.v[q], f_has_lo, f_has_hi, -di, smin, smax);
                 }
                 Pack<T> xt, gt, pt;
                 if (!FUSE && A.xout) {
@@ -356,7 +372,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
 #pragma unroll
                     for (int q = 0; q < VEC; ++q) {
                         T xi = px.v[q] + T(-1) * v.v[q];
-                        if (A.bounded) xi = fastclamp(xi, pl.v[q], ph_.v[q]);
+                        if (f_bounded) xi = fastclamp(xi, pl.v[q], ph_.v[q]);
                         xt.v[q] = xi;
                     }
                 }
@@ -370,7 +386,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
 #pragma unroll
                     for (int q = 0; q < VEC; ++q) {
                         T xi = px.v[q] + T(-1) * v.v[q];
-                        if (A.bounded) xi = fastclamp(xi, pl.v[q], ph_.v[q]);
+                        if (f_bounded) xi = fastclamp(xi, pl.v[q], ph_.v[q]);
                         xt.v[q] = xi;
                     }
                     if (FUSE == OPKB_OBJ_ROSENBROCK) {
@@ -388,7 +404,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
 #pragma unroll
                     for (int q = 0; q < VEC; ++q) {
                         const T xi = xt.v[q], gi = gt.v[q];
-                        const T pi = A.bounded ? projdir_m1(!A.has_lo | (xi > pl.v[q]), !A.has_hi | (xi < ph_.v[q]), gi)
+                        const T pi = f_bounded ? projdir_m1(!f_has_lo | (xi > pl.v[q]), !f_has_hi | (xi < ph_.v[q]), gi)
                                                : gi;
                         pt.v[q] = pi;
                         if (ok[q]) {
@@ -410,7 +426,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                     for (int q = 0; q < VEC; ++q) {
                         sn.v[q] = px.v[q] - xt.v[q];
                         yn.v[q] = pg.v[q] - gt.v[q];
-                        const bool frn = !A.masked || (pt.v[q] != T(0));
+                        const bool frn = !f_masked || (pt.v[q] != T(0));
                         v0n[q] = ok[q] ? pt.v[q] : T(0);                 // v0' = p' (g' for L-BFGS)
                         ynm[q] = (ok[q] && frn) ? yn.v[q] : T(0);        // y' on the new free set
                     }
@@ -458,7 +474,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                         cd[4 * MB + 2] = fma(sd, ynd[q], cd[4 * MB + 2]);
                         cd[4 * MB + 3] = fma(yd, ynd[q], cd[4 * MB + 3]);
                     }
-                    if (A.masked) {
+                    if (f_masked) {
                         // elements that enter (+) or leave (-) the free set: signed products
                         // between the stored pairs, one element at a time, whole warp
 #pragma unroll
@@ -559,7 +575,18 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                 }
             }
             // (SPLIT: rows 0 and 2, HISTORY: the pair rows were written through the generic proxy)
-            if (partial || SPLIT || A.hist) fence_proxy_async();
+            if (partial || SPLIT || f_hist) fence_proxy_async();
+        };
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= (uint32_t)(++s == NSTAGE), s = (s == NSTAGE) ? 0 : s) {
+            st = stage0 + s * stage_elems;
+            base = tile * TILE;
+            mbar_wait_a(full_a + 8u * s, ph);
+            if constexpr (SPEC != 0) {
+                if (base + TILE > A.n) tile_body(std::true_type{});
+                else tile_body(std::false_type{});
+            } else {
+                tile_body(Dir2RtBool{base + TILE > A.n});
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive_a(empty_a + 8u * s);
         }

@@ -1,5 +1,7 @@
 // opkb_direction2_carry.cu -- instances of k_direction2 with the incremental Gram
 // (direction + speculative first trial + the next Gram block, see opkb_direction2.cuh).
+#include <stdlib.h>
+
 #include "opkb_internal.cuh"
 #include "opkb_direction2.cuh"
 
@@ -23,16 +25,29 @@ int dir2_launch_carry(opkb_context* ctx, const Dir2Args<T>& B, int fuse, int mb,
     if (B.tile != ((mb == 5) ? TC5 : TC))
         return opkb_set_error(OPKB_EINVAL, "carry instances use %d / %d-byte rows", DIR2_CARRY_ROWB5, DIR2_CARRY_ROWB);
     // (MB, EXACT) instances: m < 5: (5, 0); m = 5: (5, 1); m <= 8: (8, 0); m = 10: (10, 1); else (12, 0)
-#define DIR2_PICK(F)                                                              \
-    do {                                                                          \
-        if (mb == 5 && B.m == 5) kern = k_direction2<T, F, 5, TC5, 1, 1, 11>;     \
-        else if (mb == 5) kern = k_direction2<T, F, 5, TC5, 1, 0, 11>;            \
-        else if (mb == 8) kern = k_direction2<T, F, 8, TC, 1, 0>;                 \
-        else if (mb == 10 && B.m == 10) kern = k_direction2<T, F, 10, TC, 1, 1>;  \
-        else if (mb == 12) kern = k_direction2<T, F, 12, TC, 1, 0>;               \
+#define DIR2_PICK(F, SPEC)                                                                  \
+    do {                                                                                    \
+        if (mb == 5 && B.m == 5) kern = k_direction2<T, F, 5, TC5, 1, 1, 11, 0, SPEC>;      \
+        else if (mb == 5) kern = k_direction2<T, F, 5, TC5, 1, 0, 11, 0, SPEC>;             \
+        else if (mb == 8) kern = k_direction2<T, F, 8, TC, 1, 0, 7, 0, SPEC>;               \
+        else if (mb == 10 && B.m == 10) kern = k_direction2<T, F, 10, TC, 1, 1, 7, 0, SPEC>; \
+        else if (mb == 12) kern = k_direction2<T, F, 12, TC, 1, 0, 7, 0, SPEC>;             \
     } while (0)
-    if (fuse == OPKB_OBJ_ROSENBROCK) DIR2_PICK(OPKB_OBJ_ROSENBROCK);
-    else if (fuse == OPKB_OBJ_QUADRATIC) DIR2_PICK(OPKB_OBJ_QUADRATIC);
+    // SPEC = 1 (Float64): VMLMB on a box given by two arrays with the iterate history -- the flags are
+    // compile-time constants and the whole tiles run a body without the partial-tile predicates
+    static const int spec_on = getenv("OPKB_DIR_SPEC") ? atoi(getenv("OPKB_DIR_SPEC")) : 1;
+    const bool spec = sizeof(T) == 8 && spec_on && B.hist && B.bounded && B.masked && B.has_lo && B.has_hi &&
+                      B.r_lo == 3 && B.r_hi == 4 && B.r_ysrc < 0 && B.v0_from_g;
+    if constexpr (sizeof(T) == 8) {
+        if (spec) {
+            if (fuse == OPKB_OBJ_ROSENBROCK) DIR2_PICK(OPKB_OBJ_ROSENBROCK, 1);
+            else if (fuse == OPKB_OBJ_QUADRATIC) DIR2_PICK(OPKB_OBJ_QUADRATIC, 1);
+        }
+    }
+    if (!kern) {
+        if (fuse == OPKB_OBJ_ROSENBROCK) DIR2_PICK(OPKB_OBJ_ROSENBROCK, 0);
+        else if (fuse == OPKB_OBJ_QUADRATIC) DIR2_PICK(OPKB_OBJ_QUADRATIC, 0);
+    }
 #undef DIR2_PICK
     return dir2_do_launch<T>(ctx, kern, B, (mb == 5) ? 384 : DIR2_NTHREADS(1), smem, grid);
 }
