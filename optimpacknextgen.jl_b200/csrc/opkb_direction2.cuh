@@ -99,7 +99,7 @@ template <int MB> struct Dir2Carry {
 // accumulators per thread instead of 4 MB + 4: 10 consumer warps instead of 7, no Float32 ->
 // Float64 conversion of the pair rows.  Fixed item -> warp map and fixed part order: deterministic.
 //
-// SPEC = 1 (the headline instances): the grid-uniform flags of the common case -- VMLMB on a box
+// SPEC = 1 (the headline instances; 2: the same with stored differences): the grid-uniform flags of the common case -- VMLMB on a box
 // given by two arrays (bounded, masked, both bounds present as rows 3 and 4, v0 recomputed from g,
 // y = g differences), pairs kept as the iterate history -- are compile-time constants, and the tile
 // body is instantiated twice: without the per-element "is this a real element" predicates for the
@@ -146,6 +146,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
     // 8 g'.d; 9 |x'|^2; 10 |s|^2; 11 number of free variables at x'
     constexpr int NACC = FUSE ? 12 : 4;
     T smin = T(INFINITY), smax = T(0);
+    int nfree_i = 0;
     double acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
         const int f_has_lo = SPEC ? 1 : A.has_lo, f_has_hi = SPEC ? 1 : A.has_hi;
         const int r_lo = SPEC ? 3 : A.r_lo, r_hi = SPEC ? 4 : A.r_hi, r_ysrc = SPEC ? -1 : A.r_ysrc;
         const int f_v0g = SPEC ? 1 : A.v0_from_g;
-        const bool f_hist = SPEC ? true : (A.hist != 0);
+        const bool f_hist = (SPEC == 1) ? true : ((SPEC == 2) ? false : (A.hist != 0));   // SPEC 2: stored differences
         const int prow = 3 + (r_lo >= 0) + (r_hi >= 0) + (r_ysrc >= 0);  // first pair row
         int s = 0;
         uint32_t ph = 0;
@@ -414,7 +415,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                             acc[8] = dacc(gi, v.v[q], acc[8]);      // g'.d (:434)
                             acc[9] = dacc(xi, xi, acc[9]);          // |x'|^2 (:446)
                             acc[10] = dacc(si, si, acc[10]);        // |s|^2 (:448)
-                            acc[11] += (pi != T(0)) ? 1.0 : 0.0;
+                            nfree_i += (pi != T(0)) ? 1 : 0;        // |sel| of the trial point (an integer add)
                         }
                     }
                 }
@@ -593,6 +594,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
     }
     acc[2] = (double)smin;
     acc[3] = (double)smax;
+    if (FUSE) acc[NACC - 1] = (double)nfree_i;
     __syncthreads();
     if constexpr (!CARRY) {
         block_reduce_publish<NACC, 8u, 4u>(acc, rs);  // slot 2: min, slot 3: max

@@ -15,10 +15,17 @@ int dir2_launch_carry(opkb_context* ctx, const Dir2Args<T>& B, int fuse, int mb,
         // Float32, up to 8 pairs: the dense sums of the stored pairs in a second phase by the warp
         // that owns the pair (SPLIT, opkb_direction2.cuh): 10 consumer warps on 5 KB rows
         if (mb == 8 && B.tile == TS) {
+            // SPEC = 2: VMLMB on a box given by two arrays, stored differences: flags as constants,
+            // whole tiles without the partial-tile predicates
+            static const int spec_on32 = getenv("OPKB_DIR_SPEC") ? atoi(getenv("OPKB_DIR_SPEC")) : 1;
+            const bool spec2 = spec_on32 && !B.hist && B.bounded && B.masked && B.has_lo && B.has_hi && B.r_lo == 3 &&
+                               B.r_hi == 4 && B.r_ysrc < 0 && B.v0_from_g;
             if (fuse == OPKB_OBJ_ROSENBROCK)
-                kern = k_direction2<T, OPKB_OBJ_ROSENBROCK, 8, TS, 1, 0, DIR2_SPLIT_CW, 1>;
+                kern = spec2 ? k_direction2<T, OPKB_OBJ_ROSENBROCK, 8, TS, 1, 0, DIR2_SPLIT_CW, 1, 2>
+                             : k_direction2<T, OPKB_OBJ_ROSENBROCK, 8, TS, 1, 0, DIR2_SPLIT_CW, 1, 0>;
             else if (fuse == OPKB_OBJ_QUADRATIC)
-                kern = k_direction2<T, OPKB_OBJ_QUADRATIC, 8, TS, 1, 0, DIR2_SPLIT_CW, 1>;
+                kern = spec2 ? k_direction2<T, OPKB_OBJ_QUADRATIC, 8, TS, 1, 0, DIR2_SPLIT_CW, 1, 2>
+                             : k_direction2<T, OPKB_OBJ_QUADRATIC, 8, TS, 1, 0, DIR2_SPLIT_CW, 1, 0>;
             return dir2_do_launch<T>(ctx, kern, B, (DIR2_SPLIT_CW + 1) * 32, smem, grid);
         }
     }
