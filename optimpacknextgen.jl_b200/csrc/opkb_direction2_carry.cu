@@ -18,14 +18,17 @@ int dir2_launch_carry(opkb_context* ctx, const Dir2Args<T>& B, int fuse, int mb,
             // SPEC = 2: VMLMB on a box given by two arrays, stored differences: flags as constants,
             // whole tiles without the partial-tile predicates
             static const int spec_on32 = getenv("OPKB_DIR_SPEC") ? atoi(getenv("OPKB_DIR_SPEC")) : 1;
-            const bool spec2 = spec_on32 && !B.hist && B.bounded && B.masked && B.has_lo && B.has_hi && B.r_lo == 3 &&
-                               B.r_hi == 4 && B.r_ysrc < 0 && B.v0_from_g;
+            const bool box = spec_on32 && B.bounded && B.masked && B.has_lo && B.has_hi && B.r_lo == 3 &&
+                             B.r_hi == 4 && B.r_ysrc < 0 && B.v0_from_g;
+            const int spec = !box ? 0 : (B.hist ? 1 : 2);
             if (fuse == OPKB_OBJ_ROSENBROCK)
-                kern = spec2 ? k_direction2<T, OPKB_OBJ_ROSENBROCK, 8, TS, 1, 0, DIR2_SPLIT_CW, 1, 2>
-                             : k_direction2<T, OPKB_OBJ_ROSENBROCK, 8, TS, 1, 0, DIR2_SPLIT_CW, 1, 0>;
+                kern = spec == 1 ? k_direction2<T, OPKB_OBJ_ROSENBROCK, 8, TS, 1, 0, DIR2_SPLIT_CW, 1, 1>
+                     : spec == 2 ? k_direction2<T, OPKB_OBJ_ROSENBROCK, 8, TS, 1, 0, DIR2_SPLIT_CW, 1, 2>
+                                 : k_direction2<T, OPKB_OBJ_ROSENBROCK, 8, TS, 1, 0, DIR2_SPLIT_CW, 1, 0>;
             else if (fuse == OPKB_OBJ_QUADRATIC)
-                kern = spec2 ? k_direction2<T, OPKB_OBJ_QUADRATIC, 8, TS, 1, 0, DIR2_SPLIT_CW, 1, 2>
-                             : k_direction2<T, OPKB_OBJ_QUADRATIC, 8, TS, 1, 0, DIR2_SPLIT_CW, 1, 0>;
+                kern = spec == 1 ? k_direction2<T, OPKB_OBJ_QUADRATIC, 8, TS, 1, 0, DIR2_SPLIT_CW, 1, 1>
+                     : spec == 2 ? k_direction2<T, OPKB_OBJ_QUADRATIC, 8, TS, 1, 0, DIR2_SPLIT_CW, 1, 2>
+                                 : k_direction2<T, OPKB_OBJ_QUADRATIC, 8, TS, 1, 0, DIR2_SPLIT_CW, 1, 0>;
             return dir2_do_launch<T>(ctx, kern, B, (DIR2_SPLIT_CW + 1) * 32, smem, grid);
         }
     }
