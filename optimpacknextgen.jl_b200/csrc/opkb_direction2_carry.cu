@@ -46,12 +46,15 @@ int dir2_launch_carry(opkb_context* ctx, const Dir2Args<T>& B, int fuse, int mb,
     // SPEC = 1 (Float64): VMLMB on a box given by two arrays with the iterate history -- the flags are
     // compile-time constants and the whole tiles run a body without the partial-tile predicates
     static const int spec_on = getenv("OPKB_DIR_SPEC") ? atoi(getenv("OPKB_DIR_SPEC")) : 1;
-    const bool spec = sizeof(T) == 8 && spec_on && B.hist && B.bounded && B.masked && B.has_lo && B.has_hi &&
+    const bool spec = sizeof(T) == 8 && spec_on && B.bounded && B.masked && B.has_lo && B.has_hi &&
                       B.r_lo == 3 && B.r_hi == 4 && B.r_ysrc < 0 && B.v0_from_g;
     if constexpr (sizeof(T) == 8) {
-        if (spec) {
+        if (spec && B.hist) {
             if (fuse == OPKB_OBJ_ROSENBROCK) DIR2_PICK(OPKB_OBJ_ROSENBROCK, 1);
             else if (fuse == OPKB_OBJ_QUADRATIC) DIR2_PICK(OPKB_OBJ_QUADRATIC, 1);
+        } else if (spec) {      // stored differences (OPKB_HISTORY=0)
+            if (fuse == OPKB_OBJ_ROSENBROCK) DIR2_PICK(OPKB_OBJ_ROSENBROCK, 2);
+            else if (fuse == OPKB_OBJ_QUADRATIC) DIR2_PICK(OPKB_OBJ_QUADRATIC, 2);
         }
     }
     if (!kern) {
