@@ -70,7 +70,7 @@ struct opkb_vmlmb_ {
     int opt_xspec;      // OPKB_XSPEC (default 1)
     int opt_maskb;      // OPKB_MASKB (default 1)
     int opt_carry_check;
-    int opt_history;    // OPKB_HISTORY: 1 default (Float64 only), 0 off, 2 also Float32
+    int opt_history;    // OPKB_HISTORY: 1 default (Float64, mem <= 8), 0 off, 2 always
     // Representation of the pairs on the Gram path.  hist = 1: slot k keeps the ITERATE (x_k, g_k)
     // saved when line search k started (src/quasinewton.jl:562-563) and is never turned into the
     // difference of :512-513: pair k is S[k] - S[succ(k)] (succ: the slot saved next, (x, g) for
@@ -176,10 +176,13 @@ extern "C" int opkb_vmlmb_create(opkb_context* ctx, int eltype, int64_t n, int m
     ws->opt_maskb = env_int("OPKB_MASKB", 1);
     ws->opt_carry_check = getenv("OPKB_CARRY_CHECK") ? 1 : 0;
     ws->opt_history = env_int("OPKB_HISTORY", 1);
-    // Float64: on (C4 +1 %, C2 +2.4 %: two writes less on an HBM-bound kernel).  Float32: off unless
-    // OPKB_HISTORY=2 -- those instances are issue-bound and the extra subtractions cost more than
-    // the two passes save (C5 shard: 118 against 129 it/s).
-    ws->hist = (method == 1 || !ws->opt_history || (eltype == OPKB_FLOAT && ws->opt_history != 2)) ? 0 : -1;
+    // The history saves two passes whatever m, forming the differences costs 2m subtractions and
+    // shared-memory stores per element: measured with the SPEC instances on a power-capped box, it wins
+    // 5 % at m = 5 (C2: 3417 -> 3588 it/s) and loses 1 % at m = 10 (C4: 96.0 -> 94.9 it/s); the Float32
+    // instances, issue-bound, always lose (C5 shard: 145 -> 132 it/s).  Default: Float64 with up to 8
+    // pairs; OPKB_HISTORY=2 forces it, =0 disables it.
+    ws->hist = (method == 1 || !ws->opt_history ||
+                (ws->opt_history != 2 && (eltype == OPKB_FLOAT || mem > 8))) ? 0 : -1;
     int rc = 0;
     rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->x);
     rc = rc ? rc : opkb_vector_create(ctx, eltype, n, &ws->g);
