@@ -308,10 +308,12 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                     }
                 } else {
                     // HISTORY: y_j = g_j - g_{j+1} (the same bits as the stored difference of
-                    // src/quasinewton.jl:513), formed while the chain walks newest -> oldest, and left
-                    // in the stage in place of g_j for everything that follows (dense sums,
-                    // corrections, the second phase of SPLIT); likewise s_j = x_j - x_{j+1} oldest ->
-                    // newest.  One subtraction and one shared-memory store per row and pack.
+                    // src/quasinewton.jl:513), formed while the chain walks newest -> oldest; likewise
+                    // s_j = x_j - x_{j+1} oldest -> newest.  One subtraction per row and pack, the
+                    // predecessor kept in registers.  The dense sums and the corrections below form
+                    // them again from the same rows (registers are cheaper than shared-memory stores +
+                    // a proxy fence per tile); only the SPLIT instances, whose second phase reads the
+                    // rows of other warps, leave the differences in the stage.
                     T* wb = const_cast<T*>(pb);
                     Pack<T> gnext = pg;
 #pragma unroll
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                             Pack<T> y;
 #pragma unroll
                             for (int q = 0; q < VEC; ++q) y.v[q] = gj.v[q] - gnext.v[q];
-                            st_pack<T>(wb + 2 * j * TILE, 0, y);
+                            if (SPLIT) st_pack<T>(wb + 2 * j * TILE, 0, y);
                             gnext = gj;
                             if (all_used || ((A.use >> j) & 1u)) {
 #pragma unroll
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                             Pack<T> sv;
 #pragma unroll
                             for (int q = 0; q < VEC; ++q) sv.v[q] = xj.v[q] - xn.v[q];
-                            st_pack<T>(wb + (2 * j + 1) * TILE, 0, sv);
+                            if (SPLIT) st_pack<T>(wb + (2 * j + 1) * TILE, 0, sv);
                             xj = xn;
                             if (all_used || ((A.use >> j) & 1u)) {
 #pragma unroll
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                             }
                         }
                     }
-                    __syncwarp();   // the corrections below read the packs of the other lanes of this warp
+                    if (SPLIT) __syncwarp();   // the corrections below read the packs of the other lanes of this warp
                 }
 #pragma unroll
                 for (int q = 0; q < VEC; ++q)
@@ -440,11 +442,28 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                         ynd[q] = (double)ynm[q];
                     }
                     if constexpr (!SPLIT) {
+                        Pack<T> hg = ld_pack<T>(pb, 0), hx = ld_pack<T>(pb + TILE, 0);   // (HISTORY: g_0, x_0)
 #pragma unroll
                         for (int j = 0; j < MB; ++j) {
                             if (EXACT || j < m) {
-                                const Pack<T> y = ld_pack<T>(pb + 2 * j * TILE, 0);
-                                const Pack<T> sv = ld_pack<T>(pb + (2 * j + 1) * TILE, 0);
+                                Pack<T> y = hg, sv = hx;
+                                if (f_hist) {
+                                    Pack<T> gn = pg, xn = px;          // successor of the newest pair
+                                    if (j + 1 < MB && (EXACT || j + 1 < m)) {
+                                        gn = ld_pack<T>(pb + (2 * j + 2) * TILE, 0);
+                                        xn = ld_pack<T>(pb + (2 * j + 3) * TILE, 0);
+                                    }
+#pragma unroll
+                                    for (int q = 0; q < VEC; ++q) {
+                                        y.v[q] = hg.v[q] - gn.v[q];
+                                        sv.v[q] = hx.v[q] - xn.v[q];
+                                    }
+                                    hg = gn;
+                                    hx = xn;
+                                } else {
+                                    y = ld_pack<T>(pb + 2 * j * TILE, 0);
+                                    sv = ld_pack<T>(pb + (2 * j + 1) * TILE, 0);
+                                }
 #pragma unroll
                                 for (int q = 0; q < VEC; ++q) {
                                     const double sd = (double)sv.v[q], yd = (double)y.v[q];
@@ -494,7 +513,16 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                                 bal &= bal - 1;
                                 const int ec = (e - lane * VEC) + src * VEC + q;
                                 double val = 0.0;
-                                if (lane < 2 * m) val = (double)st[(prow + lane) * TILE + ec];
+                                if (lane < 2 * m) {
+                                    T rv = st[(prow + lane) * TILE + ec];
+                                    if (f_hist && !SPLIT) {
+                                        // row `lane` is g_j (even) or x_j (odd), j = lane / 2: minus its successor
+                                        const T nx = (lane + 2 < 2 * m) ? st[(prow + lane + 2) * TILE + ec]
+                                                                        : st[((lane & 1) ? 1 : 2) * TILE + ec];
+                                        rv = rv - nx;
+                                    }
+                                    val = (double)rv;
+                                }
                                 const double sg = ((nfb >> src) & 1u) ? 1.0 : -1.0;
 #pragma unroll
                                 for (int t = 0; t < CPL; ++t) {
@@ -576,7 +604,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                 }
             }
             // (SPLIT: rows 0 and 2, HISTORY: the pair rows were written through the generic proxy)
-            if (partial || SPLIT || f_hist) fence_proxy_async();
+            if (partial || SPLIT) fence_proxy_async();
         };
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= (uint32_t)(++s == NSTAGE), s = (s == NSTAGE) ? 0 : s) {
             st = stage0 + s * stage_elems;
