@@ -92,3 +92,19 @@ def test_group_with_per_rank_device_callbacks(opk):
         x = s.solve()
         assert np.abs(x - np.clip(target, 0, 1)).max() < 1e-5 and s.stage == 3
         s.close()
+
+
+def test_group_with_an_empty_shard(opk, oracle):
+    """A rank whose shard is EMPTY (n = 8 over 3 ranks in blocks of 4: 4 + 4 + 0) runs the same kernels on
+    no element, reduces the same slots and takes the same decisions as the others (the carry
+    decision must not depend on rank-local quantities)."""
+    pb = problem("quad_box", 8, np.float64)
+    xo, ro, _ = oracle.vmlmb(pb["oracle_obj"], pb["x0"], pb["lower"], pb["upper"], mem=3, maxiter=12)
+    lo, hi = gpu_bounds(pb)
+    with opk.Group(devices=_devices(3)) as grp:
+        s = opk.MultiVMLMB(pb["gpu_obj"], pb["x0"], group=grp, lower=lo, upper=hi, mem=3, maxiter=12)
+        assert [cnt for _, cnt in s.ranges] == [4, 4, 0]
+        x = s.solve()
+        assert (s.iter, s.eval, s.rejects, s.reason) == (ro["iter"], ro["eval"], ro["rejects"], ro["reason"])
+        assert relerr(x, xo) <= 1e-10 and abs(s.f - ro["f"]) <= 1e-10 * abs(ro["f"])
+        s.close()
