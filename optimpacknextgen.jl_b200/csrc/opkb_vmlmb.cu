@@ -1251,6 +1251,8 @@ __global__ void __launch_bounds__(OPKB_BLOCK) k_twoloop_step(StepArgs<T> A, Redu
     const int64_t nvec = A.n / VEC;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     double acc[3] = {0, 0, 0};
+    // (two packs per thread in flight: the loads of both iterations are issued before the first use)
+#pragma unroll 2
     for (int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += stride) {
         Pack<T> v = ld_pack<T>(A.vsrc, iv), z = ld_pack<T>(A.z, iv), u = v, z2 = v, z3 = v;
         if (A.u) u = ld_pack<T>(A.u, iv);
