@@ -41,10 +41,12 @@ class Group:
 
     def close(self):
         if self._h:
-            _lib.lib().opkb_group_destroy(self._h)
-            self._h = vp()
+            # the contexts die with the group: mark them first, so that whatever still refers to them
+            # (vectors, workspaces, solvers) only drops its handles from now on
             for c in self.contexts:
                 c._h = vp()
+            _lib.lib().opkb_group_destroy(self._h)
+            self._h = vp()
 
     def __del__(self):
         try:

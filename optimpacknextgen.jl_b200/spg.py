@@ -176,7 +176,8 @@ class SPG:
 
     def close(self):
         if self._h:
-            _lib.lib().opkb_spg_destroy(self._h)
+            if self.ctx is not None and self.ctx.handle:     # (not after the context itself)
+                _lib.lib().opkb_spg_destroy(self._h)
             self._h = None
 
     def __del__(self):

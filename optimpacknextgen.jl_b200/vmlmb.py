@@ -640,7 +640,10 @@ class VMLMB:
 
     def close(self):
         if self._ws:
-            _lib.lib().opkb_vmlmb_destroy(self._ws)
+            # never call into the library for a workspace whose context is gone (e.g. a Group that
+            # was closed first): its device memory went with the context
+            if self.ctx is not None and self.ctx.handle:
+                _lib.lib().opkb_vmlmb_destroy(self._ws)
             self._ws = None
 
     def __del__(self):
