@@ -115,7 +115,7 @@ class Smooth2DOperator:
         """q = A.p -> (p.q, p.p), reduced in the same pass."""
         check(_lib.lib().opkb_smooth2d_apply(
             self.ctx.handle, self.w.handle, self.mu, self.cols, p.handle,
-            self.up.handle if self.up else None, self.dn.handle if self.dn else None, q.handle, self._out))
+            self.up.handle if self.up is not None else None, self.dn.handle if self.dn is not None else None, q.handle, self._out))
         return self._out[0], self._out[1]
 
     def __call__(self, dst: Vector, src: Vector) -> Vector:

@@ -133,7 +133,7 @@ class Smooth2D:
         import ctypes as C
         _lib.check(_lib.lib().opkb_smooth2d_fg(
             self.ctx.handle, self.w.handle, self.y.handle, self.mu, self.cols, x.handle,
-            self.up.handle if self.up else None, self.dn.handle if self.dn else None, g.handle,
+            self.up.handle if self.up is not None else None, self.dn.handle if self.dn is not None else None, g.handle,
             C.byref(self._f)))
         return self._f.value
 

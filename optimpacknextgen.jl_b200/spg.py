@@ -153,7 +153,7 @@ class SPG:
                                     hi if hi_h is None else math.inf, C.byref(h)))
             self._h = h
             a, c = fg.vectors(self.ctx, n, dtype)
-            check(L.opkb_spg_set_objective(h, fg.kind, a.handle if a else None, c.handle if c else None))
+            check(L.opkb_spg_set_objective(h, fg.kind, a.handle if a is not None else None, c.handle if c is not None else None))
             xv = self._vec("x")
             if isinstance(x0, Vector):
                 vcopy_(xv, x0)

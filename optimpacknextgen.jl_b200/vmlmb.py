@@ -610,8 +610,8 @@ class VMLMB:
                 self.x.upload(x0)
             if is_builtin(fg):
                 a, c = fg.vectors(self.ctx, n, dtype)
-                check(L.opkb_vmlmb_set_objective(ws, fg.kind, a.handle if a else None,
-                                                 c.handle if c else None))
+                check(L.opkb_vmlmb_set_objective(ws, fg.kind, a.handle if a is not None else None,
+                                                 c.handle if c is not None else None))
             else:
                 check(L.opkb_vmlmb_set_objective(ws, _lib.OBJ_USER, None, None))
             self.ops = _FusedOps(self, ws, self.x)
