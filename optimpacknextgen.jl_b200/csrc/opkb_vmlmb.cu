@@ -1053,7 +1053,10 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
     // ---- the rest (tail of the ring path, or everything) with the register kernel -----
     if (done < ws->n && ws->hist == 1 && !steepest && A.m >= 1)
         return opkb_set_error(OPKB_EINVAL, "the direction ring does not fit (m = %d): set OPKB_HISTORY=0", A.m);
-    if (done < ws->n) {
+    // (nparts == 0: the ring did not run -- steepest descent, the tail of the step-by-step recursion --:
+    // this launch then runs on EVERY rank, also on one whose shard is empty, so that all ranks
+    // reduce the same slots in the same phases)
+    if (done < ws->n || nparts == 0) {
         {
             int rc = vmlmb_ensure_p(ws);   // v0 / the mask are read from p here
             if (rc) return rc;
