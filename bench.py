@@ -267,6 +267,60 @@ def bind_to_gpu_numa_node(device):
         return None
 
 
+class NumaNearGpu:
+    """For the e2e leg on ONE rank: the pinned host buffers are allocated (first-touched) on the NUMA node
+    the GPU hangs off -- `set_mempolicy(MPOL_PREFERRED, node)` for this thread, plus its CPU affinity when the
+    container owns cores there -- and both are restored afterwards (the CPU-baseline leg wants every core).
+    A buffer on the far socket crosses the socket interconnect on its way to PCIe: 25 instead of 48 GB/s
+    on these boxes (profiles/r02s_bench_n1.json vs r02n_bench_n1.json).  Best effort: any failure leaves
+    the defaults in place, and `report` says what was done."""
+
+    def __init__(self, device):
+        self.device, self.report, self._aff = int(device), {"numa_node": None}, None
+
+    def __enter__(self):
+        import ctypes
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            path = "/sys/bus/pci/devices/%s/numa_node" % bus.lower()[-12:]
+            node = int(open(path).read().strip())
+            self.report["numa_node"] = node
+            if node >= 0:
+                libc = ctypes.CDLL(None, use_errno=True)
+                mask = ctypes.c_ulong(1 << node)
+                MPOL_PREFERRED, SYS_set_mempolicy = 1, 238          # x86-64
+                rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), 64)
+                self.report["mempolicy"] = "preferred" if rc == 0 else "errno %d" % ctypes.get_errno()
+                self._libc = libc if rc == 0 else None
+                cpus = set()
+                for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                    a, _, b = part.partition("-")
+                    cpus |= set(range(int(a), int(b or a) + 1))
+                cpus &= set(os.sched_getaffinity(0))
+                if cpus:
+                    self._aff = os.sched_getaffinity(0)
+                    os.sched_setaffinity(0, cpus)
+                self.report["cpus_on_node"] = len(cpus)
+        except Exception as e:
+            self.report["error"] = repr(e)[:120]
+        return self
+
+    def __exit__(self, *exc):
+        import ctypes
+        try:
+            if self._aff:
+                os.sched_setaffinity(0, self._aff)
+            if getattr(self, "_libc", None) is not None:
+                self._libc.syscall(238, 0, None, 0)                  # MPOL_DEFAULT
+        except Exception:
+            pass
+        return False
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -452,12 +506,16 @@ def ours(args):
     e2e = None
     if not args.no_e2e:
         host = {}
-        for name, v in (("a", obj.a), ("c", obj.c), ("lo", lo), ("hi", hi), ("x0", x0)):
-            t = torch.empty(nloc, dtype=torch.float64, pin_memory=True)
-            arr = t.numpy()
-            v.download(arr)
-            host[name] = (t, arr)
-        out_t = torch.empty(nloc, dtype=torch.float64, pin_memory=True)
+        import contextlib
+        near = NumaNearGpu(local) if world == 1 else contextlib.nullcontext()   # (N > 1: bound at start-up)
+        with near:
+            for name, v in (("a", obj.a), ("c", obj.c), ("lo", lo), ("hi", hi), ("x0", x0)):
+                t = torch.empty(nloc, dtype=torch.float64, pin_memory=True)
+                arr = t.numpy()
+                v.download(arr)
+                host[name] = (t, arr)
+            out_t = torch.empty(nloc, dtype=torch.float64, pin_memory=True)
+            out_t.zero_()                                  # (first touch inside the policy)
         del obj, lo, hi, x0
         barrier()
         te0 = time.perf_counter()
@@ -483,6 +541,7 @@ def ours(args):
                "seconds": te,
                "breakdown_s": {"create_and_upload": max_over_ranks(te1 - te0), "solve": max_over_ranks(te2 - te1),
                                "download": max_over_ranks(te3 - te2),
+                               "host_buffers": (near.report if world == 1 else "rank bound to the cores next to its GPU"),
                                "note": "max over ranks of each part; create_and_upload moves 5 vectors over "
                                        "PCIe (%.1f GB/s on rank 0): with K = %d iterations the transfers, not "
                                        "the iterations, bound this figure" % (h2d_gbs, K)}}

@@ -369,6 +369,25 @@ int opkb_vmlmb_discard_trial(opkb_vmlmb* ws, int mark_next);
  * is accepted).  carry_stats: how many opkb_vmlmb_gram calls were served that way / fell
  * back although armed. */
 int opkb_vmlmb_carry_stats(const opkb_vmlmb* ws, int64_t* hits, int64_t* misses);
+/* Device-resident decisions of the native driver (opkb_solver_run with a built-in objective,
+ * Float64, mem <= 8, one rank; csrc/opkb_chain.cuh).  In steady state the last CTA of the fused
+ * launch takes the decisions the host takes between two launches -- descent test
+ * (src/quasinewton.jl:542-546), first step = 1 (:566-584), acceptance by the line search at the first
+ * trial (src/linesearches.jl:235-247, :360-381, :536-547), convergence tests (:398-423, :437-468) --
+ * and solves the two-loop coefficients of the next direction (:716-779), which the launch of the next
+ * iteration, enqueued ahead by the host, reads from device memory: the host round trip leaves the
+ * critical path.  The host still runs its own stage machine on the same scalars and adopts a launch
+ * only if its decision and coefficients are bit-identical: same trajectories with and without.
+ * Opt-in (OPKB_CHAIN=1 in the environment when the solver is created): on a B200 the round trip it
+ * removes (~8 us) is shorter than what the one-thread decision adds to the kernel (~12 us), see
+ * DESIGN.md.  chain_stats: launches
+ * that started a chain / launches adopted while already in flight / launches enqueued ahead that the
+ * device cancelled (another step length, a rejected direction, convergence: the host took over). */
+int opkb_vmlmb_chain_stats(const opkb_vmlmb* ws, int64_t* heads, int64_t* adopted, int64_t* nogo);
+/* development aid (OPKB_CHAIN_CHECK=1 when the workspace is created): how many times the host asked
+ * for the next direction right after a chained launch, and how many times the decision record of
+ * that launch's last CTA did NOT hold the same decision and coefficients bit for bit (must be 0) */
+int opkb_vmlmb_chain_check_stats(const opkb_vmlmb* ws, int64_t* checked, int64_t* failed);
 /* the Gram block the last opkb_vmlmb_gram call returned (*m = 0: none), for checks */
 int opkb_vmlmb_last_gram(const opkb_vmlmb* ws, int* m, int* slots, double* G);
 /* Sequential two-loop recursion, fused step by step (parity-grade: the

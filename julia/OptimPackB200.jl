@@ -361,6 +361,20 @@ function carry_stats(ws::Workspace)
     return (h[], m[])
 end
 
+"""
+    chain_stats(ws) -> (heads, adopted, cancelled)
+
+device-resident decisions of the native driver (`opkb200.h`, `opkb_vmlmb_chain_stats`): fused
+launches that started a chain, launches adopted while already in flight, launches enqueued ahead
+that the device cancelled.  Diagnostics only.
+"""
+function chain_stats(ws::Workspace)
+    a, b, c = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0)
+    check(ccall((:opkb_vmlmb_chain_stats, libopkb200), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}),
+                ws.ptr, a, b, c))
+    return (a[], b[], c[])
+end
+
 wsvector(ws::Workspace{T}, which::Char, slot::Integer = 0) where {T} =
     DeviceVector{T}(ws.ctx, ccall((:opkb_vmlmb_vector, libopkb200), Ptr{Cvoid},
                                   (Ptr{Cvoid}, Cint, Cint), ws.ptr, Cint(which), slot), ws.n)

@@ -126,6 +126,8 @@ _SIGNATURES = {
     "opkb_vmlmb_discard_trial": (C.c_int, [vp, C.c_int]),
     "opkb_vmlmb_history": (C.c_int, [vp]),
     "opkb_vmlmb_carry_stats": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
+    "opkb_vmlmb_chain_stats": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+    "opkb_vmlmb_chain_check_stats": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64)]),
     "opkb_vmlmb_last_gram": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(f64)]),
     "opkb_vmlmb_pair_update": (C.c_int, [vp, C.c_int, Pd]),
     "opkb_vmlmb_twoloop_step": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, f64, C.c_int, f64, C.c_int,

@@ -499,6 +499,36 @@ int opkb_finish_reduction(opkb_context* ctx, int nred, const int* kinds, double*
     return 0;
 }
 
+int opkb_chain_supported(const opkb_context* ctx)
+{
+    return ctx && ctx->nranks <= 1 && !ctx->mbox && ctx->spin && ctx->h_flag && ctx->d_res == ctx->h_res;
+}
+
+int opkb_finish_reduction_seq(opkb_context* ctx, unsigned int seq, int res_offset, int nred, double* out)
+{
+    if (!opkb_chain_supported(ctx)) return opkb_set_error(OPKB_EINVAL, "chained launches need one rank and the polled flag");
+    if (res_offset < 0 || res_offset + nred > OPKB_NRED_MAX) return opkb_set_error(OPKB_EINVAL, "too many reduced scalars");
+    volatile unsigned int* flag = ctx->h_flag;
+    opkb_backoff bo;
+    backoff_begin(&bo);
+    bool seen = false;
+    for (unsigned int it = 1;; ++it) {
+        // (sequence numbers only grow; the difference is taken modulo 2^32)
+        if ((int)(__atomic_load_n((const unsigned int*)flag, __ATOMIC_ACQUIRE) - seq) >= 0) { seen = true; break; }
+        if ((it & 4095u) == 0u && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) {
+            seen = (int)(__atomic_load_n((const unsigned int*)flag, __ATOMIC_ACQUIRE) - seq) >= 0;
+            break;
+        }
+        backoff_pause(&bo);
+    }
+    if (!seen) {
+        OPKB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return opkb_set_error(OPKB_EINVAL, "internal error: the chained launch %u published nothing", seq);
+    }
+    for (int k = 0; k < nred; ++k) out[k] = ctx->h_res[res_offset + k];
+    return 0;
+}
+
 // ---------------------------------------------------------------------------
 // vectors
 static size_t elsize(int eltype) { return eltype == OPKB_DOUBLE ? 8 : 4; }

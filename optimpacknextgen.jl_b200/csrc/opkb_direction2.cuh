@@ -14,6 +14,8 @@
 #pragma once
 #include <type_traits>
 
+#include "opkb_chain.cuh"
+
 #define DIR2_MAXSTAGE 8
 #define DIR2_CORR_SHARE 8    // a warp gives up its corrections beyond 8 / 32 changed elements on average ...
 #define DIR2_CORR_WARMUP 64  // ... over at least 64 steps (2048 elements) of its stream
@@ -56,6 +58,11 @@ template <typename T> struct Dir2Args {
     // stage (each thread for its own pack, while it walks the chain) and nothing is ever written
     // back: with the incremental Gram the iteration moves 2m + 9 passes instead of 2m + 11.
     int hist;
+    // CHAIN instances (opkb_chain.cuh): the two-loop coefficients, the `use` mask and the go / no-go
+    // of this launch are read from this device structure (left there by the last CTA of the previous
+    // launch, or by the host for the first launch of a chain) instead of ma / cc / gamma / use above,
+    // and the last CTA leaves those of the next launch there.  NULL otherwise.
+    ChainDev* chain;
 };
 
 // FUSE: 0 direction only; OPKB_OBJ_ROSENBROCK / OPKB_OBJ_QUADRATIC: + speculative trial.
@@ -106,12 +113,19 @@ template <int MB> struct Dir2Carry {
 // whole tiles, with them for the last, partial one.  The generic instances (SPEC = 0) read the
 // flags from the arguments.
 struct Dir2RtBool { bool value; };
+//
+// CHAIN = 1 (with CARRY, Float64, MB <= 8): device-resident decisions, see opkb_chain.cuh.  The
+// coefficients live in shared memory (read by the prologue from A.chain), a launch whose `go` is 0
+// returns at once, and the last CTA runs chain_decide() on the combined scalars before it
+// publishes them, followed by its decision record.
 template <typename T, int FUSE, int MB, int TILE, int CARRY, int EXACT = 0, int CW = (CARRY ? 7 : 8), int SPLIT = 0,
-          int SPEC = 0>
+          int SPEC = 0, int CHAIN = 0>
 __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, ReduceScratch rs)
 {
     constexpr int DIR2_THREADS = (CW + 1) * 32;
     static_assert(!CARRY || (FUSE != 0 && 2 * MB <= 32), "CARRY needs the fused trial and 2*MB <= 32 rows");
+    static_assert(!CHAIN || (CARRY && !SPLIT && MB <= OPKB_CHAIN_MB && sizeof(T) == 8),
+                  "CHAIN: Float64 carry instances of up to OPKB_CHAIN_MB pairs");
     static_assert(!SPLIT || (CARRY && TILE == CW * 32 * VecOf<T>::N && (TILE / VecOf<T>::N) % (5 * 32) == 0),
                   "SPLIT: one pack per thread and tile, five parts of whole warps of packs");
     constexpr int NSPLIT = 5;                                         // parts of a tile
@@ -131,7 +145,11 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
     const int stage_elems = NR * TILE;
     constexpr uint32_t rowbytes = (uint32_t)(TILE * sizeof(T));
     const int64_t ntiles = (A.n + TILE - 1) / TILE;
-    const bool all_used = (A.use == (m >= 32 ? 0xffffffffu : ((1u << m) - 1u)));
+    // CHAIN: coefficients, mask and go / no-go of this launch from the device structure
+    __shared__ T s_ma[CHAIN ? MB : 1], s_cc[CHAIN ? MB : 1];
+    __shared__ T s_gamma;
+    __shared__ unsigned s_use;
+    __shared__ int s_go;
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
@@ -140,7 +158,32 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if constexpr (CHAIN != 0) {
+        if (tid >= 32 && tid < 32 + MB) {
+            const int j = tid - 32;
+            s_ma[j] = (T)(-A.chain->alpha[j]);
+            s_cc[j] = (T)(A.chain->c[j]);
+        }
+        if (tid == 64) {
+            unsigned u = 0u;
+            for (int j = 0; j < m; ++j) {
+                const double a = A.chain->alpha[j];
+                if (a == a) u |= (1u << j);
+            }
+            s_use = u;
+            s_gamma = (T)A.chain->gamma_dir;
+            s_go = A.chain->go;
+        }
+    }
     __syncthreads();
+    if constexpr (CHAIN != 0) {
+        if (!s_go) return;     // the step this launch was enqueued for is not taken: nothing is touched
+    }
+    const unsigned use_mask = CHAIN ? s_use : A.use;
+    const bool all_used = (use_mask == (m >= 32 ? 0xffffffffu : ((1u << m) - 1u)));
+    auto MA = [&](int j) -> T { if constexpr (CHAIN != 0) return s_ma[j]; else return A.ma[j]; };
+    auto CC = [&](int j) -> T { if constexpr (CHAIN != 0) return s_cc[j]; else return A.cc[j]; };
+    const T dgamma = CHAIN ? s_gamma : A.gamma;
 
     // acc: 0 g.d; 1 |d|^2; 2 smin; 3 smax; with FUSE: 4,5 objective sums; 6 |p'|^2; 7 g'.s;
     // 8 g'.d; 9 |x'|^2; 10 |s|^2; 11 number of free variables at x'
@@ -290,20 +333,20 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
 #pragma unroll
                     for (int jj = 0; jj < MB; ++jj) {
                         const int j = MB - 1 - jj;
-                        if ((EXACT || j < m) && (all_used || ((A.use >> j) & 1u))) {
+                        if ((EXACT || j < m) && (all_used || ((use_mask >> j) & 1u))) {
                             const Pack<T> y = ld_pack<T>(pb + 2 * j * TILE, 0);
 #pragma unroll
-                            for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + A.ma[j] * y.v[q];
+                            for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + MA(j) * y.v[q];
                         }
                     }
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) v.v[q] = A.gamma * v.v[q];
+                    for (int q = 0; q < VEC; ++q) v.v[q] = dgamma * v.v[q];
 #pragma unroll
                     for (int j = 0; j < MB; ++j) {
-                        if ((EXACT || j < m) && (all_used || ((A.use >> j) & 1u))) {
+                        if ((EXACT || j < m) && (all_used || ((use_mask >> j) & 1u))) {
                             const Pack<T> sv = ld_pack<T>(pb + (2 * j + 1) * TILE, 0);
 #pragma unroll
-                            for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + A.cc[j] * sv.v[q];
+                            for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + CC(j) * sv.v[q];
                         }
                     }
                 } else {
@@ -326,14 +369,14 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                             for (int q = 0; q < VEC; ++q) y.v[q] = gj.v[q] - gnext.v[q];
                             if (SPLIT) st_pack<T>(wb + 2 * j * TILE, 0, y);
                             gnext = gj;
-                            if (all_used || ((A.use >> j) & 1u)) {
+                            if (all_used || ((use_mask >> j) & 1u)) {
 #pragma unroll
-                                for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + A.ma[j] * y.v[q];
+                                for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + MA(j) * y.v[q];
                             }
                         }
                     }
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) v.v[q] = A.gamma * v.v[q];
+                    for (int q = 0; q < VEC; ++q) v.v[q] = dgamma * v.v[q];
                     Pack<T> xj = ld_pack<T>(pb + TILE, 0);          // x_0 (m >= 1)
 #pragma unroll
                     for (int j = 0; j < MB; ++j) {
@@ -345,9 +388,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                             for (int q = 0; q < VEC; ++q) sv.v[q] = xj.v[q] - xn.v[q];
                             if (SPLIT) st_pack<T>(wb + (2 * j + 1) * TILE, 0, sv);
                             xj = xn;
-                            if (all_used || ((A.use >> j) & 1u)) {
+                            if (all_used || ((use_mask >> j) & 1u)) {
 #pragma unroll
-                                for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + A.cc[j] * sv.v[q];
+                                for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] + CC(j) * sv.v[q];
                             }
                         }
                     }
@@ -355,7 +398,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                 }
 #pragma unroll
                 for (int q = 0; q < VEC; ++q)
-                    if (!upd[q]) v.v[q] = A.gamma * pv.v[q];
+                    if (!upd[q]) v.v[q] = dgamma * pv.v[q];
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {
                     T di = v.v[q];
@@ -689,8 +732,19 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
         __syncthreads();
         if (!s_last2) return;
         __threadfence();
-        last_cta_combine(rs.part, rs.res, NTOT, gridDim.x,
-                         [](int k) { return (k == 2) ? OPKB_RMIN : ((k == 3) ? OPKB_RMAX : OPKB_RSUM); });
+        if constexpr (CHAIN != 0) {
+            // combined scalars into shared memory (the drained scratch), from there to the host, and
+            // the decision about the next launch (one thread) before the completion flag
+            double* comb = red;
+            last_cta_combine(rs.part, comb, NTOT, gridDim.x,
+                             [](int k) { return (k == 2) ? OPKB_RMIN : ((k == 3) ? OPKB_RMAX : OPKB_RSUM); });
+            __syncthreads();
+            for (int k = tid; k < NTOT; k += DIR2_THREADS) rs.res[k] = comb[k];
+            chain_decide_block<MB>(A.chain, comb, rs.res + NTOT, comb + ((NTOT + 1) & ~1), tid, DIR2_THREADS);
+        } else {
+            last_cta_combine(rs.part, rs.res, NTOT, gridDim.x,
+                             [](int k) { return (k == 2) ? OPKB_RMIN : ((k == 3) ? OPKB_RMAX : OPKB_RSUM); });
+        }
         reduce_done(rs);
     }
 }
@@ -706,15 +760,16 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
 template <typename T>
 int dir2_launch_plain(opkb_context* ctx, const Dir2Args<T>& B, int fuse, int mb, size_t smem, int grid);
 template <typename T>
-int dir2_launch_carry(opkb_context* ctx, const Dir2Args<T>& B, int fuse, int mb, size_t smem, int grid);
+int dir2_launch_carry(opkb_context* ctx, const Dir2Args<T>& B, int fuse, int mb, size_t smem, int grid,
+                      int res_offset = 0);
 
 template <typename T>
 static int dir2_do_launch(opkb_context* ctx, void (*kern)(Dir2Args<T>, ReduceScratch), const Dir2Args<T>& B,
-                          int threads, size_t smem, int grid)
+                          int threads, size_t smem, int grid, int res_offset = 0)
 {
     if (!kern) return opkb_set_error(OPKB_EINVAL, "no direction kernel instance for this shape");
     OPKB_CUDA(opkb_ensure_smem((const void*)kern, smem));
-    ReduceScratch rs = opkb_make_scratch(ctx);
+    ReduceScratch rs = opkb_make_scratch(ctx, res_offset);
     opkb_prof_begin(ctx, OPKB_K_DIRECTION);
     kern<<<grid, threads, smem, ctx->stream>>>(B, rs);
     opkb_prof_end(ctx);

@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include "opkb_internal.cuh"
+#include "opkb_chain.cuh"
 
 // ---------------------------------------------------------------------------
 // line searches (scalar, Float64): src/linesearches.jl
@@ -233,6 +234,12 @@ struct opkb_solver_ {
     opkb_fg_callback fg;
     void* fg_user;
     int fg_partial;
+    // device-resident decisions (opkb_chain.cuh): the steady-state launches of opkb_solver_run are
+    // enqueued one iteration ahead and take their coefficients from `chain_dev`
+    int chain_on;
+    ChainDev* chain_dev;
+    ChainDev* chain_stage;      // pinned: what a head launch sends to chain_dev
+    int64_t run_target;
 };
 
 extern "C" void opkb_vmlmb_default_options(opkb_vmlmb_options* o)
@@ -256,6 +263,12 @@ extern "C" void opkb_vmlmb_default_options(opkb_vmlmb_options* o)
 
 // accessors of the workspace needed here (opkb_vmlmb.cu)
 int opkb_vmlmb_info(const opkb_vmlmb* ws, int* mem, int* method, int* eltype, int* obj);
+int opkb_vmlmb_chain_possible(const opkb_vmlmb* ws);
+int opkb_vmlmb_chain_pending(const opkb_vmlmb* ws);
+int opkb_vmlmb_direction_trial_chain(opkb_vmlmb* ws, int m, const int* slots, const double* alpha,
+                                     const double* c, double gamma, int mark_next, double out[4],
+                                     double trial[8], const ChainDev* state, ChainDev* dev, ChainDev* stage,
+                                     int prelaunch_next);
 int opkb_vmlmb_trial_end_mode(opkb_vmlmb* ws, int mark, double f, int initial, int f_mode, double out[8]);
 
 extern "C" int opkb_solver_create(opkb_vmlmb* ws, const opkb_vmlmb_options* opt, opkb_solver** out)
@@ -294,12 +307,32 @@ extern "C" int opkb_solver_create(opkb_vmlmb* ws, const opkb_vmlmb_options* opt,
     s->saved_for = -1;
     s->limits[0] = s->limits[1] = INFINITY;
     s->reason[0] = 0;
+    s->run_target = INT64_MAX;
+    // Device-resident decisions (opkb_chain.cuh): built-in objective, Gram-form two-loop, Float64, up
+    // to 8 pairs, one rank.  OPT-IN (OPKB_CHAIN=1): measured on a B200 (profiles/r02u_*), the host
+    // round trip it removes is only ~8 us per iteration (polled pinned flag, results written straight
+    // to host memory), while the chained kernel is ~12 us longer (prologue 1.3, staging 1.7, the
+    // one-thread scalar part 9.5 us): C1 17.4 k -> 15.6 k it/s.  Same bits either way.
+    {
+        const int chain_env = getenv("OPKB_CHAIN") ? atoi(getenv("OPKB_CHAIN")) : 0;   // (read per solver)
+        const bool want = (chain_env > 0);
+        const bool ls_ok = (kind != LS_MORE_THUENTE) || (o.ls_ftol > 0 && o.ls_gtol > 0 && o.ls_xtol >= 0);
+        if (want && ls_ok && s->builtin && o.speculate && s->twoloop == 0 && opkb_vmlmb_chain_possible(ws)) {
+            if (cudaMalloc((void**)&s->chain_dev, sizeof(ChainDev)) == cudaSuccess &&
+                cudaMallocHost((void**)&s->chain_stage, sizeof(ChainDev)) == cudaSuccess)
+                s->chain_on = 1;
+            else
+                cudaGetLastError();
+        }
+    }
     *out = s;
     return 0;
 }
 
 extern "C" int opkb_solver_destroy(opkb_solver* s)
 {
+    if (s && s->chain_dev) cudaFree(s->chain_dev);   // (synchronises the device: no launch reads it any more)
+    if (s && s->chain_stage) cudaFreeHost(s->chain_stage);
     free(s);
     return 0;
 }
@@ -376,7 +409,37 @@ static int new_direction_gram(opkb_solver* s, bool* change, double* gd, double* 
     const int mark_next = (mark < mem - 1 ? mark + 1 : 0);
     double out4[4];
     if (s->opt.speculate && s->builtin && s->method != 1) {
-        rc = opkb_vmlmb_direction_trial(s->ws, m, slots, alpha, c, gamma, mark_next, out4, s->spec);
+        if (s->chain_on) {
+            // the solver's scalars as the last CTA needs them to take this launch's decisions
+            ChainDev st;
+            memset(&st, 0, sizeof(st));
+            st.ls_kind = s->ls.kind;
+            st.fminset = s->fminset;
+            st.epsilon = s->opt.epsilon;
+            st.fmin = s->opt.fmin;
+            st.ls_ftol = s->ls.ftol;
+            st.ls_gtol = s->ls.gtol;
+            st.xatol = s->opt.xatol;
+            st.xrtol = s->opt.xrtol;
+            st.fatol = s->opt.fatol;
+            st.frtol = s->opt.frtol;
+            st.maxiter = s->opt.maxiter;
+            st.maxeval = s->opt.maxeval;
+            st.iter = s->iter;
+            st.eval = s->eval;
+            st.f = s->f;
+            st.gnorm = s->gnorm;
+            st.bestf = s->bestf;
+            st.gtest = s->gtest;
+            st.gamma = s->gamma;
+            for (int k = 0; k < mem && k < OPKB_CHAIN_MB; ++k) st.rho[k] = s->rho[k];
+            // the launch of the iteration after this one is enqueued ahead if this run goes that far
+            const int ahead = (s->iter < s->run_target) ? 1 : 0;
+            rc = opkb_vmlmb_direction_trial_chain(s->ws, m, slots, alpha, c, gamma, mark_next, out4, s->spec,
+                                                  &st, s->chain_dev, s->chain_stage, ahead);
+        } else {
+            rc = opkb_vmlmb_direction_trial(s->ws, m, slots, alpha, c, gamma, mark_next, out4, s->spec);
+        }
         if (rc) return rc;
         s->spec_valid = (s->spec[7] == 1.0);
         s->spec_mark = mark_next;
@@ -683,6 +746,7 @@ extern "C" int opkb_solver_run(opkb_solver* s, int64_t niter, int* task)
                                   "(opkb_solver_set_fg_callback)");
         return solver_run_callback(s, target, task);
     }
+    s->run_target = target;
     while (!s->finished && s->iter < target) {
         int rc = 0;
         if (s->spec_valid && s->eval > 0 && s->spec_mark == s->mark && s->stp == 1.0) {
@@ -694,6 +758,10 @@ extern "C" int opkb_solver_run(opkb_solver* s, int64_t niter, int* task)
         }
         if (!rc) rc = after_evaluation(s);
         if (rc) { *task = OPKB_TASK_ERROR; return rc; }
+    }
+    if (s->chain_on && opkb_vmlmb_chain_pending(s->ws)) {
+        *task = OPKB_TASK_ERROR;
+        return opkb_set_error(OPKB_EINVAL, "internal error: a chained launch is still in flight at the end of the run");
     }
     *task = task_of(s);
     return 0;

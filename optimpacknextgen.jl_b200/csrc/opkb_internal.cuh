@@ -103,6 +103,12 @@ int opkb_check_cuda(cudaError_t err, const char* what);
 // gives OPKB_RSUM/RMAX/RMIN per slot (NULL = all sums).
 int opkb_finish_reduction(opkb_context* ctx, int nred, const int* kinds, double* out);
 int opkb_grid_for(const opkb_context* ctx, int64_t nwork_items, int ctas_per_sm);
+// Chained launches (opkb_chain.cuh): one rank whose reducing kernels write their results straight
+// into pinned host memory and are awaited by polling the completion flag.
+int opkb_chain_supported(const opkb_context* ctx);
+// Results of the reducing launch number `seq` (ReduceScratch::seq), written at opkb_res_ptr() +
+// res_offset: waits until the flag has REACHED seq (later launches may already be in the stream).
+int opkb_finish_reduction_seq(opkb_context* ctx, unsigned int seq, int res_offset, int nred, double* out);
 
 void opkb_mailbox_close(opkb_context* ctx);
 // NCCL (opkb_comm.cu, loaded with dlopen)

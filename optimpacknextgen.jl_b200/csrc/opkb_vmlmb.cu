@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include "opkb_internal.cuh"
+#include "opkb_chain.cuh"
 
 struct opkb_vmlmb_ {
     opkb_context* ctx;
@@ -78,7 +79,40 @@ struct opkb_vmlmb_ {
     // s', y' (2m + 9 passes instead of 2m + 11).  hist = 0: the reference's stored differences
     // (sequential two-loop, BLMVM, OPKB_HISTORY=0).  -1: not decided yet (no pair formed).
     int hist;
+    // Chained launches (opkb_chain.cuh): the fused launch of the NEXT iteration, enqueued before the
+    // results of the current one are known.  valid: it is in the stream; go: what the current
+    // launch's last CTA decided for it (-1 until its results have been collected; a launch with
+    // go = 0 is a no-op and is forgotten at once, so outside direction_run valid implies go = 1).
+    struct {
+        int valid, go;
+        int fuse, mb, nd, ncorr, m, mark_next, ran_lazy_p, resoff;
+        unsigned int seq;
+        int slots[OPKB_CHAIN_MB];
+        const void* x;                    // the (x, g) it reads: the workspace's when it is adopted
+        const void* g;
+        double rec[OPKB_CHAIN_NREC];      // decision record of its predecessor: the coefficients it runs with
+    } pend;
+    int64_t chain_adopted, chain_heads, chain_nogo;
+    // OPKB_CHAIN_CHECK=1 (development aid): the decision record of the last chained launch, compared
+    // with what the host asks for next when nothing else happened in between
+    int opt_chain_check, opt_chain_dbg, last_rec_valid, last_rec_m;
+    double last_rec[OPKB_CHAIN_NREC];
+    int64_t chain_checked, chain_check_failed;
 };
+
+// A chained launch that runs (go = 1) and is not adopted by the host would have overwritten d and
+// the buffers of the recycled slot behind the host's back: every other entry point that touches
+// the workspace checks that none is outstanding.  Cannot happen unless chain_decide() and the
+// host's stage machine disagree -- an internal error, reported loudly.
+static int chain_guard(opkb_vmlmb* ws)
+{
+    ws->last_rec_valid = 0;
+    if (!ws->pend.valid) return 0;
+    ws->pend.valid = 0;
+    cudaStreamSynchronize(ws->ctx->stream);
+    return opkb_set_error(OPKB_EINVAL, "internal error: a chained launch (device go = %d) was not adopted by the host",
+                          ws->pend.go);
+}
 
 static int env_int(const char* name, int dflt)
 {
@@ -176,6 +210,8 @@ extern "C" int opkb_vmlmb_create(opkb_context* ctx, int eltype, int64_t n, int m
     ws->opt_maskb = env_int("OPKB_MASKB", 1);
     ws->opt_carry_check = getenv("OPKB_CARRY_CHECK") ? 1 : 0;
     ws->opt_history = env_int("OPKB_HISTORY", 1);
+    ws->opt_chain_check = env_int("OPKB_CHAIN_CHECK", 0);
+    ws->opt_chain_dbg = env_int("OPKB_CHAIN_DBG", 0);
     // The history saves two passes whatever m, forming the differences costs 2m subtractions and
     // shared-memory stores per element: measured with the SPEC instances on a power-capped box, it wins
     // 5 % at m = 5 (C2: 3417 -> 3588 it/s) and loses 1 % at m = 10 (C4: 96.0 -> 94.9 it/s); the Float32
@@ -214,6 +250,7 @@ extern "C" int opkb_vmlmb_create(opkb_context* ctx, int eltype, int64_t n, int m
 extern "C" int opkb_vmlmb_destroy(opkb_vmlmb* ws)
 {
     if (!ws) return 0;
+    if (ws->pend.valid) cudaStreamSynchronize(ws->ctx->stream);   // a launch enqueued ahead may still run
     if (ws->x && ws->g) vmlmb_unalias(ws);
     opkb_vector_destroy(ws->x);
     opkb_vector_destroy(ws->g);
@@ -417,6 +454,10 @@ __global__ void __launch_bounds__(OPKB_BLOCK) k_trial(TrialArgs<T> A, ReduceScra
 template <typename T>
 static int trial_launch(opkb_vmlmb* ws, int mark, double stp, int initial, int stage, double f_partial = 0.0)
 {
+    {
+        int rcg = chain_guard(ws);
+        if (rcg) return rcg;
+    }
     opkb_context* ctx = ws->ctx;
     ws->carry_valid = 0;                 // another point than the speculated one
     if (stage != 2) vmlmb_unalias(ws);   // x, g|p are about to be overwritten
@@ -640,6 +681,8 @@ extern "C" int opkb_vmlmb_gram(opkb_vmlmb* ws, int mark, int m, const int* slots
         }
     }
     if (!carried) {
+        rc = chain_guard(ws);
+        if (rc) return rc;
         if (ws->carry_valid) ws->carry_misses += 1;
         ws->carry_valid = 0;
         rc = vmlmb_ensure_p(ws);
@@ -839,15 +882,40 @@ __global__ void __launch_bounds__(OPKB_BLOCK) k_direction(DirArgs<T> A, ReduceSc
     block_reduce_publish<4, 8u, 4u>(acc, rs);  // slot 2: min, slot 3: max
 }
 
+// How a call of direction_run takes part in a chain of launches (opkb_chain.cuh; native driver, one
+// rank).  HEAD: first launch of a chain -- the caller has sent state and coefficients to `dev`;
+// ADOPT: the launch is already in flight (ws->pend), only its results are collected; PRELAUNCH:
+// enqueue the launch and return (no result is awaited, the workspace is left as it was).
+enum { DIR_CHAIN_HEAD = 1, DIR_CHAIN_ADOPT = 2, DIR_CHAIN_PRELAUNCH = 3 };
+struct DirChain {
+    int mode;
+    ChainDev* dev;
+    int prelaunch_next;            // HEAD / ADOPT: enqueue the next iteration's launch before waiting
+    double rec[OPKB_CHAIN_NREC];   // HEAD / ADOPT: decision record of this launch (out)
+    int chained;                   // out: the launch was a chained one
+};
+
+template <typename T>
+static int chain_prelaunch_next(opkb_vmlmb* ws, int m, const int* slots, int mark_next, ChainDev* dev);
+
 template <typename T>
 static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* alpha,
                          const double* c, double gamma, int mark_next, int steepest, double out[4],
-                         const opkb_vector* pend_u = NULL, double pend_a = 0.0, double* out8 = NULL)
+                         const opkb_vector* pend_u = NULL, double pend_a = 0.0, double* out8 = NULL,
+                         DirChain* ch = NULL)
 {
     opkb_context* ctx = ws->ctx;
-    ws->carry_valid = 0;
-    ws->maskb_valid = 0;
-    ws->xspec_mark = -1;
+    int chmode = ch ? ch->mode : 0;
+    if (ch) ch->chained = 0;
+    if (chmode == 0) {
+        int rcg = chain_guard(ws);
+        if (rcg) return rcg;
+    }
+    if (chmode != DIR_CHAIN_PRELAUNCH) {
+        ws->carry_valid = 0;
+        ws->maskb_valid = 0;
+        ws->xspec_mark = -1;
+    }
     int xspec = 0;
     DirArgs<T> A;
     memset(&A, 0, sizeof(A));
@@ -935,6 +1003,9 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
             }
             carry = (A.m <= 12 && ws->Gc_valid && ws->Gc_m == A.m);
             for (int j = 0; carry && j < A.m; ++j) carry = (ws->Gc_slots[j] == slots[j]);
+            // (enqueued ahead: the Gram block of exactly these pairs is what opkb_vmlmb_gram will
+            // have assembled from the carry if the launch is ever adopted)
+            if (chmode == DIR_CHAIN_PRELAUNCH) carry = (A.m <= 12);
             // mark_next is the oldest pair when the memory is full, a free slot otherwise
             if (carry && A.m == ws->mem && slots[0] != mark_next) carry = 0;
             if (carry && A.m < ws->mem)
@@ -1015,11 +1086,84 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
             int64_t grid = ctx->sm_count;
             if (grid > ntiles) grid = ntiles;
             if (grid < 1) grid = 1;
-            int rc = carry ? dir2_launch_carry<T>(ctx, B, fuse, mb, smem, (int)grid)
+            // chained launch?  (Float64 carry instances of up to OPKB_CHAIN_MB pairs, one rank with the
+            // polled completion flag; anything else runs as it always did)
+            bool chained = false;
+            unsigned int seq = 0;
+            int resoff = 0;
+            if (chmode) {
+                chained = carry && fuse && sizeof(T) == 8 && (mb == 5 || mb == 8) && ws->mem <= OPKB_CHAIN_MB &&
+                          opkb_chain_supported(ctx);
+                if (!chained) {
+                    if (chmode == DIR_CHAIN_ADOPT)
+                        return opkb_set_error(OPKB_EINVAL, "internal error: the launch in flight is not the one the "
+                                              "workspace would enqueue now");
+                    if (chmode == DIR_CHAIN_PRELAUNCH) return 0;
+                    chmode = 0;     // (a head launch that cannot be chained is an ordinary launch)
+                }
+            }
+            int rc = 0;
+            if (chmode == DIR_CHAIN_ADOPT) {
+                if (ws->pend.fuse != fuse || ws->pend.mb != mb || ws->pend.nd != nd || ws->pend.ncorr != ncorr)
+                    return opkb_set_error(OPKB_EINVAL, "internal error: geometry of the launch in flight");
+                seq = ws->pend.seq;
+                resoff = ws->pend.resoff;
+                ran_lazy_p = ws->pend.ran_lazy_p;
+                ws->pend.valid = 0;
+                ws->chain_adopted += 1;
+            } else {
+                if (chained) {
+                    B.chain = ch->dev;
+                    resoff = ((ctx->seq + 1u) & 1u) ? OPKB_NRED_MAX / 2 : 0;   // results by sequence parity
+                }
+                rc = carry ? dir2_launch_carry<T>(ctx, B, fuse, mb, smem, (int)grid, resoff)
                            : dir2_launch_plain<T>(ctx, B, fuse, mb, smem, (int)grid);
-            if (rc) return rc;
-            rc = opkb_finish_reduction(ctx, (fuse ? 12 : 4) + nd + ncorr, kinds, part[nparts++]);
-            if (rc) return rc;
+                if (rc) return rc;
+                seq = ctx->seq;
+                if (chmode == DIR_CHAIN_HEAD) ws->chain_heads += 1;
+            }
+            if (chmode == DIR_CHAIN_PRELAUNCH) {
+                ws->pend.valid = 1;
+                ws->pend.go = -1;
+                ws->pend.fuse = fuse;
+                ws->pend.mb = mb;
+                ws->pend.nd = nd;
+                ws->pend.ncorr = ncorr;
+                ws->pend.m = A.m;
+                ws->pend.mark_next = mark_next;
+                ws->pend.ran_lazy_p = ran_lazy_p;
+                ws->pend.resoff = resoff;
+                ws->pend.seq = seq;
+                for (int j = 0; j < A.m; ++j) ws->pend.slots[j] = slots[j];
+                ws->pend.x = ws->x->data;
+                ws->pend.g = ws->g->data;
+                return 0;
+            }
+            if (chained) {
+                ch->chained = 1;
+                if (ch->prelaunch_next) {
+                    rc = chain_prelaunch_next<T>(ws, A.m, slots, mark_next, ch->dev);
+                    if (rc) return rc;
+                }
+                rc = opkb_finish_reduction_seq(ctx, seq, resoff, 12 + nd + ncorr + OPKB_CHAIN_NREC, part[nparts++]);
+                if (rc) return rc;
+                // what the last CTA decided about the next launch
+                memcpy(ch->rec, part[0] + 12 + nd + ncorr, sizeof(double) * OPKB_CHAIN_NREC);
+                memcpy(ws->last_rec, ch->rec, sizeof(ch->rec));
+                ws->last_rec_valid = 1;
+                ws->last_rec_m = (A.m + 1 < ws->mem ? A.m + 1 : ws->mem);
+                if (ws->pend.valid) {
+                    ws->pend.go = (ch->rec[0] != 0.0) ? 1 : 0;
+                    memcpy(ws->pend.rec, ch->rec, sizeof(ch->rec));
+                    if (!ws->pend.go) {     // it returns at once, nothing is touched: forgotten
+                        ws->pend.valid = 0;
+                        ws->chain_nogo += 1;
+                    }
+                }
+            } else {
+                rc = opkb_finish_reduction(ctx, (fuse ? 12 : 4) + nd + ncorr, kinds, part[nparts++]);
+                if (rc) return rc;
+            }
             done = B.n;
             if (carry) {
                 const double* r = part[0] + 12;
@@ -1050,6 +1194,9 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
         }
     }
 
+    if (chmode == DIR_CHAIN_PRELAUNCH) return 0;   // (the ring did not fit: nothing enqueued)
+    if (chmode == DIR_CHAIN_ADOPT && done < ws->n)
+        return opkb_set_error(OPKB_EINVAL, "internal error: the launch in flight did not cover the vector");
     // ---- the rest (tail of the ring path, or everything) with the register kernel -----
     if (done < ws->n && ws->hist == 1 && !steepest && A.m >= 1)
         return opkb_set_error(OPKB_EINVAL, "the direction ring does not fit (m = %d): set OPKB_HISTORY=0", A.m);
@@ -1127,6 +1274,163 @@ static int direction_run(opkb_vmlmb* ws, int m, const int* slots, const double* 
     return 0;
 }
 
+// Enqueue the fused launch of the iteration AFTER the one whose launch has just been issued (pairs
+// `slots`, saving into `mark_next`), as the workspace will look once that trial point has been
+// accepted: x, g <-> S, Y[mark_next] (the swaps at the end of direction_run) and, with stored
+// differences, S, Y[mark_next] <-> the spare buffers that received the new pair (gram_from_carry).
+// The pointers are rotated for the build and rotated back: the workspace itself is untouched.
+template <typename T>
+static int chain_prelaunch_next(opkb_vmlmb* ws, int m, const int* slots, int mark_next, ChainDev* dev)
+{
+    if (ws->aliased_slot >= 0 || ws->pend.valid) return 0;     // (not in steady state yet)
+    if (ws->hist != 1 && (!ws->carry_s || !ws->carry_y)) return 0;
+    const int mem = ws->mem, drop = (m == mem) ? 1 : 0;
+    const int m2 = (m + 1 < mem ? m + 1 : mem);
+    int slots2[OPKB_MEM_MAX];
+    for (int j = 0; j < m2 - 1; ++j) slots2[j] = slots[j + drop];
+    slots2[m2 - 1] = mark_next;
+    const int mn2 = (mark_next < mem - 1 ? mark_next + 1 : 0);
+    auto swp = [](void*& a, void*& b) { void* t = a; a = b; b = t; };
+    auto rotate = [&](bool undo) {
+        if (!undo) {
+            swp(ws->S[mark_next]->data, ws->x->data);
+            swp(ws->Y[mark_next]->data, ws->g->data);
+            if (ws->hist != 1) {
+                swp(ws->S[mark_next]->data, ws->carry_s->data);
+                swp(ws->Y[mark_next]->data, ws->carry_y->data);
+            }
+        } else {
+            if (ws->hist != 1) {
+                swp(ws->Y[mark_next]->data, ws->carry_y->data);
+                swp(ws->S[mark_next]->data, ws->carry_s->data);
+            }
+            swp(ws->Y[mark_next]->data, ws->g->data);
+            swp(ws->S[mark_next]->data, ws->x->data);
+        }
+    };
+    double zero[OPKB_MEM_MAX], o4[4], o8[8];
+    for (int j = 0; j < OPKB_MEM_MAX; ++j) zero[j] = 0.0;
+    DirChain pc;
+    memset(&pc, 0, sizeof(pc));
+    pc.mode = DIR_CHAIN_PRELAUNCH;
+    pc.dev = dev;
+    rotate(false);
+    const int rc = direction_run<T>(ws, m2, slots2, zero, zero, 1.0, mn2, 0, o4, NULL, 0.0, o8, &pc);
+    rotate(true);
+    return rc;
+}
+
+// opkb_vmlmb_direction_trial for the native driver with device-resident decisions (opkb_chain.cuh).
+// `state`: the solver's scalars as chain_decide() needs them (everything but the coefficients, the
+// pairs and the Gram block, which are filled in here); `dev`: the device copy.  If the launch this
+// call asks for is already in flight (enqueued ahead by the previous call, go = 1 from its last
+// CTA) it is adopted after a bit-for-bit comparison of the coefficients; otherwise state and
+// coefficients go to the device and the launch is the head of a new chain.  `prelaunch_next`: also
+// enqueue the launch of the following iteration before waiting.  Falls back to the ordinary launch
+// when this shape has no chained instance.
+int opkb_vmlmb_direction_trial_chain(opkb_vmlmb* ws, int m, const int* slots, const double* alpha,
+                                     const double* c, double gamma, int mark_next, double out[4],
+                                     double trial[8], const ChainDev* state, ChainDev* dev, ChainDev* stage,
+                                     int prelaunch_next)
+{
+    // (stage: one ChainDev of pinned host memory -- a head launch is awaited before this function
+    // returns, so the copy that precedes it in the stream has completed when the buffer is written again)
+    if (!ws || !state || !dev || !stage) return opkb_set_error(OPKB_EINVAL, "NULL argument");
+    if (mark_next < 0 || mark_next >= ws->mem) return opkb_set_error(OPKB_EINVAL, "mark out of range");
+    if (ws->eltype != OPKB_DOUBLE || m < 1 || m > OPKB_CHAIN_MB || ws->mem > OPKB_CHAIN_MB ||
+        !(ws->Gc_valid && ws->Gc_m == m)) {
+        int rc = chain_guard(ws);
+        if (rc) return rc;
+        return opkb_vmlmb_direction_trial(ws, m, slots, alpha, c, gamma, mark_next, out, trial);
+    }
+    DirChain ch;
+    memset(&ch, 0, sizeof(ch));
+    ch.mode = DIR_CHAIN_HEAD;
+    ch.dev = dev;
+    ch.prelaunch_next = prelaunch_next;
+    auto same_bits = [](double a, double b) { return (a != a && b != b) || memcmp(&a, &b, sizeof(double)) == 0; };
+    {
+        if (ws->opt_chain_check && ws->last_rec_valid) {
+            // the previous chained launch and nothing else since: its last CTA must have foreseen this call
+            const double* r = ws->last_rec;
+            bool ok = (r[0] == 1.0 && ws->last_rec_m == m && same_bits(gamma, r[2]));
+            for (int j = 0; ok && j < m; ++j) ok = same_bits(alpha[j], r[3 + j]) && same_bits(c[j], r[3 + OPKB_CHAIN_MB + j]);
+            ws->chain_checked += 1;
+            if (!ok) {
+                ws->chain_check_failed += 1;
+                fprintf(stderr, "[chain check] device go=%g why=%g gamma=%.17g | host m=%d gamma=%.17g", r[0], r[1], r[2], m, gamma);
+                for (int j = 0; j < m; ++j) fprintf(stderr, " a%d %.17g/%.17g c%d %.17g/%.17g", j, r[3 + j], alpha[j], j, r[3 + OPKB_CHAIN_MB + j], c[j]);
+                fprintf(stderr, "\n");
+            }
+        }
+        ws->last_rec_valid = 0;
+    }
+    if (ws->pend.valid) {
+        bool same = (ws->pend.go == 1 && ws->pend.m == m && ws->pend.mark_next == mark_next &&
+                     ws->pend.x == ws->x->data && ws->pend.g == ws->g->data && same_bits(gamma, ws->pend.rec[2]));
+        for (int j = 0; same && j < m; ++j)
+            same = (ws->pend.slots[j] == slots[j] && same_bits(alpha[j], ws->pend.rec[3 + j]) &&
+                    same_bits(c[j], ws->pend.rec[3 + OPKB_CHAIN_MB + j]));
+        if (!same) {
+            ws->pend.valid = 0;
+            cudaStreamSynchronize(ws->ctx->stream);
+            return opkb_set_error(OPKB_EINVAL, "internal error: the chained launch in flight does not match the "
+                                  "host's decision (m %d/%d, mark %d/%d, gamma %.17g/%.17g)", ws->pend.m, m,
+                                  ws->pend.mark_next, mark_next, ws->pend.rec[2], gamma);
+        }
+        ch.mode = DIR_CHAIN_ADOPT;
+    } else {
+        ChainDev& hs = *stage;
+        hs = *state;
+        hs.go = 1;
+        hs.m = m;
+        for (int j = 0; j < m; ++j) {
+            if (ws->Gc_slots[j] != slots[j]) return opkb_set_error(OPKB_EINVAL, "the Gram block is not that of these pairs");
+            hs.alpha[j] = alpha[j];
+            hs.c[j] = c[j];
+            hs.slots[j] = slots[j];
+        }
+        hs.gamma_dir = gamma;
+        hs.mark_next = mark_next;
+        hs.mem = ws->mem;
+        hs.method = ws->method;
+        hs.obj = ws->obj;
+        const Bound<double> lo = make_bound<double>(ws->lo, ws->lo_val, true), hi = make_bound<double>(ws->hi, ws->hi_val, false);
+        hs.limits_inf = (ws->method == 0 || (!lo.has && !hi.has)) ? 1 : 0;
+        hs.pad = ws->opt_chain_dbg;
+        memcpy(hs.G, ws->Gc, sizeof(double) * 2 * m * (m + 1));
+        opkb_bind_device(ws->ctx);
+        OPKB_CUDA(cudaMemcpyAsync(dev, stage, sizeof(ChainDev), cudaMemcpyHostToDevice, ws->ctx->stream));
+    }
+    return direction_run<double>(ws, m, slots, alpha, c, gamma, mark_next, 0, out, NULL, 0.0, trial, &ch);
+}
+
+int opkb_vmlmb_chain_possible(const opkb_vmlmb* ws)
+{
+    return ws && ws->eltype == OPKB_DOUBLE && ws->mem <= OPKB_CHAIN_MB && ws->method != 1 && ws->opt_carry != 0 &&
+           !ws->opt_carry_check &&
+           (ws->obj == OPKB_OBJ_ROSENBROCK || ws->obj == OPKB_OBJ_QUADRATIC) && opkb_chain_supported(ws->ctx);
+}
+
+int opkb_vmlmb_chain_pending(const opkb_vmlmb* ws) { return ws ? ws->pend.valid : 0; }
+
+extern "C" int opkb_vmlmb_chain_check_stats(const opkb_vmlmb* ws, int64_t* checked, int64_t* failed)
+{
+    if (!ws) return opkb_set_error(OPKB_EINVAL, "NULL workspace");
+    if (checked) *checked = ws->chain_checked;
+    if (failed) *failed = ws->chain_check_failed;
+    return 0;
+}
+
+extern "C" int opkb_vmlmb_chain_stats(const opkb_vmlmb* ws, int64_t* heads, int64_t* adopted, int64_t* nogo)
+{
+    if (!ws) return opkb_set_error(OPKB_EINVAL, "NULL workspace");
+    if (heads) *heads = ws->chain_heads;
+    if (adopted) *adopted = ws->chain_adopted;
+    if (nogo) *nogo = ws->chain_nogo;
+    return 0;
+}
+
 extern "C" int opkb_vmlmb_direction(opkb_vmlmb* ws, int m, const int* slots, const double* alpha,
                                     const double* c, double gamma, int mark_next, double out[4])
 {
@@ -1162,6 +1466,8 @@ extern "C" int opkb_vmlmb_discard_trial(opkb_vmlmb* ws, int mark_next)
     // because the direction was rejected (:542-546): x, g are the current
     // iterate again, S[mark'], Y[mark'] alias them, p is recomputed (:396)
     int rc = check_mark(ws, mark_next);
+    if (rc) return rc;
+    rc = chain_guard(ws);
     if (rc) return rc;
     ws->carry_valid = 0;
     ws->maskb_valid = 0;

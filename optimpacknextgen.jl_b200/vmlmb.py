@@ -826,6 +826,16 @@ class VMLMB:
         check(_lib.lib().opkb_vmlmb_carry_stats(self._ws, C.byref(h), C.byref(m)))
         return (h.value, m.value)
 
+    def chain_stats(self):
+        """(heads, adopted, cancelled) of the device-resident decisions of the native driver
+        (opkb200.h, opkb_vmlmb_chain_stats): fused launches that started a chain, launches adopted
+        while already in flight, launches enqueued ahead that the device cancelled."""
+        if not self._ws:
+            return (0, 0, 0)
+        a, b, c = _lib.i64(), _lib.i64(), _lib.i64()
+        check(_lib.lib().opkb_vmlmb_chain_stats(self._ws, C.byref(a), C.byref(b), C.byref(c)))
+        return (a.value, b.value, c.value)
+
     @property
     def history(self) -> int:
         """1: the workspace keeps the iterate history (pairs formed on the fly, nothing written

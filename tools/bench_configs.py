@@ -45,12 +45,14 @@ def run_vmlmb(ctx, name, obj, x0, lo, hi, mem, n, nglobal, K, es, walg, twoloop=
     name += " [native driver]" if NATIVE else ""
     s.iterate((mem + 1 if prime is None else prime) + 3)
     ctx.synchronize()
-    ctx.profile(True)
+    noprof = bool(int(os.environ.get("OPKB_BENCH_NOPROF", "0")))   # (no CUDA events around every launch)
+    if not noprof:
+        ctx.profile(True)
     e0, i0, l0 = s.eval, s.iter, ctx.launch_count
     ctx.timer_start()
     alive = s.iterate(K)
     ms = ctx.timer_stop()
-    prof = ctx.profile_report()
+    prof = {} if noprof else ctx.profile_report()
     ctx.profile(False)
     it = s.iter - i0
     out = {"config": name, "n": nglobal, "iterations": it, "ms_per_iteration": ms / max(it, 1),
@@ -62,6 +64,8 @@ def run_vmlmb(ctx, name, obj, x0, lo, hi, mem, n, nglobal, K, es, walg, twoloop=
            "kernel_launches_per_iteration": {k: round(v[1] / max(it, 1), 2) for k, v in prof.items()}}
     out["frac_of_measured_peak"] = out["alg_GBps_per_gpu"] / PEAK
     out["incremental_gram_hits_misses"] = list(s.carry_stats())
+    if NATIVE:   # device-resident decisions: chains started / launches adopted in flight / cancelled by the device
+        out["chain_heads_adopted_cancelled"] = list(s.chain_stats())
     s.close()
     return out
 
