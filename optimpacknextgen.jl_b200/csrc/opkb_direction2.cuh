@@ -106,6 +106,7 @@ template <int MB> struct Dir2Carry {
 // accumulators per thread instead of 4 MB + 4: 10 consumer warps instead of 7, no Float32 ->
 // Float64 conversion of the pair rows.  Fixed item -> warp map and fixed part order: deterministic.
 //
+// SPEC = 3: L-BFGS without bounds on the iterate history (C1), same idea: see the flags in the kernel.
 // SPEC = 1 (the headline instances; 2: the same with stored differences): the grid-uniform flags of the common case -- VMLMB on a box
 // given by two arrays (bounded, masked, both bounds present as rows 3 and 4, v0 recomputed from g,
 // y = g differences), pairs kept as the iterate history -- are compile-time constants, and the tile
@@ -266,12 +267,16 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
         }
     } else {
         // grid-uniform flags: constants in the SPEC instances, arguments otherwise
-        const bool f_bounded = SPEC ? true : (A.bounded != 0);
-        const bool f_masked = SPEC ? true : (A.masked != 0);
-        const int f_has_lo = SPEC ? 1 : A.has_lo, f_has_hi = SPEC ? 1 : A.has_hi;
-        const int r_lo = SPEC ? 3 : A.r_lo, r_hi = SPEC ? 4 : A.r_hi, r_ysrc = SPEC ? -1 : A.r_ysrc;
-        const int f_v0g = SPEC ? 1 : A.v0_from_g;
-        const bool f_hist = (SPEC == 1) ? true : ((SPEC == 2) ? false : (A.hist != 0));   // SPEC 2: stored differences
+        // (SPEC = 3: L-BFGS without bounds on the iterate history -- no projection, no mask, no step
+        // limits, v0 = g taken from the g row: row 0 is not even loaded)
+        constexpr bool UNB = (SPEC == 3);
+        const bool f_bounded = UNB ? false : (SPEC ? true : (A.bounded != 0));
+        const bool f_masked = UNB ? false : (SPEC ? true : (A.masked != 0));
+        const int f_has_lo = UNB ? 0 : (SPEC ? 1 : A.has_lo), f_has_hi = UNB ? 0 : (SPEC ? 1 : A.has_hi);
+        const int r_lo = UNB ? -1 : (SPEC ? 3 : A.r_lo), r_hi = UNB ? -1 : (SPEC ? 4 : A.r_hi);
+        const int r_ysrc = SPEC ? -1 : A.r_ysrc;
+        const int f_v0g = SPEC ? 1 : A.v0_from_g;       // (row 0 is not in the stage)
+        const bool f_hist = (SPEC == 1 || SPEC == 3) ? true : ((SPEC == 2) ? false : (A.hist != 0));   // SPEC 2: stored differences
         const int prow = 3 + (r_lo >= 0) + (r_hi >= 0) + (r_ysrc >= 0);  // first pair row
         int s = 0;
         uint32_t ph = 0;
@@ -311,7 +316,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) k_direction2(Dir2Args<T> A, 
                     flo[q] = !f_has_lo | (px.v[q] > pl.v[q]);
                     fhi[q] = !f_has_hi | (px.v[q] < ph_.v[q]);
                 }
-                if (f_v0g) {
+                if constexpr (UNB) {
+                    pv = pg;                        // vcopy!(d, g) (src/quasinewton.jl:528)
+                } else if (f_v0g) {
                     // p = project_direction!(p, x, lo, hi, -, g) (src/quasinewton.jl:396),
                     // bit-identical to the stored vector, without reading it
 #pragma unroll

@@ -56,6 +56,17 @@ int dir2_launch_carry(opkb_context* ctx, const Dir2Args<T>& B, int fuse, int mb,
     const bool spec = sizeof(T) == 8 && spec_on && B.bounded && B.masked && B.has_lo && B.has_hi &&
                       B.r_lo == 3 && B.r_hi == 4 && B.r_ysrc < 0 && B.v0_from_g;
     if constexpr (sizeof(T) == 8) {
+        // SPEC = 3: L-BFGS without bounds, iterate history, v0 = g (the g row serves as v0: row 0 is not loaded)
+        if (!B.chain && spec_on && !B.bounded && !B.masked && B.r_ysrc < 0 && !B.v0_from_g && B.hist &&
+            B.rows[0] == B.rows[2]) {
+            if (fuse == OPKB_OBJ_ROSENBROCK) DIR2_PICK(OPKB_OBJ_ROSENBROCK, 3);
+            else if (fuse == OPKB_OBJ_QUADRATIC) DIR2_PICK(OPKB_OBJ_QUADRATIC, 3);
+            if (kern) {
+                Dir2Args<T> U = B;
+                U.v0_from_g = 1;
+                return dir2_do_launch<T>(ctx, kern, U, (mb == 5) ? 384 : DIR2_NTHREADS(1), smem, grid);
+            }
+        }
         if (B.chain) {
             const int sp = !spec ? 0 : (B.hist ? 1 : 2);
             if (fuse == OPKB_OBJ_ROSENBROCK) {
