@@ -17,6 +17,10 @@ CASES = [
     ("quad_box", 1003, np.float64, dict(mem=12)),
     ("rosen_box", 100000, np.float64, dict(mem=7)),
     ("rosen_unc", 1000, np.float64, dict(mem=5)),
+    # L-BFGS without bounds: the SPEC = 3 instances of every shape (MB = 5, 8, 10 exact, 12)
+    ("rosen_unc", 7 * 448 * 2 + 6, np.float64, dict(mem=8)),
+    ("rosen_unc", 30000, np.float64, dict(mem=10, history=2)),
+    ("rosen_unc", 20002, np.float64, dict(mem=12, history=2)),
     ("rosen_lower0", 4096, np.float64, dict(mem=3)),
     ("quad_upper_scalar", 5000, np.float64, dict(mem=8)),
     ("quad_box", 100001, np.float32, dict(mem=5, twoloop="gram")),
@@ -34,9 +38,13 @@ def test_carried_gram_equals_sweep(kind, n, dtype, kw):
     import opkb200 as opk
     pb = problem(kind, n, dtype)
     kw = dict(kw, xtol=(0, 0), ftol=(0, 0), gtol=(0, 0))
-    # (the switch is read when a workspace is created: identical on every rank of a job)
+    hist = kw.pop("history", None)      # OPKB_HISTORY for this case (2: the iterate history also beyond 8 pairs)
+    # (the switches are read when a workspace is created: identical on every rank of a job)
     old = os.environ.get("OPKB_CARRY")
+    old_hist = os.environ.get("OPKB_HISTORY")
     try:
+        if hist is not None:
+            os.environ["OPKB_HISTORY"] = str(hist)
         os.environ["OPKB_CARRY"] = "2"    # incremental Gram (2: also for Float32 workspaces, where it is opt-in)
         a = _solver(opk, pb, **kw)
         os.environ["OPKB_CARRY"] = "0"    # a sweep every iteration
@@ -46,6 +54,10 @@ def test_carried_gram_equals_sweep(kind, n, dtype, kw):
             os.environ.pop("OPKB_CARRY", None)
         else:
             os.environ["OPKB_CARRY"] = old
+        if old_hist is None:
+            os.environ.pop("OPKB_HISTORY", None)
+        else:
+            os.environ["OPKB_HISTORY"] = old_hist
     f64 = dtype == np.float64
     # The two runs differ by the summation order of the Gram entries only; the
     # (chaotic, for Rosenbrock) trajectory then amplifies that: rounding level
