@@ -318,6 +318,7 @@ extern "C" int opkb_solver_create(opkb_vmlmb* ws, const opkb_vmlmb_options* opt,
         const bool want = (chain_env > 0);
         const bool ls_ok = (kind != LS_MORE_THUENTE) || (o.ls_ftol > 0 && o.ls_gtol > 0 && o.ls_xtol >= 0);
         if (want && ls_ok && s->builtin && o.speculate && s->twoloop == 0 && opkb_vmlmb_chain_possible(ws)) {
+            opkb_bind_device(opkb_vmlmb_vector(ws, 'x', 0)->ctx);     // (the structure lives on the workspace's GPU)
             if (cudaMalloc((void**)&s->chain_dev, sizeof(ChainDev)) == cudaSuccess &&
                 cudaMallocHost((void**)&s->chain_stage, sizeof(ChainDev)) == cudaSuccess)
                 s->chain_on = 1;
