@@ -65,6 +65,7 @@ template <typename T> struct Gram2Args {
     // (x, g) as the successor of the newest one; the consumers turn a stage into differences before
     // they accumulate, nothing is written back (2m + 3 passes, all reads)
     int hist;
+    int coop;     // several roles: the newest pair is formed by all consumer threads (OPKB_GRAM_COOP=0: by the writer role)
 };
 
 // Stage layout (rows of TILE elements of T): 0: v0, 1: x, 2: g|p, then the pairs
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
         const bool needs_pair = !writer && (bj == nb - 1);   // its columns include y_new
         const int snew = (3 + 2 * qn) * TILE, ynew = (4 + 2 * qn) * TILE;
         const bool masked = A.masked != 0;
+        const bool coop = (nroles > 1) && A.coop;    // all consumers form the newest pair (see below)
 
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -208,6 +210,35 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
                         st_pack<T>(sg, pk, dy);
                         xn = xq;
                         gn = gq;
+                    }
+                }
+                named_bar_sync(2, cthreads);
+            } else if (coop) {
+                // Several roles: EVERY consumer thread turns its packs of the newest slot into the pair
+                // (x0 - x, g0 - g), in the stage and in HBM, and the consumer warps meet at a named
+                // barrier.  (With a writer role doing it alone -- two warps -- the warps of the role
+                // whose columns hold y_new waited for it 40 % of their time: ncu source page of the
+                // Float32 sweep at m = 7, r02e_gram2_f32.)
+                constexpr int VEC = VecOf<T>::N;
+                for (int pk = tid; pk < TILE / VEC; pk += cthreads) {
+                    Pack<T> ps = ld_pack<T>(st + snew, pk), py = ld_pack<T>(st + ynew, pk);
+                    const Pack<T> px = ld_pack<T>(st + TILE, pk), pg = ld_pack<T>(st + 2 * TILE, pk);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        ps.v[q] = ps.v[q] - px.v[q];       // s_new = x0 - x (element type)
+                        py.v[q] = py.v[q] - pg.v[q];       // y_new = g0 - g
+                    }
+                    st_pack<T>(st + snew, pk, ps);
+                    st_pack<T>(st + ynew, pk, py);
+                    const int64_t e0 = base + (int64_t)pk * VEC;
+                    if (e0 + VEC <= A.n) {
+                        st_pack<T>(A.Snew, e0 / VEC, ps);
+                        st_pack<T>(A.Ynew, e0 / VEC, py);
+                    } else {
+                        for (int q = 0; q < VEC && e0 + q < A.n; ++q) {
+                            A.Snew[e0 + q] = ps.v[q];
+                            A.Ynew[e0 + q] = py.v[q];
+                        }
                     }
                 }
                 named_bar_sync(2, cthreads);
@@ -321,7 +352,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_gram2(Gram2Args<T> A, ReduceScratch
             }
             // release the stage (the writer's generic-proxy stores into it must be
             // ordered before the next bulk copy)
-            if (partial || writer || A.hist) fence_proxy_async();
+            if (partial || writer || A.hist || coop) fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive_a(empty_a + 8u * s);
         }
@@ -447,6 +478,11 @@ static int gram2_run(opkb_context* ctx, int64_t n, int m, const void* const* Sp,
     const int bs = (m + nb - 1) / nb;
     const int nroles = nb * (nb + 1) / 2;
     A.nb = nb;
+    {
+        // measured (profiles/r02g2_gram_coop_ab.txt): Float64 m = 10: 10.33 -> 10.08 ms; Float32 m = 7: 4.16 -> 4.27 ms
+        static const int coop_env = getenv("OPKB_GRAM_COOP") ? atoi(getenv("OPKB_GRAM_COOP")) : -1;
+        A.coop = (coop_env < 0) ? (sizeof(T) == 8 ? 1 : 0) : coop_env;
+    }
     // consumer warps per role: 1 role: 7; 3 roles: 2 each; 6 or 10 roles: 1 each
     A.kshare = (nroles == 1) ? 7 : ((nroles == 3) ? 2 : 1);
     if (const char* e = getenv("OPKB_GRAM_KSHARE")) {   // tuning knob
