@@ -474,7 +474,11 @@ static int gram2_run(opkb_context* ctx, int64_t n, int m, const void* const* Sp,
     A.n = n;
     A.m = m;
     A.masked = masked;
-    const int nb = (m + 4) / 5;
+    int nb = (m + 4) / 5;
+    if (const char* e = getenv("OPKB_GRAM_NB")) {   // tuning knob: more, smaller blocks (more roles, fewer accumulators each)
+        const int v = atoi(e);
+        if (v >= nb && v <= 4 && v <= m) nb = v;
+    }
     const int bs = (m + nb - 1) / nb;
     const int nroles = nb * (nb + 1) / 2;
     A.nb = nb;
