@@ -378,7 +378,7 @@ int opkb_vmlmb_carry_stats(const opkb_vmlmb* ws, int64_t* hits, int64_t* misses)
  * iteration, enqueued ahead by the host, reads from device memory: the host round trip leaves the
  * critical path.  The host still runs its own stage machine on the same scalars and adopts a launch
  * only if its decision and coefficients are bit-identical: same trajectories with and without.
- * Opt-in (OPKB_CHAIN=1 in the environment when the solver is created): on a B200 the round trip it
+ * Opt-in (opkb_solver_set_chain, or OPKB_CHAIN=1 in the environment when the solver is created): on a B200 the round trip it
  * removes (~8 us) is shorter than what the one-thread decision adds to the kernel (~12 us), see
  * DESIGN.md.  chain_stats: launches
  * that started a chain / launches adopted while already in flight / launches enqueued ahead that the
@@ -469,6 +469,13 @@ int  opkb_solver_run(opkb_solver* solver, int64_t niter, int* task);
 typedef int (*opkb_fg_callback)(void* user, int64_t n, const void* x_dev, void* g_dev, void* stream,
                                 double* f);
 int  opkb_solver_set_fg_callback(opkb_solver* solver, opkb_fg_callback fn, void* user, int f_is_partial);
+/* Device-resident decisions of opkb_solver_run (see opkb_vmlmb_chain_stats above): on = 1 asks for them, 0
+ * switches them off (the default; OPKB_CHAIN=1 in the environment asks for them at creation).  Not an
+ * error when the solver cannot use them (user objective, Float32, mem > 8, BLMVM, the step-by-step
+ * two-loop recursion, several ranks): opkb_solver_chain_enabled tells what is in effect.  Results do not
+ * depend on the switch. */
+int  opkb_solver_set_chain(opkb_solver* solver, int on);
+int  opkb_solver_chain_enabled(const opkb_solver* solver);
 int  opkb_solver_status(const opkb_solver* solver, int64_t* iter, int64_t* eval, int64_t* rejects,
                         double* f, double* gnorm, double* stp, int* stage, int* new_x);
 const char* opkb_solver_reason(const opkb_solver* solver);

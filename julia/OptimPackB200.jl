@@ -726,7 +726,7 @@ function vmlmb_native!(fg!, x::DeviceVector{T}; mem::Integer = min(5, length(x))
                        printer::Function = OptimPackNextGen.QuasiNewton.print_iteration,
                        output::IO = stdout,
                        lnsrch::Union{LineSearch{Float},Nothing} = nothing,
-                       twoloop::Symbol = :default, callback::Bool = false,
+                       twoloop::Symbol = :default, callback::Bool = false, chain::Bool = false,
                        nglobal::Integer = length(x)) where {T}
     if lower isa BoundedSet
         lower, upper = lower.lower, lower.upper
@@ -752,6 +752,8 @@ function vmlmb_native!(fg!, x::DeviceVector{T}; mem::Integer = min(5, length(x))
     check(ccall((:opkb_solver_create, libopkb200), Cint, (Ptr{Cvoid}, Ref{NativeOptions}, Ref{Ptr{Cvoid}}),
                 ws.ptr, opt, sref))
     solver = sref[]
+    # device-resident decisions of the run loop (same results; opt-in, DESIGN.md "Chained launches")
+    chain && check(ccall((:opkb_solver_set_chain, libopkb200), Cint, (Ptr{Cvoid}, Cint), solver, 1))
     task = Ref{Cint}(0)
     report() = begin
         iter, eval, rej, f, gnorm, stp, stage, newx = solver_status(solver)

@@ -142,6 +142,8 @@ _SIGNATURES = {
     "opkb_solver_iterate": (C.c_int, [vp, f64, Pi]),
     "opkb_solver_run": (C.c_int, [vp, i64, Pi]),
     "opkb_solver_set_fg_callback": (C.c_int, [vp, vp, vp, C.c_int]),
+    "opkb_solver_set_chain": (C.c_int, [vp, C.c_int]),
+    "opkb_solver_chain_enabled": (C.c_int, [vp]),
     "opkb_solver_status": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), Pd, Pd, Pd,
                                      Pi, Pi]),
     "opkb_solver_reason": (C.c_char_p, [vp]),

@@ -308,27 +308,43 @@ extern "C" int opkb_solver_create(opkb_vmlmb* ws, const opkb_vmlmb_options* opt,
     s->limits[0] = s->limits[1] = INFINITY;
     s->reason[0] = 0;
     s->run_target = INT64_MAX;
-    // Device-resident decisions (opkb_chain.cuh): built-in objective, Gram-form two-loop, Float64, up
-    // to 8 pairs, one rank.  OPT-IN (OPKB_CHAIN=1): measured on a B200 (profiles/r02u_*), the host
-    // round trip it removes is only ~8 us per iteration (polled pinned flag, results written straight
-    // to host memory), while the chained kernel is ~12 us longer (prologue 1.3, staging 1.7, the
-    // one-thread scalar part 9.5 us): C1 17.4 k -> 15.6 k it/s.  Same bits either way.
-    {
-        const int chain_env = getenv("OPKB_CHAIN") ? atoi(getenv("OPKB_CHAIN")) : 0;   // (read per solver)
-        const bool want = (chain_env > 0);
-        const bool ls_ok = (kind != LS_MORE_THUENTE) || (o.ls_ftol > 0 && o.ls_gtol > 0 && o.ls_xtol >= 0);
-        if (want && ls_ok && s->builtin && o.speculate && s->twoloop == 0 && opkb_vmlmb_chain_possible(ws)) {
-            opkb_bind_device(opkb_vmlmb_vector(ws, 'x', 0)->ctx);     // (the structure lives on the workspace's GPU)
-            if (cudaMalloc((void**)&s->chain_dev, sizeof(ChainDev)) == cudaSuccess &&
-                cudaMallocHost((void**)&s->chain_stage, sizeof(ChainDev)) == cudaSuccess)
-                s->chain_on = 1;
-            else
-                cudaGetLastError();
-        }
-    }
+    // Device-resident decisions (opkb_chain.cuh): opt-in, opkb_solver_set_chain or OPKB_CHAIN=1 in the
+    // environment (read per solver).  Measured on a B200 (profiles/r02u_*): the host round trip it removes
+    // is only ~8 us per iteration (polled pinned flag, results written straight to host memory), while
+    // the chained kernel is ~12 us longer (prologue 1.3, staging 1.7, the one-thread scalar part 9.5 us):
+    // C1 17.4 k -> 15.6 k it/s.  Same bits either way.
+    if (getenv("OPKB_CHAIN") && atoi(getenv("OPKB_CHAIN")) > 0) (void)opkb_solver_set_chain(s, 1);
     *out = s;
     return 0;
 }
+
+// Switch the device-resident decisions of opkb_solver_run on or off (include/opkb200.h).  Returns 0 also
+// when the solver cannot use them (user objective, Float32, more than 8 pairs, BLMVM, the step-by-step
+// two-loop, several ranks): `*enabled` (may be NULL) tells what is in effect.
+extern "C" int opkb_solver_set_chain(opkb_solver* s, int on)
+{
+    if (!s) return opkb_set_error(OPKB_EINVAL, "NULL solver");
+    if (opkb_vmlmb_chain_pending(s->ws)) return opkb_set_error(OPKB_EINVAL, "a chained launch is in flight");
+    if (!on) {
+        s->chain_on = 0;
+        return 0;
+    }
+    const opkb_vmlmb_options& o = s->opt;
+    const bool ls_ok = (s->ls.kind != LS_MORE_THUENTE) || (o.ls_ftol > 0 && o.ls_gtol > 0 && o.ls_xtol >= 0);
+    if (!(ls_ok && s->builtin && o.speculate && s->twoloop == 0 && opkb_vmlmb_chain_possible(s->ws))) return 0;
+    if (!s->chain_dev) {
+        opkb_bind_device(opkb_vmlmb_vector(s->ws, 'x', 0)->ctx);     // (the structure lives on the workspace's GPU)
+        if (cudaMalloc((void**)&s->chain_dev, sizeof(ChainDev)) != cudaSuccess ||
+            cudaMallocHost((void**)&s->chain_stage, sizeof(ChainDev)) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+    }
+    s->chain_on = 1;
+    return 0;
+}
+
+extern "C" int opkb_solver_chain_enabled(const opkb_solver* s) { return s ? s->chain_on : 0; }
 
 extern "C" int opkb_solver_destroy(opkb_solver* s)
 {

@@ -873,6 +873,9 @@ class NativeVMLMB(VMLMB):
         from .linesearches import ArmijoLineSearch
         ls = kw.get("lnsrch")
         kw.pop("mode", None)
+        # chain=True: device-resident decisions of the run loop (opkb_solver_set_chain; same results,
+        # opt-in, see DESIGN.md "Chained launches"); None: the library's default (OPKB_CHAIN)
+        chain = kw.pop("chain", None)
         super().__init__(fg, x0, mode="fused", **kw)
         L = _lib.lib()
         opt = _lib.VmlmbOptions()
@@ -897,6 +900,8 @@ class NativeVMLMB(VMLMB):
             raise TypeError("the native driver knows the three line searches of the reference")
         self._solver = vp()
         check(L.opkb_solver_create(self._ws, C.byref(opt), C.byref(self._solver)))
+        if chain is not None:
+            check(L.opkb_solver_set_chain(self._solver, int(bool(chain))))
         self._task = C.c_int(_lib.TASK_START)
         self._g = self.ops.vector("g")
         self._builtin = is_builtin(fg)
@@ -910,6 +915,11 @@ class NativeVMLMB(VMLMB):
             _lib.lib().opkb_solver_destroy(self._solver)
             self._solver = None
         super().close()
+
+    @property
+    def chain_enabled(self) -> bool:
+        """Whether the run loop uses the device-resident decisions (opkb_solver_chain_enabled)."""
+        return bool(self._solver) and bool(_lib.lib().opkb_solver_chain_enabled(self._solver))
 
     def _refresh(self):
         L = _lib.lib()

@@ -30,11 +30,11 @@ CASES = [
 
 def _run(pb, mem, chain, plan, **kw):
     """NativeVMLMB run following `plan` (iterations per opkb_solver_run call); -> summary."""
-    os.environ["OPKB_CHAIN"] = "1" if chain else "0"
     os.environ["OPKB_CHAIN_CHECK"] = "1"
     try:
         lo, hi = gpu_bounds(pb)
-        s = opk.NativeVMLMB(pb["gpu_obj"], pb["x0"].copy(), lower=lo, upper=hi, mem=mem, **kw)
+        s = opk.NativeVMLMB(pb["gpu_obj"], pb["x0"].copy(), lower=lo, upper=hi, mem=mem, chain=chain, **kw)
+        assert s.chain_enabled == bool(chain)
         trace = []
         for k in plan:
             alive = s.iterate(k)
@@ -46,8 +46,34 @@ def _run(pb, mem, chain, plan, **kw):
         s.close()
         return out
     finally:
-        os.environ.pop("OPKB_CHAIN", None)
         os.environ.pop("OPKB_CHAIN_CHECK", None)
+
+
+def test_chain_switches():
+    """The keyword, the environment switch, and solvers that cannot chain (not an error)."""
+    pb = problem("quad_box", 4096, np.float64)
+    lo, hi = gpu_bounds(pb)
+    s = opk.NativeVMLMB(pb["gpu_obj"], pb["x0"].copy(), lower=lo, upper=hi, mem=5)
+    assert not s.chain_enabled                      # opt-in
+    s.close()
+    os.environ["OPKB_CHAIN"] = "1"
+    try:
+        s = opk.NativeVMLMB(pb["gpu_obj"], pb["x0"].copy(), lower=lo, upper=hi, mem=5)
+        assert s.chain_enabled
+        s.close()
+    finally:
+        os.environ.pop("OPKB_CHAIN", None)
+    for kw in (dict(mem=9), dict(mem=5, blmvm=True), dict(mem=5, twoloop="sequential")):
+        s = opk.NativeVMLMB(pb["gpu_obj"], pb["x0"].copy(), lower=lo, upper=hi, chain=True, **kw)
+        assert not s.chain_enabled, kw
+        s.iterate(12)
+        assert s.chain_stats() == (0, 0, 0)
+        s.close()
+    pb32 = problem("quad_box", 4096, np.float32)
+    s = opk.NativeVMLMB(pb32["gpu_obj"], pb32["x0"].copy(), lower=lo.astype(np.float32), upper=hi.astype(np.float32),
+                        mem=5, chain=True, twoloop="gram")
+    assert not s.chain_enabled
+    s.close()
 
 
 @pytest.mark.parametrize("kind,n,mem,kw", CASES)
