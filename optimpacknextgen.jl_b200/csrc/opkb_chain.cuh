@@ -57,160 +57,186 @@ struct ChainDev {
 __device__ __forceinline__ double chain_max(double a, double b) { return a != a ? a : (b != b ? b : (a > b ? a : b)); }
 __device__ __forceinline__ double chain_min(double a, double b) { return a != a ? a : (b != b ? b : (a < b ? a : b)); }
 
-// The scalar part, one thread, everything in shared memory.  cs: this launch's copy of the
-// structure (updated in place for the next launch, G excepted); R: the combined scalars of this launch
-// (k_direction2: 12 + dense + corrections); Gn: the next Gram block, already assembled (below).
-// Mirrors, statement by statement, what the host does between two fused launches:
+// The scalar part, by ONE WARP (all 32 lanes call it), everything in shared memory.  cs: this launch's
+// copy of the structure (updated in place for the next launch, G excepted); R: the combined scalars
+// of this launch (k_direction2: 12 + dense + corrections); G: the next Gram block, already assembled
+// (below).  Mirrors, statement by statement, what the host does between two fused launches:
 // new_direction_gram (tail) -> after_evaluation (tail) -> opkb_solver_run -> after_evaluation (head)
 // -> opkb_vmlmb_gram (gram_from_carry) -> solve_two_loop of opkb_driver.cu / opkb_vmlmb.cu.
+// One thread doing all of it costs ~9.5 us (~1500 dependent instructions: measured, profiles/r02u_*).
+// Here lane 0 takes the decisions (the four square roots come from lanes 1..4), and the two
+// recurrences of the two-loop solve run with lane k owning pair k: every accumulator sees its
+// terms in the host's order (alpha: j = m-1 down to k+1; c: all alpha_j, j = m-1 down to 0, then c_j,
+// j = 0 up to k-1), each product rounded before it is added -- the same bits, ~40 dependent
+// operations and 2m divisions on the critical path instead of ~1500.
 template <int MB>
-__device__ __forceinline__ void chain_decide_serial(ChainDev* cs, const double* R, const double* G, double* rec)
+__device__ __forceinline__ void chain_decide_warp(ChainDev* cs, const double* R, const double* G, double* rec,
+                                                  int lane)
 {
+    constexpr unsigned FULL = 0xffffffffu;
     constexpr int ND = 4 * MB + 4, NENT = MB * (MB + 1), NCORR = 32 * ((NENT + 31) / 32);
-    // the NEXT launch works on up to MB + 1 pairs (this one held m <= MB)
-    constexpr int MN = (MB + 1 <= OPKB_CHAIN_MB) ? MB + 1 : OPKB_CHAIN_MB;
     const int m = cs->m, mem = cs->mem, method = cs->method;
-    int why = 0;
-    double alpha[MN], c[MN], rho[MN];
-    int slots[MN];
-    double gamma_dir = 0.0, gamma_keep = cs->gamma, f = 0.0, gnorm = 0.0;
-    long long iter = cs->iter, eval = cs->eval;
     const int mn = (m + 1 < mem ? m + 1 : mem);
-    do {
-        // -- the direction this launch assembled: descent test (:542-546, :631-632)
-        const double gd = -R[0];
-        const double dnorm = sqrt(R[1]);
-        const double smax = cs->limits_inf ? INFINITY : R[3];
-        const bool reject = !(cs->epsilon > 0 ? (gd <= -cs->epsilon * dnorm * cs->gnorm) : (gd < 0));
-        if (reject) { why = 1; break; }
-        // -- first step of the line search (:566-584): the trial point of this launch is x - 1*d
-        const double f0 = cs->f, gd0 = gd;
-        double stp = 1.0, stpmin, stpmax;
-        if (method > 0) {
-            stp = chain_min(stp, smax);
-            stpmin = 1e-20 * stp;
-            stpmax = chain_min(1e+20 * stp, smax);
-        } else {
-            stpmin = 1e-20 * stp;
-            stpmax = 1e+20 * stp;
-        }
-        if (stp != 1.0) { why = 2; break; }
-        // start! (src/linesearches.jl:331-358, :470-529): anything it would throw is the host's business
-        if (stpmax < stpmin || stpmin < 0 || !(gd0 < 0) || stp > stpmax || stp < stpmin) { why = 3; break; }
-        // -- the trial point (k_direction2, FUSE): f, |p'|^2, g'.s, g'.d, |x'|^2, |s|^2
-        f = (cs->obj == OPKB_OBJ_ROSENBROCK) ? R[4] + R[5] : 0.5 * R[4];
-        const double r1 = R[6], r2 = R[7], r3 = R[8], r4 = R[9], r5 = R[10];
-        eval += 1;
-        if (!(f < cs->bestf)) { why = 4; break; }             // (:398; a trial that does not improve: host)
-        gnorm = sqrt(r1);
-        if (gnorm <= cs->gtest) { why = 5; break; }           // converged (:409-417)
-        if (cs->fminset && f < cs->fmin) { why = 6; break; }  // (:420-423)
-        // iterate! : convergence at the first trial, or the host goes on with the search
-        bool conv;
-        if (cs->ls_kind == 3) {
-            const double g_ls = (method > 0 ? r2 / stp : -r3);                // (:432 / :434)
-            const double gtest = cs->ls_ftol * gd0, ftest = f0 + stp * gtest; // src/linesearches.jl:536-547
-            conv = (f <= ftest && fabs(g_ls) <= -cs->ls_gtol * gd0);
-        } else {
-            conv = (f <= f0 + cs->ls_ftol * stp * gd0);                       // :235-237, :360-362
-        }
-        if (!conv) { why = 7; break; }
-        iter += 1;                                                            // (:443)
-        double xtest = chain_max(cs->xatol, 0.0);                             // (:444-468)
-        if (cs->xrtol > 0) xtest = chain_max(xtest, cs->xrtol * sqrt(r4));
-        if (sqrt(r5) <= xtest) { why = 8; break; }
-        const double delta = chain_max(fabs(f - f0), stp * fabs(gd0));
-        if (delta <= cs->fatol || delta <= cs->frtol * fabs(f0)) { why = 9; break; }
-        if (iter >= cs->maxiter || eval >= cs->maxeval) { why = 10; break; }
-        // -- the next Gram block comes from what this launch carried (gram_from_carry, opkb_vmlmb.cu)
-        if (R[12 + ND + NCORR - 1] != 0.0) { why = 11; break; }              // a warp gave its corrections up
-        const int drop = (m == mem) ? 1 : 0;
-        const int W = mn + 1, nn = mn - 1;
-#pragma unroll
-        for (int a2 = 0; a2 < MN; ++a2) slots[a2] = (a2 < nn) ? cs->slots[a2 + drop] : ((a2 == nn) ? cs->mark_next : 0);
-        // -- two-loop recursion in coefficient space (solve_two_loop, opkb_driver.cu); unrolled over
-        // MB with guards, so that alpha, c, rho live in registers (one thread: every trip through
-        // local memory would be on the critical path of the whole grid)
+    // square roots the decisions need, one lane each: 1: |d|, 2: |p'| (gnorm), 3: |x'|, 4: |s|
+    double sq = 0.0;
+    if (lane >= 1 && lane <= 4) sq = sqrt(R[lane == 1 ? 1 : (lane == 2 ? 6 : (lane == 3 ? 9 : 10))]);
+    const double dnorm = __shfl_sync(FULL, sq, 1), gnorm = __shfl_sync(FULL, sq, 2);
+    const double xnorm = __shfl_sync(FULL, sq, 3), snorm = __shfl_sync(FULL, sq, 4);
+    int why = 0;
+    double f = 0.0;
+    long long iter = cs->iter, eval = cs->eval;
+    if (lane == 0) {
+        do {
+            // -- the direction this launch assembled: descent test (:542-546, :631-632)
+            const double gd = -R[0];
+            const double smax = cs->limits_inf ? INFINITY : R[3];
+            const bool reject = !(cs->epsilon > 0 ? (gd <= -cs->epsilon * dnorm * cs->gnorm) : (gd < 0));
+            if (reject) { why = 1; break; }
+            // -- first step of the line search (:566-584): the trial point of this launch is x - 1*d
+            const double f0 = cs->f, gd0 = gd;
+            double stp = 1.0, stpmin, stpmax;
+            if (method > 0) {
+                stp = chain_min(stp, smax);
+                stpmin = 1e-20 * stp;
+                stpmax = chain_min(1e+20 * stp, smax);
+            } else {
+                stpmin = 1e-20 * stp;
+                stpmax = 1e+20 * stp;
+            }
+            if (stp != 1.0) { why = 2; break; }
+            // start! (src/linesearches.jl:331-358, :470-529): anything it would throw is the host's business
+            if (stpmax < stpmin || stpmin < 0 || !(gd0 < 0) || stp > stpmax || stp < stpmin) { why = 3; break; }
+            // -- the trial point (k_direction2, FUSE): f, |p'|^2, g'.s, g'.d, |x'|^2, |s|^2
+            f = (cs->obj == OPKB_OBJ_ROSENBROCK) ? R[4] + R[5] : 0.5 * R[4];
+            const double r2 = R[7], r3 = R[8];
+            eval += 1;
+            if (!(f < cs->bestf)) { why = 4; break; }             // (:398; a trial that does not improve: host)
+            if (gnorm <= cs->gtest) { why = 5; break; }           // converged (:409-417)
+            if (cs->fminset && f < cs->fmin) { why = 6; break; }  // (:420-423)
+            // iterate! : convergence at the first trial, or the host goes on with the search
+            bool conv;
+            if (cs->ls_kind == 3) {
+                const double g_ls = (method > 0 ? r2 / stp : -r3);                // (:432 / :434)
+                const double gtest = cs->ls_ftol * gd0, ftest = f0 + stp * gtest; // src/linesearches.jl:536-547
+                conv = (f <= ftest && fabs(g_ls) <= -cs->ls_gtol * gd0);
+            } else {
+                conv = (f <= f0 + cs->ls_ftol * stp * gd0);                       // :235-237, :360-362
+            }
+            if (!conv) { why = 7; break; }
+            iter += 1;                                                            // (:443)
+            double xtest = chain_max(cs->xatol, 0.0);                             // (:444-468)
+            if (cs->xrtol > 0) xtest = chain_max(xtest, cs->xrtol * xnorm);
+            if (snorm <= xtest) { why = 8; break; }
+            const double delta = chain_max(fabs(f - f0), stp * fabs(gd0));
+            if (delta <= cs->fatol || delta <= cs->frtol * fabs(f0)) { why = 9; break; }
+            if (iter >= cs->maxiter || eval >= cs->maxeval) { why = 10; break; }
+            // -- the next Gram block comes from what this launch carried (gram_from_carry, opkb_vmlmb.cu)
+            if (R[12 + ND + NCORR - 1] != 0.0) { why = 11; break; }              // a warp gave its corrections up
+        } while (0);
+    }
+    why = __shfl_sync(FULL, why, 0);
+    // -- two-loop recursion in coefficient space (solve_two_loop, opkb_driver.cu): lane k = pair k
+    const int drop = (m == mem) ? 1 : 0;
+    const int W = mn + 1, nn = mn - 1;
+    const int k = lane;
+    const bool mine = (k < mn);
+    const int kk = mine ? k : 0;                       // (clamped: lanes beyond the pairs read valid memory)
+    const int slot = (k < nn) ? cs->slots[kk + drop] : cs->mark_next;
+    double gamma_keep = cs->gamma, gamma = 0.0, alpha = NAN, c = 0.0;
+    bool change = false;
+    if (why == 0) {
 #define CH_SV(a) G[2 * (a) * W]
 #define CH_YV(a) G[(2 * (a) + 1) * W]
 #define CH_SY(a, b) G[2 * (a) * W + 1 + (b)]
 #define CH_YY(a, b) ((b) >= (a) ? G[(2 * (a) + 1) * W + 1 + (b)] : G[(2 * (b) + 1) * W + 1 + (a)])
+        double rho;
         if (method == 2) {
-#pragma unroll
-            for (int j = 0; j < MN; ++j) rho[j] = (j < mn) ? CH_SY(j, j) : 0.0;
+            rho = mine ? CH_SY(kk, kk) : 0.0;                                    // (:758)
         } else {
-            const double rnew = CH_SY(nn, nn);
-            cs->rho[cs->mark_next] = rnew;     // (slots[nn])
-            if (rnew > 0) gamma_keep = rnew / CH_YY(nn, nn);
-#pragma unroll
-            for (int j = 0; j < MN; ++j) rho[j] = (j < mn) ? cs->rho[slots[j]] : 0.0;
+            const double rnew = CH_SY(nn, nn);                                    // (:515)
+            if (rnew > 0) gamma_keep = rnew / CH_YY(nn, nn);                      // (:518)
+            rho = !mine ? 0.0 : ((k == nn) ? rnew : cs->rho[slot]);
+            if (k == nn) cs->rho[slot] = rnew;
         }
-        double gamma = 0.0;
-        bool modif = false;
-#pragma unroll
-        for (int k = MN - 1; k >= 0; --k) {
-            alpha[k] = NAN;
-            c[k] = 0.0;
-            if (k < mn && rho[k] > 0) {
-                double acc = CH_SV(k);
-#pragma unroll
-                for (int j = MN - 1; j > k; --j)
-                    if (j < mn && rho[j] > 0) acc -= alpha[j] * CH_SY(k, j);
-                alpha[k] = acc / rho[k];
-                if (gamma == 0) gamma = rho[k] / CH_YY(k, k);
-                modif = true;
+        const bool use = mine && (rho > 0);
+        const unsigned usemask = __ballot_sync(FULL, use);
+        // first loop (:725-732 / :756-766): alpha_t newest -> oldest, every older pair takes its term
+        double acc = mine ? CH_SV(kk) : 0.0;
+        for (int t = mn - 1; t >= 0; --t) {
+            const bool ut = (usemask >> t) & 1u;                 // (uniform)
+            double at = (k == t && use) ? acc / rho : 0.0;
+            at = __shfl_sync(FULL, at, t);
+            if (ut) {
+                if (k == t) alpha = at;
+                if (mine && k < t) acc -= at * CH_SY(kk, t);
             }
+        }
+        // gamma: from the newest pair that takes part (:762-764), or the one kept between iterations
+        {
+            const double q = use ? rho / CH_YY(kk, kk) : 0.0;
+            const int top = usemask ? (31 - __clz((int)usemask)) : 0;
+            gamma = usemask ? __shfl_sync(FULL, q, top) : 0.0;
         }
         if (method < 2) gamma = gamma_keep;
-        if (!modif || gamma == 0) { why = 12; break; }
-#pragma unroll
-        for (int k = 0; k < MN; ++k) {
-            if (k < mn && rho[k] > 0) {
-                double acc = CH_YV(k);
-#pragma unroll
-                for (int j = MN - 1; j >= 0; --j)
-                    if (j < mn && rho[j] > 0) acc -= alpha[j] * CH_YY(k, j);
-                acc *= gamma;
-#pragma unroll
-                for (int j = 0; j < MN; ++j)
-                    if (j < k && rho[j] > 0) acc += c[j] * CH_SY(j, k);
-                c[k] = alpha[k] - acc / rho[k];
+        change = (usemask != 0u) && (gamma != 0);
+        if (change) {
+            // second loop (:735-741 / :769-775): every alpha_j first (newest -> oldest), the scaling, then
+            // the c_j of the older pairs oldest -> newest
+            double b = mine ? CH_YV(kk) : 0.0;
+            for (int j = mn - 1; j >= 0; --j) {
+                const double aj = __shfl_sync(FULL, alpha, j);
+                if (((usemask >> j) & 1u) && mine) b -= aj * CH_YY(kk, j);
             }
+            b *= gamma;
+            for (int t = 0; t < mn; ++t) {
+                const bool ut = (usemask >> t) & 1u;             // (uniform)
+                double ct = (k == t && use) ? alpha - b / rho : 0.0;
+                ct = __shfl_sync(FULL, ct, t);
+                if (ut) {
+                    if (k == t) c = ct;
+                    if (mine && k > t) b += ct * CH_SY(t, kk);
+                }
+            }
+        } else if (lane == 0) {
+            why = 12;
         }
 #undef CH_SV
 #undef CH_YV
 #undef CH_SY
 #undef CH_YY
-        gamma_dir = gamma;
-    } while (0);
-    for (int i = 0; i < OPKB_CHAIN_NREC; ++i) rec[i] = 0.0;
-    rec[1] = (double)why;
+    }
+    why = __shfl_sync(FULL, why, 0);
+    if (lane < OPKB_CHAIN_NREC) rec[lane] = 0.0;
+    __syncwarp();
     if (why != 0) {
-        cs->go = 0;
+        if (lane == 0) {
+            rec[1] = (double)why;
+            cs->go = 0;
+        }
         return;
     }
-#pragma unroll
-    for (int j = 0; j < MN; ++j) {
-        if (j < mn) {
-            cs->alpha[j] = alpha[j];
-            cs->c[j] = c[j];
-            cs->slots[j] = slots[j];
-            rec[3 + j] = alpha[j];
-            rec[3 + OPKB_CHAIN_MB + j] = c[j];
-        }
+    if (mine) {
+        cs->alpha[k] = alpha;
+        cs->c[k] = c;
+        rec[3 + k] = alpha;
+        rec[3 + OPKB_CHAIN_MB + k] = c;
     }
-    cs->gamma_dir = gamma_dir;
-    cs->gamma = gamma_keep;
-    cs->m = mn;
-    cs->mark_next = (cs->mark_next < mem - 1) ? cs->mark_next + 1 : 0;
-    cs->iter = iter;
-    cs->eval = eval;
-    cs->f = f;
-    cs->bestf = f;
-    cs->gnorm = gnorm;
-    cs->go = 1;
-    rec[0] = 1.0;
-    rec[2] = gamma_dir;
+    __syncwarp();                 // (every lane has read cs->slots / cs->mark_next before they change)
+    if (mine) cs->slots[k] = slot;
+    if (lane == 0) {
+        cs->gamma_dir = gamma;
+        cs->gamma = gamma_keep;
+        cs->m = mn;
+        cs->mark_next = (cs->mark_next < mem - 1) ? cs->mark_next + 1 : 0;
+        cs->iter = iter;
+        cs->eval = eval;
+        cs->f = f;
+        cs->bestf = f;
+        cs->gnorm = gnorm;
+        cs->go = 1;
+        rec[0] = 1.0;
+        rec[2] = gamma;
+    }
 }
 
 // All threads of the last CTA.  cs_g: the structure in device memory; R: the combined scalars of
@@ -222,7 +248,7 @@ __device__ __forceinline__ void chain_decide_serial(ChainDev* cs, const double* 
 #define OPKB_CHAIN_NW ((int)(sizeof(ChainDev) / 8))
 #define OPKB_CHAIN_WORK (OPKB_CHAIN_NW + 2 * OPKB_CHAIN_MB * (OPKB_CHAIN_MB + 1) + OPKB_CHAIN_NREC + 1)
 template <int MB>
-__device__ __forceinline__ void chain_decide_block(ChainDev* cs_g, const double* R, double* rec_g, double* work,
+__device__ __noinline__ void chain_decide_block(ChainDev* cs_g, const double* R, double* rec_g, double* work,
                                                    int tid, int nthreads)
 {
     static_assert(sizeof(ChainDev) % 8 == 0 && offsetof(ChainDev, G) % 8 == 0, "ChainDev is copied word by word");
@@ -265,12 +291,12 @@ __device__ __forceinline__ void chain_decide_block(ChainDev* cs_g, const double*
         }
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32) {
         if (dbg & 1) {
-            cs->go = 0;
-            for (int i = 0; i < OPKB_CHAIN_NREC; ++i) rec[i] = 0.0;
+            if (tid == 0) cs->go = 0;
+            if (tid < OPKB_CHAIN_NREC) rec[tid] = 0.0;
         } else {
-            chain_decide_serial<MB>(cs, R, Gn, rec);
+            chain_decide_warp<MB>(cs, R, Gn, rec, tid);
         }
     }
     __syncthreads();

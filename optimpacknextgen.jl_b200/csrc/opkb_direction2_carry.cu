@@ -68,6 +68,17 @@ int dir2_launch_carry(opkb_context* ctx, const Dir2Args<T>& B, int fuse, int mb,
             }
         }
         if (B.chain) {
+            const bool unb = spec_on && !B.bounded && !B.masked && B.r_ysrc < 0 && !B.v0_from_g && B.hist &&
+                             B.rows[0] == B.rows[2];
+            if (unb) {      // L-BFGS without bounds: SPEC = 3 (row 0 is not loaded)
+                if (fuse == OPKB_OBJ_ROSENBROCK) DIR2_PICK_CHAIN(OPKB_OBJ_ROSENBROCK, 3);
+                else if (fuse == OPKB_OBJ_QUADRATIC) DIR2_PICK_CHAIN(OPKB_OBJ_QUADRATIC, 3);
+                if (kern) {
+                    Dir2Args<T> U = B;
+                    U.v0_from_g = 1;
+                    return dir2_do_launch<T>(ctx, kern, U, (mb == 5) ? 384 : DIR2_NTHREADS(1), smem, grid, res_offset);
+                }
+            }
             const int sp = !spec ? 0 : (B.hist ? 1 : 2);
             if (fuse == OPKB_OBJ_ROSENBROCK) {
                 if (sp == 1) DIR2_PICK_CHAIN(OPKB_OBJ_ROSENBROCK, 1);

@@ -311,8 +311,7 @@ extern "C" int opkb_solver_create(opkb_vmlmb* ws, const opkb_vmlmb_options* opt,
     // Device-resident decisions (opkb_chain.cuh): opt-in, opkb_solver_set_chain or OPKB_CHAIN=1 in the
     // environment (read per solver).  Measured on a B200 (profiles/r02u_*): the host round trip it removes
     // is only ~8 us per iteration (polled pinned flag, results written straight to host memory), while
-    // the chained kernel is ~12 us longer (prologue 1.3, staging 1.7, the one-thread scalar part 9.5 us):
-    // C1 17.4 k -> 15.6 k it/s.  Same bits either way.
+    // the chained kernel is ~12 us longer: C1 18.9 k -> 18.2 k it/s (profiles/r02c2_*).  Same bits either way.
     if (getenv("OPKB_CHAIN") && atoi(getenv("OPKB_CHAIN")) > 0) (void)opkb_solver_set_chain(s, 1);
     *out = s;
     return 0;
