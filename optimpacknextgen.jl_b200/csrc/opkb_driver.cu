@@ -450,7 +450,8 @@ static int new_direction_gram(opkb_solver* s, bool* change, double* gd, double* 
             st.gamma = s->gamma;
             for (int k = 0; k < mem && k < OPKB_CHAIN_MB; ++k) st.rho[k] = s->rho[k];
             // the launch of the iteration after this one is enqueued ahead if this run goes that far
-            const int ahead = (s->iter < s->run_target) ? 1 : 0;
+            static const int dbg = getenv("OPKB_CHAIN_DBG") ? atoi(getenv("OPKB_CHAIN_DBG")) : 0;   // 4: never ahead
+            const int ahead = (s->iter < s->run_target && !(dbg & 4)) ? 1 : 0;
             rc = opkb_vmlmb_direction_trial_chain(s->ws, m, slots, alpha, c, gamma, mark_next, out4, s->spec,
                                                   &st, s->chain_dev, s->chain_stage, ahead);
         } else {
