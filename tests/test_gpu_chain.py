@@ -25,6 +25,12 @@ CASES = [
     ("quad_box", 4096, 3, {}),                   # the memory fills up after 3 iterations
     ("rosen_lower0", 5000, 7, {}),               # scalar bound
     ("quad_upper_scalar", 10000, 4, {}),
+    # tiny problems run to (and past) convergence with the tolerances off: pairs with rho <= 0, zero steps,
+    # everything on a bound -- the device must never say "go" where the host takes another path
+    ("quad_box", 7, 3, {}),
+    ("rosen_unc", 2, 2, {}),
+    ("rosen_box", 6, 5, {}),
+    ("quad_box", 64, 8, {}),
 ]
 
 
@@ -86,7 +92,7 @@ def test_chain_is_bit_identical(kind, n, mem, kw):
         assert a["trace"] == b["trace"], (plan, a["trace"], b["trace"])     # bit for bit
         assert np.array_equal(a["x"], b["x"]), plan
         assert b["chain"] == (0, 0, 0)
-        if plan == [30]:
+        if plan == [30] and n >= 1000:
             # launches were adopted while already in flight (otherwise this test proves nothing)
             assert a["chain"][1] >= 5, a["chain"]
         if plan == [1] * 12:
