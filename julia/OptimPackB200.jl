@@ -444,6 +444,7 @@ vmlmb(fg!, x0::DeviceVector; kwds...) = vmlmb!(fg!, vcopy(x0); kwds...)
 function vmlmb!(fg!, x::DeviceVector{T};
                 mem::Integer = min(5, length(x)),
                 lower = -Inf, upper = +Inf,
+                autodiff::Bool = false,
                 blmvm::Bool = false,
                 fmin::Real = -Inf,
                 maxiter::Integer = typemax(Int),
@@ -457,6 +458,9 @@ function vmlmb!(fg!, x::DeviceVector{T};
                 output::IO = stdout,
                 lnsrch::Union{LineSearch{Float},Nothing} = nothing,
                 nglobal::Integer = length(x)) where {T}
+    # (src/quasinewton.jl:230: the keyword exists for drop-in calls; automatic differentiation of a host
+    # closure has no meaning on device vectors -- SURVEY section 2, out of scope)
+    autodiff && throw(ArgumentError("autodiff=true is not supported on device vectors: provide fg!(x, g)"))
     if lower isa BoundedSet
         lower, upper = lower.lower, lower.upper
     end
@@ -718,7 +722,7 @@ end
 advances one iteration per `ccall`).
 """
 function vmlmb_native!(fg!, x::DeviceVector{T}; mem::Integer = min(5, length(x)),
-                       lower = -Inf, upper = +Inf, blmvm::Bool = false, fmin::Real = -Inf,
+                       lower = -Inf, upper = +Inf, autodiff::Bool = false, blmvm::Bool = false, fmin::Real = -Inf,
                        maxiter::Integer = typemax(Int), maxeval::Integer = typemax(Int),
                        xtol::NTuple{2,Real} = (0.0, 1e-7), ftol::NTuple{2,Real} = (0.0, 1e-8),
                        gtol::NTuple{2,Real} = (0.0, 1e-6), epsilon::Real = 0.0,
@@ -728,6 +732,7 @@ function vmlmb_native!(fg!, x::DeviceVector{T}; mem::Integer = min(5, length(x))
                        lnsrch::Union{LineSearch{Float},Nothing} = nothing,
                        twoloop::Symbol = :default, callback::Bool = false, chain::Bool = false,
                        nglobal::Integer = length(x)) where {T}
+    autodiff && throw(ArgumentError("autodiff=true is not supported on device vectors: provide fg!(x, g)"))
     if lower isa BoundedSet
         lower, upper = lower.lower, lower.upper
     end
@@ -818,11 +823,13 @@ function spg!(fg!, prj!, x::DeviceVector{T}, m::Integer; kwds...) where {T}
 end
 
 function fused_spg!(fg!, box::BoundedSet, x::DeviceVector{T}, m::Int;
+                    autodiff::Bool = false,
                     ws::OptimPackNextGen.SPG.Info = OptimPackNextGen.SPG.Info(),
                     maxit::Integer = typemax(Int), maxfc::Integer = typemax(Int),
                     eps1::Real = 1e-6, eps2::Real = 1e-6, eta::Real = 1.0,
                     printer::Function = OptimPackNextGen.SPG.default_printer,
                     verb::Integer = false, io::IO = stdout) where {T}
+    autodiff && throw(ArgumentError("autodiff=true is not supported on device vectors: provide fg!(x, g)"))
     ctx = x.ctx
     lo = to_device(ctx, box.lower, T); hi = to_device(ctx, box.upper, T)
     (lp, lv), (hp, hv) = bound_args(lo, -Inf), bound_args(hi, +Inf)

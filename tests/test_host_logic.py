@@ -276,3 +276,28 @@ def test_c_host_builds_and_fails_loudly_without_gpu(tmp_path):
         pytest.skip("a GPU is present: tests/test_gpu_api.py::test_c_host_runs covers the run")
     r = subprocess.run([exe, "1000"], capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_python_twin_accepts_the_reference_keywords():
+    """Drop-in surface: every keyword of the reference's `vmlmb!` (src/quasinewton.jl:226-242) and `spg!`
+    (src/spg.jl:168-178) is a keyword of the twin's solvers, with the reference's defaults where Python
+    has the same value (tests/test_julia_static.py does the same for the Julia module)."""
+    import inspect
+    import math
+
+    import opkb200 as opk
+    v = inspect.signature(opk.VMLMB.__init__).parameters
+    for kw in ("mem", "lower", "upper", "autodiff", "blmvm", "fmin", "maxiter", "maxeval", "xtol", "ftol", "gtol",
+               "epsilon", "verb", "printer", "output", "lnsrch"):
+        assert kw in v and v[kw].kind is inspect.Parameter.KEYWORD_ONLY, kw
+    assert (v["mem"].default, v["lower"].default, v["upper"].default) == (5, -math.inf, math.inf)
+    assert (v["xtol"].default, v["ftol"].default, v["gtol"].default) == ((0.0, 1e-7), (0.0, 1e-8), (0.0, 1e-6))
+    assert v["autodiff"].default is False and v["blmvm"].default is False and v["epsilon"].default == 0.0
+    s = inspect.signature(opk.SPG.__init__).parameters
+    for kw in ("autodiff", "ws", "maxit", "maxfc", "eps1", "eps2", "eta", "printer", "verb", "io"):
+        assert kw in s and s[kw].kind is inspect.Parameter.KEYWORD_ONLY, kw
+    assert (s["eps1"].default, s["eps2"].default, s["eta"].default) == (1e-6, 1e-6, 1.0)
+    # the names north_star lists
+    for name in ("vmlmb", "vmlmb_", "spg", "spg_", "BoundedSet", "MoreThuenteLineSearch", "ArmijoLineSearch",
+                 "MoreToraldoLineSearch", "conjgrad", "conjgrad_"):
+        assert hasattr(opk, name), name

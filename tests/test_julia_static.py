@@ -206,3 +206,64 @@ def test_static_checker_catches_breakage(tmp_path):
     p.write_text(good.replace("    return x[end] + y[1]\nend\n", "    return x[end] + y[1]\n"))
     with pytest.raises(AssertionError):
         check_blocks(str(p))
+
+
+# ---------------------------------------------------------------------------
+# Drop-in signatures: every keyword of the reference's entry points is accepted by the module.
+# The lists are the reference's (src/quasinewton.jl:226-242, src/spg.jl:168-178); when the reference
+# tree is at hand (the build container, not the GPU box) they are re-read from it.
+REF_VMLMB_KW = ["mem", "lower", "upper", "autodiff", "blmvm", "fmin", "maxiter", "maxeval", "xtol", "ftol", "gtol",
+                "epsilon", "verb", "printer", "output", "lnsrch"]
+REF_SPG_KW = ["autodiff", "ws", "maxit", "maxfc", "eps1", "eps2", "eta", "printer", "verb", "io"]
+
+
+def _signature_keywords(src, head):
+    """Keyword names of the Julia method whose definition starts with `head` (up to `) where` / `)`)."""
+    i = src.index(head)
+    j = src.index(";", i)
+    depth, k = 1, j
+    # the signature ends at the parenthesis that closes the one opened by `head`
+    depth = 0
+    for k in range(i + len("function"), len(src)):
+        ch = src[k]
+        if ch == "(":
+            depth += 1
+        elif ch == ")":
+            depth -= 1
+            if depth == 0:
+                break
+    sig = src[j + 1:k]
+    names, depth, tok = [], 0, ""
+    for ch in sig + ",":
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            name = re.match(r"\s*([A-Za-z_][A-Za-z_0-9!]*)", tok)
+            if name:
+                names.append(name.group(1))
+            tok = ""
+        else:
+            tok += ch
+    return names
+
+
+def test_julia_entry_points_accept_the_reference_keywords():
+    src = open(MODULE).read()
+    vm = _signature_keywords(src, "function vmlmb!(fg!, x::DeviceVector{T};")
+    vn = _signature_keywords(src, "function vmlmb_native!(fg!, x::DeviceVector{T};")
+    sp = _signature_keywords(src, "function fused_spg!(fg!, box::BoundedSet, x::DeviceVector{T}, m::Int;")
+    for kw in REF_VMLMB_KW:
+        assert kw in vm, ("vmlmb!", kw, vm)
+        assert kw in vn, ("vmlmb_native!", kw, vn)
+    for kw in REF_SPG_KW:
+        assert kw in sp, ("spg!", kw, sp)
+    # the generic entry points forward every keyword
+    assert "vmlmb(fg!, x0::Array; kwds...)" in src and "spg!(fg!, prj!, x::DeviceVector{T}, m::Integer; kwds...)" in src
+    ref = "/root/reference/src"
+    if os.path.isdir(ref):
+        q = open(os.path.join(ref, "quasinewton.jl")).read()
+        s = open(os.path.join(ref, "spg.jl")).read()
+        assert _signature_keywords(q, "function vmlmb!(fg!, x::T;") == REF_VMLMB_KW
+        assert _signature_keywords(s, "function spg!(fg!, prj!, x, m::Integer;") == REF_SPG_KW
