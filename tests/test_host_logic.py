@@ -301,3 +301,84 @@ def test_python_twin_accepts_the_reference_keywords():
     for name in ("vmlmb", "vmlmb_", "spg", "spg_", "BoundedSet", "MoreThuenteLineSearch", "ArmijoLineSearch",
                  "MoreToraldoLineSearch", "conjgrad", "conjgrad_"):
         assert hasattr(opk, name), name
+
+
+def _random_case(seed):
+    """A random small problem + option set in both vocabularies (oracle keywords, twin keywords)."""
+    rng = np.random.default_rng(1000 + seed)
+    dtype = np.float64 if rng.random() < 0.7 else np.float32
+    rosen = rng.random() < 0.5
+    n = int(rng.choice([2, 6, 50, 200])) if rosen else int(rng.choice([1, 3, 7, 51, 333]))
+    if rosen:
+        x0 = opk.Rosenbrock.x0(n, dtype, perturb_seed=int(rng.integers(1, 99)) if n > 2 else None)
+        obj_o, obj_t = "rosenbrock", opk.Rosenbrock()
+    else:
+        a, c = opk.Quadratic.synthetic(n, dtype, kappa=float(rng.choice([10.0, 1e3])))
+        x0 = rng.random(n).astype(dtype)
+        obj_o, obj_t = ("quadratic", a, c), opk.Quadratic(a, c)
+    # bounds: none | scalar / array, one- or two-sided, around the start
+    def bound(kind, val):
+        if kind == 0:
+            return None
+        if kind == 1:
+            return float(val)
+        return (np.full(n, val) + 0.2 * rng.random(n)).astype(dtype)
+    lk, uk = int(rng.integers(0, 3)), int(rng.integers(0, 3))
+    base = float(x0.min()) if rosen else 0.0
+    top = float(x0.max()) if rosen else 1.0
+    lower = bound(lk, base - 0.3 + 0.5 * rng.random())
+    upper = bound(uk, top + 0.1 + 0.8 * rng.random())
+    bounded = lower is not None or upper is not None
+    okw, tkw = {}, {}
+    mem = int(rng.choice([1, 2, 3, 5, 8]))
+    okw["mem"] = tkw["mem"] = mem
+    if bounded and rng.random() < 0.35:
+        okw["blmvm"] = tkw["blmvm"] = True
+    if rng.random() < 0.3:
+        okw["epsilon"] = tkw["epsilon"] = 0.01
+    if rng.random() < 0.2:
+        okw["fmin"] = tkw["fmin"] = -1.0 if rosen else -1e6
+    r = rng.random()
+    if r < 0.2:
+        ft = float(rng.choice([1e-4, 1e-2]))
+        okw.update(lnsrch=1, ls_ftol=ft); tkw["lnsrch"] = opk.ArmijoLineSearch(ftol=ft)
+    elif r < 0.45:
+        ft, gt = float(rng.choice([1e-3, 1e-2])), float(rng.choice([0.9, 0.5]))
+        okw.update(lnsrch=3, ls_ftol=ft, ls_gtol=gt, ls_xtol=0.1)
+        tkw["lnsrch"] = opk.MoreThuenteLineSearch(ftol=ft, gtol=gt, xtol=0.1)
+    elif r < 0.65:
+        ft, strict = float(rng.choice([1e-3, 1e-4])), bool(rng.random() < 0.5)
+        g1 = float(rng.choice([0.1, 0.25]))
+        okw.update(lnsrch=2, ls_ftol=ft, ls_gamma=(g1, 0.5), ls_strict=strict)
+        tkw["lnsrch"] = opk.MoreToraldoLineSearch(ftol=ft, strict=strict, gamma=(g1, 0.5))
+    if rng.random() < 0.5:
+        okw["maxiter"] = tkw["maxiter"] = int(rng.integers(3, 40))
+    else:
+        okw["maxeval"] = tkw["maxeval"] = int(rng.integers(3, 60))
+    pb = dict(x0=x0, lower=lower, upper=upper, oracle_obj=obj_o, gpu_obj=obj_t)
+    return pb, okw, tkw
+
+
+@pytest.mark.parametrize("seed", range(80))
+def test_stage_machine_equals_oracle_driver_on_random_options(oracle, seed):
+    """The twin's `_vmlmb!` (the same Python that drives the GPU phases) against the oracle's C driver on
+    random combinations of what src/quasinewton.jl:226-293 accepts -- element type, scalar / array / one-sided
+    bounds, mem, BLMVM, epsilon, fmin, the three line searches with their parameters, maxiter / maxeval --:
+    same counts, same reason, the same bits at every iteration."""
+    pb, okw, tkw = _random_case(seed)
+    try:
+        xo, ro, tro = oracle.vmlmb(pb["oracle_obj"], pb["x0"], pb["lower"], pb["upper"], trace=True, **okw)
+        oerr = None
+    except Exception as e:      # (a line search that refuses its start: the twin must refuse too)
+        oerr = e
+    if oerr is not None:
+        with pytest.raises(Exception):
+            _run_host(pb, NumpyOps, **tkw)
+        return
+    s, tr = _run_host(pb, NumpyOps, **tkw)
+    assert (s.iter, s.eval, s.rejects, s.reason) == (ro["iter"], ro["eval"], ro["rejects"], ro["reason"]), (okw, pb["lower"] is None, pb["upper"] is None)
+    assert len(tr) == len(tro)
+    for g, w in zip(tr, tro):
+        assert (g["iter"], g["eval"], g["f"], g["gnorm"], g["stp"]) == (w["iter"], w["eval"], w["f"], w["gnorm"], w["stp"]), (g["iter"], okw)
+        assert np.array_equal(g["x"], w["x"]) and np.array_equal(g["mask"], w["mask"])
+    assert np.array_equal(s.result(), xo)
