@@ -6,11 +6,11 @@
 // (src/quasinewton.jl:542-546), is the step the driver tries exactly 1 (:566-584), does the line
 // search accept it at once (src/linesearches.jl:235-247, :360-381, :536-547), do the convergence
 // tests let the loop go on (:398-423, :437-468), and what are the two-loop coefficients of the next
-// direction (apply_lbfgs!, :716-779) -- and then the next launch.  For small problems that round
-// trip (completion flag over PCIe, host, launch) is a third of the iteration (C1: 20 of 59 us).
+// direction (apply_lbfgs!, :716-779) -- and then the next launch.  That round trip (completion flag
+// over PCIe, host, launch) measures ~8 us on a B200 (C1: 53 us per iteration).
 //
 // CHAIN instances of the kernel take it out of the critical path: the last CTA, once it has combined
-// the partials, runs chain_decide() below -- the very same tests and the same coefficient-space
+// the partials, runs chain_decide_block() below -- the very same tests and the same coefficient-space
 // two-loop recursion, in the same order, on the same Float64 scalars -- and leaves `go` and the
 // coefficients of the NEXT direction in a small device structure.  The host has ALREADY enqueued
 // that next launch (pointers rotated as an accepted step rotates them); its prologue reads the
@@ -20,6 +20,8 @@
 // on them, and ADOPTS the launch that is already in flight only if its own decision and its own
 // coefficients are bit-identical to what the device published (anything else is an internal error,
 // reported loudly).  Trajectories are therefore the same bits with and without the chain.
+// Opt-in (opkb_solver_set_chain): the decision's 2m + 1 dependent Float64 divisions cost ~6.5 us on the
+// GPU, the prologue and the staging ~4.5 us more -- about what the round trip costs.
 #pragma once
 #include <math.h>
 
